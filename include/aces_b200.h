@@ -1,0 +1,134 @@
+/*
+ * aces_b200.h — C ABI of libaces_b200.so: the B200 (sm_100a) implementation of the
+ * ACES estimation hot path of QuantumACES.jl.
+ *
+ * The reference has no FFI for this path (it is plain Julia); the entry points below are
+ * what a Julia shim binds with `ccall` (see INTEGRATION.md and
+ * quantumaces.jl_b200/julia/ACESB200.jl) and what the Python host mirror binds with
+ * ctypes (quantumaces.jl_b200/_lib.py).  Every entry point cites the reference code it
+ * replaces as file:line relative to the reference repository root.
+ *
+ * Conventions
+ *  - All functions return 0 on success, a negative ACES_E_* code on failure; the message
+ *    is available from aces_last_error().
+ *  - The caller owns every buffer it passes in and keeps it alive across the call
+ *    (Julia: GC.@preserve).  The library owns device memory and never keeps a host
+ *    pointer after returning.
+ *  - Pointers marked "host or device" are classified with cudaPointerGetAttributes.
+ *  - Calls are blocking unless stated otherwise and serialised per context; use one
+ *    context per GPU (one process per GPU for multi-GPU runs).
+ *  - There is no CPU fallback anywhere in this library.
+ */
+#ifndef ACES_B200_H
+#define ACES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACES_OK 0
+#define ACES_E_INVALID (-1)    /* bad argument */
+#define ACES_E_CUDA (-2)       /* CUDA runtime/driver error */
+#define ACES_E_NOMEM (-3)      /* allocation failure */
+#define ACES_E_NOT_PD (-4)     /* a covariance block / Gram matrix is not positive definite
+                                  (reference fallback: src/merit.jl:403-424) */
+#define ACES_E_UNSUPPORTED (-5)
+
+typedef struct aces_ctx aces_ctx;
+typedef struct aces_tables aces_tables;
+
+/* ---- context ------------------------------------------------------------------------- */
+
+/* Library ABI version (major*1000 + minor). */
+int32_t aces_version(void);
+
+/* Creates a context on CUDA device `device` (streams, workspaces).  Fails with
+ * ACES_E_CUDA when no sm_100 device is present: there is no CPU path. */
+int32_t aces_init(int32_t device, aces_ctx** out);
+int32_t aces_destroy(aces_ctx* ctx);
+
+/* Last error message of `ctx` (or of the last failed aces_init when ctx == NULL). */
+const char* aces_last_error(const aces_ctx* ctx);
+
+/* Run the library's kernels and copies on `cuda_stream` (a cudaStream_t) instead of the
+ * context's own stream; NULL restores the context's stream.  Lets a host that owns a
+ * stream (e.g. torch) time and order the work. */
+int32_t aces_set_stream(aces_ctx* ctx, void* cuda_stream);
+int32_t aces_synchronize(aces_ctx* ctx);
+
+/* Pinned host memory for sample matrices that are uploaded every call. */
+int32_t aces_host_alloc(aces_ctx* ctx, int64_t bytes, void** out);
+int32_t aces_host_free(aces_ctx* ctx, void* ptr);
+
+/* Number of kernels this context has launched since creation (bench bookkeeping). */
+int64_t aces_kernel_launches(const aces_ctx* ctx);
+
+/* ---- K1: shot records -> odd-parity counts --------------------------------------------
+ *
+ * Replaces pauli_estimate + estimate_experiment (src/estimate.jl:239-301) and the
+ * per-budget inner loop of simulate_stim_estimate (src/simulate.jl:195-234).
+ *
+ * A *Pauli table* lists, per experiment, the measured Paulis as lists of record bits.
+ * Record bit b (0-based) is bit (b % 8) of byte column (b / 8) of a shot record, i.e.
+ * qubit m = b + 1 of src/estimate.jl:249.  It is what get_experiment_data /
+ * get_covariance_experiment_data (src/estimate.jl:308-428) produce from a Design, flattened
+ * once per Design:
+ *   exp_ptr   [n_experiments + 1]  Paulis of experiment e are exp_ptr[e] .. exp_ptr[e+1]-1
+ *   pauli_ptr [n_paulis + 1]       support of Pauli p is pauli_bits[pauli_ptr[p] .. pauli_ptr[p+1]-1]
+ *   pauli_bits                     0-based record bits, each < n_qubits
+ * A bit listed twice in one support cancels (as in the reference, where the per-shot sum is
+ * reduced mod 2).  An empty support is the identity: its odd count is 0.
+ */
+int32_t aces_tables_create(aces_ctx* ctx, int32_t n_qubits, int32_t n_experiments,
+                           const int64_t* exp_ptr, const int64_t* pauli_ptr,
+                           const int32_t* pauli_bits, aces_tables** out);
+int32_t aces_tables_destroy(aces_ctx* ctx, aces_tables* tables);
+
+/* Odd-parity counts of a batch of sample matrices in ONE kernel launch.
+ *
+ *   item i: experiment experiment_ids[i]; sample matrix counts[i] of rows[i] shots,
+ *           column-major bytes, ld[i] bytes between byte columns (Julia Matrix{UInt8}:
+ *           ld = size(counts, 1)), at least ceil(n_qubits / 8) columns; host or device.
+ *   prefix_shots[i*K + k], k < K: nondecreasing shot counts <= rows[i]; count k is taken
+ *           over rows 0 .. prefix_shots[i*K+k]-1 (src/simulate.jl:206-213).
+ *   odd_counts (host or device): for item i a block of E_i * K int64 placed after the
+ *           blocks of items 0..i-1; entry [k * E_i + p] = number of shots among the first
+ *           prefix_shots[i*K+k] whose parity over Pauli p's record bits is odd.
+ *           The reference's pauli_shots (src/estimate.jl:251) is shots - 2 * odd.
+ *   accumulate != 0: add to the values already in odd_counts (batched sampling,
+ *           src/simulate.jl:174-186, without concatenating the batches).
+ *
+ * Device matrices with 16-byte aligned base and ld % 16 == 0 are read in place through the
+ * TMA engine; anything else is first copied into a pitched device buffer.
+ */
+int32_t aces_parity_counts(aces_ctx* ctx, const aces_tables* tables, int32_t n_items,
+                           const int32_t* experiment_ids, const uint8_t* const* counts,
+                           const int64_t* rows, const int64_t* ld, int32_t K,
+                           const int64_t* prefix_shots, int64_t* odd_counts,
+                           int32_t accumulate);
+
+/* Same launch as aces_parity_counts but asynchronous on the context's stream, device
+ * matrices only, odd_counts must be a device pointer.  Used to time the kernel with CUDA
+ * events and to feed NCCL without a host round trip. */
+int32_t aces_parity_counts_async(aces_ctx* ctx, const aces_tables* tables, int32_t n_items,
+                                 const int32_t* experiment_ids, const uint8_t* const* counts,
+                                 const int64_t* rows, const int64_t* ld, int32_t K,
+                                 const int64_t* prefix_shots, int64_t* odd_counts,
+                                 int32_t accumulate);
+
+/* Drop-in for estimate_experiment(counts::Matrix{UInt8}, experiment_meas_indices,
+ * experiment_pauli_signs, shots_value) (src/estimate.jl:284-301): meas_indices are the
+ * reference's 1-based qubit indices in CSR form (meas_ptr [E+1]); est[p] =
+ * ((-1)^sign[p] * (shots_value - 2*odd[p])) / shots_value, the division done in IEEE
+ * double on the host exactly as the reference does. */
+int32_t aces_estimate_experiment(aces_ctx* ctx, const uint8_t* counts, int64_t rows,
+                                 int64_t ld, int32_t n_cols, int32_t E,
+                                 const int64_t* meas_ptr, const int32_t* meas_indices,
+                                 const uint8_t* signs, int64_t shots_value, double* est);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACES_B200_H */

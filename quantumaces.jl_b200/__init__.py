@@ -1,0 +1,9 @@
+"""aces_b200 -- B200-native ACES estimation hot path (K1 parity counts, LS fit, covariance).
+
+The directory is named `quantumaces.jl_b200` (not importable by that name); import it as
+`aces_b200` through the loader module at the repository root.
+"""
+from . import _lib  # noqa: F401
+from ._lib import AcesError, Context, NotPositiveDefinite, PauliTables  # noqa: F401
+from .design import FlatDesign, build_pauli_tables, shots_divide, synthetic_design  # noqa: F401
+from .estimate import DesignEstimator, estimate_experiment  # noqa: F401

@@ -1,0 +1,64 @@
+// aces_common.h — internal definitions shared by the translation units of libaces_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/aces_b200.h"
+
+#define ACES_VERSION 1000
+
+// Growable device / pinned-host buffers owned by the context.
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+};
+
+struct aces_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int smem_optin = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;  // stream in use (own_stream or caller's)
+    cudaEvent_t ev = nullptr;
+    int64_t launches = 0;
+    std::string err;
+
+    // K1 workspaces
+    DevBuf d_arena;    // pitched copies of sample matrices that cannot be read in place
+    DevBuf d_streams;  // stream table + item prefix
+    DevBuf d_seg;      // per-segment odd counts (uint64)
+    DevBuf d_odd;      // cumulative odd counts when the caller's output is on the host
+    DevBuf h_stage;    // pinned staging for the small per-call tables / outputs
+    // fit workspaces are added by fit.cu through this generic pool
+    DevBuf d_work[8];
+};
+
+int aces_fail(aces_ctx* ctx, int code, const char* fmt, ...);
+int aces_reserve_dev(aces_ctx* ctx, DevBuf& b, size_t bytes);
+int aces_reserve_host(aces_ctx* ctx, DevBuf& b, size_t bytes);
+bool aces_is_device_ptr(const void* p);
+
+#define ACES_CUDA(ctx, call)                                                              \
+    do {                                                                                  \
+        cudaError_t _e = (call);                                                          \
+        if (_e != cudaSuccess)                                                            \
+            return aces_fail((ctx), ACES_E_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, \
+                             __LINE__, cudaGetErrorString(_e));                           \
+    } while (0)
+
+#define ACES_CHECK(ctx, cond, ...)                                    \
+    do {                                                              \
+        if (!(cond)) return aces_fail((ctx), ACES_E_INVALID, __VA_ARGS__); \
+    } while (0)
+
+#define ACES_TRY(expr)               \
+    do {                             \
+        int _rc = (expr);            \
+        if (_rc != ACES_OK) return _rc; \
+    } while (0)

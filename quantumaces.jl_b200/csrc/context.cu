@@ -1,0 +1,177 @@
+// context.cu — context lifetime, error reporting and buffer management of libaces_b200.so.
+#include "aces_common.h"
+
+static std::string g_init_err;
+
+int aces_fail(aces_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx)
+        ctx->err = buf;
+    else
+        g_init_err = buf;
+    return code;
+}
+
+int aces_reserve_dev(aces_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return ACES_OK;
+    if (b.ptr) {
+        // The buffer may still be read by work queued on the stream.
+        ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ACES_CUDA(ctx, cudaFree(b.ptr));
+        b.ptr = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.ptr, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&b.ptr, want);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        b.ptr = nullptr;
+        return aces_fail(ctx, ACES_E_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes,
+                         cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return ACES_OK;
+}
+
+int aces_reserve_host(aces_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return ACES_OK;
+    if (b.ptr) {
+        ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ACES_CUDA(ctx, cudaFreeHost(b.ptr));
+        b.ptr = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMallocHost(&b.ptr, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        b.ptr = nullptr;
+        return aces_fail(ctx, ACES_E_NOMEM, "cudaMallocHost of %zu bytes failed: %s", bytes,
+                         cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return ACES_OK;
+}
+
+bool aces_is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+extern "C" {
+
+int32_t aces_version(void) { return ACES_VERSION; }
+
+int32_t aces_init(int32_t device, aces_ctx** out) {
+    if (!out) return aces_fail(nullptr, ACES_E_INVALID, "aces_init: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return aces_fail(nullptr, ACES_E_CUDA,
+                         "aces_init: no CUDA device available (%s); libaces_b200 has no CPU path",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= count)
+        return aces_fail(nullptr, ACES_E_INVALID, "aces_init: device %d out of range [0,%d)",
+                         device, count);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess)
+        return aces_fail(nullptr, ACES_E_CUDA, "cudaGetDeviceProperties: %s",
+                         cudaGetErrorString(e));
+    if (prop.major != 10)
+        return aces_fail(nullptr, ACES_E_UNSUPPORTED,
+                         "aces_init: device %d is sm_%d%d; this library is built for sm_100a only",
+                         device, prop.major, prop.minor);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess)
+        return aces_fail(nullptr, ACES_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    aces_ctx* ctx = new aces_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        int rc = aces_fail(nullptr, ACES_E_CUDA, "stream/event creation: %s", cudaGetErrorString(e));
+        delete ctx;
+        return rc;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return ACES_OK;
+}
+
+int32_t aces_destroy(aces_ctx* ctx) {
+    if (!ctx) return ACES_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* dev[] = {&ctx->d_arena, &ctx->d_streams, &ctx->d_seg, &ctx->d_odd};
+    for (DevBuf* b : dev)
+        if (b->ptr) cudaFree(b->ptr);
+    for (DevBuf& b : ctx->d_work)
+        if (b.ptr) cudaFree(b.ptr);
+    if (ctx->h_stage.ptr) cudaFreeHost(ctx->h_stage.ptr);
+    if (ctx->ev) cudaEventDestroy(ctx->ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return ACES_OK;
+}
+
+const char* aces_last_error(const aces_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_init_err.c_str();
+}
+
+int32_t aces_set_stream(aces_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return ACES_E_INVALID;
+    ACES_CUDA(ctx, cudaSetDevice(ctx->device));
+    ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return ACES_OK;
+}
+
+int32_t aces_synchronize(aces_ctx* ctx) {
+    if (!ctx) return ACES_E_INVALID;
+    ACES_CUDA(ctx, cudaSetDevice(ctx->device));
+    ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ACES_OK;
+}
+
+int32_t aces_host_alloc(aces_ctx* ctx, int64_t bytes, void** out) {
+    if (!ctx || !out || bytes < 0) return ACES_E_INVALID;
+    ACES_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMallocHost(out, (size_t)(bytes > 0 ? bytes : 1));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return aces_fail(ctx, ACES_E_NOMEM, "cudaMallocHost(%lld): %s", (long long)bytes,
+                         cudaGetErrorString(e));
+    }
+    return ACES_OK;
+}
+
+int32_t aces_host_free(aces_ctx* ctx, void* ptr) {
+    if (!ctx) return ACES_E_INVALID;
+    if (ptr) ACES_CUDA(ctx, cudaFreeHost(ptr));
+    return ACES_OK;
+}
+
+int64_t aces_kernel_launches(const aces_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

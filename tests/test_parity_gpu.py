@@ -1,0 +1,310 @@
+"""GPU parity tests for K1: the CUDA kernel (through the C ABI) against the CPU oracle, the
+golden fixture and size-independent properties.  Integer work: the bar is bit-exact."""
+import numpy as np
+import pytest
+
+import oracle_bindings as ob
+from golden_util import parity_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def rand_supports(rng, n, E, max_w=9):
+    sup = []
+    for p in range(E):
+        w = int(rng.choice([1, 1, 1, 2, 2, 2, 3, 4, 5, 7, max_w]))
+        sup.append(sorted((rng.choice(n, size=min(w, n), replace=False) + 1).tolist()))
+    return sup
+
+
+def test_golden_fixture(ctx):
+    import aces_b200
+
+    for case in parity_cases():
+        for k, S in enumerate(case["prefixes"]):
+            est = aces_b200.estimate_experiment(ctx, case["counts"], case["supports"], case["signs"], int(S))
+            assert np.array_equal(est, case["est"][k])
+
+
+@pytest.mark.parametrize("n,rows", [(17, 1), (17, 15), (17, 16), (17, 4097), (49, 1023), (49, 70001),
+                                    (161, 1025), (161, 33333), (577, 257), (577, 5000), (1200, 3000)])
+def test_estimate_experiment_vs_oracle(ctx, n, rows):
+    import aces_b200
+
+    rng = np.random.default_rng(n * 1000 + rows)
+    B = (n + 7) // 8
+    counts = np.asfortranarray(rng.integers(0, 256, size=(rows, B), dtype=np.uint8))
+    sup = rand_supports(rng, n, 97)
+    sup[3] = []                       # identity: eigenvalue (+-)1
+    sup[4] = [sup[5][0], sup[5][0]]   # repeated qubit cancels
+    signs = rng.integers(0, 2, size=len(sup))
+    for S in sorted({1, rows, max(1, rows // 3)}):
+        got = aces_b200.estimate_experiment(ctx, counts, sup, signs, S)
+        want, _ = ob.estimate_experiment(counts, sup, signs, S)
+        assert np.array_equal(got, want)
+
+
+def test_row_major_input_is_accepted(ctx):
+    import aces_b200
+
+    rng = np.random.default_rng(3)
+    counts = rng.integers(0, 256, size=(777, 7), dtype=np.uint8)  # C order, as numpy/Stim produce
+    sup = rand_supports(rng, 49, 20)
+    got = aces_b200.estimate_experiment(ctx, counts, sup, [0] * 20, 777)
+    want, _ = ob.estimate_experiment(counts, sup, [0] * 20, 777)
+    assert np.array_equal(got, want)
+
+
+def test_noiseless_known_answer(ctx):
+    # test/device_tests.jl:144-155 through the CUDA path
+    import aces_b200
+
+    rec = np.zeros((12345, 21), dtype=np.uint8, order="F")
+    sup = [[1], [2, 3], [161], [5, 6, 7, 8], []]
+    assert np.all(aces_b200.estimate_experiment(ctx, rec, sup, [0] * 5, 12345) == 1.0)
+    got = aces_b200.estimate_experiment(ctx, rec, sup, [1, 0, 1, 0, 1], 12345)
+    assert np.array_equal(got, np.array([-1.0, 1.0, -1.0, 1.0, -1.0]))
+
+
+def test_error_behaviour(ctx):
+    import aces_b200
+
+    rec = np.zeros((10, 3), dtype=np.uint8, order="F")
+    with pytest.raises(AssertionError):      # src/estimate.jl:292
+        aces_b200.estimate_experiment(ctx, rec, [[1], [2]], [0], 10)
+    with pytest.raises(aces_b200.AcesError):  # qubit outside the record (Julia: BoundsError)
+        aces_b200.estimate_experiment(ctx, rec, [[25]], [0], 10)
+    with pytest.raises(aces_b200.AcesError):  # more shots than rows (Julia: BoundsError)
+        aces_b200.estimate_experiment(ctx, rec, [[1]], [0], 11)
+
+
+def make_batch(rng, est, fd, shots_set, pad_ld=0):
+    import aces_b200
+
+    shots_divided, shots_max = aces_b200.shots_divide(fd, shots_set)
+    mats, rows, ld, prefix = [], [], [], []
+    for e in range(fd.experiment_number):
+        t = int(est.tuple_of_experiment[e])
+        S = int(shots_max[t])
+        full = np.asfortranarray(rng.integers(0, 256, size=(S + pad_ld, fd.n_bytes), dtype=np.uint8))
+        mats.append(full[:S] if pad_ld else full)
+        rows.append(S)
+        ld.append(S + pad_ld)
+        prefix.append(shots_divided[t])
+    return mats, rows, ld, np.asarray(prefix, dtype=np.int64)
+
+
+@pytest.mark.parametrize("d,gls,stress", [(3, False, False), (3, True, True), (5, True, False)])
+def test_design_batch_vs_oracle(ctx, d, gls, stress):
+    import aces_b200
+
+    fd = aces_b200.synthetic_design("rotated", d, full_covariance=gls, stress_weights=stress)
+    est = aces_b200.DesignEstimator(ctx, fd)
+    rng = np.random.default_rng(d)
+    mats, rows, ld, prefix = make_batch(rng, est, fd, [3_000, 41_111, 200_003])
+    got = est.odd_counts([m.ctypes.data for m in mats], rows, ld, prefix)
+    want = ob.oracle_odd_counts(est, mats, prefix)
+    assert np.array_equal(got, want)
+    # prefix properties: nondecreasing in k and bounded by the prefix length
+    off = 0
+    for e in range(fd.experiment_number):
+        E = est.tables.experiment_size(e)
+        blk = got[off:off + 3 * E].reshape(3, E)
+        assert np.all(np.diff(blk, axis=0) >= 0)
+        assert np.all(blk <= prefix[e][:, None])
+        off += 3 * E
+
+
+def test_simulate_estimate_matches_reference_nesting(ctx):
+    import aces_b200
+
+    fd = aces_b200.synthetic_design("rotated", 3, full_covariance=True)
+    est = aces_b200.DesignEstimator(ctx, fd)
+    rng = np.random.default_rng(9)
+    shots_set = [10_000, 2_000, 77_777]  # deliberately unsorted budgets
+    mats, rows, ld, prefix = make_batch(rng, est, fd, shots_set)
+    eig_set, cov_set = est.simulate_estimate(mats, shots_set)
+    shots_divided, _ = aces_b200.shots_divide(fd, shots_set)
+    # restate src/simulate.jl:195-234 with the oracle
+    e = 0
+    for t in range(fd.tuple_number):
+        want_eig = [[[] for _ in range(int(fd.mapping_lengths[t]))] for _ in shots_set]
+        want_cov = [[[] for _ in range(len(fd.cov_keys[t]))] for _ in shots_set]
+        for j in range(int(fd.experiment_numbers[t])):
+            exp = fd.experiment_ensemble[t][j]
+            cexp = fd.cov_experiment_ensemble[t][j]
+            for s in range(len(shots_set)):
+                S = int(shots_divided[t, s])
+                ee, _ = ob.estimate_experiment(mats[e], [fd.meas_indices[t][p] for p in exp],
+                                               fd.pauli_signs[t][exp], S)
+                for idx, p in enumerate(exp):
+                    want_eig[s][int(p)].append(ee[idx])
+                ce, _ = ob.estimate_experiment(mats[e], [fd.cov_meas_indices[t][c] for c in cexp],
+                                               fd.cov_signs[t][cexp], S)
+                for idx, c in enumerate(cexp):
+                    want_cov[s][int(c)].append(ce[idx])
+            e += 1
+        for s in range(len(shots_set)):
+            assert eig_set[s][t] == want_eig[s]
+            assert cov_set[s][t] == want_cov[s]
+
+
+def test_prefix_edge_cases(ctx):
+    import aces_b200
+
+    rng = np.random.default_rng(21)
+    n, rows = 49, 5000
+    sup = rand_supports(rng, n, 40)
+    ptr, flat = ob._csr(sup)
+    tables = aces_b200.PauliTables(ctx, n, [0, 40], ptr, flat - 1)
+    m = np.asfortranarray(rng.integers(0, 256, size=(rows, 7), dtype=np.uint8))
+    for prefixes in ([0, 0, 5000], [1, 1, 1], [1024, 2048, 4096], [1023, 1025, 4999], [5000], [0],
+                     [17, 17, 17, 900, 5000]):
+        got = aces_b200._lib.parity_counts(ctx, tables, [0], [m], [rows], [rows], [prefixes])
+        K = len(prefixes)
+        want = np.zeros((K, 40), dtype=np.int64)
+        for k, S in enumerate(prefixes):
+            if S > 0:
+                _, ps = ob.estimate_experiment(m, sup, [0] * 40, S)
+                want[k] = (S - ps) // 2
+        assert np.array_equal(got.reshape(K, 40), want)
+    with pytest.raises(aces_b200.AcesError):
+        aces_b200._lib.parity_counts(ctx, tables, [0], [m], [rows], [rows], [[10, 5]])
+    with pytest.raises(aces_b200.AcesError):
+        aces_b200._lib.parity_counts(ctx, tables, [0], [m], [rows], [rows], [[5001]])
+    # empty batch and zero-row matrix
+    got = aces_b200._lib.parity_counts(ctx, tables, [0], [m], [0], [0], [[0, 0]])
+    assert np.array_equal(got, np.zeros(80, dtype=np.int64))
+
+
+def test_batched_accumulate_equals_concatenated(ctx):
+    # src/simulate.jl:174-186: batches are vcat'ed; accumulating per-batch counts must agree
+    import aces_b200
+
+    rng = np.random.default_rng(33)
+    n = 161
+    sup = rand_supports(rng, n, 300)
+    ptr, flat = ob._csr(sup)
+    tables = aces_b200.PauliTables(ctx, n, [0, 300], ptr, flat - 1)
+    batches = ob.batch_shots(10_000, n, 600_000)
+    assert len(batches) > 1
+    mats = [np.asfortranarray(rng.integers(0, 256, size=(int(b), 21), dtype=np.uint8)) for b in batches]
+    whole = np.asfortranarray(np.concatenate(mats, axis=0))
+    prefixes = np.array([700, 4100, 10_000])
+    want = aces_b200._lib.parity_counts(ctx, tables, [0], [whole], [10_000], [10_000], [prefixes])
+    acc = np.zeros(3 * 300, dtype=np.int64)
+    start = 0
+    for mtx in mats:
+        local = np.clip(prefixes - start, 0, mtx.shape[0])
+        aces_b200._lib.parity_counts(ctx, tables, [0], [mtx], [mtx.shape[0]], [mtx.shape[0]], [local],
+                                     out=acc, accumulate=True)
+        start += mtx.shape[0]
+    assert np.array_equal(acc, want)
+    _, odd = ob.simulate_estimate(whole, sup, [0] * 300, prefixes)
+    assert np.array_equal(want.reshape(3, 300), odd)
+
+
+@pytest.mark.parametrize("E", [513, 1500, 2049, 5000])
+def test_many_paulis_per_experiment(ctx, E):
+    # more Paulis than threads: several per thread (PPT 2/4) and Pauli slices beyond 2048
+    import aces_b200
+
+    rng = np.random.default_rng(E)
+    n, rows = 97, 2100
+    sup = rand_supports(rng, n, E)
+    ptr, flat = ob._csr(sup)
+    tables = aces_b200.PauliTables(ctx, n, [0, E], ptr, flat - 1)
+    m = np.asfortranarray(rng.integers(0, 256, size=(rows, 13), dtype=np.uint8))
+    got = aces_b200._lib.parity_counts(ctx, tables, [0], [m], [rows], [rows], [[100, rows]])
+    _, odd = ob.simulate_estimate(m, sup, [0] * E, [100, rows])
+    assert np.array_equal(got.reshape(2, E), odd)
+
+
+def test_device_resident_inputs(ctx):
+    # device matrices: in place (aligned ld) and through the pitched copy (odd ld); device output
+    import torch
+
+    import aces_b200
+
+    rng = np.random.default_rng(55)
+    n, E = 161, 241
+    sup = rand_supports(rng, n, E)
+    ptr, flat = ob._csr(sup)
+    tables = aces_b200.PauliTables(ctx, n, [0, E, 2 * E], np.concatenate([ptr, ptr[1:] + ptr[-1]]),
+                                   np.concatenate([flat, flat]) - 1)
+    for rows, ld in [(40_000, 40_000), (40_001, 40_016), (39_999, 39_999), (12_345, 20_000)]:
+        host = [np.asfortranarray(rng.integers(0, 256, size=(ld, 21), dtype=np.uint8)) for _ in range(2)]
+        dev = [torch.from_numpy(np.ascontiguousarray(h.T)).cuda() for h in host]  # [21, ld] row-major == col-major [ld,21]
+        prefixes = [[rows // 7, rows // 2, rows], [1, 2, rows]]
+        out = torch.zeros(2 * 3 * E, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        aces_b200._lib.parity_counts(ctx, tables, [0, 1], [d.data_ptr() for d in dev], [rows, rows],
+                                     [ld, ld], prefixes, out=out.data_ptr(), asynchronous=True)
+        ctx.synchronize()
+        got = out.cpu().numpy()
+        want = np.concatenate([
+            ob.simulate_estimate(host[i][:rows], sup, [0] * E, prefixes[i])[1].reshape(-1) for i in range(2)
+        ])
+        assert np.array_equal(got, want)
+
+
+def test_full_size_properties(ctx):
+    """BASELINE config 3 size (rotated d=9, 1e8 shots, 2.1 GB): size-independent properties."""
+    import torch
+
+    import aces_b200
+
+    fd = aces_b200.synthetic_design("rotated", 9)
+    est = aces_b200.DesignEstimator(ctx, fd)
+    shots_set = [10**6, 10**7, 10**8]
+    shots_divided, shots_max = aces_b200.shots_divide(fd, shots_set)
+    n_exp, B = fd.experiment_number, fd.n_bytes
+    rows = [int(shots_max[int(est.tuple_of_experiment[e])]) for e in range(n_exp)]
+    ld = [(r + 127) // 128 * 128 for r in rows]
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    dev = [torch.randint(0, 256, (B, ld[e]), dtype=torch.uint8, device="cuda", generator=g) for e in range(n_exp)]
+    prefix = np.stack([shots_divided[int(est.tuple_of_experiment[e])] for e in range(n_exp)])
+    total = int(np.sum(est.experiment_sizes()) * 3)
+    out = torch.zeros(total, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+
+    def run():
+        est.odd_counts([d.data_ptr() for d in dev], rows, ld, prefix, out=out.data_ptr(), asynchronous=True)
+        ctx.synchronize()
+        return out.cpu().numpy().copy()
+
+    got = run()
+    # (1) independent check of a sample of Paulis with plain torch bit arithmetic
+    rng = np.random.default_rng(0)
+    off = np.concatenate([[0], np.cumsum(est.experiment_sizes() * 3)])
+    for e in rng.choice(n_exp, size=6, replace=False):
+        E = est.tables.experiment_size(int(e))
+        sup = ob.table_supports(est, int(e))
+        for p in rng.choice(E, size=5, replace=False):
+            acc = torch.zeros(rows[e], dtype=torch.uint8, device="cuda")
+            for q in sup[p]:
+                acc ^= (dev[e][(q - 1) // 8, :rows[e]] >> ((q - 1) % 8)) & 1
+            csum = torch.cumsum(acc.to(torch.int64), 0)
+            for k in range(3):
+                S = int(prefix[e, k])
+                assert got[off[e] + k * E + p] == int(csum[S - 1])
+    # (2) idempotence / determinism of the atomics-based reduction
+    assert np.array_equal(got, run())
+    # (3) complement: flipping every record bit maps odd -> S - odd for odd-weight Paulis and
+    #     leaves even-weight Paulis unchanged
+    for d in dev:
+        d.bitwise_not_()
+    torch.cuda.synchronize()  # the library runs on its own stream
+    flipped = run()
+    for e in range(n_exp):
+        E = est.tables.experiment_size(e)
+        w = np.array([len(s) for s in ob.table_supports(est, e)])
+        a = got[off[e]:off[e + 1]].reshape(3, E)
+        b = flipped[off[e]:off[e + 1]].reshape(3, E)
+        S = prefix[e][:, None]
+        assert np.array_equal(np.where(w % 2 == 1, S - a, a), b)
+    # (4) all-zero records: no odd parities at all (noiseless known answer at full size)
+    for d in dev:
+        d.zero_()
+    torch.cuda.synchronize()
+    assert not run().any()
