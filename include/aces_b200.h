@@ -65,6 +65,12 @@ int32_t aces_host_free(aces_ctx* ctx, void* ptr);
 /* Number of kernels this context has launched since creation (bench bookkeeping). */
 int64_t aces_kernel_launches(const aces_ctx* ctx);
 
+/* With timing on, the dominant kernel of each call (K1: the parity kernel) is bracketed by
+ * CUDA events on the stream it is launched on; aces_last_kernel_ms waits for the last one
+ * and returns its duration.  Used by bench.py for the roofline figure. */
+int32_t aces_set_timing(aces_ctx* ctx, int32_t on);
+int32_t aces_last_kernel_ms(aces_ctx* ctx, float* ms);
+
 /* ---- K1: shot records -> odd-parity counts --------------------------------------------
  *
  * Replaces pauli_estimate + estimate_experiment (src/estimate.jl:239-301) and the

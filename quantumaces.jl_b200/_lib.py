@@ -49,6 +49,8 @@ SIGNATURES = {
     "aces_host_alloc": (_i32, [_vp, _i64, _p(_vp)]),
     "aces_host_free": (_i32, [_vp, _vp]),
     "aces_kernel_launches": (_i64, [_vp]),
+    "aces_set_timing": (_i32, [_vp, _i32]),
+    "aces_last_kernel_ms": (_i32, [_vp, _p(C.c_float)]),
     "aces_tables_create": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _p(_vp)]),
     "aces_tables_destroy": (_i32, [_vp, _vp]),
     "aces_parity_counts": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32]),
@@ -132,6 +134,14 @@ class Context:
 
     def kernel_launches(self) -> int:
         return int(self.lib.aces_kernel_launches(self.handle))
+
+    def set_timing(self, on: bool) -> None:
+        self.check(self.lib.aces_set_timing(self.handle, 1 if on else 0))
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        self.check(self.lib.aces_last_kernel_ms(self.handle, C.byref(ms)))
+        return float(ms.value)
 
     def host_alloc(self, nbytes: int) -> np.ndarray:
         """Pinned host buffer as a uint8 numpy array (freed with host_free)."""

@@ -26,6 +26,9 @@ struct aces_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;  // stream in use (own_stream or caller's)
     cudaEvent_t ev = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;  // bracket the dominant kernel when timing is on
+    int timing = 0;
+    int timed = 0;
     int64_t launches = 0;
     std::string err;
 

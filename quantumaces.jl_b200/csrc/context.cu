@@ -108,6 +108,8 @@ int32_t aces_init(int32_t device, aces_ctx** out) {
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->t0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->t1);
     if (e != cudaSuccess) {
         int rc = aces_fail(nullptr, ACES_E_CUDA, "stream/event creation: %s", cudaGetErrorString(e));
         delete ctx;
@@ -129,6 +131,8 @@ int32_t aces_destroy(aces_ctx* ctx) {
         if (b.ptr) cudaFree(b.ptr);
     if (ctx->h_stage.ptr) cudaFreeHost(ctx->h_stage.ptr);
     if (ctx->ev) cudaEventDestroy(ctx->ev);
+    if (ctx->t0) cudaEventDestroy(ctx->t0);
+    if (ctx->t1) cudaEventDestroy(ctx->t1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return ACES_OK;
@@ -173,5 +177,21 @@ int32_t aces_host_free(aces_ctx* ctx, void* ptr) {
 }
 
 int64_t aces_kernel_launches(const aces_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t aces_set_timing(aces_ctx* ctx, int32_t on) {
+    if (!ctx) return ACES_E_INVALID;
+    ctx->timing = on ? 1 : 0;
+    ctx->timed = 0;
+    return ACES_OK;
+}
+
+int32_t aces_last_kernel_ms(aces_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return ACES_E_INVALID;
+    ACES_CHECK(ctx, ctx->timed, "last_kernel_ms: no timed kernel (call aces_set_timing(ctx, 1) first)");
+    ACES_CUDA(ctx, cudaSetDevice(ctx->device));
+    ACES_CUDA(ctx, cudaEventSynchronize(ctx->t1));
+    ACES_CUDA(ctx, cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return ACES_OK;
+}
 
 }  // extern "C"

@@ -431,8 +431,13 @@ int launch_parity(aces_ctx* ctx, const ParityParams& P, const TileCfg& cfg) {
                          cfg.smem);
     int64_t grid = (int64_t)ctx->sm_count * per_sm;
     if (grid > P.total_items) grid = P.total_items;
+    if (ctx->timing) ACES_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
     kern<<<(unsigned)grid, NT, cfg.smem, ctx->stream>>>(P);
     ACES_CUDA(ctx, cudaGetLastError());
+    if (ctx->timing) {
+        ACES_CUDA(ctx, cudaEventRecord(ctx->t1, ctx->stream));
+        ctx->timed = 1;
+    }
     ctx->launches += 1;
     return ACES_OK;
 }
