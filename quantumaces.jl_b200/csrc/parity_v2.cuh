@@ -1,0 +1,367 @@
+// parity_v2.cuh -- K1 kernel, warp-autonomous variant (the default path).
+//
+// One CTA = NW consumer warps + 1 producer warp around a shared-memory ring of NS stages.
+//   producer warp : per work item (one TS = NW*SUB shot tile of a stream) waits for the stage to
+//                   be empty, writes the item descriptor, arms the stage's "full" mbarrier with
+//                   the byte count and issues B bulk-async copies (TMA engine, SASS UBLKCP),
+//                   one per byte column.
+//   consumer warp w: owns rows [w*SUB, (w+1)*SUB) of every tile.  It waits on "full", runs
+//                   phase A (8x32-bit butterfly transposition of its rows into private bit
+//                   planes), arrives on "empty" (the raw stage is no longer needed), then runs
+//                   phase B: lane l owns Paulis l, l+32, ... of the experiment; each is the XOR
+//                   of a few plane rows (128-bit shared loads) + popcount into a register.
+// There is no CTA-wide barrier in steady state: warps drift up to NS tiles apart, which absorbs
+// the imbalance of either phase.  Consumers meet on a named barrier only when the stream
+// (experiment, budget segment) changes, to flush the per-Pauli counts: registers -> shared
+// (atomics across the NW warps) -> one 64-bit global atomic per Pauli.
+#pragma once
+#include "parity_common.cuh"
+
+namespace k1 {
+
+constexpr int V2_MAX_STAGES = 8;
+constexpr int V2_OFF_EMPTY = 64;
+constexpr int V2_OFF_DESC = 128;
+constexpr int V2_OFF_SACC = V2_OFF_DESC + V2_MAX_STAGES * 64;  // 640
+
+__host__ __device__ constexpr uint32_t v2_planes_off(int rmax) {
+    return (uint32_t)((V2_OFF_SACC + 4 * 32 * rmax + 127) & ~127);
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// Phase A for one warp: rows [row0, row0 + SUB) of every byte column of the stage -> the warp's
+// private planes.  Plane row of record bit q = 8c + k is row (k * B + c) (k-major: lanes of a
+// warp then store to consecutive words), SUB/8 bytes per row.
+template <int SUB, bool MASKED>
+__device__ __forceinline__ void v2_phase_a(uint32_t stage_s, uint32_t planes_s, int B, int CS,
+                                           int lane, int lo, int hi) {
+    constexpr int UPS = SUB / 32;  // 32-shot units per byte column
+    const int nunits = B * UPS;
+    const uint32_t kstride = (uint32_t)(B * UPS * 4);
+    for (int unit = lane; unit < nunits; unit += 32) {
+        const int c = unit / UPS;
+        const int u = unit - c * UPS;
+        const uint32_t col = stage_s + (uint32_t)(c * CS + 16 * u);
+        uint4 a = lds128(col);
+        uint4 b = lds128(col + SUB / 2);
+        if (MASKED) {
+            a = mask_rows(a, 16 * u, lo, hi);
+            b = mask_rows(b, SUB / 2 + 16 * u, lo, hi);
+        }
+        uint32_t w0 = a.x, w1 = a.y, w2 = a.z, w3 = a.w;
+        uint32_t w4 = b.x, w5 = b.y, w6 = b.z, w7 = b.w;
+        ACES_BFLY(w0, w1, 0x55555555u, 1) ACES_BFLY(w2, w3, 0x55555555u, 1)
+        ACES_BFLY(w4, w5, 0x55555555u, 1) ACES_BFLY(w6, w7, 0x55555555u, 1)
+        ACES_BFLY(w0, w2, 0x33333333u, 2) ACES_BFLY(w1, w3, 0x33333333u, 2)
+        ACES_BFLY(w4, w6, 0x33333333u, 2) ACES_BFLY(w5, w7, 0x33333333u, 2)
+        ACES_BFLY(w0, w4, 0x0F0F0F0Fu, 4) ACES_BFLY(w1, w5, 0x0F0F0F0Fu, 4)
+        ACES_BFLY(w2, w6, 0x0F0F0F0Fu, 4) ACES_BFLY(w3, w7, 0x0F0F0F0Fu, 4)
+        const uint32_t pl = planes_s + (uint32_t)((c * UPS + u) * 4);
+        sts32(pl + 0 * kstride, w0); sts32(pl + 1 * kstride, w1);
+        sts32(pl + 2 * kstride, w2); sts32(pl + 3 * kstride, w3);
+        sts32(pl + 4 * kstride, w4); sts32(pl + 5 * kstride, w5);
+        sts32(pl + 6 * kstride, w6); sts32(pl + 7 * kstride, w7);
+    }
+}
+
+template <int NW, int SUB, int RMAX>
+__global__ void __launch_bounds__((NW + 1) * 32) parity_kernel_v2(const ParityParams P) {
+    constexpr int TS = NW * SUB;
+    constexpr int CS = TS + 64;     // raw column stride: +64 B keeps quarter-warp LDS.128 conflict-free
+    constexpr int V = SUB / 128;    // 128-shot vectors per plane row
+    constexpr int ROWB = SUB / 8;   // bytes per plane row
+    constexpr int NCT = NW * 32;    // consumer threads
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = reinterpret_cast<uint64_t*>(smem + V2_OFF_EMPTY);
+    ItemDesc* sdesc = reinterpret_cast<ItemDesc*>(smem + V2_OFF_DESC);
+    uint32_t* sacc = reinterpret_cast<uint32_t*>(smem + V2_OFF_SACC);
+    const int B = P.B;
+    const int NS = P.NS;
+    const uint32_t planes_bytes = (uint32_t)((8 * B + 1) * ROWB);  // + one all-zero row
+    const uint32_t planes_off = v2_planes_off(RMAX);
+    const uint32_t raw_off = (planes_off + NW * planes_bytes + 127u) & ~127u;
+    const uint32_t stage_bytes = (uint32_t)(B * CS);
+    const uint32_t smem_s = smem_u32(smem);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
+
+    const int64_t i0 = (P.total_items * (int64_t)blockIdx.x) / gridDim.x;
+    const int64_t i1 = (P.total_items * (int64_t)(blockIdx.x + 1)) / gridDim.x;
+    if (i0 >= i1) return;
+    const int n_my = (int)(i1 - i0);
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int p = tid; p < 32 * RMAX; p += (NW + 1) * 32) sacc[p] = 0;
+    __syncthreads();
+
+    if (warp == NW) {
+        // ================================ producer warp ========================================
+        uint64_t policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        int prod_stream = 0;
+        int stage = 0;
+        uint32_t parity = 1;  // a fresh mbarrier passes a wait on parity 1
+        for (int it = 0; it < n_my; ++it) {
+            mbar_wait(&empty[stage], parity);
+            ItemDesc* d = &sdesc[stage];
+            if (lane == 0) {
+                const int64_t item = i0 + it;
+                int s = prod_stream;
+                if (!(P.item_start[s] <= item && item < P.item_start[s + 1])) {
+                    int a = 0, b = P.n_streams;
+                    while (b - a > 1) {
+                        int m = (a + b) >> 1;
+                        if (P.item_start[m] <= item) a = m; else b = m;
+                    }
+                    s = a;
+                    prod_stream = s;
+                }
+                const StreamDesc sd = P.streams[s];
+                const int64_t r0 = (sd.tile_first + (item - P.item_start[s])) * TS;
+                const int64_t avail = sd.copy_rows - r0;
+                const uint32_t bytes = (uint32_t)(avail < TS ? avail : TS);
+                const int64_t lo = sd.lo - r0, hi = sd.hi - r0;
+                d->stream = s;
+                d->lo_rel = (int32_t)(lo > 0 ? lo : 0);
+                d->hi_rel = (int32_t)(hi < TS ? hi : TS);
+                d->boundary = (lo > 0) || (hi < TS);
+                d->src = sd.base + r0;
+                d->ld = sd.ld;
+                d->bytes = bytes;
+                mbar_arrive_expect_tx(&full[stage], bytes * (uint32_t)B);
+            }
+            __syncwarp();
+            const uint8_t* src = d->src;
+            const int64_t ld = d->ld;
+            const uint32_t bytes = d->bytes;
+            uint8_t* dst = smem + raw_off + (size_t)stage * stage_bytes;
+            for (int c = lane; c < B; c += 32)
+                bulk_g2s(dst + c * CS, src + (int64_t)c * ld, bytes, &full[stage], policy);
+            if (++stage == NS) { stage = 0; parity ^= 1u; }
+        }
+        return;
+    }
+
+    // ================================== consumer warps =========================================
+    const uint32_t planes_s = smem_s + planes_off + (uint32_t)warp * planes_bytes;
+    uint32_t acc[RMAX];
+    uint32_t dx[RMAX];  // weight-1 rounds: plane-row offset; weight<=2 rounds: a0 | a1 << 16
+    const uint32_t zero_row = (uint32_t)(8 * B * ROWB);
+    for (int i = lane; i < ROWB / 4; i += 32) sts32(planes_s + zero_row + 4 * i, 0u);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) { acc[r] = 0; dx[r] = 0; }
+    // rounds whose Paulis all have weight 1 / weight <= 2 (a missing second bit, an identity
+    // Pauli or a lane past the end of the table points at the all-zero row)
+    uint32_t w1mask = 0, w2mask = 0;
+    int R = 0;                        // rounds in use
+    int E = 0;
+    int cur_stream = -1;
+    int64_t cur_out = 0, cur_poff = 0;
+    uint32_t tiles_since_flush = 0;
+
+    auto row_off = [&](uint32_t q) -> uint32_t {  // plane-row byte offset of record bit q
+        return ((q & 7u) * (uint32_t)B + (q >> 3)) * (uint32_t)ROWB;
+    };
+
+    // registers -> shared -> global; then (optionally) load the Pauli slice of stream `ns`
+    auto change_stream = [&](int ns) {
+        if (cur_stream >= 0) {
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                const int p = r * 32 + lane;
+                if (r < R && p < E && acc[r] != 0) atomicAdd(&sacc[p], acc[r]);
+                acc[r] = 0;
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
+        if (cur_stream >= 0) {
+            for (int p = tid; p < E; p += NCT) {
+                const uint32_t v = sacc[p];
+                if (v != 0) {
+                    const int orig = P.pauli[cur_poff + p].orig;
+                    atomicAdd(&P.seg[cur_out + orig], (unsigned long long)v);
+                    sacc[p] = 0;
+                }
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
+        tiles_since_flush = 0;
+        if (ns < 0 || ns == cur_stream) return;
+        cur_stream = ns;
+        const StreamDesc* sd = &P.streams[ns];
+        cur_out = sd->out_off;
+        cur_poff = sd->pauli_off;
+        E = sd->E;
+        R = (E + 31) >> 5;
+        w1mask = 0;
+        w2mask = 0;
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            const int p = r * 32 + lane;
+            int w = 0;
+            uint32_t a0 = zero_row, a1 = zero_row;
+            if (r < R && p < E) {
+                const uint4* pd4 = reinterpret_cast<const uint4*>(&P.pauli[cur_poff + p]);
+                const uint4 qa = __ldg(pd4);
+                w = (int)__ldg(reinterpret_cast<const uint32_t*>(pd4 + 1));
+                if (w >= 1) a0 = row_off(qa.x);
+                if (w >= 2) a1 = row_off(qa.y);
+            }
+            const bool all1 = __all_sync(0xffffffffu, w == 1);
+            const bool all2 = __all_sync(0xffffffffu, w <= 2);
+            dx[r] = all1 ? a0 : (a0 | (a1 << 16));
+            if (all1) w1mask |= 1u << r;
+            else if (all2) w2mask |= 1u << r;
+        }
+    };
+
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int it = 0; it < n_my; ++it) {
+        mbar_wait(&full[stage], parity);
+        const int4 d = *reinterpret_cast<const int4*>(&sdesc[stage]);  // stream, lo_rel, hi_rel, boundary
+        if (d.x != cur_stream || tiles_since_flush >= (1u << 19)) change_stream(d.x);
+        ++tiles_since_flush;
+
+        // rows of this warp relative to its sub-tile start
+        const int lo = d.y - warp * SUB, hi = d.z - warp * SUB;
+        const bool any = (hi > 0) && (lo < SUB);
+        const uint32_t stage_s = smem_s + raw_off + (uint32_t)stage * stage_bytes + (uint32_t)(warp * SUB);
+        if (any) {
+            if (lo > 0 || hi < SUB)
+                v2_phase_a<SUB, true>(stage_s, planes_s, B, CS, lane, lo, hi);
+            else
+                v2_phase_a<SUB, false>(stage_s, planes_s, B, CS, lane, 0, SUB);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);  // the raw stage may be refilled
+
+        if (any) {
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                if (r < R) {
+                    uint32_t cnt = 0;
+                    if ((w1mask >> r) & 1u) {
+                        const uint32_t a0 = planes_s + dx[r];
+#pragma unroll
+                        for (int v = 0; v < V; ++v) cnt += popc4(lds128(a0 + 16 * v));
+                    } else if ((w2mask >> r) & 1u) {
+                        const uint32_t a0 = planes_s + (dx[r] & 0xFFFFu);
+                        const uint32_t a1 = planes_s + (dx[r] >> 16);
+#pragma unroll
+                        for (int v = 0; v < V; ++v)
+                            cnt += popc4(xor4(lds128(a0 + 16 * v), lds128(a1 + 16 * v)));
+                    } else {
+                        // mixed weights or supports wider than two bits: table-driven
+                        const int p = r * 32 + lane;
+                        if (p < E) {
+                            const PauliDesc* pd = &P.pauli[cur_poff + p];
+                            const int w = pd->w;
+                            const int ext = pd->ext;
+                            for (int v = 0; v < V && w > 0; ++v) {
+                                uint4 x = make_uint4(0, 0, 0, 0);
+                                for (int k = 0; k < w; ++k) {
+                                    const uint32_t q = (uint32_t)__ldg(&P.bits[ext + k]);
+                                    x = xor4(x, lds128(planes_s + row_off(q) + 16 * v));
+                                }
+                                cnt += popc4(x);
+                            }
+                        }
+                    }
+                    acc[r] += cnt;
+                }
+            }
+        }
+        __syncwarp();  // every lane is done with the planes before the next phase A overwrites them
+        if (++stage == NS) { stage = 0; parity ^= 1u; }
+    }
+    change_stream(-1);
+}
+
+struct V2Cfg {
+    int NW, SUB, RMAX, NS;
+    size_t smem;
+};
+
+// Chooses the v2 tiling for B byte columns and up to max_E Paulis per slice.  Returns false when
+// the shape is outside what v2 covers (the caller falls back to the v1 kernel).
+inline bool v2_pick(int B, int max_E, int smem_optin, V2Cfg* cfg) {
+    int SUB;
+    if (B <= 6) SUB = 512;
+    else if (B <= 12) SUB = 256;
+    else if (B <= 40) SUB = 128;
+    else return false;
+    const int NW = 8;
+    if ((8 * B + 1) * (SUB / 8) >= 65536) return false;  // plane-row offsets are packed in 16 bits
+    const int RMAX = max_E <= 256 ? 8 : (max_E <= 512 ? 16 : 32);
+    const size_t planes = (size_t)NW * (8 * B + 1) * (SUB / 8);
+    const size_t raw_off = (v2_planes_off(RMAX) + planes + 127) & ~(size_t)127;
+    const size_t stage = (size_t)B * (NW * SUB + 64);
+    const char* env_ns = getenv("ACES_K1_NS");
+    const char* env_cta = getenv("ACES_K1_CTAS");
+    const int want_ctas = env_cta ? atoi(env_cta) : 2;
+    const size_t budget = ((size_t)smem_optin + 1024) / (size_t)(want_ctas > 0 ? want_ctas : 1) - 1024;
+    int ns = 0;
+    for (int s = (env_ns ? atoi(env_ns) : 4); s >= 2; --s)
+        if (raw_off + s * stage <= budget) { ns = s; break; }
+    if (ns == 0)
+        for (int s = 4; s >= 2; --s)
+            if (raw_off + s * stage <= (size_t)smem_optin) { ns = s; break; }
+    if (ns == 0) return false;
+    cfg->NW = NW;
+    cfg->SUB = SUB;
+    cfg->RMAX = RMAX;
+    cfg->NS = ns;
+    cfg->smem = raw_off + ns * stage;
+    return true;
+}
+
+template <int NW, int SUB, int RMAX>
+int v2_launch_t(aces_ctx* ctx, const ParityParams& P, const V2Cfg& cfg) {
+    auto kern = parity_kernel_v2<NW, SUB, RMAX>;
+    ACES_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    int per_sm = 0;
+    ACES_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (NW + 1) * 32, cfg.smem));
+    if (per_sm < 1)
+        return aces_fail(ctx, ACES_E_UNSUPPORTED, "parity kernel v2 does not fit on an SM (smem %zu)", cfg.smem);
+    int64_t grid = (int64_t)ctx->sm_count * per_sm;
+    if (grid > P.total_items) grid = P.total_items;
+    if (ctx->timing) ACES_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
+    kern<<<(unsigned)grid, (NW + 1) * 32, cfg.smem, ctx->stream>>>(P);
+    ACES_CUDA(ctx, cudaGetLastError());
+    if (ctx->timing) {
+        ACES_CUDA(ctx, cudaEventRecord(ctx->t1, ctx->stream));
+        ctx->timed = 1;
+    }
+    ctx->launches += 1;
+    return ACES_OK;
+}
+
+inline int v2_launch(aces_ctx* ctx, const ParityParams& P, const V2Cfg& cfg) {
+#define ACES_V2_R(NWV, SUBV)                                                            \
+    (cfg.RMAX == 8 ? v2_launch_t<NWV, SUBV, 8>(ctx, P, cfg)                             \
+                   : cfg.RMAX == 16 ? v2_launch_t<NWV, SUBV, 16>(ctx, P, cfg)           \
+                                    : v2_launch_t<NWV, SUBV, 32>(ctx, P, cfg))
+    if (cfg.SUB == 128) return ACES_V2_R(8, 128);
+    if (cfg.SUB == 256) return ACES_V2_R(8, 256);
+    return ACES_V2_R(8, 512);
+#undef ACES_V2_R
+}
+
+}  // namespace k1
