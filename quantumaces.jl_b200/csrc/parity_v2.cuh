@@ -35,15 +35,17 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+
 // Phase A for one warp: rows [row0, row0 + SUB) of every byte column of the stage -> the warp's
-// private planes.  Plane row of record bit q = 8c + k is row (k * B + c) (k-major: lanes of a
-// warp then store to consecutive words), SUB/8 bytes per row.
-template <int SUB, bool MASKED>
+// private planes.  Plane row of record bit q = 8c + k is row (k * BMAX + c) (k-major: lanes of a
+// warp then store to consecutive words; the compile-time row stride keeps the eight stores of a
+// unit on immediate offsets), SUB/8 bytes per row.
+template <int SUB, int BMAX, bool MASKED>
 __device__ __forceinline__ void v2_phase_a(uint32_t stage_s, uint32_t planes_s, int B, int CS,
                                            int lane, int lo, int hi) {
     constexpr int UPS = SUB / 32;  // 32-shot units per byte column
     const int nunits = B * UPS;
-    const uint32_t kstride = (uint32_t)(B * UPS * 4);
+    constexpr uint32_t kstride = (uint32_t)(BMAX * UPS * 4);
     for (int unit = lane; unit < nunits; unit += 32) {
         const int c = unit / UPS;
         const int u = unit - c * UPS;
@@ -70,7 +72,8 @@ __device__ __forceinline__ void v2_phase_a(uint32_t stage_s, uint32_t planes_s, 
     }
 }
 
-template <int NW, int SUB, int RMAX>
+// BMAX = byte columns the plane layout is dimensioned for (B <= BMAX).
+template <int NW, int SUB, int BMAX, int RMAX>
 __global__ void __launch_bounds__((NW + 1) * 32) parity_kernel_v2(const ParityParams P) {
     constexpr int TS = NW * SUB;
     constexpr int CS = TS + 64;     // raw column stride: +64 B keeps quarter-warp LDS.128 conflict-free
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__((NW + 1) * 32) parity_kernel_v2(const ParityPa
     uint32_t* sacc = reinterpret_cast<uint32_t*>(smem + V2_OFF_SACC);
     const int B = P.B;
     const int NS = P.NS;
-    const uint32_t planes_bytes = (uint32_t)((8 * B + 1) * ROWB);  // + one all-zero row
+    constexpr uint32_t planes_bytes = (uint32_t)((8 * BMAX + 1) * ROWB);  // + one all-zero row
     const uint32_t planes_off = v2_planes_off(RMAX);
     const uint32_t raw_off = (planes_off + NW * planes_bytes + 127u) & ~127u;
     const uint32_t stage_bytes = (uint32_t)(B * CS);
@@ -161,14 +164,14 @@ __global__ void __launch_bounds__((NW + 1) * 32) parity_kernel_v2(const ParityPa
     const uint32_t planes_s = smem_s + planes_off + (uint32_t)warp * planes_bytes;
     uint32_t acc[RMAX];
     uint32_t dx[RMAX];  // weight-1 rounds: plane-row offset; weight<=2 rounds: a0 | a1 << 16
-    const uint32_t zero_row = (uint32_t)(8 * B * ROWB);
+    constexpr uint32_t zero_row = (uint32_t)(8 * BMAX * ROWB);
     for (int i = lane; i < ROWB / 4; i += 32) sts32(planes_s + zero_row + 4 * i, 0u);
     __syncwarp();
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) { acc[r] = 0; dx[r] = 0; }
     // rounds whose Paulis all have weight 1 / weight <= 2 (a missing second bit, an identity
     // Pauli or a lane past the end of the table points at the all-zero row)
-    uint32_t w1mask = 0, w2mask = 0;
+    int n1 = 0, n12 = 0;  // rounds [0,n1): weight 1; [n1,n12): weight <= 2; [n12,R): table-driven
     int R = 0;                        // rounds in use
     int E = 0;
     int cur_stream = -1;
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__((NW + 1) * 32) parity_kernel_v2(const ParityPa
     uint32_t tiles_since_flush = 0;
 
     auto row_off = [&](uint32_t q) -> uint32_t {  // plane-row byte offset of record bit q
-        return ((q & 7u) * (uint32_t)B + (q >> 3)) * (uint32_t)ROWB;
+        return ((q & 7u) * (uint32_t)BMAX + (q >> 3)) * (uint32_t)ROWB;
     };
 
     // registers -> shared -> global; then (optionally) load the Pauli slice of stream `ns`
@@ -209,8 +212,8 @@ __global__ void __launch_bounds__((NW + 1) * 32) parity_kernel_v2(const ParityPa
         cur_poff = sd->pauli_off;
         E = sd->E;
         R = (E + 31) >> 5;
-        w1mask = 0;
-        w2mask = 0;
+        n1 = 0;
+        n12 = 0;
 #pragma unroll
         for (int r = 0; r < RMAX; ++r) {
             const int p = r * 32 + lane;
@@ -225,9 +228,10 @@ __global__ void __launch_bounds__((NW + 1) * 32) parity_kernel_v2(const ParityPa
             }
             const bool all1 = __all_sync(0xffffffffu, w == 1);
             const bool all2 = __all_sync(0xffffffffu, w <= 2);
-            dx[r] = all1 ? a0 : (a0 | (a1 << 16));
-            if (all1) w1mask |= 1u << r;
-            else if (all2) w2mask |= 1u << r;
+            // the table is sorted by weight, so the classes are prefixes of the round list
+            if (all1 && n1 == r) n1 = r + 1;
+            if (all2 && n12 == r && r < R) n12 = r + 1;
+            dx[r] = (a0 | (a1 << 16));
         }
     };
 
@@ -245,9 +249,9 @@ __global__ void __launch_bounds__((NW + 1) * 32) parity_kernel_v2(const ParityPa
         const uint32_t stage_s = smem_s + raw_off + (uint32_t)stage * stage_bytes + (uint32_t)(warp * SUB);
         if (any) {
             if (lo > 0 || hi < SUB)
-                v2_phase_a<SUB, true>(stage_s, planes_s, B, CS, lane, lo, hi);
+                v2_phase_a<SUB, BMAX, true>(stage_s, planes_s, B, CS, lane, lo, hi);
             else
-                v2_phase_a<SUB, false>(stage_s, planes_s, B, CS, lane, 0, SUB);
+                v2_phase_a<SUB, BMAX, false>(stage_s, planes_s, B, CS, lane, 0, SUB);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);  // the raw stage may be refilled
@@ -255,36 +259,41 @@ __global__ void __launch_bounds__((NW + 1) * 32) parity_kernel_v2(const ParityPa
         if (any) {
 #pragma unroll
             for (int r = 0; r < RMAX; ++r) {
-                if (r < R) {
+                if (r < n12) {
+                    const uint32_t a0 = planes_s + (dx[r] & 0xFFFFu);
                     uint32_t cnt = 0;
-                    if ((w1mask >> r) & 1u) {
-                        const uint32_t a0 = planes_s + dx[r];
+                    if (r < n1) {
 #pragma unroll
                         for (int v = 0; v < V; ++v) cnt += popc4(lds128(a0 + 16 * v));
-                    } else if ((w2mask >> r) & 1u) {
-                        const uint32_t a0 = planes_s + (dx[r] & 0xFFFFu);
+                    } else {
                         const uint32_t a1 = planes_s + (dx[r] >> 16);
 #pragma unroll
                         for (int v = 0; v < V; ++v)
                             cnt += popc4(xor4(lds128(a0 + 16 * v), lds128(a1 + 16 * v)));
-                    } else {
-                        // mixed weights or supports wider than two bits: table-driven
-                        const int p = r * 32 + lane;
-                        if (p < E) {
-                            const PauliDesc* pd = &P.pauli[cur_poff + p];
-                            const int w = pd->w;
-                            const int ext = pd->ext;
-                            for (int v = 0; v < V && w > 0; ++v) {
-                                uint4 x = make_uint4(0, 0, 0, 0);
-                                for (int k = 0; k < w; ++k) {
-                                    const uint32_t q = (uint32_t)__ldg(&P.bits[ext + k]);
-                                    x = xor4(x, lds128(planes_s + row_off(q) + 16 * v));
-                                }
-                                cnt += popc4(x);
-                            }
-                        }
                     }
                     acc[r] += cnt;
+                }
+            }
+            if (n12 < R) {
+                // supports wider than two bits: table-driven
+#pragma unroll
+                for (int r = 0; r < RMAX; ++r) {
+                    const int p = r * 32 + lane;
+                    if (r >= n12 && r < R && p < E) {
+                        const PauliDesc* pd = &P.pauli[cur_poff + p];
+                        const int w = pd->w;
+                        const int ext = pd->ext;
+                        uint32_t cnt = 0;
+                        for (int v = 0; v < V && w > 0; ++v) {
+                            uint4 x = make_uint4(0, 0, 0, 0);
+                            for (int k = 0; k < w; ++k) {
+                                const uint32_t q = (uint32_t)__ldg(&P.bits[ext + k]);
+                                x = xor4(x, lds128(planes_s + row_off(q) + 16 * v));
+                            }
+                            cnt += popc4(x);
+                        }
+                        acc[r] += cnt;
+                    }
                 }
             }
         }
@@ -295,27 +304,28 @@ __global__ void __launch_bounds__((NW + 1) * 32) parity_kernel_v2(const ParityPa
 }
 
 struct V2Cfg {
-    int NW, SUB, RMAX, NS;
+    int NW, SUB, BMAX, RMAX, NS;
     size_t smem;
 };
 
 // Chooses the v2 tiling for B byte columns and up to max_E Paulis per slice.  Returns false when
 // the shape is outside what v2 covers (the caller falls back to the v1 kernel).
 inline bool v2_pick(int B, int max_E, int smem_optin, V2Cfg* cfg) {
-    int SUB;
-    if (B <= 6) SUB = 512;
-    else if (B <= 12) SUB = 256;
-    else if (B <= 40) SUB = 128;
+    int SUB, BMAX;
+    if (B <= 7) { SUB = 512; BMAX = 7; }
+    else if (B <= 13) { SUB = 256; BMAX = 13; }
+    else if (B <= 25) { SUB = 128; BMAX = 25; }
+    else if (B <= 41) { SUB = 128; BMAX = 41; }
     else return false;
     const int NW = 8;
-    if ((8 * B + 1) * (SUB / 8) >= 65536) return false;  // plane-row offsets are packed in 16 bits
+    if ((8 * BMAX + 1) * (SUB / 8) >= 65536) return false;  // plane-row offsets are packed in 16 bits
     const int RMAX = max_E <= 256 ? 8 : (max_E <= 512 ? 16 : 32);
-    const size_t planes = (size_t)NW * (8 * B + 1) * (SUB / 8);
+    const size_t planes = (size_t)NW * (8 * BMAX + 1) * (SUB / 8);
     const size_t raw_off = (v2_planes_off(RMAX) + planes + 127) & ~(size_t)127;
     const size_t stage = (size_t)B * (NW * SUB + 64);
     const char* env_ns = getenv("ACES_K1_NS");
     const char* env_cta = getenv("ACES_K1_CTAS");
-    const int want_ctas = env_cta ? atoi(env_cta) : 2;
+    const int want_ctas = env_cta ? atoi(env_cta) : 3;
     const size_t budget = ((size_t)smem_optin + 1024) / (size_t)(want_ctas > 0 ? want_ctas : 1) - 1024;
     int ns = 0;
     for (int s = (env_ns ? atoi(env_ns) : 4); s >= 2; --s)
@@ -326,15 +336,16 @@ inline bool v2_pick(int B, int max_E, int smem_optin, V2Cfg* cfg) {
     if (ns == 0) return false;
     cfg->NW = NW;
     cfg->SUB = SUB;
+    cfg->BMAX = BMAX;
     cfg->RMAX = RMAX;
     cfg->NS = ns;
     cfg->smem = raw_off + ns * stage;
     return true;
 }
 
-template <int NW, int SUB, int RMAX>
+template <int NW, int SUB, int BMAX, int RMAX>
 int v2_launch_t(aces_ctx* ctx, const ParityParams& P, const V2Cfg& cfg) {
-    auto kern = parity_kernel_v2<NW, SUB, RMAX>;
+    auto kern = parity_kernel_v2<NW, SUB, BMAX, RMAX>;
     ACES_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
     int per_sm = 0;
     ACES_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (NW + 1) * 32, cfg.smem));
@@ -354,13 +365,14 @@ int v2_launch_t(aces_ctx* ctx, const ParityParams& P, const V2Cfg& cfg) {
 }
 
 inline int v2_launch(aces_ctx* ctx, const ParityParams& P, const V2Cfg& cfg) {
-#define ACES_V2_R(NWV, SUBV)                                                            \
-    (cfg.RMAX == 8 ? v2_launch_t<NWV, SUBV, 8>(ctx, P, cfg)                             \
-                   : cfg.RMAX == 16 ? v2_launch_t<NWV, SUBV, 16>(ctx, P, cfg)           \
-                                    : v2_launch_t<NWV, SUBV, 32>(ctx, P, cfg))
-    if (cfg.SUB == 128) return ACES_V2_R(8, 128);
-    if (cfg.SUB == 256) return ACES_V2_R(8, 256);
-    return ACES_V2_R(8, 512);
+#define ACES_V2_R(SUBV, BMV)                                                             \
+    (cfg.RMAX == 8 ? v2_launch_t<8, SUBV, BMV, 8>(ctx, P, cfg)                           \
+                   : cfg.RMAX == 16 ? v2_launch_t<8, SUBV, BMV, 16>(ctx, P, cfg)         \
+                                    : v2_launch_t<8, SUBV, BMV, 32>(ctx, P, cfg))
+    if (cfg.SUB == 128 && cfg.BMAX == 25) return ACES_V2_R(128, 25);
+    if (cfg.SUB == 128) return ACES_V2_R(128, 41);
+    if (cfg.SUB == 256) return ACES_V2_R(256, 13);
+    return ACES_V2_R(512, 7);
 #undef ACES_V2_R
 }
 
