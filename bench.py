@@ -313,7 +313,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "parity_kernel<1024,1>", "kernel_ms": k_ms,
+                         "kernel": "k1::parity_kernel_v2<8,128,25,8>", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": alg_bytes},
         }
         if not args.no_cpu:
