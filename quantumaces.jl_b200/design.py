@@ -43,6 +43,8 @@ class FlatDesign:
     cov_counts: List[np.ndarray] = field(default_factory=list)         # [T][C_t]
     matrix: Optional[sp.csc_matrix] = None  # d.matrix, M x N, int32
     gate_eigenvalues: Optional[np.ndarray] = None  # d.c.gate_eigenvalues (true values, synthetic)
+    # design rows of the covariance Paulis (covariance_dict[key][1].design_row), CSR per tuple
+    cov_rows: List = field(default_factory=list)
     name: str = ""
 
     @property
@@ -264,4 +266,89 @@ def synthetic_design(
             for ce in fd.cov_experiment_ensemble[t]:
                 c[ce] += 1
             fd.cov_counts.append(c)
+    if with_matrix:
+        _attach_synthetic_matrix(fd, shape["N"], rng)
     return fd
+
+
+def _attach_synthetic_matrix(fd: FlatDesign, N: int, rng) -> None:
+    """Synthetic design matrix of SURVEY.md section 8d ("Fit synthetic input").
+
+    A is M x N Int32 in T row blocks.  N rows spread over the blocks form a permuted identity
+    (one row e_j per gate eigenvalue: full column rank, like the SPAM rows of a real design);
+    every other row has 2-6 entries inside its block's column window with values in
+    {1, r, (r-1)/2, (r+1)/2}, r the repeat number of the block (src/design.jl:475-531: an
+    entry counts how often a gate eigenvalue enters the circuit eigenvalue).  Gate eigenvalues
+    are log-normal around 1 - O(r_1, r_2, r_m) (src/noises/lognormal.jl:157-235, std 0.5).
+    The covariance Paulis get design rows row_p + row_q +- e_j so that lambda_pq differs from
+    lambda_p * lambda_q by one gate eigenvalue (a small, well-conditioned off-diagonal).
+    """
+    T, M = fd.tuple_number, fd.M
+    m_t = np.asarray(fd.mapping_lengths, dtype=np.int64)
+    assert M >= N, "the synthetic design needs at least as many circuit as gate eigenvalues"
+    # identity rows per block, proportional to the block size
+    ident = np.floor(N * m_t / M).astype(np.int64)
+    ident[: int(N - ident.sum())] += 1
+    assert ident.sum() == N and np.all(ident <= m_t)
+    col_start = np.concatenate([[0], np.cumsum(ident)])
+    repeat = [1] * 9 + [63, 143, 63, 143, 143, 63, 143] if T == 16 else [1] * 7 + [63, 143, 143, 143, 183]
+    perm = rng.permutation(N)
+    rows, cols, vals = [], [], []
+    row0 = 0
+    for t in range(T):
+        width = int(min(N, max(N // 4, 2 * ident[t])))
+        lo = int(min(max(col_start[t] - (width - ident[t]) // 2, 0), N - width))
+        r = repeat[t]
+        choices = np.array([1, r, max((r - 1) // 2, 1), (r + 1) // 2], dtype=np.int64)
+        for i in range(int(m_t[t])):
+            if i < ident[t]:
+                rows.append(row0 + i)
+                cols.append(int(perm[col_start[t] + i]))
+                vals.append(1)
+            else:
+                k = int(rng.integers(2, 7))
+                cc = lo + rng.choice(width, size=k, replace=False)
+                rows.extend([row0 + i] * k)
+                cols.extend(int(perm[c]) for c in cc)
+                vals.extend(int(v) for v in rng.choice(choices, size=k))
+        row0 += int(m_t[t])
+    A = sp.csc_matrix((np.asarray(vals, dtype=np.int32), (np.asarray(rows), np.asarray(cols))),
+                      shape=(M, N), dtype=np.int32)
+    A.sum_duplicates()
+    A.sort_indices()
+    fd.matrix = A
+    # gate eigenvalues: 1 - error with log-normal errors of scale ~0.4% / repeat (keeps the
+    # circuit eigenvalues of the repeated blocks away from the 0.1 clipping threshold)
+    err = 0.004 / 30.0 * np.exp(0.5 * rng.standard_normal(N) - 0.125)
+    clean = rng.permutation(N)[: max(N // 20, 1)]  # a few very clean gates (see cov_rows below)
+    err[clean] *= 0.02
+    fd.gate_eigenvalues = 1.0 - err
+    if fd.full_covariance:
+        Acsr = sp.csr_matrix(A).astype(np.int64)
+        lam = np.exp(Acsr.astype(np.float64) @ np.log(fd.gate_eigenvalues))
+        order = np.argsort(err)
+        err_sorted = err[order]
+        cov_rows = []
+        row0 = 0
+        for t in range(T):
+            keys = fd.cov_keys[t]
+            if len(keys):
+                Rp = Acsr[row0 + keys[:, 0]]
+                Rq = Acsr[row0 + keys[:, 1]]
+                # The extra gate of a pair is one whose error is at most a tenth of the smaller
+                # of the two variances 1 - lambda^2 (none if no gate is that clean): every
+                # covariance block is then diagonally dominant, hence positive definite.
+                var = 1.0 - lam[row0:row0 + int(m_t[t])] ** 2
+                thr = 0.1 * np.minimum(var[keys[:, 0]], var[keys[:, 1]])
+                n_ok = np.searchsorted(err_sorted, thr, side="right")
+                has = n_ok > 0
+                pick = np.maximum(n_ok - 1 - rng.integers(0, 50, size=len(keys)), 0)
+                extra_cols = order[pick]
+                sign = np.where(rng.integers(0, 2, size=len(keys)) == 1, 1, -1) * has
+                extra = sp.csr_matrix((sign, (np.arange(len(keys)), extra_cols)), shape=(len(keys), N))
+                extra.eliminate_zeros()
+                cov_rows.append((Rp + Rq + extra).tocsr())
+            else:
+                cov_rows.append(sp.csr_matrix((0, N), dtype=np.int64))
+            row0 += int(m_t[t])
+        fd.cov_rows = cov_rows

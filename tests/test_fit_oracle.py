@@ -1,0 +1,135 @@
+"""CPU tests: the numpy/scipy fit oracle against the reference's own identities."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import aces_b200
+from fit_util import fo, noisy_ensembles
+
+
+def approx(x, y, rtol=np.sqrt(np.finfo(float).eps)):
+    """Julia's `x ≈ y` for arrays: norm(x - y) <= rtol * max(norm(x), norm(y))."""
+    x, y = np.asarray(x), np.asarray(y)
+    return np.linalg.norm(x - y) <= rtol * max(np.linalg.norm(x), np.linalg.norm(y))
+
+
+@pytest.fixture(scope="module")
+def design():
+    return aces_b200.synthetic_design("rotated", 3, full_covariance=True, with_matrix=True)
+
+
+def test_shapes(design):
+    assert design.matrix.shape == (1248, 659)
+    assert np.linalg.matrix_rank(design.matrix.toarray().astype(float)) == 659
+
+
+def test_covariance_closed_forms(design):
+    # src/merit.jl:245-279 including the epsilon floor at lambda = +-1
+    fd = design
+    lam = [np.full(int(m), 0.9) for m in fd.mapping_lengths]
+    lam[0][0] = 1.0
+    lam[0][1] = -1.0
+    lam12 = [np.full(len(k), 0.83) for k in fd.cov_keys]
+    cov = fo.calc_covariance(fd, lam, lam12, weight_time=False).toarray()
+    X, w, cd = fd.experiment_numbers[0], fd.shot_weights[0], fd.diag_counts[0]
+    assert cov[0, 0] == (1 / w) * (X / cd[0]) * 1e-10
+    assert cov[1, 1] == (1 / w) * (X / cd[1]) * 1e-10
+    assert cov[2, 2] == (1 / w) * (X / cd[2]) * max(1 - 0.9 ** 2, 1e-10)
+    p, q = fd.cov_keys[0][-1]
+    c = fd.cov_counts[0][-1]
+    want = (1 / w) * ((X * c) / (cd[p] * cd[q])) * (0.83 - 0.9 * 0.9)
+    assert cov[p, q] == want and cov[q, p] == want
+    tf = float(np.sum(fd.shot_weights * fd.tuple_times))
+    assert np.allclose(fo.calc_covariance(fd, lam, lam12, weight_time=True).toarray(), tf * cov, rtol=1e-15)
+
+
+def test_inverse_factor_identities(design):
+    # test/merit_tests.jl:531-549: F'F == inv(chol(dense)); whitened solves agree
+    fd = design
+    eig, cov = noisy_ensembles(fd, seed=1)
+    lam = np.concatenate(fo.mean_ensemble(eig))
+    cl = fo.calc_covariance_log(fo.calc_covariance_from_experiments(fd, eig, cov), lam)
+    F = fo.sparse_covariance_inv_factor(cl, fd.mapping_lengths)
+    inv = fo.sparse_covariance_inv(cl, fd.mapping_lengths)
+    dense_inv = np.linalg.inv(cl.toarray())
+    assert np.allclose(inv.toarray(), (F.T @ F).toarray(), rtol=1e-12, atol=0)
+    assert approx(inv.toarray(), dense_inv)
+    assert np.allclose((inv @ cl).toarray(), np.eye(cl.shape[0]), atol=1e-9)
+    rng = np.random.default_rng(2)
+    M = cl.shape[0]
+    data, mat = rng.random(M), rng.random((M, 40))
+    Ld = np.linalg.inv(np.linalg.cholesky(cl.toarray()))
+    x1 = np.linalg.lstsq(F @ mat, F @ data, rcond=None)[0]
+    x2 = np.linalg.lstsq(Ld @ mat, Ld @ data, rcond=None)[0]
+    assert approx(x1, x2)
+
+
+def test_inverse_factor_after_clipping(design):
+    # test/merit_tests.jl:569-591
+    fd = design
+    eig, cov = noisy_ensembles(fd, seed=3)
+    lam = np.concatenate(fo.mean_ensemble(eig))
+    cl = fo.calc_covariance_log(fo.calc_covariance_from_experiments(fd, eig, cov), lam)
+    rng = np.random.default_rng(4)
+    test_data = rng.random(cl.shape[0])
+    ci = fo.get_clipped_indices(test_data)
+    cml = fo.get_clipped_mapping_lengths(fd.mapping_lengths, ci)
+    assert cml.sum() == len(ci) and len(ci) < cl.shape[0]
+    ccl = cl[ci, :][:, ci]
+    inv = fo.sparse_covariance_inv(ccl, cml)
+    assert np.allclose((inv @ ccl).toarray(), np.eye(len(ci)), atol=1e-9)
+    with pytest.raises(ValueError):
+        fo.get_clipped_indices(np.array([0.5, 1.2]))
+
+
+def test_precision_is_inverse_of_gls_covariance(design):
+    # test/merit_tests.jl:561-567
+    fd = design
+    g = fd.gate_eigenvalues
+    lam = fo.get_eigenvalues(fd, g)
+    cov = fo.calc_covariance(fd, fo.get_eigenvalues_ensemble(fd, g), fo.calc_covariance_eigenvalues(fd, g))
+    cl = fo.calc_covariance_log(cov, lam)
+    prec = fo.calc_precision_matrix(fd.matrix, g, fo.sparse_covariance_inv(cl, fd.mapping_lengths)).toarray()
+    gls = fo.calc_gls_covariance(fd, cl)
+    assert approx(prec, np.linalg.inv(gls))
+    cld = sp.diags(cl.diagonal()).tocsc()
+    wls_diag = fo.calc_wls_covariance(fd, cld)
+    prec_d = fo.calc_precision_matrix(fd.matrix, g, sp.diags(1 / cl.diagonal())).toarray()
+    assert approx(prec_d, np.linalg.inv(wls_diag))
+    # merit ordering GLS <= WLS <= OLS (test/design_tests.jl:175-188) on the NRMSE expectation
+    e = [fo.nrmse_moments(f(fd, cl))[0] for f in (fo.calc_gls_covariance, fo.calc_wls_covariance, fo.calc_ols_covariance)]
+    assert e[0] <= e[1] * (1 + 1e-12) and e[1] <= e[2] * (1 + 1e-12)
+
+
+def test_fit_known_answers(design):
+    fd = design
+    A = fd.matrix
+    # noiseless records => y == 1 => b == 0 => x == 0 => g == 1.0 exactly (test/device_tests.jl:144-155)
+    ones = np.ones(A.shape[0])
+    F = sp.identity(A.shape[0], format="csc") * 3.0
+    assert np.all(fo.estimate_gate_eigenvalues(A, ones) == 1.0)
+    assert np.all(fo.estimate_gate_eigenvalues(A, ones, F) == 1.0)
+    # noiseless y = exp(A log g) recovers g (full column rank)
+    y = fo.get_eigenvalues(fd, fd.gate_eigenvalues)
+    assert np.allclose(fo.estimate_gate_eigenvalues(A, y), fd.gate_eigenvalues, rtol=1e-11)
+    # GLS with a diagonal covariance == WLS; WLS with unit weights == OLS (test/design_tests.jl:243-246)
+    eig, cov = noisy_ensembles(fd, seed=5)
+    lam = np.concatenate(fo.mean_ensemble(eig))
+    cl = fo.calc_covariance_log(fo.calc_covariance_from_experiments(fd, eig, cov), lam)
+    cld = sp.diags(cl.diagonal()).tocsc()
+    gls_d = fo.estimate_gate_eigenvalues(A, lam, fo.sparse_covariance_inv_factor(cld, fd.mapping_lengths))
+    wls = fo.estimate_gate_eigenvalues(A, lam, sp.diags(cl.diagonal() ** -0.5))
+    assert np.allclose(gls_d, wls, rtol=1e-11)
+    assert np.allclose(fo.estimate_gate_eigenvalues(A, lam, sp.identity(A.shape[0])), fo.estimate_gate_eigenvalues(A, lam), rtol=1e-12)
+    # constrain clamps negative log-eigenvalues (gate eigenvalues > 1) to exactly 1
+    gc = fo.estimate_gate_eigenvalues(A, lam, constrain=True)
+    assert np.all(gc <= 1.0)
+
+
+def test_gate_noise_core_statistics(design):
+    fd = design
+    eig, cov = noisy_ensembles(fd, shots=10**9, seed=6)
+    out = fo.estimate_gate_noise_core(fd, eig, cov)
+    for k in ("ols", "wls", "gls"):
+        err = np.linalg.norm(out[k] - fd.gate_eigenvalues) / np.sqrt(len(fd.gate_eigenvalues))
+        assert err < 5e-4, (k, err)
