@@ -134,6 +134,36 @@ int32_t aces_estimate_experiment(aces_ctx* ctx, const uint8_t* counts, int64_t r
                                  const int64_t* meas_ptr, const int32_t* meas_indices,
                                  const uint8_t* signs, int64_t shots_value, double* est);
 
+/* ---- K4/K5: least-squares fit of the gate eigenvalues -------------------------------------------
+ *
+ * Drop-in for estimate_gate_eigenvalues(design_matrix::SparseMatrixCSC{Float64,Int},
+ * est_covariance_log_inv_factor::SparseMatrixCSC{Float64,Int}, est_eigenvalues; constrain)
+ * (src/estimate.jl:492-524) and its two-argument OLS form (:510-524, pass F_* = NULL):
+ *     b = -log(est_eigenvalues);  x = (F*A) \ (F*b);  constrain: x[x < 0] = 0;  g = exp(-x).
+ * A is M x N, F is M x M, both CSC exactly as Julia stores them (colptr [ncols+1], rowval,
+ * nzval); index_base = 1 for Julia's 1-based colptr/rowval, 0 for C.  The whitened matrix F*A is
+ * formed densely on the device, its Gram matrix accumulated on the FP64 tensor pipe, factorised
+ * by a blocked Cholesky and the solution refined twice with FP64 residuals.  Returns
+ * ACES_E_NOT_PD when F*A is numerically rank deficient. */
+int32_t aces_estimate_gate_eigenvalues(aces_ctx* ctx, int64_t M, int64_t N, const int64_t* A_colptr,
+                                       const int64_t* A_rowval, const double* A_nzval,
+                                       const int64_t* F_colptr, const int64_t* F_rowval,
+                                       const double* F_nzval, int32_t index_base,
+                                       const double* est_eigenvalues, int32_t constrain,
+                                       double* gate_eigenvalues);
+
+/* Dense N x N (column-major, host or device) matrices derived from the Gram matrix
+ * G = (F*A)' (F*A) of the same arguments:
+ *   want_gram == 0: out = S * inv(G) * S   -- calc_gls_covariance (src/merit.jl:556-568) with
+ *                   S = diag(scale) = diag(gate eigenvalues) and F'F = inv(covariance_log);
+ *   want_gram != 0: out = S * G * S        -- calc_precision_matrix (src/merit.jl:754-770) with
+ *                   scale_inverse != 0 (S = diag(1 ./ scale)).
+ * scale == NULL means S = I. */
+int32_t aces_gram_inverse(aces_ctx* ctx, int64_t M, int64_t N, const int64_t* A_colptr,
+                          const int64_t* A_rowval, const double* A_nzval, const int64_t* F_colptr,
+                          const int64_t* F_rowval, const double* F_nzval, int32_t index_base,
+                          const double* scale, int32_t scale_inverse, int32_t want_gram, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,3 +7,8 @@ from . import _lib  # noqa: F401
 from ._lib import AcesError, Context, NotPositiveDefinite, PauliTables  # noqa: F401
 from .design import FlatDesign, build_pauli_tables, shots_divide, synthetic_design  # noqa: F401
 from .estimate import DesignEstimator, estimate_experiment  # noqa: F401
+from . import merit  # noqa: F401
+from .merit import (  # noqa: F401
+    calc_gls_covariance_from_factor, calc_precision_matrix_from_factor, estimate_gate_eigenvalues,
+    get_clipped_indices, get_clipped_mapping_lengths,
+)
