@@ -164,6 +164,80 @@ int32_t aces_gram_inverse(aces_ctx* ctx, int64_t M, int64_t N, const int64_t* A_
                           const int64_t* F_rowval, const double* F_nzval, int32_t index_base,
                           const double* scale, int32_t scale_inverse, int32_t want_gram, double* out);
 
+/* ---- design-resident fit path ---------------------------------------------------------------------
+ *
+ * Everything the numeric core of estimate_gate_noise (src/estimate.jl:703-743, 820-831) and the
+ * estimator covariances of src/merit.jl:556-629 need, with the Design uploaded once instead of
+ * per call.  An aces_design holds what those functions read from a `Design`:
+ *   mapping_lengths [T]        length.(d.mapping_ensemble)                    (block sizes m_t)
+ *   A_colptr/A_rowval/A_nzval  d.matrix exactly as stored: SparseMatrixCSC{Int32,Int32}, M x N
+ *   experiment_numbers [T], shot_weights [T], tuple_times [T]
+ *   diag_counts [M]            covariance_dict_ensemble[t][(p,p)][2]  (src/design.jl:803-817)
+ *   cov_ptr [T+1], cov_p/cov_q/cov_counts [C]
+ *                              the off-diagonal keys of covariance_dict_ensemble[t] in the sorted
+ *                              order of get_covariance_mapping_data (src/merit.jl:144-163), as
+ *                              block-local Pauli indices, with their experiment counts; the c-th
+ *                              entry is the c-th covariance circuit eigenvalue.  cov_ptr == NULL:
+ *                              diagonal covariance (full_covariance = false).
+ * index_base = 1 when colptr / rowval / cov_p / cov_q are Julia's 1-based indices, 0 for C.
+ *
+ * The covariance matrices of this path all share one sparsity pattern (the diagonal plus both
+ * orientations of every key); they are exchanged as the nzval array of a CSC matrix whose
+ * colptr / rowval come from aces_design_covariance_pattern (0-based, rows sorted).
+ */
+typedef struct aces_design aces_design;
+
+int32_t aces_design_create(aces_ctx* ctx, int32_t T, const int64_t* mapping_lengths, int64_t N,
+                           const int32_t* A_colptr, const int32_t* A_rowval, const int32_t* A_nzval,
+                           int32_t index_base, const int64_t* experiment_numbers,
+                           const double* shot_weights, const double* tuple_times,
+                           const int64_t* diag_counts, const int64_t* cov_ptr, const int64_t* cov_p,
+                           const int64_t* cov_q, const int64_t* cov_counts, aces_design** out);
+int32_t aces_design_destroy(aces_ctx* ctx, aces_design* design);
+int64_t aces_design_covariance_nnz(const aces_design* design);
+int32_t aces_design_covariance_pattern(const aces_design* design, int64_t* colptr /* [M+1] */,
+                                       int64_t* rowval /* [nnz] */);
+
+/* K2.  calc_covariance(d, eigenvalues_ensemble, covariance_ensemble; epsilon, weight_time)
+ * (src/merit.jl:206-291): eigenvalues [M] (tuples concatenated), covariance_eigenvalues [C].
+ * log_form != 0 additionally applies calc_covariance_log(covariance, eigenvalues)
+ * (src/merit.jl:356-365) with the same eigenvalues.  nzval [nnz] host or device. */
+int32_t aces_calc_covariance(aces_ctx* ctx, aces_design* design, const double* eigenvalues,
+                             const double* covariance_eigenvalues, double epsilon,
+                             int32_t weight_time, int32_t log_form, double* nzval);
+
+/* K3.  sparse_covariance_inv_factor(covariance_log[kept, kept], clipped_mapping_lengths)
+ * (src/merit.jl:378-427, called at src/estimate.jl:823): covariance_log_nzval in the design's
+ * pattern; kept_rows (sorted, unique; NULL = all M rows) are the clipped indices of
+ * src/estimate.jl:435-460.  factor_blocks receives, for every tuple, the dense lower-triangular
+ * block inv(L_t) (k_t x k_t column-major, k_t = kept rows of the tuple, blocks concatenated) with
+ * covariance_log_t = L_t L_t'; block_lengths [T] receives k_t.  The reference's CHOLMOD factor is
+ * a row permutation of this one; F'F = inv(covariance_log) is the same.  Returns ACES_E_NOT_PD
+ * when a block is not positive definite (the caller applies src/merit.jl:403-424). */
+int32_t aces_design_inv_factor(aces_ctx* ctx, aces_design* design, const double* covariance_log_nzval,
+                               const int64_t* kept_rows, int64_t n_kept, int32_t index_base,
+                               double* factor_blocks, int64_t* block_lengths);
+
+/* K2-K5 fused: the gate eigenvalues of one estimator from the circuit-eigenvalue estimates, as
+ * estimate_gate_noise computes them (src/estimate.jl:711-743, 820-831): covariance of the
+ * estimates (weight_time = false), log-covariance, clipping to kept_rows, inverse factor
+ * (ls_type 2 = GLS: block Cholesky; 1 = WLS: diagonal; 0 = OLS: identity), whitened
+ * least-squares solve, g = exp(-x).  est_eigenvalues [M] are the unclipped means
+ * (mean.(est_eigenvalues_experiment_ensemble)), est_covariance_eigenvalues [C] likewise. */
+int32_t aces_design_fit(aces_ctx* ctx, aces_design* design, int32_t ls_type,
+                        const double* est_eigenvalues, const double* est_covariance_eigenvalues,
+                        const int64_t* kept_rows, int64_t n_kept, int32_t index_base, double epsilon,
+                        int32_t constrain, double* gate_eigenvalues);
+
+/* K6.  calc_gls_covariance / calc_wls_covariance / calc_ols_covariance(d, covariance_log)
+ * (src/merit.jl:556-629) for ls_type 2 / 1 / 0: gate_eigenvalues [N] = get_gate_eigenvalues(d),
+ * covariance_log_nzval in the design's pattern.  sigma (N x N column-major, host or device) may be
+ * NULL when only the moments are wanted: trace = tr(sigma), trace_sq = tr(sigma^2), the inputs
+ * of nrmse_moments (src/merit.jl:672-682). */
+int32_t aces_design_ls_covariance(aces_ctx* ctx, aces_design* design, int32_t ls_type,
+                                  const double* gate_eigenvalues, const double* covariance_log_nzval,
+                                  double* sigma, double* trace, double* trace_sq);
+
 #ifdef __cplusplus
 }
 #endif

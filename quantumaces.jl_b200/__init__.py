@@ -10,5 +10,6 @@ from .estimate import DesignEstimator, estimate_experiment  # noqa: F401
 from . import merit  # noqa: F401
 from .merit import (  # noqa: F401
     calc_gls_covariance_from_factor, calc_precision_matrix_from_factor, estimate_gate_eigenvalues,
-    get_clipped_indices, get_clipped_mapping_lengths,
+    get_clipped_indices, get_clipped_mapping_lengths, DeviceDesign, estimate_gate_noise_core, mean_ensemble,
+    nrmse_moments,
 )

@@ -58,6 +58,14 @@ SIGNATURES = {
     "aces_estimate_experiment": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
     "aces_estimate_gate_eigenvalues": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp]),
     "aces_gram_inverse": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _vp]),
+    "aces_design_create": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _p(_vp)]),
+    "aces_design_destroy": (_i32, [_vp, _vp]),
+    "aces_design_covariance_nnz": (_i64, [_vp]),
+    "aces_design_covariance_pattern": (_i32, [_vp, _vp, _vp]),
+    "aces_calc_covariance": (_i32, [_vp, _vp, _vp, _vp, C.c_double, _i32, _i32, _vp]),
+    "aces_design_inv_factor": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "aces_design_fit": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, C.c_double, _i32, _vp]),
+    "aces_design_ls_covariance": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

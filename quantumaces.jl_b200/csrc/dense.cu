@@ -1,5 +1,5 @@
 // dense.cu -- FP64 dense engine: DMMA (mma.sync m8n8k4 f64, SASS DMMA) GEMM and the blocked
-// Cholesky / triangular inverse / triangular solve built on it.  See dense.cuh for the
+// Cholesky / triangular inverse / triangular solves built on it.  See dense.cuh for the
 // conventions (column-major, padded to multiples of 128, no edge handling).
 //
 // Replaces, for the fit path, what the reference gets from LAPACK / SuiteSparse:
@@ -26,7 +26,6 @@ struct GemmP {
     int64_t lda, ldb, ldc;
     int k;
     double alpha, beta;
-    int lower_only;
 };
 
 __device__ __forceinline__ void cp_async16(double* dst, const double* src) {
@@ -47,13 +46,10 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-// One CTA computes one 128x128 tile of C.  8 warps as 2 (m) x 4 (n), warp tile 64x32 =
+// One CTA computes the 128x128 tile (bm, bn) of C.  8 warps as 2 (m) x 4 (n), warp tile 64x32 =
 // 8x4 DMMA tiles; operands staged by cp.async in a 3-stage ring.
 template <bool A_KC, bool B_KC>
-__global__ void __launch_bounds__(GT, 1) gemm_kernel(const GemmP p) {
-    const int bm = blockIdx.x, bn = blockIdx.y;
-    if (p.lower_only && bn > bm) return;
-    extern __shared__ __align__(16) double sm[];
+__device__ __forceinline__ void gemm_tile(const GemmP& p, const int bm, const int bn, double* sm) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
@@ -143,77 +139,315 @@ __global__ void __launch_bounds__(GT, 1) gemm_kernel(const GemmP p) {
         }
 }
 
-// Unblocked Cholesky of one 128x128 diagonal block in shared memory; writes L (strict upper
-// triangle zeroed) back in place.  1024 threads.
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(GT, 1) gemm_kernel(const GemmP p, const int lower_only) {
+    if (lower_only && blockIdx.y > blockIdx.x) return;
+    extern __shared__ __align__(16) double sm[];
+    gemm_tile<A_KC, B_KC>(p, blockIdx.x, blockIdx.y, sm);
+}
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(GT, 1) gemm_batched_kernel(const GemmDesc* __restrict__ descs) {
+    const GemmDesc& d = descs[blockIdx.z];
+    const int bm = blockIdx.x, bn = blockIdx.y;
+    if (d.k == 0 || bm >= d.tiles_m || bn >= d.tiles_n || (d.lower_only && bn > bm)) return;
+    GemmP p{d.A, d.B, d.C, d.lda, d.ldb, d.ldc, d.k, d.alpha, d.beta};
+    extern __shared__ __align__(16) double sm[];
+    gemm_tile<A_KC, B_KC>(p, bm, bn, sm);
+}
+
+// ---- 128 x 128 diagonal block: Cholesky factor and its inverse, one CTA of 512 threads ---------
+//
+// The block lives in shared memory (column-major, odd row pitch).  Factorisation: right-looking
+// with 16-wide panels -- the 16 x 16 diagonal piece by one warp, the panel rows one thread per
+// row, the trailing update as static 4 x 8 register tiles per thread.  Inverse: in place, the
+// eight 16 x 16 diagonal pieces by eight warps at once, then block columns from right to left
+// (X21 = -X22 * L21 * X11).
 constexpr int PLD = DB + 1;
-__global__ void __launch_bounds__(1024, 1) potf2_kernel(double* A, int64_t lda, int* flag, int blk,
-                                                        const double* diag0, double rel_tol) {
-    extern __shared__ double s[];  // s[j*PLD + i] = A(i, j)
-    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-    for (int e = tid; e < DB * DB; e += 1024) {
-        const int i = e & (DB - 1), j = e >> 7;
-        s[j * PLD + i] = A[i + (int64_t)j * lda];
+constexpr int PW = 16;
+constexpr int DIAG_THREADS = 512;
+constexpr size_t DIAG_SMEM = (size_t)(DB * PLD + PW * PLD + 2 * DB) * sizeof(double);
+
+// Cholesky of the 16 x 16 piece at (k0, k0) of the shared-memory block by ONE warp, rows in
+// registers (lane i holds row i; lanes 16..31 mirror 0..15 so that every shuffle source is
+// defined).  Kept out of line so that its registers are allocated separately from the caller's
+// tile accumulators.  Returns true when a pivot was not above its floor (and was replaced by 1).
+__device__ __noinline__ bool diag16(double* s, double* rdiag, const double* pfloor, int k0, int lane) {
+    const int li = lane & (PW - 1);
+    double a[PW];
+    bool bad = false;
+#pragma unroll
+    for (int c = 0; c < PW; ++c) a[c] = s[(k0 + c) * PLD + k0 + li];
+    // Square-root-free elimination: column k stays unscaled (a_ik) while the update uses
+    // a_ik * a_jk / d_k, so that the only operation on the critical path of a pivot is one
+    // reciprocal; the 1/sqrt(d_k) scaling of all columns is applied once at the end.
+    double dmine = 1.0;  // pivot of row li
+#pragma unroll
+    for (int k = 0; k < PW; ++k) {
+        double dkk = __shfl_sync(0xffffffffu, a[k], k);
+        if (!(dkk > pfloor[k0 + k])) {
+            bad = true;
+            dkk = 1.0;
+        }
+        if (li == k) dmine = dkk;
+        const double tk = a[k] * (1.0 / dkk);  // a_ik / d_k
+#pragma unroll
+        for (int j = k + 1; j < PW; ++j) {
+            const double ajk = __shfl_sync(0xffffffffu, a[k], j);
+            if (li >= j) a[j] -= tk * ajk;
+        }
     }
-    for (int k = 0; k < DB; ++k) {
-        __syncthreads();
-        double d = s[k * PLD + k];
-        // a pivot that is not positive, or negligible against the original diagonal entry,
-        // means the matrix is numerically not positive definite
-        const double floor_k = diag0 ? rel_tol * fabs(diag0[k]) : 0.0;
-        if (!(d > floor_k)) {
-            if (tid == 0) atomicCAS(flag, 0, blk + 1);
-            d = 1.0;
+    const double rmine = rsqrt(dmine);
+#pragma unroll
+    for (int c = 0; c < PW; ++c) {
+        const double rc = __shfl_sync(0xffffffffu, rmine, c);
+        a[c] = (li == c) ? dmine * rc : a[c] * rc;  // L(c, c) = sqrt(d_c); L(i, c) = a_ic / sqrt(d_c)
+    }
+    if (lane < PW) {
+        rdiag[k0 + lane] = rmine;
+#pragma unroll
+        for (int c = 0; c < PW; ++c)
+            if (c <= li) s[(k0 + c) * PLD + k0 + li] = a[c];
+    }
+    return bad;
+}
+
+__device__ __forceinline__ void diag_block(const DiagDesc& d, const double rel_tol, double* sh) {
+    double* s = sh;                  // s[j*PLD + i] = A(i, j)
+    double* tmp = sh + DB * PLD;     // [PW][PLD] scratch of the inverse
+    double* rdiag = tmp + PW * PLD;  // reciprocals of the diagonal of L
+    double* pfloor = rdiag + DB;     // smallest acceptable pivot per column
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        // 32 elements per thread, loads issued in batches of 8 before their shared-memory stores
+        const int i = tid & (DB - 1), jb = tid >> 7;  // 4 columns in flight per pass
+#pragma unroll
+        for (int j0 = 0; j0 < DB; j0 += 32) {
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = d.A[i + (int64_t)(j0 + 4 * q + jb) * d.lda];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s[(j0 + 4 * q + jb) * PLD + i] = v[q];
         }
-        d = sqrt(d);
+    }
+    if (tid < DB) pfloor[tid] = d.diag0 ? rel_tol * fabs(d.diag0[tid]) : 0.0;
+    __syncthreads();
+    for (int k0 = 0; k0 < DB; k0 += PW) {
+        // (a) 16 x 16 diagonal piece, one warp, rows in registers (lane i holds row i; lanes
+        //     16..31 mirror 0..15 so that every shuffle source is defined)
+        if (warp == 0 && diag16(s, rdiag, pfloor, k0, lane) && lane == 0 && d.flag) atomicCAS(d.flag, 0, d.code);
         __syncthreads();
-        if (tid < DB) {
-            if (tid > k) s[k * PLD + tid] /= d;
-            else if (tid == k) s[k * PLD + k] = d;
+        const int r0 = k0 + PW;  // first trailing row / column
+        if (r0 >= DB) break;
+        // (b) panel rows: x * L_dd' = a, one thread per row
+        if (tid < DB - r0) {
+            const int i = r0 + tid;
+            double a[PW];
+#pragma unroll
+            for (int c = 0; c < PW; ++c) a[c] = s[(k0 + c) * PLD + i];
+#pragma unroll
+            for (int c = 0; c < PW; ++c) {
+                double v = a[c];
+#pragma unroll
+                for (int k = 0; k < c; ++k) v -= a[k] * s[(k0 + k) * PLD + k0 + c];
+                a[c] = v * rdiag[k0 + c];
+            }
+#pragma unroll
+            for (int c = 0; c < PW; ++c) s[(k0 + c) * PLD + i] = a[c];
         }
         __syncthreads();
-        for (int j = k + 1 + ty; j < DB; j += 32) {
-            const double lkj = s[k * PLD + j];
-            for (int i = k + 1 + tx; i < DB; i += 32)
-                if (i >= j) s[j * PLD + i] -= s[k * PLD + i] * lkj;
+        // (c) trailing update: thread (tx, ty) owns rows tx + 32a, columns ty + 16b
+        {
+            const int tx = lane, ty = warp;
+            double acc[4][8];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+#pragma unroll 4
+            for (int k = 0; k < PW; ++k) {
+                const double* col = s + (k0 + k) * PLD;
+                double ra[4], cb[8];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) ra[a] = (32 * a + 31 >= r0) ? col[tx + 32 * a] : 0.0;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) cb[b] = (ty + 16 * b >= r0) ? col[ty + 16 * b] : 0.0;
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) acc[a][b] += ra[a] * cb[b];
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const int i = tx + 32 * a, j = ty + 16 * b;
+                    if (j >= r0 && i >= j) s[j * PLD + i] -= acc[a][b];
+                }
         }
+        __syncthreads();
+    }
+    // L -> global (strict upper triangle zeroed)
+    for (int e = tid; e < DB * DB; e += DIAG_THREADS) {
+        const int i = e & (DB - 1), j = e >> 7;
+        d.A[i + (int64_t)j * d.lda] = (i >= j) ? s[j * PLD + i] : 0.0;
     }
     __syncthreads();
-    for (int e = tid; e < DB * DB; e += 1024) {
+    // ---- in-place inverse ------------------------------------------------------------------
+    if (warp < DB / PW) {
+        const int b0 = warp * PW;
+        const int c = lane & (PW - 1);  // lanes 16..31 mirror 0..15 (no divergence), only 0..15 store
+        double x[PW];
+#pragma unroll
+        for (int i = 0; i < PW; ++i) {
+            double v = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < i; ++k) v -= s[(b0 + k) * PLD + b0 + i] * x[k];
+            x[i] = (i < c) ? 0.0 : v * rdiag[b0 + i];
+        }
+        __syncwarp();
+        if (lane < PW)
+#pragma unroll
+            for (int i = 0; i < PW; ++i)
+                if (i >= c) s[(b0 + c) * PLD + b0 + i] = x[i];
+    }
+    __syncthreads();
+    for (int j0 = DB - 2 * PW; j0 >= 0; j0 -= PW) {
+        const int r0 = j0 + PW, nr = DB - r0;
+        const int item = tid;
+        const bool active = item < nr * 4;
+        const int il = active ? item % nr : 0, cq = active ? item / nr : 0;
+        const int i = r0 + il;
+        if (active) {
+            // T[i][c] = sum_{k=r0..i} X22[i][k] * L21[k][c]
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+            const double* c0 = s + (j0 + 4 * cq) * PLD;
+            for (int k = r0; k <= i; ++k) {
+                const double xv = s[k * PLD + i];
+                t0 += xv * c0[k];
+                t1 += xv * c0[PLD + k];
+                t2 += xv * c0[2 * PLD + k];
+                t3 += xv * c0[3 * PLD + k];
+            }
+            tmp[(4 * cq + 0) * PLD + il] = t0;
+            tmp[(4 * cq + 1) * PLD + il] = t1;
+            tmp[(4 * cq + 2) * PLD + il] = t2;
+            tmp[(4 * cq + 3) * PLD + il] = t3;
+        }
+        __syncthreads();
+        if (active) {
+            // X21[i][c] = -sum_{c' >= c} T[i][c'] * X11[c'][c]
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = 4 * cq + u;
+                double y = 0.0;
+                for (int cp = c; cp < PW; ++cp) y += tmp[cp * PLD + il] * s[(j0 + c) * PLD + j0 + cp];
+                s[(j0 + c) * PLD + i] = -y;
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < DB * DB; e += DIAG_THREADS) {
         const int i = e & (DB - 1), j = e >> 7;
-        A[i + (int64_t)j * lda] = (i >= j) ? s[j * PLD + i] : 0.0;
+        d.dinv[i + j * DB] = (i >= j) ? s[j * PLD + i] : 0.0;
     }
 }
 
-// X = inv(L) for one 128x128 lower-triangular block.  512 threads: column j is solved by four
-// threads that each keep 32 entries of it in registers (forward substitution, all threads in
-// lock step; entries not yet computed are zero, so no masking is needed).
-__global__ void __launch_bounds__(512, 1) trtri128_kernel(const double* L, int64_t ldl, double* X) {
-    extern __shared__ double s[];  // s[k*PLD + i] = L(i, k)
-    const int tid = threadIdx.x;
-    for (int e = tid; e < DB * DB; e += 512) {
-        const int i = e & (DB - 1), j = e >> 7;
-        s[j * PLD + i] = (i >= j) ? L[i + (int64_t)j * ldl] : 0.0;
-    }
+__global__ void __launch_bounds__(DIAG_THREADS, 1) diag_kernel(const DiagDesc* __restrict__ descs,
+                                                               const DiagDesc one, const double rel_tol) {
+    extern __shared__ __align__(16) double sh[];
+    const DiagDesc d = descs ? descs[blockIdx.x] : one;
+    if (!d.A) return;
+    diag_block(d, rel_tol, sh);
+}
+
+// ---- blocked triangular solves with one right-hand side ------------------------------------------
+constexpr int TRSV_THREADS = 256;
+
+// Step k of y = inv(L) b: every CTA recomputes y_k = inv(L_kk) b_k (the block inverse is in L2);
+// CTA 0 publishes y_k, CTA q >= 1 updates b_{k+q} -= L[k+q, k] y_k.
+__global__ void __launch_bounds__(TRSV_THREADS) trsv_fwd_kernel(const double* __restrict__ L, int64_t ldl,
+                                                                const double* __restrict__ dinv,
+                                                                double* __restrict__ b,
+                                                                double* __restrict__ y, int k) {
+    __shared__ double bk[DB], yk[DB], part[TRSV_THREADS];
+    const int tid = threadIdx.x, i = tid & (DB - 1), h = tid >> 7;
+    if (tid < DB) bk[tid] = b[(int64_t)k * DB + tid];
     __syncthreads();
-    const int j = tid >> 2, l = tid & 3;
-    double x[32];
+    const double* X = dinv + (int64_t)k * DB * DB;
+    double s = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 4
+    for (int j = h * 64; j < h * 64 + 64; j += 4) {  // X is zero above the diagonal
+        s += X[i + j * DB] * bk[j];
+        s1 += X[i + (j + 1) * DB] * bk[j + 1];
+        s2 += X[i + (j + 2) * DB] * bk[j + 2];
+        s3 += X[i + (j + 3) * DB] * bk[j + 3];
+    }
+    part[tid] = (s + s1) + (s2 + s3);
+    __syncthreads();
+    if (tid < DB) yk[tid] = part[tid] + part[tid + DB];
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        if (tid < DB) y[(int64_t)k * DB + tid] = yk[tid];
+        return;
+    }
+    const int64_t r = k + blockIdx.x;
+    const double* T = L + r * DB + (int64_t)k * DB * ldl;
+    s = s1 = s2 = s3 = 0.0;
+#pragma unroll 4
+    for (int j = h * 64; j < h * 64 + 64; j += 4) {
+        s += T[i + (int64_t)j * ldl] * yk[j];
+        s1 += T[i + (int64_t)(j + 1) * ldl] * yk[j + 1];
+        s2 += T[i + (int64_t)(j + 2) * ldl] * yk[j + 2];
+        s3 += T[i + (int64_t)(j + 3) * ldl] * yk[j + 3];
+    }
+    part[tid] = (s + s1) + (s2 + s3);
+    __syncthreads();
+    if (tid < DB) b[r * DB + tid] -= part[tid] + part[tid + DB];
+}
+
+// out[c] = sum_r T[r + c*ld] * v[r] for one 128 x 128 tile; warp w handles columns w, w+8, ...
+// All 64 loads of a lane are issued before the reductions (the tile comes from L2 / HBM).
+__device__ __forceinline__ void tile_t_times_vec(const double* __restrict__ T, int64_t ld,
+                                                 const double* v, double* out, int lane, int warp) {
+    double s[16];
 #pragma unroll
-    for (int q = 0; q < 32; ++q) x[q] = 0.0;
-    for (int i = 0; i < DB; ++i) {
-        double sum = 0.0;
-#pragma unroll
-        for (int q = 0; q < 32; ++q) sum += s[(4 * q + l) * PLD + i] * x[q];
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        const double val = ((i == j ? 1.0 : 0.0) - sum) / s[i * PLD + i];
-        const int qi = i >> 2;
-        const bool mine = (i & 3) == l;
-#pragma unroll
-        for (int q = 0; q < 32; ++q)
-            if (mine && q == qi) x[q] = val;
+    for (int cc = 0; cc < 16; ++cc) {
+        const double* col = T + (int64_t)(warp + 8 * cc) * ld;
+        s[cc] = col[lane] * v[lane] + col[lane + 32] * v[lane + 32] + col[lane + 64] * v[lane + 64] +
+                col[lane + 96] * v[lane + 96];
     }
 #pragma unroll
-    for (int q = 0; q < 32; ++q) X[(4 * q + l) + j * DB] = x[q];
+    for (int cc = 0; cc < 16; ++cc) {
+        double t = s[cc];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) out[warp + 8 * cc] = t;
+    }
+}
+
+// Step k (descending) of x = inv(L') y: x_k = inv(L_kk)' y_k; CTA q >= 1 updates
+// y_{q-1} -= L[k, q-1]' x_k.
+__global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_kernel(const double* __restrict__ L, int64_t ldl,
+                                                                const double* __restrict__ dinv,
+                                                                double* __restrict__ y,
+                                                                double* __restrict__ x, int k) {
+    __shared__ double yk[DB], xk[DB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < DB) yk[tid] = y[(int64_t)k * DB + tid];
+    __syncthreads();
+    const double* X = dinv + (int64_t)k * DB * DB;
+    tile_t_times_vec(X, DB, yk, xk, lane, warp);
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        if (tid < DB) x[(int64_t)k * DB + tid] = xk[tid];
+        return;
+    }
+    const int64_t j = blockIdx.x - 1;
+    const double* T = L + (int64_t)k * DB + j * DB * ldl;
+    tile_t_times_vec(T, ldl, xk, yk, lane, warp);  // yk is free now: reuse it for the product
+    __syncthreads();
+    if (tid < DB) y[j * DB + tid] -= yk[tid];
 }
 
 __global__ void set_identity_kernel(int64_t n, double* A, int64_t lda) {
@@ -246,25 +480,48 @@ __global__ void transpose_kernel(int64_t m, int64_t n, const double* A, int64_t 
         if (i < m && j < n) B[j + i * ldb] = tile[threadIdx.x][r];
     }
 }
+// A(i, j) = A(j, i) for i < j, tile-wise through shared memory so that both sides are coalesced.
 __global__ void symmetrize_kernel(int64_t n, double* A, int64_t lda) {
-    const int64_t total = n * n;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
-         e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = e % n, j = e / n;
-        if (i < j) A[i + j * lda] = A[j + i * lda];
+    __shared__ double tile[32][33];
+    const int64_t bi = blockIdx.x, bj = blockIdx.y;
+    if (bj > bi) return;  // (bi, bj) is a lower tile; it is mirrored into (bj, bi)
+    const int64_t i0 = bi * 32, j0 = bj * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t i = i0 + threadIdx.x, j = j0 + r;
+        tile[r][threadIdx.x] = (i < n && j < n) ? A[i + j * lda] : 0.0;  // tile[r][c] = A(i0+c, j0+r)
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        // write A(j0 + c, i0 + r) = A(i0 + r, j0 + c) = tile[c][r]
+        const int64_t row = j0 + threadIdx.x, col = i0 + r;
+        if (row < n && col < n && row < col) A[row + col * lda] = tile[threadIdx.x][r];
     }
 }
 
+template <typename K>
+int set_smem(aces_ctx* ctx, K kern, size_t bytes) {
+    ACES_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return ACES_OK;
+}
+
+int configure(aces_ctx* ctx) {
+    static bool done = false;
+    if (done) return ACES_OK;
+    ACES_TRY(set_smem(ctx, gemm_kernel<false, false>, GEMM_SMEM));
+    ACES_TRY(set_smem(ctx, gemm_kernel<false, true>, GEMM_SMEM));
+    ACES_TRY(set_smem(ctx, gemm_kernel<true, true>, GEMM_SMEM));
+    ACES_TRY(set_smem(ctx, gemm_batched_kernel<false, false>, GEMM_SMEM));
+    ACES_TRY(set_smem(ctx, gemm_batched_kernel<false, true>, GEMM_SMEM));
+    ACES_TRY(set_smem(ctx, gemm_batched_kernel<true, true>, GEMM_SMEM));
+    ACES_TRY(set_smem(ctx, diag_kernel, DIAG_SMEM));
+    done = true;
+    return ACES_OK;
+}
+
 template <bool A_KC, bool B_KC>
-int launch_gemm(aces_ctx* ctx, const GemmP& p, int64_t m, int64_t n) {
-    auto kern = gemm_kernel<A_KC, B_KC>;
-    static bool configured = false;
-    if (!configured) {
-        ACES_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-        configured = true;
-    }
+int launch_gemm(aces_ctx* ctx, const GemmP& p, int64_t m, int64_t n, int lower_only) {
     dim3 grid((unsigned)(m / BM), (unsigned)(n / BN));
-    kern<<<grid, GT, GEMM_SMEM, ctx->stream>>>(p);
+    gemm_kernel<A_KC, B_KC><<<grid, GT, GEMM_SMEM, ctx->stream>>>(p, lower_only);
     ACES_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return ACES_OK;
@@ -279,43 +536,97 @@ int gemm(aces_ctx* ctx, GemmForm form, int64_t m, int64_t n, int64_t k, double a
     ACES_CHECK(ctx, m % BM == 0 && n % BN == 0 && k % BK == 0 && k > 0,
                "dense::gemm: dimensions %lld x %lld x %lld are not padded", (long long)m, (long long)n, (long long)k);
     ACES_CHECK(ctx, lda % 2 == 0 && ldb % 2 == 0, "dense::gemm: odd leading dimension");
-    GemmP p{A, B, C, lda, ldb, ldc, (int)k, alpha, beta, lower_only};
+    ACES_TRY(configure(ctx));
+    GemmP p{A, B, C, lda, ldb, ldc, (int)k, alpha, beta};
     switch (form) {
-        case GEMM_NT: return launch_gemm<false, false>(ctx, p, m, n);
-        case GEMM_NN: return launch_gemm<false, true>(ctx, p, m, n);
-        case GEMM_TN: return launch_gemm<true, true>(ctx, p, m, n);
+        case GEMM_NT: return launch_gemm<false, false>(ctx, p, m, n, lower_only);
+        case GEMM_NN: return launch_gemm<false, true>(ctx, p, m, n, lower_only);
+        case GEMM_TN: return launch_gemm<true, true>(ctx, p, m, n, lower_only);
     }
     return aces_fail(ctx, ACES_E_INVALID, "dense::gemm: unknown form");
+}
+
+int gemm_batched(aces_ctx* ctx, GemmForm form, const GemmDesc* descs, int count, int max_tiles_m,
+                 int max_tiles_n) {
+    if (count <= 0 || max_tiles_m <= 0 || max_tiles_n <= 0) return ACES_OK;
+    ACES_TRY(configure(ctx));
+    dim3 grid((unsigned)max_tiles_m, (unsigned)max_tiles_n, (unsigned)count);
+    switch (form) {
+        case GEMM_NT: gemm_batched_kernel<false, false><<<grid, GT, GEMM_SMEM, ctx->stream>>>(descs); break;
+        case GEMM_NN: gemm_batched_kernel<false, true><<<grid, GT, GEMM_SMEM, ctx->stream>>>(descs); break;
+        case GEMM_TN: gemm_batched_kernel<true, true><<<grid, GT, GEMM_SMEM, ctx->stream>>>(descs); break;
+    }
+    ACES_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return ACES_OK;
+}
+
+int diag_blocks(aces_ctx* ctx, const DiagDesc* descs, int count, double rel_tol) {
+    if (count <= 0) return ACES_OK;
+    ACES_TRY(configure(ctx));
+    DiagDesc none{};
+    diag_kernel<<<(unsigned)count, DIAG_THREADS, DIAG_SMEM, ctx->stream>>>(descs, none, rel_tol);
+    ACES_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return ACES_OK;
 }
 
 int potrf(aces_ctx* ctx, int64_t n, double* A, int64_t lda, double* dinv, int* flag, const double* diag0,
           double rel_tol) {
     ACES_CHECK(ctx, n % DB == 0, "dense::potrf: n=%lld is not padded", (long long)n);
-    static bool configured = false;
-    const size_t smem = (size_t)DB * PLD * sizeof(double);
-    if (!configured) {
-        ACES_CUDA(ctx, cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ACES_CUDA(ctx, cudaFuncSetAttribute(trtri128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    const int64_t nb = n / DB;
-    for (int64_t k = 0; k < nb; ++k) {
-        double* Akk = A + k * DB * (lda + 1);
-        double* dk = dinv + k * DB * DB;
-        potf2_kernel<<<1, 1024, smem, ctx->stream>>>(Akk, lda, flag, (int)k, diag0 ? diag0 + k * DB : nullptr, rel_tol);
-        trtri128_kernel<<<1, 512, smem, ctx->stream>>>(Akk, lda, dk);
-        ACES_CUDA(ctx, cudaGetLastError());
-        ctx->launches += 2;
-        const int64_t rows = n - (k + 1) * DB;
-        if (rows > 0) {
+    ACES_TRY(configure(ctx));
+    constexpr int64_t NB2 = 4 * DB;  // outer panel: the bulk of the flops runs as K = 512 updates
+    for (int64_t K0 = 0; K0 < n; K0 += NB2) {
+        const int64_t kb = std::min(NB2, n - K0);
+        for (int64_t k = K0; k < K0 + kb; k += DB) {
+            double* Akk = A + k * (lda + 1);
+            double* dk = dinv + (k / DB) * DB * DB;
+            DiagDesc one{Akk, lda, dk, diag0 ? diag0 + k : nullptr, flag, (int32_t)(k / DB) + 1, 0};
+            diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, ctx->stream>>>(nullptr, one, rel_tol);
+            ACES_CUDA(ctx, cudaGetLastError());
+            ctx->launches += 1;
+            const int64_t rows = n - (k + DB);
+            if (rows <= 0) continue;
             double* panel = Akk + DB;
-            // panel <- panel * inv(L_kk)'   (in place: one CTA per 128-row tile reads exactly what it writes)
+            // panel <- panel * inv(L_kk)'  (in place: a CTA reads exactly the tile it writes)
             ACES_TRY(gemm(ctx, GEMM_NT, rows, DB, DB, 1.0, panel, lda, dk, DB, 0.0, panel, lda, 0));
-            // trailing (lower tiles) -= panel * panel'
-            ACES_TRY(gemm(ctx, GEMM_NT, rows, rows, DB, -1.0, panel, lda, panel, lda, 1.0,
-                          Akk + DB * (lda + 1), lda, 1));
+            // update the rest of the outer panel (columns k+128 .. K0+kb)
+            const int64_t cols = K0 + kb - (k + DB);
+            if (cols > 0)
+                ACES_TRY(gemm(ctx, GEMM_NT, rows, cols, DB, -1.0, panel, lda, panel, lda, 1.0,
+                              Akk + DB * (lda + 1), lda, 1));
+        }
+        const int64_t rows = n - (K0 + kb);
+        if (rows > 0) {
+            const double* P = A + (K0 + kb) + K0 * lda;  // rows below the panel, its kb columns
+            ACES_TRY(gemm(ctx, GEMM_NT, rows, rows, kb, -1.0, P, lda, P, lda, 1.0,
+                          A + (K0 + kb) * (lda + 1), lda, 1));
         }
     }
+    return ACES_OK;
+}
+
+int trsv_lower(aces_ctx* ctx, int64_t n, const double* L, int64_t ldl, const double* dinv, double* b,
+               double* y) {
+    ACES_CHECK(ctx, n % DB == 0, "dense::trsv_lower: not padded");
+    const int nb = (int)(n / DB);
+    for (int k = 0; k < nb; ++k) {
+        trsv_fwd_kernel<<<(unsigned)(nb - k), TRSV_THREADS, 0, ctx->stream>>>(L, ldl, dinv, b, y, k);
+        ctx->launches += 1;
+    }
+    ACES_CUDA(ctx, cudaGetLastError());
+    return ACES_OK;
+}
+
+int trsv_lower_t(aces_ctx* ctx, int64_t n, const double* L, int64_t ldl, const double* dinv, double* y,
+                 double* x) {
+    ACES_CHECK(ctx, n % DB == 0, "dense::trsv_lower_t: not padded");
+    const int nb = (int)(n / DB);
+    for (int k = nb - 1; k >= 0; --k) {
+        trsv_bwd_kernel<<<(unsigned)(k + 1), TRSV_THREADS, 0, ctx->stream>>>(L, ldl, dinv, y, x, k);
+        ctx->launches += 1;
+    }
+    ACES_CUDA(ctx, cudaGetLastError());
     return ACES_OK;
 }
 
@@ -383,7 +694,9 @@ int transpose(aces_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda,
 }
 int symmetrize_from_lower(aces_ctx* ctx, int64_t n, double* A, int64_t lda) {
     if (n == 0) return ACES_OK;
-    symmetrize_kernel<<<(unsigned)std::min<int64_t>((n * n + 255) / 256, 148 * 16), 256, 0, ctx->stream>>>(n, A, lda);
+    const unsigned nt = (unsigned)((n + 31) / 32);
+    dim3 grid(nt, nt), block(32, 8);
+    symmetrize_kernel<<<grid, block, 0, ctx->stream>>>(n, A, lda);
     ACES_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return ACES_OK;

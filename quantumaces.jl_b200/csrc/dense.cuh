@@ -20,16 +20,52 @@ enum GemmForm {
     GEMM_TN = 2,  // A: k x m col-major,       B: k x n col-major            C = A' * B
 };
 
+// One GEMM of a batched launch (device-resident table, one entry per blockIdx.z).
+struct GemmDesc {
+    const double* A;
+    const double* B;
+    double* C;
+    int64_t lda, ldb, ldc;
+    int32_t k;           // inner dimension (multiple of 16); 0 = inactive entry
+    int32_t tiles_m;     // m / 128
+    int32_t tiles_n;     // n / 128
+    int32_t lower_only;  // compute only tiles with bn <= bm
+    double alpha, beta;
+};
+
+// One 128 x 128 diagonal block of a (batched) Cholesky step.
+struct DiagDesc {
+    double* A;           // the block inside the matrix being factorised (NULL = inactive)
+    int64_t lda;
+    double* dinv;        // receives inv(L_kk), 128 x 128 col-major
+    const double* diag0; // original diagonal of the block (pivot test), may be NULL
+    int32_t* flag;       // set to code when a pivot fails (must be 0 before), may be NULL
+    int32_t code;
+    int32_t pad;
+};
+
 // C (m x n, ldc) = alpha * op(A) op(B) + beta * C.  m, n multiples of 128, k a multiple of 16.
 // lower_only != 0: only tiles on or below the block diagonal are computed (symmetric updates).
 int gemm(aces_ctx* ctx, GemmForm form, int64_t m, int64_t n, int64_t k, double alpha,
          const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,
          int64_t ldc, int lower_only);
 
+// `count` GEMMs of the same form in one launch; descs is a DEVICE array.  max_tiles_m/n bound
+// the grid (entries with fewer tiles leave the surplus CTAs idle).
+int gemm_batched(aces_ctx* ctx, GemmForm form, const GemmDesc* descs, int count, int max_tiles_m,
+                 int max_tiles_n);
+
+// Factorises `count` 128 x 128 diagonal blocks (descs: DEVICE array) in one launch: L_kk in place
+// (strict upper triangle zeroed) and inv(L_kk) into dinv.  A pivot that is not positive or, with
+// diag0, not above rel_tol * |diag0|, sets *flag = code (first failure wins) and is replaced by 1.
+int diag_blocks(aces_ctx* ctx, const DiagDesc* descs, int count, double rel_tol);
+
 // In-place lower Cholesky of the n x n matrix A (n a multiple of 128).  dinv receives the
 // inverses of the 128 x 128 diagonal blocks of L ([n/128][128*128], col-major).  flag (device
 // int, must be zero on entry) is set to 1 + the failing block when a pivot is not positive or,
 // with diag0 (the diagonal of A before the call, device), not above rel_tol * |diag0|.
+// descs: device scratch for n/128 DiagDesc entries (filled here through `stage`, a pinned or
+// pageable host array of the same length that must stay alive until the stream has consumed it).
 int potrf(aces_ctx* ctx, int64_t n, double* A, int64_t lda, double* dinv, int* flag,
           const double* diag0 = nullptr, double rel_tol = 0.0);
 int get_diag(aces_ctx* ctx, int64_t n, const double* A, int64_t lda, double* d);
@@ -38,6 +74,14 @@ int get_diag(aces_ctx* ctx, int64_t n, const double* A, int64_t lda, double* d);
 // (ldx); only its lower triangle is written, the strict upper triangle is zeroed.
 int trtri(aces_ctx* ctx, int64_t n, const double* L, int64_t ldl, const double* dinv, double* X,
           int64_t ldx);
+
+// Blocked triangular solves with one right-hand side, one launch per 128-block:
+//   trsv_lower:   y = inv(L)  * b   (b is destroyed)
+//   trsv_lower_t: x = inv(L') * y   (y is destroyed)
+int trsv_lower(aces_ctx* ctx, int64_t n, const double* L, int64_t ldl, const double* dinv, double* b,
+               double* y);
+int trsv_lower_t(aces_ctx* ctx, int64_t n, const double* L, int64_t ldl, const double* dinv, double* y,
+                 double* x);
 
 // B (n x nrhs, ldb) <- inv(L) * B by blocked forward substitution (nrhs a multiple of 128).
 int trsm_lower(aces_ctx* ctx, int64_t n, int64_t nrhs, const double* L, int64_t ldl,

@@ -1,0 +1,973 @@
+// design.cu -- the design-resident fit path: everything estimate_gate_noise needs from the GPU
+// with the Design uploaded once.
+//
+// Reference functions replaced (paths relative to the QuantumACES.jl root):
+//   calc_covariance / calc_covariance_log          src/merit.jl:206-291, 356-365   (K2)
+//   sparse_covariance_inv_factor                   src/merit.jl:378-427            (K3)
+//   estimate_gate_eigenvalues (OLS / WLS / GLS)    src/estimate.jl:492-524         (K4/K5)
+//   calc_gls / wls / ols_covariance, nrmse_moments src/merit.jl:556-629, 672-682   (K6)
+// as they are called from estimate_gate_noise (src/estimate.jl:703-743, 820-831).
+//
+// Layout.  The M circuit eigenvalues are grouped in T tuple blocks of m_t rows.  Every block gets
+// a dense column-major tile of mp_t x mp_t doubles (mp_t = m_t rounded up to 128) for its
+// log-covariance, which is factorised in place (L_t) and inverted (X_t = inv(L_t), the
+// reference's F block) by batched launches over all tuples at once.  The "padded row space" of
+// dimension Mp = sum mp_t stacks the blocks; clipped rows (src/estimate.jl:435-460) are
+// compacted inside their block through row_map and the freed rows become identity padding, so
+// the launch sequence does not depend on what was clipped.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "dense.cuh"
+
+using dense::DB;
+using dense::DiagDesc;
+using dense::GemmDesc;
+using dense::pad_up;
+
+struct aces_design {
+    int T = 0;
+    int64_t M = 0, N = 0, Mp = 0, Np = 0, C = 0, nnz_cov = 0, nnzA = 0;
+    int max_nb = 0;
+    double times_factor = 0.0;
+    std::vector<int64_t> m, mp, row0, prow0, tile_off, dinv_off, key0;
+    std::vector<int64_t> h_cov_colptr, h_cov_rowval;  // covariance pattern (0-based), host copy
+    std::vector<int32_t> h_blk_of_row;
+    // --- device: design data ---
+    int64_t *a_colptr = nullptr, *a_rowptr = nullptr;  // CSC / CSR of A
+    int32_t *a_rowval = nullptr, *a_colidx = nullptr;
+    double *a_nzval = nullptr, *a_vals = nullptr;
+    int64_t *cov_colptr = nullptr, *cov_rowval = nullptr;
+    int32_t *cov_src = nullptr;    // per stored entry: -1 = variance, else key index
+    int32_t *blk_of_row = nullptr;
+    double *dfac = nullptr;        // per row: (1 / w_t) * (X_t / c_pp)
+    double *kfac = nullptr;        // per key: (1 / w_t) * ((X_t * c_pq) / (c_pp * c_qq))
+    int64_t *key_p = nullptr, *key_q = nullptr;  // global rows of each key
+    int64_t *d_row0 = nullptr, *d_prow0 = nullptr, *d_tile_off = nullptr, *d_mp = nullptr;
+    // --- device: batched descriptor tables (built once) ---
+    DiagDesc* dd = nullptr;        // [max_nb][T]
+    GemmDesc *g_panel = nullptr, *g_trail = nullptr, *g_tri1 = nullptr, *g_tri2 = nullptr;  // [max_nb][T]
+    // --- device: workspaces (allocated on first use) ---
+    double *tilesL = nullptr, *tilesX = nullptr, *dinvT = nullptr;
+    double *At = nullptr, *G = nullptr, *Xn = nullptr, *Cn = nullptr, *dinvG = nullptr;
+    double *vec = nullptr;         // vector workspace
+    double *mom = nullptr;         // partial sums of the trace moments
+    double *covval = nullptr;      // [nnz_cov]
+    int32_t *row_map = nullptr;    // [M] compacted local row or -1
+    int32_t *flags = nullptr;      // [T + 1] not-PD flags (blocks, then the Gram matrix)
+    std::vector<void*> owned;
+};
+
+namespace {
+
+// ---- small device helpers -------------------------------------------------------------------------
+
+template <typename Tp>
+int dev_alloc(aces_ctx* ctx, aces_design* d, Tp** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, sizeof(Tp) * std::max<size_t>(count, 1));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return aces_fail(ctx, ACES_E_NOMEM, "design: cudaMalloc of %zu bytes failed: %s", sizeof(Tp) * count,
+                         cudaGetErrorString(e));
+    }
+    d->owned.push_back(q);
+    *p = (Tp*)q;
+    return ACES_OK;
+}
+template <typename Tp>
+int dev_upload(aces_ctx* ctx, aces_design* d, Tp** p, const std::vector<Tp>& h) {
+    ACES_TRY(dev_alloc(ctx, d, p, h.size()));
+    if (!h.empty()) ACES_CUDA(ctx, cudaMemcpy(*p, h.data(), sizeof(Tp) * h.size(), cudaMemcpyHostToDevice));
+    return ACES_OK;
+}
+
+// ---- K2: covariance values ------------------------------------------------------------------------
+// One thread per stored entry of the block-diagonal covariance (src/merit.jl:245-279).  The
+// arithmetic is written with explicit round-to-nearest intrinsics so that no multiply-add is
+// contracted: the values are the ones the reference's Float64 expressions produce.
+__global__ void cov_values_kernel(int64_t nnz, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval,
+                                  const int32_t* __restrict__ src, int64_t M, const double* __restrict__ lam,
+                                  const double* __restrict__ lam_cov, const double* __restrict__ dfac,
+                                  const double* __restrict__ kfac, const int64_t* __restrict__ key_p,
+                                  const int64_t* __restrict__ key_q, double epsilon, double times_factor,
+                                  int weight_time, int log_form, double* __restrict__ out) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = rowval[e];
+        // column of entry e: last c with colptr[c] <= e
+        int64_t lo = 0, hi = M;
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (colptr[mid] <= e) lo = mid; else hi = mid;
+        }
+        const int64_t c = lo;
+        const int32_t k = src[e];
+        double v;
+        if (k < 0) {
+            const double l = lam[r];
+            v = __dmul_rn(dfac[r], fmax(__dsub_rn(1.0, __dmul_rn(l, l)), epsilon));
+        } else {
+            v = __dmul_rn(kfac[k], __dsub_rn(lam_cov[k], __dmul_rn(lam[key_p[k]], lam[key_q[k]])));
+        }
+        if (weight_time) v = __dmul_rn(times_factor, v);
+        if (log_form) {
+            // sparse(Symmetric(D^-1 * cov * D^-1)): the upper triangle, mirrored (src/merit.jl:361-363)
+            const int64_t i = r < c ? r : c, j = r < c ? c : r;
+            v = __dmul_rn(__dmul_rn(__ddiv_rn(1.0, lam[i]), v), __ddiv_rn(1.0, lam[j]));
+        }
+        out[e] = v;
+    }
+}
+
+// ---- K3: scatter the (clipped) covariance into dense tiles ---------------------------------------
+__global__ void tiles_init_kernel(int T, const int64_t* __restrict__ tile_off, const int64_t* __restrict__ mp,
+                                  double* __restrict__ tiles, int identity) {
+    const int t = blockIdx.y;
+    if (t >= T) return;
+    const int64_t n = mp[t], total = n * n;
+    double* tile = tiles + tile_off[t];
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+        tile[e] = (identity && (e % n) == (e / n)) ? 1.0 : 0.0;
+}
+// One thread per column c of the M x M block-diagonal sparse matrix; entries outside the diagonal
+// blocks are ignored (the reference slices the blocks out, src/merit.jl:393).  row_map == NULL:
+// nothing is clipped.  Rows past the kept ones get a unit diagonal.
+__global__ void tiles_scatter_kernel(int64_t M, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval,
+                                     const double* __restrict__ val, const int32_t* __restrict__ blk_of_row,
+                                     const int64_t* __restrict__ row0, const int64_t* __restrict__ tile_off,
+                                     const int64_t* __restrict__ mp, const int32_t* __restrict__ row_map,
+                                     double* __restrict__ tiles) {
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < M; c += (int64_t)gridDim.x * blockDim.x) {
+        const int t = blk_of_row[c];
+        const int64_t lc = row_map ? row_map[c] : c - row0[t];
+        if (lc < 0) continue;
+        double* tile = tiles + tile_off[t];
+        const int64_t n = mp[t];
+        for (int64_t e = colptr[c]; e < colptr[c + 1]; ++e) {
+            const int64_t r = rowval[e];
+            if (blk_of_row[r] != t) continue;
+            const int64_t lr = row_map ? row_map[r] : r - row0[t];
+            if (lr < 0) continue;
+            tile[lr + lc * n] = val[e];
+        }
+    }
+}
+// unit diagonal on rows kept[t] .. mp[t]-1 of every tile
+__global__ void tiles_pad_kernel(int T, const int64_t* __restrict__ tile_off, const int64_t* __restrict__ mp,
+                                 const int64_t* __restrict__ kept, double* __restrict__ tiles) {
+    const int t = blockIdx.y;
+    if (t >= T) return;
+    const int64_t n = mp[t];
+    double* tile = tiles + tile_off[t];
+    for (int64_t i = kept[t] + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        tile[i + i * n] = 1.0;
+}
+// dense lower-triangular tiles -> caller layout (m_t x m_t col-major blocks, concatenated)
+__global__ void tiles_export_kernel(int T, const int64_t* __restrict__ tile_off, const int64_t* __restrict__ mp,
+                                    const int64_t* __restrict__ kept, const int64_t* __restrict__ out_off,
+                                    const double* __restrict__ tiles, double* __restrict__ out) {
+    const int t = blockIdx.y;
+    if (t >= T) return;
+    const int64_t n = mp[t], k = kept[t], total = k * k;
+    const double* tile = tiles + tile_off[t];
+    double* o = out + out_off[t];
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e % k, j = e / k;
+        o[e] = (i >= j) ? tile[i + j * n] : 0.0;
+    }
+}
+
+// ---- operators on the padded row space --------------------------------------------------------------
+// u[prow] = b_r - sum_j A[r, j] x[j] for kept rows (b_r = -log y_r), zero elsewhere.  x == NULL: u = b.
+__global__ void residual_kernel(int64_t M, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                const double* __restrict__ vals, const int32_t* __restrict__ blk_of_row,
+                                const int64_t* __restrict__ row0, const int64_t* __restrict__ prow0,
+                                const int32_t* __restrict__ row_map, const double* __restrict__ y,
+                                const double* __restrict__ x, double* __restrict__ u) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < M; r += (int64_t)gridDim.x * blockDim.x) {
+        const int t = blk_of_row[r];
+        const int64_t lr = row_map ? row_map[r] : r - row0[t];
+        if (lr < 0) continue;
+        double s = -log(y[r]);
+        if (x)
+            for (int64_t e = rowptr[r]; e < rowptr[r + 1]; ++e) s -= vals[e] * x[colidx[e]];
+        u[prow0[t] + lr] = s;
+    }
+}
+// g[j] = sum_r A[r, j] v[prow(r)]
+__global__ void at_times_kernel(int64_t N, const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval,
+                                const double* __restrict__ nzval, const int32_t* __restrict__ blk_of_row,
+                                const int64_t* __restrict__ row0, const int64_t* __restrict__ prow0,
+                                const int32_t* __restrict__ row_map, const double* __restrict__ v,
+                                double* __restrict__ g) {
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < N; j += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int64_t e = colptr[j]; e < colptr[j + 1]; ++e) {
+            const int64_t r = rowval[e];
+            const int t = blk_of_row[r];
+            const int64_t lr = row_map ? row_map[r] : r - row0[t];
+            if (lr >= 0) s += nzval[e] * v[prow0[t] + lr];
+        }
+        g[j] = s;
+    }
+}
+// out = F u with F = blockdiag(X_t) (lower triangular tiles): one thread per padded row
+__global__ void apply_f_kernel(int T, const int64_t* __restrict__ prow0, const int64_t* __restrict__ tile_off,
+                               const int64_t* __restrict__ mp, const double* __restrict__ tiles,
+                               const double* __restrict__ u, double* __restrict__ out) {
+    const int t = blockIdx.y;
+    if (t >= T) return;
+    const int64_t n = mp[t];
+    const double* X = tiles + tile_off[t];
+    const double* ut = u + prow0[t];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int64_t c = 0; c <= i; ++c) s += X[i + c * n] * ut[c];
+        out[prow0[t] + i] = s;
+    }
+}
+// out = F' v: one warp per padded column
+__global__ void apply_ft_kernel(int T, const int64_t* __restrict__ prow0, const int64_t* __restrict__ tile_off,
+                                const int64_t* __restrict__ mp, const double* __restrict__ tiles,
+                                const double* __restrict__ v, double* __restrict__ out) {
+    const int t = blockIdx.y;
+    if (t >= T) return;
+    const int64_t n = mp[t];
+    const double* X = tiles + tile_off[t];
+    const double* vt = v + prow0[t];
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = warp; c < n; c += nwarps) {
+        double s = 0.0;
+        for (int64_t i = c + lane; i < n; i += 32) s += X[i + c * n] * vt[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) out[prow0[t] + c] = s;
+    }
+}
+// diagonal F (WLS): f[prow] = cov_log[r, r]^(-1/2) for kept rows (src/estimate.jl:729-731), 0 elsewhere
+__global__ void diag_factor_kernel(int64_t M, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval,
+                                   const double* __restrict__ val, const int32_t* __restrict__ blk_of_row,
+                                   const int64_t* __restrict__ row0, const int64_t* __restrict__ prow0,
+                                   const int32_t* __restrict__ row_map, int unit, double* __restrict__ f) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < M; r += (int64_t)gridDim.x * blockDim.x) {
+        const int t = blk_of_row[r];
+        const int64_t lr = row_map ? row_map[r] : r - row0[t];
+        if (lr < 0) continue;
+        double d = 1.0;
+        if (!unit)
+            for (int64_t e = colptr[r]; e < colptr[r + 1]; ++e)
+                if (rowval[e] == r) d = pow(val[e], -0.5);
+        f[prow0[t] + lr] = d;
+    }
+}
+__global__ void mul_vec_kernel(int64_t n, const double* __restrict__ f, const double* __restrict__ u, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = f[i] * u[i];
+}
+__global__ void axpy_kernel(int64_t n, double a, const double* __restrict__ x, double* __restrict__ y) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] += a * x[i];
+}
+__global__ void exp_neg_kernel(int64_t n, const double* __restrict__ x, double* __restrict__ g, int constrain) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = x[i];
+        if (constrain && v < 0.0) v = 0.0;  // src/estimate.jl:504-506
+        g[i] = exp(-v);
+    }
+}
+
+// ---- whitened design matrix (GLS) --------------------------------------------------------------------
+// At[:, j] = sum over the entries (r, a) of column j of A of a * X_t[:, lr]  (one CTA per column j;
+// row i of a block is always handled by thread i % blockDim, so no two threads touch one entry).
+__global__ void whiten_tiles_kernel(int64_t N, const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval,
+                                    const double* __restrict__ nzval, const int32_t* __restrict__ blk_of_row,
+                                    const int64_t* __restrict__ row0, const int64_t* __restrict__ prow0,
+                                    const int64_t* __restrict__ tile_off, const int64_t* __restrict__ mp,
+                                    const int32_t* __restrict__ row_map, const double* __restrict__ tiles,
+                                    double* __restrict__ At, int64_t ld) {
+    const int64_t j = blockIdx.x;
+    if (j >= N) return;
+    double* col = At + j * ld;
+    const int bd = blockDim.x, tid = threadIdx.x;
+    for (int64_t e = colptr[j]; e < colptr[j + 1]; ++e) {
+        const int64_t r = rowval[e];
+        const int t = blk_of_row[r];
+        const int64_t lr = row_map ? row_map[r] : r - row0[t];
+        if (lr < 0) continue;
+        const double a = nzval[e];
+        const int64_t n = mp[t];
+        const double* X = tiles + tile_off[t] + lr * n;  // column lr of X_t: nonzero for rows >= lr
+        double* out = col + prow0[t];
+        int64_t i = lr - (lr % bd) + tid;
+        if (i < lr) i += bd;
+        for (; i < n; i += bd) out[i] += a * X[i];
+    }
+}
+
+// ---- sparse sandwich C = A' diag(w) S diag(w) A (lower triangle of C only) --------------------------
+// S is an M x M sparse matrix in CSC (the covariance pattern, or NULL for the identity); w is
+// given on the padded row space (0 for clipped rows).  One thread per column b of C.
+__global__ void sandwich_kernel(int64_t N, const int64_t* __restrict__ a_colptr, const int32_t* __restrict__ a_rowval,
+                                const double* __restrict__ a_nzval, const int64_t* __restrict__ a_rowptr,
+                                const int32_t* __restrict__ a_colidx, const double* __restrict__ a_vals,
+                                const int64_t* __restrict__ s_colptr, const int64_t* __restrict__ s_rowval,
+                                const double* __restrict__ s_val, const int32_t* __restrict__ blk_of_row,
+                                const int64_t* __restrict__ row0, const int64_t* __restrict__ prow0,
+                                const int32_t* __restrict__ row_map, const double* __restrict__ w,
+                                double* __restrict__ Cm, int64_t ldc) {
+    for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < N; b += (int64_t)gridDim.x * blockDim.x) {
+        double* col = Cm + b * ldc;
+        for (int64_t e = a_colptr[b]; e < a_colptr[b + 1]; ++e) {
+            const int64_t j = a_rowval[e];
+            const int tj = blk_of_row[j];
+            const int64_t lj = row_map ? row_map[j] : j - row0[tj];
+            if (lj < 0) continue;
+            const double ajb = a_nzval[e] * w[prow0[tj] + lj];
+            const int64_t f0 = s_colptr ? s_colptr[j] : 0, f1 = s_colptr ? s_colptr[j + 1] : 1;
+            for (int64_t f = f0; f < f1; ++f) {
+                const int64_t i = s_colptr ? s_rowval[f] : j;
+                const int ti = blk_of_row[i];
+                const int64_t li = row_map ? row_map[i] : i - row0[ti];
+                if (li < 0) continue;
+                const double sij = (s_colptr ? s_val[f] : 1.0) * w[prow0[ti] + li] * ajb;
+                for (int64_t q = a_rowptr[i]; q < a_rowptr[i + 1]; ++q) {
+                    const int64_t a = a_colidx[q];
+                    if (a >= b) col[a] += a_vals[q] * sij;
+                }
+            }
+        }
+    }
+}
+
+__global__ void scale_sym_kernel(int64_t n, double* S, int64_t lds, const double* d) {
+    const int64_t total = n * n;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e % n, j = e / n;
+        S[i + j * lds] = S[i + j * lds] * (d[i] * d[j]);  // (di*dj) commutes: the result stays exactly symmetric
+    }
+}
+// tr(S) and tr(S^2) = sum_ij S_ij^2 of a symmetric n x n matrix (src/merit.jl:674-675)
+__global__ void moments_kernel(int64_t n, const double* __restrict__ S, int64_t lds, double* __restrict__ out) {
+    double tr = 0.0, sq = 0.0;
+    const int64_t total = n * n;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e % n, j = e / n;
+        const double v = S[i + j * lds];
+        sq += v * v;
+        if (i == j) tr += v;
+    }
+    __shared__ double s_tr[256], s_sq[256];
+    s_tr[threadIdx.x] = tr;
+    s_sq[threadIdx.x] = sq;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            s_tr[threadIdx.x] += s_tr[threadIdx.x + o];
+            s_sq[threadIdx.x] += s_sq[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {  // per-CTA partial sums: the final order of additions is fixed
+        out[2 + 2 * blockIdx.x] = s_tr[0];
+        out[3 + 2 * blockIdx.x] = s_sq[0];
+    }
+}
+__global__ void moments_final_kernel(int nparts, double* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double tr = 0.0, sq = 0.0;
+        for (int i = 0; i < nparts; ++i) {
+            tr += out[2 + 2 * i];
+            sq += out[3 + 2 * i];
+        }
+        out[0] = tr;
+        out[1] = sq;
+    }
+}
+
+inline unsigned grid_for(int64_t n, int threads, int64_t cap = 148 * 16) {
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, cap));
+}
+
+// ---- host orchestration -------------------------------------------------------------------------------
+
+int ensure_workspaces(aces_ctx* ctx, aces_design* d, bool need_tiles, bool need_at, bool need_inverse, bool need_c) {
+    const size_t tiles = (size_t)(d->tile_off.back());
+    if (need_tiles && !d->tilesL) {
+        ACES_TRY(dev_alloc(ctx, d, &d->tilesL, tiles));
+        ACES_TRY(dev_alloc(ctx, d, &d->tilesX, tiles));
+        ACES_TRY(dev_alloc(ctx, d, &d->dinvT, (size_t)d->dinv_off.back()));
+    }
+    if (need_at && !d->At) ACES_TRY(dev_alloc(ctx, d, &d->At, (size_t)d->Mp * d->Np));
+    if (!d->G) {
+        ACES_TRY(dev_alloc(ctx, d, &d->G, (size_t)d->Np * d->Np));
+        ACES_TRY(dev_alloc(ctx, d, &d->dinvG, (size_t)d->Np * DB));
+        ACES_TRY(dev_alloc(ctx, d, &d->vec, (size_t)(8 * std::max(d->Mp, d->Np) + 64)));
+        ACES_TRY(dev_alloc(ctx, d, &d->covval, (size_t)d->nnz_cov));
+        ACES_TRY(dev_alloc(ctx, d, &d->mom, (size_t)(2 + 2 * 148 * 4)));
+        ACES_TRY(dev_alloc(ctx, d, &d->row_map, (size_t)d->M));
+        ACES_TRY(dev_alloc(ctx, d, &d->flags, (size_t)d->T + 2));
+    }
+    if (need_inverse && !d->Xn) ACES_TRY(dev_alloc(ctx, d, &d->Xn, (size_t)d->Np * d->Np));
+    if (need_c && !d->Cn) ACES_TRY(dev_alloc(ctx, d, &d->Cn, (size_t)d->Np * d->Np));
+    return ACES_OK;
+}
+
+// Cholesky factors L_t (tilesL, in place) and their inverses X_t (tilesX) of every tile, batched.
+int factor_tiles(aces_ctx* ctx, aces_design* d) {
+    const int T = d->T;
+    for (int k = 0; k < d->max_nb; ++k) {
+        ACES_TRY(dense::diag_blocks(ctx, d->dd + (size_t)k * T, T, 0.0));
+        if (k + 1 < d->max_nb) {
+            ACES_TRY(dense::gemm_batched(ctx, dense::GEMM_NT, d->g_panel + (size_t)k * T, T, d->max_nb - k - 1, 1));
+            ACES_TRY(dense::gemm_batched(ctx, dense::GEMM_NT, d->g_trail + (size_t)k * T, T, d->max_nb - k - 1,
+                                         d->max_nb - k - 1));
+        }
+    }
+    // X_t = inv(L_t): forward substitution on the identity, block row by block row
+    {
+        dim3 grid(148, (unsigned)T);
+        tiles_init_kernel<<<grid, 256, 0, ctx->stream>>>(T, d->d_tile_off, d->d_mp, d->tilesX, 1);
+        ACES_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
+    for (int k = 0; k < d->max_nb; ++k) {
+        ACES_TRY(dense::gemm_batched(ctx, dense::GEMM_NN, d->g_tri1 + (size_t)k * T, T, 1, k + 1));
+        if (k + 1 < d->max_nb)
+            ACES_TRY(dense::gemm_batched(ctx, dense::GEMM_NN, d->g_tri2 + (size_t)k * T, T, d->max_nb - k - 1, k + 1));
+    }
+    return ACES_OK;
+}
+
+// Uploads row_map / kept counts for a kept-row list (NULL = all rows) and returns the device kept array.
+int upload_clipping(aces_ctx* ctx, aces_design* d, const int64_t* kept_rows, int64_t n_kept, int index_base,
+                    std::vector<int64_t>* kept_count, bool* clipped) {
+    kept_count->assign(d->m.begin(), d->m.end());
+    *clipped = false;
+    if (!kept_rows) return ACES_OK;
+    std::vector<int32_t> map((size_t)d->M, -1);
+    std::vector<int64_t> cnt((size_t)d->T, 0);
+    int64_t prev = -1;
+    for (int64_t i = 0; i < n_kept; ++i) {
+        const int64_t r = kept_rows[i] - index_base;
+        ACES_CHECK(ctx, r > prev && r < d->M, "design: kept rows must be sorted, unique and inside 0..M-1");
+        prev = r;
+        const int t = d->h_blk_of_row[(size_t)r];
+        map[(size_t)r] = (int32_t)cnt[(size_t)t]++;
+    }
+    *clipped = n_kept != d->M;
+    if (!*clipped) return ACES_OK;
+    *kept_count = cnt;
+    ACES_CUDA(ctx, cudaMemcpyAsync(d->row_map, map.data(), sizeof(int32_t) * (size_t)d->M, cudaMemcpyHostToDevice,
+                                   ctx->stream));
+    ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `map` dies at return
+    return ACES_OK;
+}
+
+int launch_cov_values(aces_ctx* ctx, aces_design* d, const double* lam_dev, const double* lamcov_dev, double epsilon,
+                      int weight_time, int log_form, double* out_dev) {
+    if (d->nnz_cov == 0) return ACES_OK;
+    cov_values_kernel<<<grid_for(d->nnz_cov, 256), 256, 0, ctx->stream>>>(
+        d->nnz_cov, d->cov_colptr, d->cov_rowval, d->cov_src, d->M, lam_dev, lamcov_dev, d->dfac, d->kfac, d->key_p,
+        d->key_q, epsilon, d->times_factor, weight_time, log_form, out_dev);
+    ACES_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return ACES_OK;
+}
+
+// Fills tilesL with the (clipped) log-covariance blocks held in `val` (pattern order), factorises.
+int build_and_factor_tiles(aces_ctx* ctx, aces_design* d, const double* val_dev, const int32_t* row_map,
+                           const std::vector<int64_t>& kept_count) {
+    const int T = d->T;
+    dim3 grid(148, (unsigned)T);
+    tiles_init_kernel<<<grid, 256, 0, ctx->stream>>>(T, d->d_tile_off, d->d_mp, d->tilesL, 0);
+    tiles_scatter_kernel<<<grid_for(d->M, 128), 128, 0, ctx->stream>>>(d->M, d->cov_colptr, d->cov_rowval, val_dev,
+                                                                      d->blk_of_row, d->d_row0, d->d_tile_off, d->d_mp,
+                                                                      row_map, d->tilesL);
+    // kept counts -> device (small, reuse the tail of vec)
+    int64_t* kept_dev = (int64_t*)(d->vec + 8 * std::max(d->Mp, d->Np));
+    ACES_CHECK(ctx, T <= 60, "design: more than 60 tuples are not supported by the workspace layout");
+    ACES_CUDA(ctx, cudaMemcpyAsync(kept_dev, kept_count.data(), sizeof(int64_t) * (size_t)T, cudaMemcpyHostToDevice,
+                                   ctx->stream));
+    dim3 gpad(4, (unsigned)T);
+    tiles_pad_kernel<<<gpad, 128, 0, ctx->stream>>>(T, d->d_tile_off, d->d_mp, kept_dev, d->tilesL);
+    ACES_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 3;
+    ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // kept_count may be a temporary of the caller
+    return factor_tiles(ctx, d);
+}
+
+struct FitVectors {
+    double *u, *v, *w, *g, *x, *t1, *t2, *f;
+};
+FitVectors fit_vectors(aces_design* d) {
+    const int64_t n = std::max(d->Mp, d->Np);
+    FitVectors fv;
+    fv.u = d->vec; fv.v = d->vec + n; fv.w = d->vec + 2 * n; fv.g = d->vec + 3 * n; fv.x = d->vec + 4 * n;
+    fv.t1 = d->vec + 5 * n; fv.t2 = d->vec + 6 * n; fv.f = d->vec + 7 * n;
+    return fv;
+}
+
+// out (padded row space) = F u  /  out = F' v for the chosen estimator
+int apply_F(aces_ctx* ctx, aces_design* d, int ls_type, const FitVectors& fv, const double* u, double* out, bool transpose) {
+    if (ls_type == 2) {
+        dim3 grid(16, (unsigned)d->T);
+        if (!transpose)
+            apply_f_kernel<<<grid, 128, 0, ctx->stream>>>(d->T, d->d_prow0, d->d_tile_off, d->d_mp, d->tilesX, u, out);
+        else
+            apply_ft_kernel<<<grid, 256, 0, ctx->stream>>>(d->T, d->d_prow0, d->d_tile_off, d->d_mp, d->tilesX, u, out);
+    } else {
+        mul_vec_kernel<<<grid_for(d->Mp, 256), 256, 0, ctx->stream>>>(d->Mp, fv.f, u, out);
+    }
+    ACES_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return ACES_OK;
+}
+
+// G = (F A)' (F A) (lower triangle) for the chosen estimator; fv.f must hold the diagonal factor
+// for OLS / WLS, tilesX the block factors for GLS.
+int build_gram(aces_ctx* ctx, aces_design* d, int ls_type, const FitVectors& fv, const int32_t* row_map) {
+    const int64_t Np = d->Np, Mp = d->Mp;
+    if (ls_type == 2) {
+        ACES_CUDA(ctx, cudaMemsetAsync(d->At, 0, sizeof(double) * (size_t)Mp * Np, ctx->stream));
+        whiten_tiles_kernel<<<(unsigned)d->N, 256, 0, ctx->stream>>>(d->N, d->a_colptr, d->a_rowval, d->a_nzval,
+                                                                    d->blk_of_row, d->d_row0, d->d_prow0, d->d_tile_off,
+                                                                    d->d_mp, row_map, d->tilesX, d->At, Mp);
+        ACES_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+        if (ctx->timing) ACES_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
+        ACES_TRY(dense::gemm(ctx, dense::GEMM_TN, Np, Np, Mp, 1.0, d->At, Mp, d->At, Mp, 0.0, d->G, Np, 1));
+        if (ctx->timing) {
+            ACES_CUDA(ctx, cudaEventRecord(ctx->t1, ctx->stream));
+            ctx->timed = 1;
+        }
+    } else {
+        ACES_CUDA(ctx, cudaMemsetAsync(d->G, 0, sizeof(double) * (size_t)Np * Np, ctx->stream));
+        sandwich_kernel<<<grid_for(d->N, 64), 64, 0, ctx->stream>>>(
+            d->N, d->a_colptr, d->a_rowval, d->a_nzval, d->a_rowptr, d->a_colidx, d->a_vals, nullptr, nullptr, nullptr,
+            d->blk_of_row, d->d_row0, d->d_prow0, row_map, fv.f, d->G, Np);
+        ACES_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
+    ACES_TRY(dense::fill_diag_range(ctx, d->G, Np, d->N, Np, 1.0));
+    return ACES_OK;
+}
+
+int check_flags(aces_ctx* ctx, aces_design* d, const char* what) {
+    std::vector<int32_t> fl((size_t)d->T + 1);
+    ACES_CUDA(ctx, cudaMemcpyAsync(fl.data(), d->flags, sizeof(int32_t) * fl.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int t = 0; t < d->T; ++t)
+        if (fl[(size_t)t])
+            return aces_fail(ctx, ACES_E_NOT_PD, "%s: the covariance block of tuple %d is not positive definite", what, t);
+    if (fl[(size_t)d->T])
+        return aces_fail(ctx, ACES_E_NOT_PD,
+                         "%s: the Gram matrix is not positive definite (diagonal block %d): the whitened design "
+                         "matrix is rank deficient", what, fl[(size_t)d->T] - 1);
+    return ACES_OK;
+}
+
+// Prepares the estimator: covariance values (from eigenvalue estimates, or given), factor (GLS) or
+// diagonal weights (OLS / WLS), Gram matrix and its Cholesky factor.
+int prepare_estimator(aces_ctx* ctx, aces_design* d, int ls_type, const double* val_dev, const int32_t* row_map,
+                      const std::vector<int64_t>& kept_count, const FitVectors& fv) {
+    ACES_CUDA(ctx, cudaMemsetAsync(d->flags, 0, sizeof(int32_t) * ((size_t)d->T + 2), ctx->stream));
+    ACES_CUDA(ctx, cudaMemsetAsync(d->vec, 0, sizeof(double) * (size_t)(8 * std::max(d->Mp, d->Np)), ctx->stream));
+    if (ls_type == 2) {
+        ACES_TRY(build_and_factor_tiles(ctx, d, val_dev, row_map, kept_count));
+    } else {
+        diag_factor_kernel<<<grid_for(d->M, 256), 256, 0, ctx->stream>>>(d->M, d->cov_colptr, d->cov_rowval, val_dev,
+                                                                        d->blk_of_row, d->d_row0, d->d_prow0, row_map,
+                                                                        ls_type == 0 ? 1 : 0, fv.f);
+        ACES_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
+    ACES_TRY(build_gram(ctx, d, ls_type, fv, row_map));
+    ACES_TRY(dense::get_diag(ctx, d->Np, d->G, d->Np, fv.t2));
+    ACES_CUDA(ctx, cudaMemcpyAsync(fv.t1, fv.t2, sizeof(double) * (size_t)d->Np, cudaMemcpyDeviceToDevice, ctx->stream));
+    ACES_TRY(dense::potrf(ctx, d->Np, d->G, d->Np, d->dinvG, d->flags + d->T, fv.t1, 1e-13));
+    return ACES_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t aces_design_create(aces_ctx* ctx, int32_t T, const int64_t* mapping_lengths, int64_t N,
+                           const int32_t* A_colptr, const int32_t* A_rowval, const int32_t* A_nzval,
+                           int32_t index_base, const int64_t* experiment_numbers, const double* shot_weights,
+                           const double* tuple_times, const int64_t* diag_counts, const int64_t* cov_ptr,
+                           const int64_t* cov_p, const int64_t* cov_q, const int64_t* cov_counts,
+                           aces_design** out) {
+    if (!ctx) return ACES_E_INVALID;
+    ACES_CHECK(ctx, out != nullptr, "design_create: out is NULL");
+    *out = nullptr;
+    ACES_CHECK(ctx, T >= 1 && N >= 1, "design_create: T=%d N=%lld", T, (long long)N);
+    ACES_CHECK(ctx, mapping_lengths && A_colptr && A_rowval && A_nzval && experiment_numbers && shot_weights &&
+                        tuple_times && diag_counts, "design_create: NULL argument");
+    ACES_CHECK(ctx, index_base == 0 || index_base == 1, "design_create: index_base must be 0 or 1");
+    ACES_CUDA(ctx, cudaSetDevice(ctx->device));
+    aces_design* d = new aces_design();
+    auto fail = [&](int rc) {
+        for (void* p : d->owned) cudaFree(p);
+        delete d;
+        return rc;
+    };
+    d->T = T;
+    d->N = N;
+    d->Np = pad_up(N);
+    d->m.assign(mapping_lengths, mapping_lengths + T);
+    d->mp.resize(T); d->row0.resize(T + 1); d->prow0.resize(T + 1); d->tile_off.resize(T + 1);
+    d->dinv_off.resize(T + 1); d->key0.resize(T + 1);
+    d->row0[0] = d->prow0[0] = d->tile_off[0] = d->dinv_off[0] = 0;
+    for (int t = 0; t < T; ++t) {
+        if (d->m[t] < 0) return fail(aces_fail(ctx, ACES_E_INVALID, "design_create: negative mapping length"));
+        d->mp[t] = std::max<int64_t>(pad_up(d->m[t]), DB);
+        d->row0[t + 1] = d->row0[t] + d->m[t];
+        d->prow0[t + 1] = d->prow0[t] + d->mp[t];
+        d->tile_off[t + 1] = d->tile_off[t] + d->mp[t] * d->mp[t];
+        d->dinv_off[t + 1] = d->dinv_off[t] + d->mp[t] * DB;
+        d->max_nb = std::max<int>(d->max_nb, (int)(d->mp[t] / DB));
+        d->times_factor += shot_weights[t] * tuple_times[t];  // sum(d.shot_weights .* d.tuple_times)
+    }
+    d->M = d->row0[T];
+    d->Mp = d->prow0[T];
+    const int64_t M = d->M;
+    d->h_blk_of_row.resize((size_t)M);
+    for (int t = 0; t < T; ++t)
+        for (int64_t r = d->row0[t]; r < d->row0[t + 1]; ++r) d->h_blk_of_row[(size_t)r] = t;
+
+    // ---- design matrix: CSC (as given) and CSR -------------------------------------------------
+    const int64_t nnzA = (int64_t)A_colptr[N] - index_base;
+    d->nnzA = nnzA;
+    std::vector<int64_t> colptr((size_t)N + 1), rowptr((size_t)M + 1, 0);
+    std::vector<int32_t> rowval((size_t)nnzA), colidx((size_t)nnzA);
+    std::vector<double> nzval((size_t)nnzA), vals((size_t)nnzA);
+    for (int64_t j = 0; j <= N; ++j) colptr[(size_t)j] = (int64_t)A_colptr[j] - index_base;
+    for (int64_t e = 0; e < nnzA; ++e) {
+        const int64_t r = (int64_t)A_rowval[e] - index_base;
+        if (r < 0 || r >= M) return fail(aces_fail(ctx, ACES_E_INVALID, "design_create: design-matrix row %lld outside 0..%lld", (long long)r, (long long)M - 1));
+        rowval[(size_t)e] = (int32_t)r;
+        nzval[(size_t)e] = (double)A_nzval[e];
+        rowptr[(size_t)r + 1]++;
+    }
+    for (int64_t r = 0; r < M; ++r) rowptr[(size_t)r + 1] += rowptr[(size_t)r];
+    {
+        std::vector<int64_t> fill(rowptr.begin(), rowptr.end() - 1);
+        for (int64_t j = 0; j < N; ++j)
+            for (int64_t e = colptr[(size_t)j]; e < colptr[(size_t)j + 1]; ++e) {
+                const int64_t p = fill[(size_t)rowval[(size_t)e]]++;
+                colidx[(size_t)p] = (int32_t)j;
+                vals[(size_t)p] = nzval[(size_t)e];
+            }
+    }
+    // ---- covariance pattern: the diagonal plus both orientations of every key ----------------------
+    const int64_t C = cov_ptr ? cov_ptr[T] : 0;
+    d->C = C;
+    std::vector<int64_t> key_p((size_t)C), key_q((size_t)C);
+    std::vector<double> dfac((size_t)M), kfac((size_t)C);
+    for (int t = 0; t < T; ++t) {
+        const double w = shot_weights[t];
+        const double X = (double)experiment_numbers[t];
+        for (int64_t r = d->row0[t]; r < d->row0[t + 1]; ++r) {
+            if (diag_counts[r] < 1) return fail(aces_fail(ctx, ACES_E_INVALID, "design_create: diag_counts[%lld] < 1", (long long)r));
+            dfac[(size_t)r] = (1.0 / w) * (X / (double)diag_counts[r]);  // src/merit.jl:250-251
+        }
+        d->key0[t] = cov_ptr ? cov_ptr[t] : 0;
+    }
+    d->key0[T] = C;
+    std::vector<std::vector<std::pair<int64_t, int32_t>>> cols((size_t)M);  // per column: (row, src)
+    for (int64_t r = 0; r < M; ++r) cols[(size_t)r].push_back({r, -1});
+    for (int t = 0; t < T; ++t) {
+        const double w = shot_weights[t];
+        for (int64_t k = d->key0[t]; k < d->key0[t + 1]; ++k) {
+            const int64_t p = cov_p[k] - index_base, q = cov_q[k] - index_base;
+            if (p < 0 || q < 0 || p >= d->m[t] || q >= d->m[t] || p == q)
+                return fail(aces_fail(ctx, ACES_E_INVALID, "design_create: covariance key %lld = (%lld, %lld) invalid for tuple %d", (long long)k, (long long)p, (long long)q, t));
+            const int64_t gp = d->row0[t] + p, gq = d->row0[t] + q;
+            key_p[(size_t)k] = gp;
+            key_q[(size_t)k] = gq;
+            // src/merit.jl:269-273: (1 / w) * ((X * c_pq) / (c_pp * c_qq)), integer products first
+            kfac[(size_t)k] = (1.0 / w) * ((double)(experiment_numbers[t] * cov_counts[k]) /
+                                           (double)(diag_counts[gp] * diag_counts[gq]));
+            cols[(size_t)gq].push_back({gp, (int32_t)k});
+            cols[(size_t)gp].push_back({gq, (int32_t)k});
+        }
+    }
+    std::vector<int64_t> cov_colptr((size_t)M + 1, 0), cov_rowval;
+    std::vector<int32_t> cov_src;
+    for (int64_t c = 0; c < M; ++c) {
+        auto& v = cols[(size_t)c];
+        std::sort(v.begin(), v.end());
+        for (size_t i = 0; i < v.size(); ++i) {
+            if (i > 0 && v[i].first == v[i - 1].first)
+                return fail(aces_fail(ctx, ACES_E_INVALID, "design_create: duplicate covariance key at (%lld, %lld)", (long long)v[i].first, (long long)c));
+            cov_rowval.push_back(v[i].first);
+            cov_src.push_back(v[i].second);
+        }
+        cov_colptr[(size_t)c + 1] = (int64_t)cov_rowval.size();
+    }
+    d->nnz_cov = (int64_t)cov_rowval.size();
+    d->h_cov_colptr = cov_colptr;
+    d->h_cov_rowval = cov_rowval;
+
+    int rc;
+#define UP(field, vecname) if ((rc = dev_upload(ctx, d, &d->field, vecname)) != ACES_OK) return fail(rc)
+    UP(a_colptr, colptr); UP(a_rowval, rowval); UP(a_nzval, nzval);
+    UP(a_rowptr, rowptr); UP(a_colidx, colidx); UP(a_vals, vals);
+    UP(cov_colptr, cov_colptr); UP(cov_rowval, cov_rowval); UP(cov_src, cov_src);
+    UP(blk_of_row, d->h_blk_of_row); UP(dfac, dfac); UP(kfac, kfac); UP(key_p, key_p); UP(key_q, key_q);
+    UP(d_row0, d->row0); UP(d_prow0, d->prow0); UP(d_tile_off, d->tile_off); UP(d_mp, d->mp);
+#undef UP
+    *out = d;
+    return ACES_OK;
+}
+
+int32_t aces_design_destroy(aces_ctx* ctx, aces_design* d) {
+    if (!ctx) return ACES_E_INVALID;
+    if (!d) return ACES_OK;
+    ACES_CUDA(ctx, cudaSetDevice(ctx->device));
+    ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (void* p : d->owned) cudaFree(p);
+    delete d;
+    return ACES_OK;
+}
+
+int64_t aces_design_covariance_nnz(const aces_design* d) { return d ? d->nnz_cov : -1; }
+
+int32_t aces_design_covariance_pattern(const aces_design* d, int64_t* colptr, int64_t* rowval) {
+    if (!d || !colptr || !rowval) return ACES_E_INVALID;
+    std::copy(d->h_cov_colptr.begin(), d->h_cov_colptr.end(), colptr);
+    std::copy(d->h_cov_rowval.begin(), d->h_cov_rowval.end(), rowval);
+    return ACES_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// Descriptor tables of the batched tile factorisation (built on first use: they hold workspace addresses).
+int build_tile_descs(aces_ctx* ctx, aces_design* d) {
+    if (d->dd) return ACES_OK;
+    const int T = d->T, nbm = d->max_nb;
+    std::vector<DiagDesc> dd((size_t)nbm * T);
+    std::vector<GemmDesc> gp((size_t)nbm * T), gt((size_t)nbm * T), g1((size_t)nbm * T), g2((size_t)nbm * T);
+    for (int k = 0; k < nbm; ++k)
+        for (int t = 0; t < T; ++t) {
+            const size_t idx = (size_t)k * T + t;
+            const int64_t n = d->mp[t];
+            const int nb = (int)(n / DB);
+            DiagDesc& a = dd[idx];
+            GemmDesc z{};
+            gp[idx] = gt[idx] = g1[idx] = g2[idx] = z;
+            a = DiagDesc{};
+            if (k >= nb) continue;
+            double* L = d->tilesL + d->tile_off[t];
+            double* X = d->tilesX + d->tile_off[t];
+            double* dk = d->dinvT + d->dinv_off[t] + (int64_t)k * DB * DB;
+            double* Akk = L + (int64_t)k * DB * (n + 1);
+            a.A = Akk; a.lda = n; a.dinv = dk; a.diag0 = nullptr; a.flag = d->flags + t; a.code = 1;
+            const int rows_t = nb - k - 1;  // 128-row tiles below the diagonal block
+            if (rows_t > 0) {
+                double* panel = Akk + DB;
+                gp[idx] = GemmDesc{panel, dk, panel, n, DB, n, DB, rows_t, 1, 0, 1.0, 0.0};
+                gt[idx] = GemmDesc{panel, panel, Akk + (int64_t)DB * (n + 1), n, n, n, DB, rows_t, rows_t, 1, -1.0, 1.0};
+            }
+            double* Xk = X + (int64_t)k * DB;  // block row k of X, columns 0 .. (k+1)*128
+            g1[idx] = GemmDesc{dk, Xk, Xk, DB, n, n, DB, 1, k + 1, 0, 1.0, 0.0};
+            if (rows_t > 0)
+                g2[idx] = GemmDesc{L + (int64_t)(k + 1) * DB + (int64_t)k * DB * n, Xk, Xk + DB, n, n, n, DB, rows_t, k + 1, 0, -1.0, 1.0};
+        }
+    ACES_TRY(dev_upload(ctx, d, &d->dd, dd));
+    ACES_TRY(dev_upload(ctx, d, &d->g_panel, gp));
+    ACES_TRY(dev_upload(ctx, d, &d->g_trail, gt));
+    ACES_TRY(dev_upload(ctx, d, &d->g_tri1, g1));
+    ACES_TRY(dev_upload(ctx, d, &d->g_tri2, g2));
+    return ACES_OK;
+}
+
+int check_design(aces_ctx* ctx, const aces_design* d, const char* what) {
+    if (!ctx) return ACES_E_INVALID;
+    ACES_CHECK(ctx, d != nullptr, "%s: design is NULL", what);
+    ACES_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ACES_OK;
+}
+
+// device copies of the eigenvalue vectors; returns pointers inside the vector workspace tail
+int upload_eigenvalues(aces_ctx* ctx, aces_design* d, const double* eig, const double* cov_eig, double** lam_dev,
+                       double** lamcov_dev) {
+    // the covariance value buffer is followed by nothing else, so keep the inputs in their own buffers
+    static_assert(sizeof(double) == 8, "");
+    ACES_TRY(aces_reserve_dev(ctx, ctx->d_work[0], sizeof(double) * (size_t)(d->M + d->C + 2)));
+    double* base = (double*)ctx->d_work[0].ptr;
+    *lam_dev = base;
+    *lamcov_dev = base + d->M;
+    ACES_CUDA(ctx, cudaMemcpyAsync(*lam_dev, eig, sizeof(double) * (size_t)d->M, cudaMemcpyDefault, ctx->stream));
+    if (d->C > 0) {
+        ACES_CHECK(ctx, cov_eig != nullptr, "design: the design has covariance keys but covariance eigenvalues are NULL");
+        ACES_CUDA(ctx, cudaMemcpyAsync(*lamcov_dev, cov_eig, sizeof(double) * (size_t)d->C, cudaMemcpyDefault, ctx->stream));
+    }
+    return ACES_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t aces_calc_covariance(aces_ctx* ctx, aces_design* d, const double* eigenvalues,
+                             const double* covariance_eigenvalues, double epsilon, int32_t weight_time,
+                             int32_t log_form, double* nzval) {
+    ACES_TRY(check_design(ctx, d, "calc_covariance"));
+    ACES_CHECK(ctx, eigenvalues && nzval, "calc_covariance: NULL argument");
+    ACES_TRY(ensure_workspaces(ctx, d, false, false, false, false));
+    double *lam, *lamcov;
+    ACES_TRY(upload_eigenvalues(ctx, d, eigenvalues, covariance_eigenvalues, &lam, &lamcov));
+    ACES_TRY(launch_cov_values(ctx, d, lam, lamcov, epsilon, weight_time, log_form, d->covval));
+    ACES_CUDA(ctx, cudaMemcpyAsync(nzval, d->covval, sizeof(double) * (size_t)d->nnz_cov, cudaMemcpyDefault, ctx->stream));
+    ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ACES_OK;
+}
+
+int32_t aces_design_inv_factor(aces_ctx* ctx, aces_design* d, const double* covariance_log_nzval,
+                               const int64_t* kept_rows, int64_t n_kept, int32_t index_base,
+                               double* factor_blocks, int64_t* block_lengths) {
+    ACES_TRY(check_design(ctx, d, "design_inv_factor"));
+    ACES_CHECK(ctx, covariance_log_nzval && factor_blocks, "design_inv_factor: NULL argument");
+    ACES_TRY(ensure_workspaces(ctx, d, true, false, false, false));
+    ACES_TRY(build_tile_descs(ctx, d));
+    std::vector<int64_t> kept;
+    bool clipped;
+    ACES_TRY(upload_clipping(ctx, d, kept_rows, n_kept, index_base, &kept, &clipped));
+    ACES_CUDA(ctx, cudaMemsetAsync(d->flags, 0, sizeof(int32_t) * ((size_t)d->T + 2), ctx->stream));
+    ACES_CUDA(ctx, cudaMemcpyAsync(d->covval, covariance_log_nzval, sizeof(double) * (size_t)d->nnz_cov, cudaMemcpyDefault,
+                                   ctx->stream));
+    ACES_TRY(build_and_factor_tiles(ctx, d, d->covval, clipped ? d->row_map : nullptr, kept));
+    // export: blocks of kept[t] x kept[t], concatenated
+    std::vector<int64_t> out_off((size_t)d->T + 1, 0);
+    for (int t = 0; t < d->T; ++t) out_off[(size_t)t + 1] = out_off[(size_t)t] + kept[(size_t)t] * kept[(size_t)t];
+    int64_t* meta = (int64_t*)(d->vec + 8 * std::max(d->Mp, d->Np));  // [kept | out_off]
+    ACES_CUDA(ctx, cudaMemcpyAsync(meta, kept.data(), sizeof(int64_t) * (size_t)d->T, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t hdr = ((size_t)d->T + 2) & ~(size_t)1;  // int64 slots before the (8-byte aligned) blocks
+    ACES_TRY(aces_reserve_dev(ctx, ctx->d_work[1], sizeof(int64_t) * hdr + sizeof(double) * (size_t)out_off.back()));
+    int64_t* off_dev = (int64_t*)ctx->d_work[1].ptr;
+    double* out_dev = (double*)(off_dev + hdr);
+    ACES_CUDA(ctx, cudaMemcpyAsync(off_dev, out_off.data(), sizeof(int64_t) * ((size_t)d->T + 1), cudaMemcpyHostToDevice, ctx->stream));
+    dim3 grid(148, (unsigned)d->T);
+    tiles_export_kernel<<<grid, 256, 0, ctx->stream>>>(d->T, d->d_tile_off, d->d_mp, meta, off_dev, d->tilesX, out_dev);
+    ACES_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    ACES_CUDA(ctx, cudaMemcpyAsync(factor_blocks, out_dev, sizeof(double) * (size_t)out_off.back(), cudaMemcpyDefault, ctx->stream));
+    if (block_lengths) std::copy(kept.begin(), kept.end(), block_lengths);
+    return check_flags(ctx, d, "design_inv_factor");
+}
+
+int32_t aces_design_fit(aces_ctx* ctx, aces_design* d, int32_t ls_type, const double* est_eigenvalues,
+                        const double* est_covariance_eigenvalues, const int64_t* kept_rows, int64_t n_kept,
+                        int32_t index_base, double epsilon, int32_t constrain, double* gate_eigenvalues) {
+    ACES_TRY(check_design(ctx, d, "design_fit"));
+    ACES_CHECK(ctx, ls_type >= 0 && ls_type <= 2, "design_fit: ls_type must be 0 (OLS), 1 (WLS) or 2 (GLS)");
+    ACES_CHECK(ctx, est_eigenvalues && gate_eigenvalues, "design_fit: NULL argument");
+    const bool gls = ls_type == 2;
+    ACES_TRY(ensure_workspaces(ctx, d, gls, gls, false, false));
+    if (gls) ACES_TRY(build_tile_descs(ctx, d));
+    std::vector<int64_t> kept;
+    bool clipped;
+    ACES_TRY(upload_clipping(ctx, d, kept_rows, n_kept, index_base, &kept, &clipped));
+    const int32_t* row_map = clipped ? d->row_map : nullptr;
+    double *lam, *lamcov;
+    ACES_TRY(upload_eigenvalues(ctx, d, est_eigenvalues, est_covariance_eigenvalues, &lam, &lamcov));
+    FitVectors fv = fit_vectors(d);
+    // K2: log-covariance of the estimates, weight_time = false (src/estimate.jl:713-720)
+    if (ls_type != 0) ACES_TRY(launch_cov_values(ctx, d, lam, lamcov, epsilon, 0, 1, d->covval));
+    ACES_TRY(prepare_estimator(ctx, d, ls_type, d->covval, row_map, kept, fv));
+    // right-hand side: g = A' F' F b
+    const unsigned gm = grid_for(d->M, 128), gn = grid_for(d->N, 128);
+    auto normal_rhs = [&](const double* x_or_null) -> int {
+        residual_kernel<<<gm, 128, 0, ctx->stream>>>(d->M, d->a_rowptr, d->a_colidx, d->a_vals, d->blk_of_row, d->d_row0,
+                                                    d->d_prow0, row_map, lam, x_or_null, fv.u);
+        ctx->launches += 1;
+        ACES_TRY(apply_F(ctx, d, ls_type, fv, fv.u, fv.v, false));
+        ACES_TRY(apply_F(ctx, d, ls_type, fv, fv.v, fv.w, true));
+        at_times_kernel<<<gn, 128, 0, ctx->stream>>>(d->N, d->a_colptr, d->a_rowval, d->a_nzval, d->blk_of_row, d->d_row0,
+                                                    d->d_prow0, row_map, fv.w, fv.g);
+        ACES_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+        return ACES_OK;
+    };
+    ACES_TRY(normal_rhs(nullptr));
+    ACES_TRY(dense::trsv_lower(ctx, d->Np, d->G, d->Np, d->dinvG, fv.g, fv.t1));
+    ACES_TRY(dense::trsv_lower_t(ctx, d->Np, d->G, d->Np, d->dinvG, fv.t1, fv.x));
+    for (int it = 0; it < 2; ++it) {
+        // corrected semi-normal equations: r = F (b - A x) in FP64, x += inv(G) A' F' r
+        ACES_TRY(normal_rhs(fv.x));
+        ACES_TRY(dense::trsv_lower(ctx, d->Np, d->G, d->Np, d->dinvG, fv.g, fv.t1));
+        ACES_TRY(dense::trsv_lower_t(ctx, d->Np, d->G, d->Np, d->dinvG, fv.t1, fv.t2));
+        axpy_kernel<<<gn, 128, 0, ctx->stream>>>(d->N, 1.0, fv.t2, fv.x);
+        ctx->launches += 1;
+    }
+    exp_neg_kernel<<<gn, 128, 0, ctx->stream>>>(d->N, fv.x, fv.t1, constrain);
+    ACES_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    ACES_CUDA(ctx, cudaMemcpyAsync(gate_eigenvalues, fv.t1, sizeof(double) * (size_t)d->N, cudaMemcpyDefault, ctx->stream));
+    return check_flags(ctx, d, "design_fit");
+}
+
+int32_t aces_design_ls_covariance(aces_ctx* ctx, aces_design* d, int32_t ls_type, const double* gate_eigenvalues,
+                                  const double* covariance_log_nzval, double* sigma, double* trace,
+                                  double* trace_sq) {
+    ACES_TRY(check_design(ctx, d, "design_ls_covariance"));
+    ACES_CHECK(ctx, ls_type >= 0 && ls_type <= 2, "design_ls_covariance: ls_type must be 0 (OLS), 1 (WLS) or 2 (GLS)");
+    ACES_CHECK(ctx, gate_eigenvalues && covariance_log_nzval, "design_ls_covariance: NULL argument");
+    const bool gls = ls_type == 2;
+    ACES_TRY(ensure_workspaces(ctx, d, gls, gls, true, !gls));
+    if (gls) ACES_TRY(build_tile_descs(ctx, d));
+    FitVectors fv = fit_vectors(d);
+    const int64_t Np = d->Np, N = d->N;
+    std::vector<int64_t> kept(d->m.begin(), d->m.end());
+    ACES_CUDA(ctx, cudaMemcpyAsync(d->covval, covariance_log_nzval, sizeof(double) * (size_t)d->nnz_cov, cudaMemcpyDefault,
+                                   ctx->stream));
+    ACES_TRY(prepare_estimator(ctx, d, ls_type, d->covval, nullptr, kept, fv));
+    // inv(G) = X' X with X = inv(L): lower tiles on the tensor pipe, then mirrored
+    ACES_TRY(dense::trtri(ctx, Np, d->G, Np, d->dinvG, d->Xn, Np));
+    ACES_TRY(dense::gemm(ctx, dense::GEMM_TN, Np, Np, Np, 1.0, d->Xn, Np, d->Xn, Np, 0.0, d->G, Np, 1));
+    ACES_TRY(dense::symmetrize_from_lower(ctx, Np, d->G, Np));
+    double* S = d->G;
+    if (!gls) {
+        // sandwich: est * cov_log * est' = H (A' W cov_log W A) H with H = inv(A' W A)
+        // (src/merit.jl:584-596, 614-622); the middle matrix is assembled sparsely, W = f^2
+        mul_vec_kernel<<<grid_for(d->Mp, 256), 256, 0, ctx->stream>>>(d->Mp, fv.f, fv.f, fv.v);
+        ACES_CUDA(ctx, cudaMemsetAsync(d->Cn, 0, sizeof(double) * (size_t)Np * Np, ctx->stream));
+        sandwich_kernel<<<grid_for(N, 64), 64, 0, ctx->stream>>>(
+            N, d->a_colptr, d->a_rowval, d->a_nzval, d->a_rowptr, d->a_colidx, d->a_vals, d->cov_colptr, d->cov_rowval,
+            d->covval, d->blk_of_row, d->d_row0, d->d_prow0, nullptr, fv.v, d->Cn, Np);
+        ACES_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 2;
+        ACES_TRY(dense::symmetrize_from_lower(ctx, Np, d->Cn, Np));
+        // Xn <- H * C ; Cn <- (H C) * H
+        ACES_TRY(dense::gemm(ctx, dense::GEMM_NN, Np, Np, Np, 1.0, d->G, Np, d->Cn, Np, 0.0, d->Xn, Np, 0));
+        ACES_TRY(dense::gemm(ctx, dense::GEMM_NN, Np, Np, Np, 1.0, d->Xn, Np, d->G, Np, 0.0, d->Cn, Np, 1));
+        ACES_TRY(dense::symmetrize_from_lower(ctx, Np, d->Cn, Np));
+        S = d->Cn;
+    }
+    double* gdev = fv.t2;
+    ACES_CUDA(ctx, cudaMemcpyAsync(gdev, gate_eigenvalues, sizeof(double) * (size_t)N, cudaMemcpyDefault, ctx->stream));
+    scale_sym_kernel<<<148 * 8, 256, 0, ctx->stream>>>(N, S, Np, gdev);
+    double* mom = d->mom;
+    moments_kernel<<<148 * 4, 256, 0, ctx->stream>>>(N, S, Np, mom);
+    moments_final_kernel<<<1, 32, 0, ctx->stream>>>(148 * 4, mom);
+    ACES_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 3;
+    double hm[2] = {0.0, 0.0};
+    ACES_CUDA(ctx, cudaMemcpyAsync(hm, mom, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sigma)
+        ACES_CUDA(ctx, cudaMemcpy2DAsync(sigma, sizeof(double) * (size_t)N, S, sizeof(double) * (size_t)Np,
+                                         sizeof(double) * (size_t)N, (size_t)N, cudaMemcpyDefault, ctx->stream));
+    ACES_TRY(check_flags(ctx, d, "design_ls_covariance"));
+    if (trace) *trace = hm[0];
+    if (trace_sq) *trace_sq = hm[1];
+    return ACES_OK;
+}
+
+}  // extern "C"

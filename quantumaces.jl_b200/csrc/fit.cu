@@ -174,13 +174,14 @@ struct LsqState {
     double* x;     // Np   solution
     double* t1;    // max(Mp, Np) scratch
     double* t2;    // Np scratch
+    double* t3;    // Np scratch
     int* flag;
 };
 
 // Builds At = F*A (dense), bt = F*(-log y), G = At'At, factorises it and inverts the factor.
 int lsq_setup(aces_ctx* ctx, int64_t M, int64_t N, const int64_t* A_colptr, const int64_t* A_rowval,
               const double* A_nzval, const int64_t* F_colptr, const int64_t* F_rowval, const double* F_nzval,
-              const double* y, int base, LsqState* st) {
+              const double* y, int base, LsqState* st, bool with_inverse) {
     ACES_CHECK(ctx, M >= 1 && N >= 1, "lsq: M=%lld N=%lld", (long long)M, (long long)N);
     ACES_CHECK(ctx, A_colptr && A_rowval && A_nzval, "lsq: NULL design matrix");
     const int64_t Mp = pad_up(M), Np = pad_up(N);
@@ -191,20 +192,21 @@ int lsq_setup(aces_ctx* ctx, int64_t M, int64_t N, const int64_t* A_colptr, cons
     if (hasF) ACES_TRY(upload_csc(ctx, ctx->d_work[W_F], M, F_colptr, F_rowval, F_nzval, base, &F));
     ACES_TRY(aces_reserve_dev(ctx, ctx->d_work[W_AT], sizeof(double) * (size_t)Mp * Np));
     ACES_TRY(aces_reserve_dev(ctx, ctx->d_work[W_G], sizeof(double) * (size_t)Np * Np));
-    ACES_TRY(aces_reserve_dev(ctx, ctx->d_work[W_X], sizeof(double) * (size_t)Np * Np));
+    if (with_inverse) ACES_TRY(aces_reserve_dev(ctx, ctx->d_work[W_X], sizeof(double) * (size_t)Np * Np));
     ACES_TRY(aces_reserve_dev(ctx, ctx->d_work[W_DINV], sizeof(double) * (size_t)Np * DB));
     const size_t vec = (size_t)std::max(Mp, Np);
-    ACES_TRY(aces_reserve_dev(ctx, ctx->d_work[W_VEC], sizeof(double) * (vec * 6 + 64)));
+    ACES_TRY(aces_reserve_dev(ctx, ctx->d_work[W_VEC], sizeof(double) * (vec * 7 + 64)));
     st->At = (double*)ctx->d_work[W_AT].ptr;
     st->G = (double*)ctx->d_work[W_G].ptr;
     st->X = (double*)ctx->d_work[W_X].ptr;
     st->dinv = (double*)ctx->d_work[W_DINV].ptr;
     double* v = (double*)ctx->d_work[W_VEC].ptr;
     st->bt = v; st->g = v + vec; st->x = v + 2 * vec; st->t1 = v + 3 * vec; st->t2 = v + 4 * vec;
-    double* ydev = v + 5 * vec;
-    st->flag = (int*)(v + 6 * vec);
+    st->t3 = v + 5 * vec;
+    double* ydev = v + 6 * vec;
+    st->flag = (int*)(v + 7 * vec);
     ACES_CUDA(ctx, cudaMemsetAsync(st->At, 0, sizeof(double) * (size_t)Mp * Np, ctx->stream));
-    ACES_CUDA(ctx, cudaMemsetAsync(v, 0, sizeof(double) * (vec * 6 + 64), ctx->stream));
+    ACES_CUDA(ctx, cudaMemsetAsync(v, 0, sizeof(double) * (vec * 7 + 64), ctx->stream));
     ACES_CUDA(ctx, cudaMemcpyAsync(ydev, y, sizeof(double) * (size_t)M, cudaMemcpyDefault, ctx->stream));
     whiten_kernel<<<(unsigned)N, 128, 0, ctx->stream>>>(N, A.colptr, A.rowval, A.nzval, hasF ? F.colptr : nullptr,
                                                         hasF ? F.rowval : nullptr, hasF ? F.nzval : nullptr, st->At, Mp);
@@ -230,14 +232,15 @@ int lsq_setup(aces_ctx* ctx, int64_t M, int64_t N, const int64_t* A_colptr, cons
         return aces_fail(ctx, ACES_E_NOT_PD,
                          "lsq: the Gram matrix is not positive definite (diagonal block %d): the whitened "
                          "design matrix is rank deficient", flag - 1);
-    ACES_TRY(dense::trtri(ctx, Np, st->G, Np, st->dinv, st->X, Np));
+    if (with_inverse) ACES_TRY(dense::trtri(ctx, Np, st->G, Np, st->dinv, st->X, Np));
     return ACES_OK;
 }
 
-// out = inv(G) v = X' (X v)
+// out = inv(G) v = inv(L') inv(L) v by two blocked triangular solves (v is kept)
 int lsq_apply_inverse(aces_ctx* ctx, const LsqState& st, const double* v, double* out) {
-    ACES_TRY(gemv_n(ctx, st.Np, st.Np, st.X, st.Np, v, st.t2, 1.0, 0.0));
-    ACES_TRY(gemv_t(ctx, st.Np, st.Np, st.X, st.Np, st.t2, out, 1.0, 0.0));
+    ACES_CUDA(ctx, cudaMemcpyAsync(st.t2, v, sizeof(double) * (size_t)st.Np, cudaMemcpyDeviceToDevice, ctx->stream));
+    ACES_TRY(dense::trsv_lower(ctx, st.Np, st.G, st.Np, st.dinv, st.t2, st.t3));
+    ACES_TRY(dense::trsv_lower_t(ctx, st.Np, st.G, st.Np, st.dinv, st.t3, out));
     return ACES_OK;
 }
 
@@ -272,7 +275,7 @@ int32_t aces_estimate_gate_eigenvalues(aces_ctx* ctx, int64_t M, int64_t N, cons
     ACES_CUDA(ctx, cudaSetDevice(ctx->device));
     LsqState st;
     ACES_TRY(lsq_setup(ctx, M, N, A_colptr, A_rowval, A_nzval, F_colptr, F_rowval, F_nzval, est_eigenvalues,
-                       index_base, &st));
+                       index_base, &st, false));
     ACES_TRY(lsq_solve(ctx, st, 2));
     exp_neg_kernel<<<(unsigned)std::min<int64_t>((N + 255) / 256, 1024), 256, 0, ctx->stream>>>(N, st.x, st.t1, constrain);
     ACES_CUDA(ctx, cudaGetLastError());
@@ -316,7 +319,7 @@ int32_t aces_gram_inverse(aces_ctx* ctx, int64_t M, int64_t N, const int64_t* A_
     } else {
         std::vector<double> ones((size_t)M, 1.0);
         ACES_TRY(lsq_setup(ctx, M, N, A_colptr, A_rowval, A_nzval, F_colptr, F_rowval, F_nzval, ones.data(),
-                           index_base, &st));
+                           index_base, &st, true));
         // inv(G) = X' X  (lower tiles on the tensor pipe, then mirrored) -> reuse the G buffer
         ACES_TRY(dense::gemm(ctx, dense::GEMM_TN, Np, Np, Np, 1.0, st.X, Np, st.X, Np, 0.0, st.G, Np, 1));
         ACES_TRY(dense::symmetrize_from_lower(ctx, Np, st.G, Np));

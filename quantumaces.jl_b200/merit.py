@@ -96,3 +96,193 @@ def calc_precision_matrix_from_factor(ctx, design_matrix, gate_eigenvalues, cova
 def calc_gls_covariance_from_factor(ctx, design_matrix, gate_eigenvalues, covariance_log_inv_factor):
     """calc_gls_covariance (src/merit.jl:556-568): D * inv(cholesky(A' inv(cov_log) A)) * D."""
     return _gram(ctx, design_matrix, covariance_log_inv_factor, gate_eigenvalues, False, False)
+
+
+# ---------------------------------------------------------------------------------------------
+# Design-resident path (aces_design_*): the Design is uploaded once
+# ---------------------------------------------------------------------------------------------
+
+LS_TYPES = {"ols": 0, "wls": 1, "gls": 2}
+
+
+def mean_ensemble(experiment_ensemble):
+    """mean.(ensemble[i]) (src/estimate.jl:711-712): left-to-right sum, then one division -- plain
+    host arithmetic on one to a few values per Pauli, exactly as the reference forms it."""
+    out = []
+    for tup in experiment_ensemble:
+        v = np.empty(len(tup), dtype=np.float64)
+        for i, vals in enumerate(tup):
+            s = 0.0
+            for x in vals:
+                s += x
+            v[i] = s / len(vals)
+        out.append(v)
+    return out
+
+
+class DeviceDesign:
+    """A `Design` resident on the GPU (aces_design_create): what calc_covariance,
+    sparse_covariance_inv_factor, estimate_gate_eigenvalues and calc_*_covariance read from it."""
+
+    def __init__(self, ctx: _lib.Context, fd):
+        self.ctx, self.fd = ctx, fd
+        A = sp.csc_matrix(fd.matrix)
+        A.sort_indices()
+        self.M, self.N = A.shape
+        T = fd.tuple_number
+        self.T = T
+        self._keep = dict(
+            ml=np.ascontiguousarray(fd.mapping_lengths, dtype=np.int64),
+            cp=np.ascontiguousarray(A.indptr, dtype=np.int32), rv=np.ascontiguousarray(A.indices, dtype=np.int32),
+            nz=np.ascontiguousarray(A.data, dtype=np.int32),
+            X=np.ascontiguousarray(fd.experiment_numbers, dtype=np.int64),
+            w=np.ascontiguousarray(fd.shot_weights, dtype=np.float64),
+            tau=np.ascontiguousarray(fd.tuple_times, dtype=np.float64),
+            dc=np.ascontiguousarray(np.concatenate(fd.diag_counts), dtype=np.int64),
+        )
+        k = self._keep
+        assert np.array_equal(k["nz"], A.data), "design matrix entries must be integers (d.matrix is Int32)"
+        has_cov = bool(fd.full_covariance and fd.cov_keys)
+        if has_cov:
+            ptr = np.zeros(T + 1, dtype=np.int64)
+            ptr[1:] = np.cumsum([len(c) for c in fd.cov_keys])
+            keys = np.concatenate([np.asarray(c, dtype=np.int64).reshape(-1, 2) for c in fd.cov_keys])
+            k.update(ptr=ptr, p=np.ascontiguousarray(keys[:, 0]), q=np.ascontiguousarray(keys[:, 1]),
+                     cc=np.ascontiguousarray(np.concatenate(fd.cov_counts), dtype=np.int64))
+            self.C = int(ptr[-1])
+        else:
+            k.update(ptr=None, p=None, q=None, cc=None)
+            self.C = 0
+        h = C.c_void_p()
+        ctx.check(ctx.lib.aces_design_create(
+            ctx.handle, T, _ptr(k["ml"]), self.N, _ptr(k["cp"]), _ptr(k["rv"]), _ptr(k["nz"]), 0, _ptr(k["X"]),
+            _ptr(k["w"]), _ptr(k["tau"]), _ptr(k["dc"]), _ptr(k["ptr"]), _ptr(k["p"]), _ptr(k["q"]), _ptr(k["cc"]),
+            C.byref(h)))
+        self.handle = h
+        nnz = int(ctx.lib.aces_design_covariance_nnz(h))
+        self.cov_colptr = np.zeros(self.M + 1, dtype=np.int64)
+        self.cov_rowval = np.zeros(nnz, dtype=np.int64)
+        ctx.check(ctx.lib.aces_design_covariance_pattern(h, _ptr(self.cov_colptr), _ptr(self.cov_rowval)))
+
+    def close(self):
+        if getattr(self, "handle", None) and self.ctx.handle:
+            self.ctx.lib.aces_design_destroy(self.ctx.handle, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- containers ---------------------------------------------------------------------------
+    def _sparse(self, nzval):
+        return sp.csc_matrix((nzval, self.cov_rowval, self.cov_colptr), shape=(self.M, self.M))
+
+    def pattern_values(self, matrix) -> np.ndarray:
+        """nzval of `matrix` (M x M sparse) laid out in the design's covariance pattern."""
+        m = sp.csc_matrix(matrix)
+        pat = self._sparse(np.ones(len(self.cov_rowval)))
+        extra = (abs(m) - abs(m).multiply(pat)).count_nonzero()
+        assert extra == 0, "the matrix has entries outside the design's covariance pattern"
+        rows = self.cov_rowval
+        cols = np.repeat(np.arange(self.M), np.diff(self.cov_colptr))
+        return np.ascontiguousarray(np.asarray(m[rows, cols]).ravel(), dtype=np.float64)
+
+    # -- K2 -------------------------------------------------------------------------------------
+    def calc_covariance(self, eigenvalues_ensemble, covariance_ensemble=None, epsilon: float = 1e-10,
+                        weight_time: bool = True, log_form: bool = False):
+        """calc_covariance(d, eigenvalues_ensemble, covariance_ensemble; epsilon, weight_time)
+        (src/merit.jl:206-291); with log_form also calc_covariance_log (src/merit.jl:356-365)."""
+        lam = np.ascontiguousarray(np.concatenate([np.asarray(e, dtype=np.float64) for e in eigenvalues_ensemble]))
+        assert lam.shape == (self.M,)
+        lc = None
+        if self.C:
+            lc = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.float64) for c in covariance_ensemble]))
+            assert lc.shape == (self.C,)
+        out = np.zeros(len(self.cov_rowval), dtype=np.float64)
+        self.ctx.check(self.ctx.lib.aces_calc_covariance(
+            self.ctx.handle, self.handle, _ptr(lam), _ptr(lc), float(epsilon), 1 if weight_time else 0,
+            1 if log_form else 0, _ptr(out)))
+        return self._sparse(out)
+
+    # -- K3 -------------------------------------------------------------------------------------
+    def sparse_covariance_inv_factor(self, covariance_log, clipped_indices=None):
+        """sparse_covariance_inv_factor(covariance_log[clipped, clipped], clipped_mapping_lengths)
+        (src/merit.jl:378-427).  `covariance_log` is the unclipped M x M matrix; returns the
+        block-diagonal factor over the kept rows."""
+        val = self.pattern_values(covariance_log)
+        ml = self._keep["ml"]
+        if clipped_indices is None:
+            kept, n_kept, lens = None, 0, ml
+        else:
+            kept = np.ascontiguousarray(clipped_indices, dtype=np.int64)
+            n_kept = len(kept)
+            lens = get_clipped_mapping_lengths(ml, kept)
+        blocks = np.zeros(int(np.sum(lens.astype(np.int64) ** 2)), dtype=np.float64)
+        got = np.zeros(self.T, dtype=np.int64)
+        self.ctx.check(self.ctx.lib.aces_design_inv_factor(
+            self.ctx.handle, self.handle, _ptr(val), _ptr(kept), n_kept, 0, _ptr(blocks), _ptr(got)))
+        assert np.array_equal(got, lens)
+        mats, off = [], 0
+        for k in lens:
+            k = int(k)
+            mats.append(sp.csc_matrix(blocks[off:off + k * k].reshape(k, k, order="F")))
+            off += k * k
+        return sp.block_diag(mats, format="csc")
+
+    # -- K2-K5 fused ------------------------------------------------------------------------------
+    def fit(self, ls_type: str, est_eigenvalues, est_covariance_eigenvalues=None, clipped_indices=None,
+            epsilon: float = 1e-10, constrain: bool = False) -> np.ndarray:
+        """Unprojected gate eigenvalues of one estimator as estimate_gate_noise computes them
+        (src/estimate.jl:711-743, 820-831)."""
+        lam = np.ascontiguousarray(est_eigenvalues, dtype=np.float64)
+        assert lam.shape == (self.M,)
+        lc = None
+        if self.C:
+            lc = np.ascontiguousarray(est_covariance_eigenvalues, dtype=np.float64)
+            assert lc.shape == (self.C,)
+        kept = None if clipped_indices is None else np.ascontiguousarray(clipped_indices, dtype=np.int64)
+        g = np.zeros(self.N, dtype=np.float64)
+        self.ctx.check(self.ctx.lib.aces_design_fit(
+            self.ctx.handle, self.handle, LS_TYPES[ls_type], _ptr(lam), _ptr(lc), _ptr(kept),
+            0 if kept is None else len(kept), 0, float(epsilon), 1 if constrain else 0, _ptr(g)))
+        return g
+
+    # -- K6 -------------------------------------------------------------------------------------
+    def calc_ls_covariance(self, ls_type: str, covariance_log, gate_eigenvalues=None, want_matrix: bool = True):
+        """calc_gls_covariance / calc_wls_covariance / calc_ols_covariance(d, covariance_log)
+        (src/merit.jl:556-629).  Returns (sigma or None, trace, trace of the square)."""
+        g = np.ascontiguousarray(self.fd.gate_eigenvalues if gate_eigenvalues is None else gate_eigenvalues,
+                                 dtype=np.float64)
+        val = self.pattern_values(covariance_log)
+        sigma = np.zeros((self.N, self.N), dtype=np.float64, order="F") if want_matrix else None
+        tr, trsq = C.c_double(), C.c_double()
+        self.ctx.check(self.ctx.lib.aces_design_ls_covariance(
+            self.ctx.handle, self.handle, LS_TYPES[ls_type], _ptr(g), _ptr(val), _ptr(sigma), C.byref(tr),
+            C.byref(trsq)))
+        return sigma, float(tr.value), float(trsq.value)
+
+
+def nrmse_moments(sigma_tr: float, sigma_sq_tr: float, N: int):
+    """nrmse_moments (src/merit.jl:672-682) from tr(sigma) and tr(sigma^2)."""
+    expectation = np.sqrt(sigma_tr) * (1 - sigma_sq_tr / (4 * sigma_tr ** 2)) / np.sqrt(N)
+    variance = (sigma_sq_tr / (2 * sigma_tr)) * (1 - sigma_sq_tr / (8 * sigma_tr ** 2)) / N
+    return expectation, variance
+
+
+def estimate_gate_noise_core(dd: DeviceDesign, est_eigenvalues_experiment_ensemble,
+                             est_covariance_experiment_ensemble, min_eigenvalue: float = 0.1,
+                             clip_warning: bool = True):
+    """The numeric core of estimate_gate_noise (src/estimate.jl:703-743, 820-831): means, clipping
+    and the unprojected OLS / WLS / GLS gate eigenvalues.  Projection onto the simplex and the
+    NoiseEstimate bookkeeping stay in the reference."""
+    fd = dd.fd
+    est = np.concatenate(mean_ensemble(est_eigenvalues_experiment_ensemble))
+    cov = np.concatenate(mean_ensemble(est_covariance_experiment_ensemble)) if dd.C else None
+    clipped = get_clipped_indices(est, min_eigenvalue=min_eigenvalue, warning=clip_warning)
+    kept = None if len(clipped) == dd.M else clipped
+    out = {"est_eigenvalues": est, "clipped_indices": clipped,
+           "ols": dd.fit("ols", est, cov, kept), "wls": dd.fit("wls", est, cov, kept)}
+    out["gls"] = dd.fit("gls", est, cov, kept) if fd.full_covariance else out["wls"]
+    return out

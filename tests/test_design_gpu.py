@@ -1,0 +1,185 @@
+"""GPU parity tests of the design-resident fit path (aces_design_*): covariance assembly (K2), block
+inverse factor (K3), fused OLS / WLS / GLS fit (K4/K5) and estimator covariances (K6) against the
+numpy/scipy oracle.  Floating point: relative tolerance 1e-9 in fp64 (BASELINE.json north_star);
+the covariance values are element-wise products and are compared to 1e-15."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from fit_util import fo, noisy_ensembles
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+def rel(x, y):
+    x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    return np.linalg.norm(x - y) / max(np.linalg.norm(y), 1e-300)
+
+
+def dense(m):
+    return m.toarray() if sp.issparse(m) else np.asarray(m)
+
+
+@pytest.fixture(scope="module", params=[(3, True), (5, True), (3, False)], ids=["d3_gls", "d5_gls", "d3_diag"])
+def setup(request, ctx):
+    import aces_b200
+
+    d, full = request.param
+    fd = aces_b200.synthetic_design("rotated", d, full_covariance=full, with_matrix=True)
+    dd = aces_b200.DeviceDesign(ctx, fd)
+    eig, cov = noisy_ensembles(fd, seed=7 + d)
+    yield fd, dd, eig, cov
+    dd.close()
+
+
+def test_pattern(setup):
+    fd, dd, _, _ = setup
+    n_keys = sum(len(k) for k in fd.cov_keys) if fd.full_covariance else 0
+    assert len(dd.cov_rowval) == fd.M + 2 * n_keys
+    pat = dd._sparse(np.ones(len(dd.cov_rowval)))
+    assert (pat - pat.T).count_nonzero() == 0
+    assert np.all(pat.diagonal() == 1.0)
+
+
+@pytest.mark.parametrize("weight_time", [True, False])
+def test_calc_covariance_vs_oracle(setup, weight_time):
+    import aces_b200
+
+    fd, dd, eig, cov = setup
+    lam_ens = aces_b200.mean_ensemble(eig)
+    cov_ens = aces_b200.mean_ensemble(cov) if fd.full_covariance else None
+    got = dd.calc_covariance(lam_ens, cov_ens, weight_time=weight_time)
+    want = fo.calc_covariance_from_experiments(fd, eig, cov, weight_time=weight_time)
+    assert np.max(np.abs(dense(got) - dense(want))) <= 1e-15 * np.max(np.abs(dense(want)))
+    lam = np.concatenate(lam_ens)
+    got_log = dd.calc_covariance(lam_ens, cov_ens, weight_time=weight_time, log_form=True)
+    want_log = fo.calc_covariance_log(want, lam)
+    assert rel(dense(got_log), dense(want_log)) < 1e-15
+    assert (got_log - got_log.T).count_nonzero() == 0
+    # the epsilon floor at eigenvalues of exactly +-1 (src/merit.jl:253)
+    ones = [np.ones(int(m)) for m in fd.mapping_lengths]
+    ones[0][::2] = -1.0
+    c1 = [np.ones(len(k)) for k in fd.cov_keys] if fd.full_covariance else None
+    got1 = dd.calc_covariance(ones, c1, epsilon=1e-10, weight_time=False)
+    want1 = fo.calc_covariance(fd, ones, c1 if c1 is not None else [[] for _ in ones], weight_time=False)
+    assert np.array_equal(got1.diagonal(), want1.diagonal())
+    assert np.all(got1.diagonal() > 0)
+
+
+def test_inverse_factor_identities(setup):
+    fd, dd, eig, cov = setup
+    if not fd.full_covariance:
+        pytest.skip("diagonal design")
+    lam = np.concatenate(fo.mean_ensemble(eig))
+    cl = fo.calc_covariance_log(fo.calc_covariance_from_experiments(fd, eig, cov, weight_time=False), lam)
+    F = dd.sparse_covariance_inv_factor(cl)
+    Fo = fo.sparse_covariance_inv_factor(cl, fd.mapping_lengths)
+    # test/merit_tests.jl:531-543: F'F == inv(cholesky(covariance_log))
+    assert rel(dense(F.T @ F), dense(Fo.T @ Fo)) < RTOL
+    assert rel(dense(F @ cl @ F.T), np.eye(fd.M)) < RTOL
+    assert sp.tril(F, -1).count_nonzero() > 0 and sp.triu(F, 1).count_nonzero() == 0
+    # after clipping (test/merit_tests.jl:569-591)
+    rng = np.random.default_rng(3)
+    clipped = np.sort(rng.choice(fd.M, size=fd.M - 37, replace=False))
+    Fc = dd.sparse_covariance_inv_factor(cl, clipped)
+    ccl = sp.csc_matrix(cl)[clipped, :][:, clipped]
+    assert Fc.shape == (len(clipped), len(clipped))
+    assert rel(dense(Fc @ ccl @ Fc.T), np.eye(len(clipped))) < RTOL
+
+
+def test_fused_fit_vs_oracle(setup):
+    import aces_b200
+
+    fd, dd, eig, cov = setup
+    want = fo.estimate_gate_noise_core(fd, eig, cov)
+    got = aces_b200.estimate_gate_noise_core(dd, eig, cov, clip_warning=False)
+    assert np.array_equal(got["est_eigenvalues"], want["est_eigenvalues"])
+    assert np.array_equal(got["clipped_indices"], want["clipped_indices"])
+    for k in ("ols", "wls", "gls"):
+        assert rel(got[k], want[k]) < RTOL, k
+        assert rel(np.log(got[k]), np.log(want[k])) < 1e-7, k
+
+
+def test_fused_fit_after_clipping(setup):
+    import aces_b200
+
+    fd, dd, eig, cov = setup
+    eig = [[list(v) for v in t] for t in eig]
+    rng = np.random.default_rng(5)
+    # clip rows with several entries only: the single-entry rows carry the column rank
+    multi = np.nonzero(np.diff(sp.csr_matrix(fd.matrix).indptr) >= 2)[0]
+    off = np.concatenate([[0], np.cumsum(fd.mapping_lengths)])
+    for r in rng.choice(multi, size=25, replace=False):
+        t = int(np.searchsorted(off, r, side="right") - 1)
+        p = int(r - off[t])
+        eig[t][p] = [0.05 for _ in eig[t][p]]  # below the 0.1 threshold
+    want = fo.estimate_gate_noise_core(fd, eig, cov)
+    got = aces_b200.estimate_gate_noise_core(dd, eig, cov, clip_warning=False)
+    assert len(got["clipped_indices"]) == fd.M - 25
+    assert np.array_equal(got["clipped_indices"], want["clipped_indices"])
+    for k in ("ols", "wls", "gls"):
+        assert rel(got[k], want[k]) < RTOL, k
+
+
+def test_fit_known_answers(setup):
+    fd, dd, _, _ = setup
+    ones = np.ones(fd.M)
+    c1 = np.ones(dd.C) if dd.C else None
+    # noiseless records => every gate eigenvalue exactly 1.0 (test/device_tests.jl:144-155)
+    for k in ("ols", "wls", "gls"):
+        assert np.all(dd.fit(k, ones, c1) == 1.0), k
+    # exact recovery from noiseless circuit eigenvalues
+    lam = fo.get_eigenvalues(fd, fd.gate_eigenvalues)
+    lc = np.concatenate(fo.calc_covariance_eigenvalues(fd, fd.gate_eigenvalues)) if dd.C else None
+    for k in ("ols", "wls", "gls"):
+        assert np.max(np.abs(dd.fit(k, lam, lc) - fd.gate_eigenvalues)) < 1e-12, k
+
+
+def test_ls_covariances_vs_oracle(setup):
+    import aces_b200
+
+    fd, dd, _, _ = setup
+    g = fd.gate_eigenvalues
+    lam = fo.get_eigenvalues(fd, g)
+    cov_eig = fo.calc_covariance_eigenvalues(fd, g) if fd.full_covariance else [[] for _ in range(fd.tuple_number)]
+    cl = fo.calc_covariance_log(fo.calc_covariance(fd, fo.get_eigenvalues_ensemble(fd, g), cov_eig), lam)
+    for k, ref in (("gls", fo.calc_gls_covariance), ("wls", fo.calc_wls_covariance), ("ols", fo.calc_ols_covariance)):
+        want = ref(fd, cl)
+        sigma, tr, trsq = dd.calc_ls_covariance(k, cl)
+        assert rel(sigma, want) < RTOL, k
+        assert np.array_equal(sigma, sigma.T), k
+        assert abs(tr - np.trace(want)) < RTOL * np.trace(want), k
+        assert abs(trsq - np.sum(want * want.T)) < RTOL * np.sum(want * want.T), k
+        e_got = aces_b200.nrmse_moments(tr, trsq, fd.matrix.shape[1])
+        e_want = fo.nrmse_moments(want)
+        assert np.allclose(e_got, e_want, rtol=1e-9), k
+        _, tr2, trsq2 = dd.calc_ls_covariance(k, cl, want_matrix=False)
+        assert tr2 == tr and trsq2 == trsq
+
+
+def test_not_positive_definite_block_is_reported(setup):
+    import aces_b200
+
+    fd, dd, eig, cov = setup
+    if not fd.full_covariance:
+        pytest.skip("diagonal design")
+    lam = np.concatenate(fo.mean_ensemble(eig))
+    cl = sp.lil_matrix(fo.calc_covariance_log(fo.calc_covariance_from_experiments(fd, eig, cov, weight_time=False), lam))
+    p, q = (int(x) for x in fd.cov_keys[0][0])
+    big = 10.0 * max(cl[p, p], cl[q, q])
+    cl[p, q] = big
+    cl[q, p] = big
+    with pytest.raises(aces_b200.NotPositiveDefinite):
+        dd.sparse_covariance_inv_factor(sp.csc_matrix(cl))
+
+
+def test_design_create_rejects_bad_input(ctx):
+    import aces_b200
+
+    fd = aces_b200.synthetic_design("rotated", 3, full_covariance=True, with_matrix=True)
+    fd.cov_keys[0] = np.vstack([fd.cov_keys[0], fd.cov_keys[0][:1]])  # duplicate key
+    fd.cov_counts[0] = np.concatenate([fd.cov_counts[0], fd.cov_counts[0][:1]])
+    with pytest.raises(aces_b200.AcesError):
+        aces_b200.DeviceDesign(ctx, fd)
