@@ -212,11 +212,16 @@ int32_t aces_calc_covariance(aces_ctx* ctx, aces_design* design, const double* e
  * src/estimate.jl:435-460.  factor_blocks receives, for every tuple, the dense lower-triangular
  * block inv(L_t) (k_t x k_t column-major, k_t = kept rows of the tuple, blocks concatenated) with
  * covariance_log_t = L_t L_t'; block_lengths [T] receives k_t.  The reference's CHOLMOD factor is
- * a row permutation of this one; F'F = inv(covariance_log) is the same.  Returns ACES_E_NOT_PD
- * when a block is not positive definite (the caller applies src/merit.jl:403-424). */
+ * a row permutation of this one; F'F = inv(covariance_log) is the same.
+ * A block whose factorisation fails gets the reference's fallback (src/merit.jl:403-424) when
+ * fallback_epsilon > 0 (the reference's default epsilon is 1e-12): elementwise absolute value,
+ * then the smallest eigenvalue raised to fallback_epsilon by a diagonal shift (found by bisection
+ * on the shift instead of ARPACK).  fallback_epsilon <= 0: such a block returns ACES_E_NOT_PD.
+ * aces_design_fallback_count reports how many blocks took the fallback in the last call. */
 int32_t aces_design_inv_factor(aces_ctx* ctx, aces_design* design, const double* covariance_log_nzval,
                                const int64_t* kept_rows, int64_t n_kept, int32_t index_base,
-                               double* factor_blocks, int64_t* block_lengths);
+                               double fallback_epsilon, double* factor_blocks, int64_t* block_lengths);
+int32_t aces_design_fallback_count(const aces_design* design);
 
 /* K2-K5 fused: the gate eigenvalues of one estimator from the circuit-eigenvalue estimates, as
  * estimate_gate_noise computes them (src/estimate.jl:711-743, 820-831): covariance of the

@@ -56,6 +56,7 @@ struct aces_design {
     double *covval = nullptr;      // [nnz_cov]
     int32_t *row_map = nullptr;    // [M] compacted local row or -1
     int32_t *flags = nullptr;      // [T + 1] not-PD flags (blocks, then the Gram matrix)
+    int fallback_blocks = 0;       // blocks that needed the not-PD fallback in the last call
     std::vector<void*> owned;
 };
 
@@ -150,6 +151,25 @@ __global__ void tiles_scatter_kernel(int64_t M, const int64_t* __restrict__ colp
             const int64_t lr = row_map ? row_map[r] : r - row0[t];
             if (lr < 0) continue;
             tile[lr + lc * n] = val[e];
+        }
+    }
+}
+// Rebuilds the tile of ONE block from the pattern values for the not-positive-definite fallback
+// (src/merit.jl:403-424): elementwise absolute value and `shift` added to the kept diagonal.
+__global__ void tile_rebuild_kernel(int64_t c0, int64_t c1, const int64_t* __restrict__ colptr,
+                                    const int64_t* __restrict__ rowval, const double* __restrict__ val,
+                                    const int32_t* __restrict__ blk_of_row, int t, int64_t row0_t,
+                                    const int32_t* __restrict__ row_map, double shift, double* __restrict__ tile,
+                                    int64_t n) {
+    for (int64_t c = c0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < c1; c += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t lc = row_map ? row_map[c] : c - row0_t;
+        if (lc < 0) continue;
+        for (int64_t e = colptr[c]; e < colptr[c + 1]; ++e) {
+            const int64_t r = rowval[e];
+            if (blk_of_row[r] != t) continue;
+            const int64_t lr = row_map ? row_map[r] : r - row0_t;
+            if (lr < 0) continue;
+            tile[lr + lc * n] = fabs(val[e]) + (lr == lc ? shift : 0.0);
         }
     }
 }
@@ -555,6 +575,73 @@ int build_gram(aces_ctx* ctx, aces_design* d, int ls_type, const FitVectors& fv,
     return ACES_OK;
 }
 
+// The reference's fallback for a block whose Cholesky factorisation fails (src/merit.jl:403-424):
+// take the elementwise absolute value and, if the smallest eigenvalue is then below epsilon, add
+// (epsilon - eig_min) * I.  The reference gets eig_min from ARPACK; here it is located by bisection
+// on the shift mu for which the block + mu * I is still factorisable (accurate to about
+// n * eps * |block|, the same order as epsilon = 1e-12 -- this path is "parity unpinned").
+int fallback_tiles(aces_ctx* ctx, aces_design* d, const double* val_dev, const int32_t* row_map,
+                   const std::vector<int64_t>& kept_count, double epsilon) {
+    std::vector<int32_t> fl((size_t)d->T);
+    ACES_CUDA(ctx, cudaMemcpyAsync(fl.data(), d->flags, sizeof(int32_t) * fl.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    d->fallback_blocks = 0;
+    std::vector<double> hval;
+    for (int t = 0; t < d->T; ++t) {
+        if (!fl[(size_t)t]) continue;
+        d->fallback_blocks += 1;
+        if (hval.empty()) {
+            hval.resize((size_t)d->nnz_cov);
+            ACES_CUDA(ctx, cudaMemcpy(hval.data(), val_dev, sizeof(double) * hval.size(), cudaMemcpyDeviceToHost));
+        }
+        // infinity norm of the block bounds every eigenvalue
+        double norm = 0.0;
+        for (int64_t c = d->row0[t]; c < d->row0[t + 1]; ++c) {
+            double sum = 0.0;
+            for (int64_t e = d->h_cov_colptr[(size_t)c]; e < d->h_cov_colptr[(size_t)c + 1]; ++e) sum += std::fabs(hval[(size_t)e]);
+            norm = std::max(norm, sum);
+        }
+        const int64_t n = d->mp[t];
+        double* tile = d->tilesL + d->tile_off[t];
+        double* dinv = d->dinvT + d->dinv_off[t];
+        int32_t* flag = d->flags + t;
+        auto attempt = [&](double mu, bool* ok) -> int {
+            ACES_CUDA(ctx, cudaMemsetAsync(tile, 0, sizeof(double) * (size_t)n * n, ctx->stream));
+            ACES_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int32_t), ctx->stream));
+            tile_rebuild_kernel<<<grid_for(d->m[t], 128), 128, 0, ctx->stream>>>(
+                d->row0[t], d->row0[t + 1], d->cov_colptr, d->cov_rowval, val_dev, d->blk_of_row, t, d->row0[t], row_map,
+                mu, tile, n);
+            ACES_CUDA(ctx, cudaGetLastError());
+            ctx->launches += 1;
+            ACES_TRY(dense::fill_diag_range(ctx, tile, n, kept_count[(size_t)t], n, 1.0));
+            ACES_TRY(dense::potrf(ctx, n, tile, n, dinv, flag));
+            int32_t f = 0;
+            ACES_CUDA(ctx, cudaMemcpyAsync(&f, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            *ok = f == 0;
+            return ACES_OK;
+        };
+        bool ok = false;
+        double shift = 0.0;
+        ACES_TRY(attempt(-epsilon, &ok));  // factorisable: the smallest eigenvalue is already >= epsilon
+        if (!ok) {
+            double lo = -epsilon, hi = 2.0 * norm + epsilon;
+            for (int it = 0; it < 64 && hi - lo > 1e-16 * norm; ++it) {
+                const double mid = 0.5 * (lo + hi);
+                ACES_TRY(attempt(mid, &ok));
+                if (ok) hi = mid; else lo = mid;
+            }
+            shift = hi + epsilon;  // hi ~ -eig_min
+        }
+        ACES_TRY(attempt(shift, &ok));
+        if (!ok)
+            return aces_fail(ctx, ACES_E_NOT_PD, "covariance block of tuple %d is not positive definite even after the "
+                             "absolute-value / eigenvalue-shift fallback", t);
+        ACES_TRY(dense::trtri(ctx, n, tile, n, dinv, d->tilesX + d->tile_off[t], n));
+    }
+    return ACES_OK;
+}
+
 int check_flags(aces_ctx* ctx, aces_design* d, const char* what) {
     std::vector<int32_t> fl((size_t)d->T + 1);
     ACES_CUDA(ctx, cudaMemcpyAsync(fl.data(), d->flags, sizeof(int32_t) * fl.size(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -573,10 +660,13 @@ int check_flags(aces_ctx* ctx, aces_design* d, const char* what) {
 // diagonal weights (OLS / WLS), Gram matrix and its Cholesky factor.
 int prepare_estimator(aces_ctx* ctx, aces_design* d, int ls_type, const double* val_dev, const int32_t* row_map,
                       const std::vector<int64_t>& kept_count, const FitVectors& fv) {
+    d->fallback_blocks = 0;
     ACES_CUDA(ctx, cudaMemsetAsync(d->flags, 0, sizeof(int32_t) * ((size_t)d->T + 2), ctx->stream));
     ACES_CUDA(ctx, cudaMemsetAsync(d->vec, 0, sizeof(double) * (size_t)(8 * std::max(d->Mp, d->Np)), ctx->stream));
     if (ls_type == 2) {
         ACES_TRY(build_and_factor_tiles(ctx, d, val_dev, row_map, kept_count));
+        // sparse_covariance_inv_factor's default epsilon (src/merit.jl:381)
+        ACES_TRY(fallback_tiles(ctx, d, val_dev, row_map, kept_count, 1e-12));
     } else {
         diag_factor_kernel<<<grid_for(d->M, 256), 256, 0, ctx->stream>>>(d->M, d->cov_colptr, d->cov_rowval, val_dev,
                                                                         d->blk_of_row, d->d_row0, d->d_prow0, row_map,
@@ -736,6 +826,7 @@ int32_t aces_design_destroy(aces_ctx* ctx, aces_design* d) {
 }
 
 int64_t aces_design_covariance_nnz(const aces_design* d) { return d ? d->nnz_cov : -1; }
+int32_t aces_design_fallback_count(const aces_design* d) { return d ? d->fallback_blocks : -1; }
 
 int32_t aces_design_covariance_pattern(const aces_design* d, int64_t* colptr, int64_t* rowval) {
     if (!d || !colptr || !rowval) return ACES_E_INVALID;
@@ -832,7 +923,7 @@ int32_t aces_calc_covariance(aces_ctx* ctx, aces_design* d, const double* eigenv
 
 int32_t aces_design_inv_factor(aces_ctx* ctx, aces_design* d, const double* covariance_log_nzval,
                                const int64_t* kept_rows, int64_t n_kept, int32_t index_base,
-                               double* factor_blocks, int64_t* block_lengths) {
+                               double fallback_epsilon, double* factor_blocks, int64_t* block_lengths) {
     ACES_TRY(check_design(ctx, d, "design_inv_factor"));
     ACES_CHECK(ctx, covariance_log_nzval && factor_blocks, "design_inv_factor: NULL argument");
     ACES_TRY(ensure_workspaces(ctx, d, true, false, false, false));
@@ -843,7 +934,10 @@ int32_t aces_design_inv_factor(aces_ctx* ctx, aces_design* d, const double* cova
     ACES_CUDA(ctx, cudaMemsetAsync(d->flags, 0, sizeof(int32_t) * ((size_t)d->T + 2), ctx->stream));
     ACES_CUDA(ctx, cudaMemcpyAsync(d->covval, covariance_log_nzval, sizeof(double) * (size_t)d->nnz_cov, cudaMemcpyDefault,
                                    ctx->stream));
+    d->fallback_blocks = 0;
     ACES_TRY(build_and_factor_tiles(ctx, d, d->covval, clipped ? d->row_map : nullptr, kept));
+    if (fallback_epsilon > 0.0)
+        ACES_TRY(fallback_tiles(ctx, d, d->covval, clipped ? d->row_map : nullptr, kept, fallback_epsilon));
     // export: blocks of kept[t] x kept[t], concatenated
     std::vector<int64_t> out_off((size_t)d->T + 1, 0);
     for (int t = 0; t < d->T; ++t) out_off[(size_t)t + 1] = out_off[(size_t)t] + kept[(size_t)t] * kept[(size_t)t];

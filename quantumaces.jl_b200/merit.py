@@ -207,7 +207,12 @@ class DeviceDesign:
         return self._sparse(out)
 
     # -- K3 -------------------------------------------------------------------------------------
-    def sparse_covariance_inv_factor(self, covariance_log, clipped_indices=None):
+    def fallback_count(self) -> int:
+        """Blocks that took the not-positive-definite fallback (src/merit.jl:403-424) in the last call."""
+        return int(self.ctx.lib.aces_design_fallback_count(self.handle))
+
+    def sparse_covariance_inv_factor(self, covariance_log, clipped_indices=None, epsilon: float = 1e-12,
+                                     fallback: bool = True):
         """sparse_covariance_inv_factor(covariance_log[clipped, clipped], clipped_mapping_lengths)
         (src/merit.jl:378-427).  `covariance_log` is the unclipped M x M matrix; returns the
         block-diagonal factor over the kept rows."""
@@ -222,7 +227,8 @@ class DeviceDesign:
         blocks = np.zeros(int(np.sum(lens.astype(np.int64) ** 2)), dtype=np.float64)
         got = np.zeros(self.T, dtype=np.int64)
         self.ctx.check(self.ctx.lib.aces_design_inv_factor(
-            self.ctx.handle, self.handle, _ptr(val), _ptr(kept), n_kept, 0, _ptr(blocks), _ptr(got)))
+            self.ctx.handle, self.handle, _ptr(val), _ptr(kept), n_kept, 0, float(epsilon) if fallback else 0.0,
+            _ptr(blocks), _ptr(got)))
         assert np.array_equal(got, lens)
         mats, off = [], 0
         for k in lens:

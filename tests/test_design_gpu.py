@@ -171,8 +171,22 @@ def test_not_positive_definite_block_is_reported(setup):
     big = 10.0 * max(cl[p, p], cl[q, q])
     cl[p, q] = big
     cl[q, p] = big
+    cl = sp.csc_matrix(cl)
     with pytest.raises(aces_b200.NotPositiveDefinite):
-        dd.sparse_covariance_inv_factor(sp.csc_matrix(cl))
+        dd.sparse_covariance_inv_factor(cl, fallback=False)
+    # the reference's fallback (src/merit.jl:403-424): |block|, smallest eigenvalue raised to epsilon
+    eps = 1e-6
+    F = dd.sparse_covariance_inv_factor(cl, epsilon=eps)
+    assert dd.fallback_count() == 1
+    Fo = fo.sparse_covariance_inv_factor(cl, fd.mapping_lengths, epsilon=eps)
+    m0 = int(fd.mapping_lengths[0])
+    inv_got, inv_want = dense(F.T @ F), dense(Fo.T @ Fo)
+    # the shifted block has condition number ~ 1e7: compare the inverses loosely, the other blocks tightly
+    assert rel(inv_got[m0:, m0:], inv_want[m0:, m0:]) < RTOL
+    assert rel(inv_got[:m0, :m0], inv_want[:m0, :m0]) < 1e-4
+    shifted = np.abs(dense(cl)[:m0, :m0])
+    w = np.linalg.eigvalsh(np.linalg.inv(inv_got[:m0, :m0]))
+    assert abs(w[0] - eps) < 0.05 * eps, (w[0], np.linalg.norm(shifted, np.inf))
 
 
 def test_design_create_rejects_bad_input(ctx):

@@ -13,5 +13,7 @@ lam = np.concatenate(fo.mean_ensemble(eig))
 cl = fo.calc_covariance_log(fo.calc_covariance_from_experiments(fd, eig, cov, weight_time=False), lam)
 F = fo.sparse_covariance_inv_factor(cl, fd.mapping_lengths)
 with aces_b200.Context(0) as ctx:
-    g = aces_b200.estimate_gate_eigenvalues(ctx, fd.matrix, lam, F)
+    dd = aces_b200.DeviceDesign(ctx, fd)
+    lc = np.concatenate(aces_b200.mean_ensemble(cov))
+    g = dd.fit(sys.argv[2] if len(sys.argv) > 2 else "gls", lam, lc)
     print("fit ok", float(np.max(np.abs(g - fd.gate_eigenvalues))))
