@@ -9,6 +9,12 @@ nested budgets 1e6/1e7/1e8): 2.1 GB of bit-packed shot records -> 96 x 241 x 3 o
 counts.  Multi-GPU: one repetition per rank per step (repetitions are independent,
 src/simulate.jl:371), the per-repetition count vectors all-gathered with NCCL ("weak").
 
+The JSON line also carries a `fit` object: GLS / WLS fits per second at the rotated d=9 shape
+through aces_design_fit (host vectors in, host gate eigenvalues out), the Gram kernel's FP64
+rate against the cuBLAS DGEMM rate measured in the same run, and the CPU restatement's time for
+one fit.  Multi-GPU: fits are independent per budget and repetition (src/simulate.jl:393), so
+every rank runs its own (replicas).
+
 `--impl reference` times the CPU restatement of the reference algorithm (oracle/, OpenMP over
 Paulis like the reference's @threads :static) -- Julia is not available in this image.
 """
@@ -145,6 +151,111 @@ def cpu_sample(fd, est_sizes, seconds_target=12.0):
     }
 
 
+def dgemm_peak_tflops(torch, n=8192, reps=5):
+    """cuBLAS DGEMM n^3 on this GPU (the FP64 roofline denominator)."""
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        a @ b
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        a @ b
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def fit_inputs():
+    """Rotated d=9 design with a full covariance pattern and estimates whose covariance blocks are
+    positive definite (the common case; the not-PD fallback is covered by the tests)."""
+    import numpy as np
+
+    import aces_b200
+
+    fd = aces_b200.synthetic_design("rotated", 9, full_covariance=True, with_matrix=True)
+    eig, cov = aces_b200.synthetic_estimates(fd, shots=10**8, seed=11)
+    lam = np.concatenate(aces_b200.mean_ensemble(eig))
+    lc = np.concatenate(aces_b200.mean_ensemble(cov))
+    return fd, eig, cov, lam, lc
+
+
+def fit_leg(ctx, torch, dist, world, rank, steps, warmup, with_cpu):
+    """GLS / WLS fits per second at the rotated d=9 shape, through the C ABI with host buffers."""
+    import numpy as np
+
+    import aces_b200
+
+    fd, eig, cov, lam, lc = fit_inputs()
+    dd = aces_b200.DeviceDesign(ctx, fd)
+    out = {"workload": "rotated_d9 GLS (full covariance pattern)", "M": int(fd.M), "N": int(fd.matrix.shape[1]),
+           "tuples": int(fd.tuple_number), "covariance_keys": int(dd.C),
+           "api": "aces_design_fit: host estimate vectors in, host gate eigenvalues out (H2D + D2H inside)"}
+    res = {}
+    for name in ("gls", "wls"):
+        for _ in range(warmup):
+            g = dd.fit(name, lam, lc)
+        assert dd.fallback_count() == 0
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            g = dd.fit(name, lam, lc)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[name] = (world * steps / float(t.item()), g)
+        out[f"{name}_fits_per_s"] = res[name][0]
+        out[f"{name}_ms_per_fit"] = 1e3 * float(t.item()) / steps
+    out["max_abs_error_vs_truth"] = float(np.max(np.abs(res["gls"][1] - fd.gate_eigenvalues)))
+    # Gram kernel of the GLS fit on the FP64 tensor pipe (lower tiles of At' At)
+    ctx.set_timing(True)
+    ks = []
+    for _ in range(3):
+        dd.fit("gls", lam, lc)
+        ks.append(ctx.last_kernel_ms())
+    ctx.set_timing(False)
+    k_ms = sorted(ks)[1]
+    Np = -(-fd.matrix.shape[1] // 128) * 128
+    Mp = int(sum(-(-int(m) // 128) * 128 for m in fd.mapping_lengths))
+    tiles = (Np // 128) * (Np // 128 + 1) // 2
+    flops = 2.0 * tiles * 128 * 128 * Mp
+    peak = dgemm_peak_tflops(torch)
+    out["roofline"] = {"bound": "tensor", "kernel": "dense::gemm_kernel<TN> (Gram, DMMA m8n8k4 f64)",
+                       "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                       "frac": flops / (k_ms * 1e-3) / 1e12 / peak, "kernel_ms": k_ms,
+                       "executed_flops_per_launch": flops,
+                       "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (burst, best of 5)",
+                       "share_of_fit": k_ms / out["gls_ms_per_fit"], "traffic": None}
+    if with_cpu and rank == 0:
+        out["cpu_baseline"] = cpu_fit_sample(fd, eig, cov)
+    dd.close()
+    return out
+
+
+def cpu_fit_sample(fd, eig, cov):
+    """One GLS fit of the same inputs by the CPU restatement (numpy / LAPACK QR as the SPQR stand-in)."""
+    import fit_util  # noqa: F401  (puts oracle/ on the path)
+    import fit_oracle as fo
+
+    t0 = time.perf_counter()
+    r = fo.estimate_gate_noise_core(fd, eig, cov)
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": "estimate_gate_noise cores/s (OLS + WLS + GLS fits of one estimate set)",
+            "cores": os.cpu_count(), "kind": "port", "seconds": dt,
+            "sample": "one estimate_gate_noise numeric core (covariance, block factor, OLS + WLS + GLS solves) at "
+                      "rotated d=9; dense LAPACK QR stands in for SPQR", "gls_fits_per_s_equivalent": 3.0 / dt,
+            "checksum": float(r["gls"].sum())}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -169,6 +280,9 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_fit:
+        f_fd, f_eig, f_cov, _, _ = fit_inputs()
+        line["fit"] = {"workload": "rotated_d9 GLS (full covariance pattern)", "cpu_baseline": cpu_fit_sample(f_fd, f_eig, f_cov)}
     print(json.dumps(line))
 
 
@@ -180,6 +294,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-fit", action="store_true")
+    ap.add_argument("--fit-steps", type=int, default=5)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -287,6 +403,11 @@ def main():
     e2e_s = float(t.item())
     e2e_value = world * shot_parities * args.e2e_steps / e2e_s
 
+    fit = None
+    if not args.no_fit:
+        ctx.set_stream(None)
+        fit = fit_leg(ctx, torch, dist, world, rank, args.fit_steps, 2, not args.no_cpu)
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         k_ms = sorted(kernel_ms)[len(kernel_ms) // 2]
@@ -318,6 +439,8 @@ def main():
         }
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_sample(fd, sizes)
+        if fit is not None:
+            line["fit"] = fit
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

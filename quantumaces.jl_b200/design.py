@@ -352,3 +352,39 @@ def _attach_synthetic_matrix(fd: FlatDesign, N: int, rng) -> None:
                 cov_rows.append(sp.csr_matrix((0, N), dtype=np.int64))
             row0 += int(m_t[t])
         fd.cov_rows = cov_rows
+
+
+def synthetic_estimates(fd: FlatDesign, shots: float = 10**8, seed: int = 0, noise: bool = True):
+    """Synthetic per-experiment estimate ensembles for a design with a matrix: what
+    simulate_stim_estimate returns for one budget ([t][pauli] -> one value per experiment that
+    measures it), drawn around the true circuit eigenvalues exp(A log g) (src/design.jl:255-258)
+    with the shot-noise variance of src/merit.jl:245-254.  Input generator for tests and bench.py
+    (Stim sampling is not part of the hot path)."""
+    rng = np.random.default_rng(seed)
+    lg = np.log(fd.gate_eigenvalues)
+    lam = np.exp(fd.matrix.astype(np.float64) @ lg)
+    off = np.concatenate([[0], np.cumsum(fd.mapping_lengths)])
+    lam_ens = [lam[off[t]:off[t + 1]] for t in range(fd.tuple_number)]
+    eig, cov = [], []
+    for t in range(fd.tuple_number):
+        sig = np.sqrt(np.maximum(1 - lam_ens[t] ** 2, 1e-10) / (shots * fd.shot_weights[t] / fd.experiment_numbers[t]))
+        eig_t = []
+        for p in range(int(fd.mapping_lengths[t])):
+            k = int(fd.diag_counts[t][p])
+            v = lam_ens[t][p] + (sig[p] * rng.standard_normal(k) if noise else np.zeros(k))
+            eig_t.append(list(np.minimum(v, 1.0)))
+        eig.append(eig_t)
+        cov_t = []
+        if fd.full_covariance and len(fd.cov_keys[t]):
+            # the pair estimate follows the two single estimates (they come from the same shots):
+            # lambda_pq_hat = lambda_p_hat * lambda_q_hat * (true ratio) + a little noise, which
+            # keeps the estimated covariance blocks positive definite as in a real experiment
+            cov_lam = np.exp(fd.cov_rows[t].astype(np.float64) @ lg)
+            for c, (p, q) in enumerate(fd.cov_keys[t]):
+                k = max(int(fd.cov_counts[t][c]), 1)
+                s = 1e-9 if noise else 0.0
+                ratio = cov_lam[c] / (lam_ens[t][p] * lam_ens[t][q])
+                base = np.mean(eig_t[p]) * np.mean(eig_t[q]) * ratio
+                cov_t.append(list(np.minimum(base + s * rng.standard_normal(k), 1.0)))
+        cov.append(cov_t)
+    return eig, cov

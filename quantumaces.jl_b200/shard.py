@@ -1,0 +1,76 @@
+"""Sharding of the ACES estimation path over GPUs (one process per GPU, torch.distributed).
+
+The path partitions along three axes, none of which needs a data-path
+collective -- only the small count / estimate vectors are exchanged:
+
+* repetitions (src/simulate.jl:371) are independent: round-robin over ranks, results gathered;
+* experiments of one repetition (src/simulate.jl:145-155) are independent sample matrices:
+  balanced over ranks by bytes, the odd-parity counts combined with all_reduce(sum, int64);
+* shots of one experiment are additive: contiguous row ranges per rank with the budget prefixes
+  (src/simulate.jl:206-213) clamped into each range, counts combined with all_reduce(sum, int64).
+
+Integer sums are exact, so the combined counts equal the single-GPU counts bit for bit whatever
+the sharding.  Backend: NCCL over NVLink for device tensors, gloo for the CPU tests.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+
+def shard_repetitions(repetitions: int, world: int, rank: int) -> List[int]:
+    """Repetition indices (0-based) handled by `rank`: round-robin."""
+    assert 0 <= rank < world
+    return list(range(rank, repetitions, world))
+
+
+def shard_experiments(experiment_bytes: Sequence[int], world: int) -> List[List[int]]:
+    """Greedy longest-processing-time split of experiments by sample-matrix bytes
+    (shots_maximum[t] * ceil(n / 8)).  Returns the experiment ids of every rank, ascending."""
+    order = np.argsort(-np.asarray(experiment_bytes, dtype=np.int64), kind="stable")
+    load = np.zeros(world, dtype=np.int64)
+    out: List[List[int]] = [[] for _ in range(world)]
+    for e in order:
+        r = int(np.argmin(load))
+        out[r].append(int(e))
+        load[r] += int(experiment_bytes[int(e)])
+    return [sorted(x) for x in out]
+
+
+def shard_shots(rows: int, prefix_shots: Sequence[int], world: int, rank: int,
+                align: int = 128) -> Tuple[int, int, np.ndarray]:
+    """Contiguous row range [lo, hi) of `rank` for a sample matrix of `rows` shots and the budget
+    prefixes restricted to it: local_prefix[k] = clamp(prefix[k] - lo, 0, hi - lo).  Range starts
+    are multiples of `align` rows so that every shard can be read in place through the TMA path
+    (16-byte aligned columns).  The per-rank counts add up to the counts of the whole matrix."""
+    assert 0 <= rank < world and rows >= 0
+    per = -(-rows // world)
+    per = -(-per // align) * align
+    lo = min(rank * per, rows)
+    hi = min(lo + per, rows)
+    pre = np.asarray(prefix_shots, dtype=np.int64)
+    return lo, hi, np.clip(pre - lo, 0, hi - lo)
+
+
+def all_reduce_counts(counts, group=None):
+    """In-place all_reduce(sum) of an int64 count tensor (device tensor: NCCL; CPU tensor: gloo)."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return counts
+
+
+def all_gather_vectors(vec, group=None):
+    """Gathers one equally sized vector per rank (per-repetition counts or estimates) into a
+    [world, len] tensor on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return vec.reshape(1, -1)
+    world = dist.get_world_size(group)
+    out = torch.empty((world, vec.numel()), dtype=vec.dtype, device=vec.device)
+    dist.all_gather_into_tensor(out.reshape(-1), vec.reshape(-1).contiguous(), group=group)
+    return out
