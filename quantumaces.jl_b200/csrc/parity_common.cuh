@@ -34,7 +34,7 @@ struct ItemDesc {  // lives in shared memory, one per pipeline stage
     // first 16 bytes: what every thread needs (one 128-bit shared load)
     int32_t stream;
     int32_t lo_rel, hi_rel;  // segment rows relative to the tile start, clamped to [0, TS]
-    int32_t boundary;        // the tile is not entirely inside the segment
+    int32_t boundary;        // bit 0: the tile is not entirely inside the segment; bit 1: flush first
     // producer warp only
     const uint8_t* src;
     int64_t ld;
@@ -53,6 +53,7 @@ struct ParityParams {
     int32_t n_streams;
     int32_t B;
     int32_t NS;
+    int32_t dbg;  // development only: bit 0 skips phase A, bit 1 skips phase B
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -66,18 +67,21 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                  "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!done);
+// Blocks until the phase with the given parity completes.  try_wait suspends the thread in
+// hardware until the phase flips or the time hint (in ns) expires, so a waiting warp does not
+// burn issue slots re-polling; the loop only covers the (rare) expiry of the hint.
+__device__ __forceinline__ void mbar_wait_s(uint32_t addr, uint32_t parity);
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_s(smem_u32(bar), parity); }
+__device__ __forceinline__ void mbar_wait_s(const uint32_t addr, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "ACES_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra ACES_DONE_%=;\n\t"
+        "bra ACES_WAIT_%=;\n\t"
+        "ACES_DONE_%=:\n\t}"
+        ::"r"(addr), "r"(parity), "r"(0x989680u)
+        : "memory");
 }
 // One bulk-async (TMA engine) copy global -> shared, completing `bytes` on the mbarrier.
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,

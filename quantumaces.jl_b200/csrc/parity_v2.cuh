@@ -117,6 +117,8 @@ __global__ void __launch_bounds__((NW + 1) * 32) parity_kernel_v2(const ParityPa
         uint64_t policy;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
         int prod_stream = 0;
+        int last_stream = -1;
+        uint32_t since_flush = 0;
         int stage = 0;
         uint32_t parity = 1;  // a fresh mbarrier passes a wait on parity 1
         for (int it = 0; it < n_my; ++it) {
@@ -142,7 +144,13 @@ __global__ void __launch_bounds__((NW + 1) * 32) parity_kernel_v2(const ParityPa
                 d->stream = s;
                 d->lo_rel = (int32_t)(lo > 0 ? lo : 0);
                 d->hi_rel = (int32_t)(hi < TS ? hi : TS);
-                d->boundary = (lo > 0) || (hi < TS);
+                // bit 0: the tile is not entirely inside the segment; bit 1: the consumers must
+                // flush their counters first (new stream, or 2^19 tiles since the last flush so
+                // that the 32-bit shared counters cannot overflow)
+                const bool flush = (s != last_stream) || (since_flush >= (1u << 19));
+                since_flush = flush ? 1u : since_flush + 1u;
+                last_stream = s;
+                d->boundary = (((lo > 0) || (hi < TS)) ? 1 : 0) | (flush ? 2 : 0);
                 d->src = sd.base + r0;
                 d->ld = sd.ld;
                 d->bytes = bytes;
@@ -161,35 +169,55 @@ __global__ void __launch_bounds__((NW + 1) * 32) parity_kernel_v2(const ParityPa
     }
 
     // ================================== consumer warps =========================================
-    const uint32_t planes_s = smem_s + planes_off + (uint32_t)warp * planes_bytes;
+    uint32_t planes_s = smem_s + planes_off + (uint32_t)warp * planes_bytes;
+    uint32_t empty_s = smem_u32(&empty[0]), full_s = smem_u32(&full[0]);
+    uint32_t raw_s = smem_s + raw_off + (uint32_t)(warp * SUB), lane_r = (uint32_t)lane;
+    // keep the loop invariants in registers (the compiler would otherwise rematerialise them from
+    // the special registers every tile)
+    asm volatile("" : "+r"(planes_s), "+r"(empty_s), "+r"(full_s), "+r"(raw_s), "+r"(lane_r));
+    const int lane_c = (int)lane_r;
     uint32_t acc[RMAX];
-    uint32_t dx[RMAX];  // weight-1 rounds: plane-row offset; weight<=2 rounds: a0 | a1 << 16
+    // per register slot: weight-1 slots hold the shared-memory address of their plane row;
+    // weight-2 slots hold the two plane-row offsets packed as a0 | a1 << 16
+    uint32_t dx[RMAX];
     constexpr uint32_t zero_row = (uint32_t)(8 * BMAX * ROWB);
     for (int i = lane; i < ROWB / 4; i += 32) sts32(planes_s + zero_row + 4 * i, 0u);
     __syncwarp();
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) { acc[r] = 0; dx[r] = 0; }
-    // rounds whose Paulis all have weight 1 / weight <= 2 (a missing second bit, an identity
-    // Pauli or a lane past the end of the table points at the all-zero row)
-    int n1 = 0, n12 = 0;  // rounds [0,n1): weight 1; [n1,n12): weight <= 2; [n12,R): table-driven
+    // The Paulis of a slice are sorted by weight; lane l owns Paulis l, l+32, ... ("rounds").
+    // Rounds [0,n1) hold only weight-1 Paulis, [n1,n12) only weight <= 2 (a missing second bit,
+    // an identity Pauli or a lane past the end of the table points at the all-zero row),
+    // [n12,R) are table-driven.  The classes live in fixed register slots so that each class runs
+    // as straight-line code entered through one computed jump (no per-round branches):
+    //   weight-2 rounds  -> slots [0, n2),  n2 = n12 - n1          round = n1 + slot
+    //   table rounds     -> slots [n2, n2 + ng), ng = R - n12       round = n12 + (slot - n2)
+    //   weight-1 rounds  -> slots [RMAX - n1, RMAX)                 round = slot - (RMAX - n1)
+    int n1 = 0, n2 = 0, ng = 0;
     int R = 0;                        // rounds in use
     int E = 0;
     int cur_stream = -1;
     int64_t cur_out = 0, cur_poff = 0;
-    uint32_t tiles_since_flush = 0;
 
     auto row_off = [&](uint32_t q) -> uint32_t {  // plane-row byte offset of record bit q
         return ((q & 7u) * (uint32_t)BMAX + (q >> 3)) * (uint32_t)ROWB;
+    };
+    auto round_of_slot = [&](int slot) -> int {  // -1: slot not in use
+        if (slot < n2) return n1 + slot;
+        if (slot < n2 + ng) return n1 + slot;  // n12 + (slot - n2) == n1 + slot
+        if (slot >= RMAX - n1) return slot - (RMAX - n1);
+        return -1;
     };
 
     // registers -> shared -> global; then (optionally) load the Pauli slice of stream `ns`
     auto change_stream = [&](int ns) {
         if (cur_stream >= 0) {
 #pragma unroll
-            for (int r = 0; r < RMAX; ++r) {
+            for (int sl = 0; sl < RMAX; ++sl) {
+                const int r = round_of_slot(sl);
                 const int p = r * 32 + lane;
-                if (r < R && p < E && acc[r] != 0) atomicAdd(&sacc[p], acc[r]);
-                acc[r] = 0;
+                if (r >= 0 && p < E && acc[sl] != 0) atomicAdd(&sacc[p], acc[sl]);
+                acc[sl] = 0;
             }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
@@ -204,7 +232,6 @@ __global__ void __launch_bounds__((NW + 1) * 32) parity_kernel_v2(const ParityPa
             }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
-        tiles_since_flush = 0;
         if (ns < 0 || ns == cur_stream) return;
         cur_stream = ns;
         const StreamDesc* sd = &P.streams[ns];
@@ -212,74 +239,104 @@ __global__ void __launch_bounds__((NW + 1) * 32) parity_kernel_v2(const ParityPa
         cur_poff = sd->pauli_off;
         E = sd->E;
         R = (E + 31) >> 5;
-        n1 = 0;
-        n12 = 0;
+        // pass 1: classify the rounds (the table is sorted by weight: classes are prefixes)
+        int c1 = 0, c12 = 0;
 #pragma unroll
         for (int r = 0; r < RMAX; ++r) {
             const int p = r * 32 + lane;
             int w = 0;
-            uint32_t a0 = zero_row, a1 = zero_row;
-            if (r < R && p < E) {
-                const uint4* pd4 = reinterpret_cast<const uint4*>(&P.pauli[cur_poff + p]);
-                const uint4 qa = __ldg(pd4);
-                w = (int)__ldg(reinterpret_cast<const uint32_t*>(pd4 + 1));
-                if (w >= 1) a0 = row_off(qa.x);
-                if (w >= 2) a1 = row_off(qa.y);
-            }
+            if (r < R && p < E) w = (int)__ldg(&P.pauli[cur_poff + p].w);
             const bool all1 = __all_sync(0xffffffffu, w == 1);
             const bool all2 = __all_sync(0xffffffffu, w <= 2);
-            // the table is sorted by weight, so the classes are prefixes of the round list
-            if (all1 && n1 == r) n1 = r + 1;
-            if (all2 && n12 == r && r < R) n12 = r + 1;
-            dx[r] = (a0 | (a1 << 16));
+            if (all1 && c1 == r) c1 = r + 1;
+            if (all2 && c12 == r && r < R) c12 = r + 1;
+        }
+        n1 = c1;
+        n2 = c12 - c1;
+        ng = R - c12;
+        // pass 2: plane rows of every slot
+#pragma unroll
+        for (int sl = 0; sl < RMAX; ++sl) {
+            const int r = round_of_slot(sl);
+            const int p = r * 32 + lane;
+            uint32_t a0 = zero_row, a1 = zero_row;
+            if (r >= 0 && p < E) {
+                const PauliDesc* pd = &P.pauli[cur_poff + p];
+                const int w = (int)__ldg(&pd->w);
+                if (w >= 1) a0 = row_off((uint32_t)__ldg(&pd->q[0]));
+                if (w >= 2) a1 = row_off((uint32_t)__ldg(&pd->q[1]));
+            }
+            dx[sl] = (sl >= RMAX - n1) ? planes_s + a0 : (a0 | (a1 << 16));
         }
     };
 
     int stage = 0;
     uint32_t parity = 0;
     for (int it = 0; it < n_my; ++it) {
-        mbar_wait(&full[stage], parity);
-        const int4 d = *reinterpret_cast<const int4*>(&sdesc[stage]);  // stream, lo_rel, hi_rel, boundary
-        if (d.x != cur_stream || tiles_since_flush >= (1u << 19)) change_stream(d.x);
-        ++tiles_since_flush;
-
-        // rows of this warp relative to its sub-tile start
-        const int lo = d.y - warp * SUB, hi = d.z - warp * SUB;
-        const bool any = (hi > 0) && (lo < SUB);
-        const uint32_t stage_s = smem_s + raw_off + (uint32_t)stage * stage_bytes + (uint32_t)(warp * SUB);
-        if (any) {
-            if (lo > 0 || hi < SUB)
-                v2_phase_a<SUB, BMAX, true>(stage_s, planes_s, B, CS, lane, lo, hi);
-            else
-                v2_phase_a<SUB, BMAX, false>(stage_s, planes_s, B, CS, lane, 0, SUB);
+        mbar_wait_s(full_s + 8u * (uint32_t)stage, parity);
+        const int4 d = *reinterpret_cast<const int4*>(&sdesc[stage]);  // stream, lo_rel, hi_rel, flags
+        if (d.w & 2) change_stream(d.x);
+        const uint32_t stage_s = raw_s + (uint32_t)stage * stage_bytes;
+        bool any = true;
+        if (d.w & 1) {
+            // rows of this warp relative to its sub-tile start
+            const int lo = d.y - warp * SUB, hi = d.z - warp * SUB;
+            any = (hi > 0) && (lo < SUB);
+            if (any) {
+                if (lo > 0 || hi < SUB)
+                    v2_phase_a<SUB, BMAX, true>(stage_s, planes_s, B, CS, lane_c, lo, hi);
+                else
+                    v2_phase_a<SUB, BMAX, false>(stage_s, planes_s, B, CS, lane_c, 0, SUB);
+            }
+        } else {
+            v2_phase_a<SUB, BMAX, false>(stage_s, planes_s, B, CS, lane_c, 0, SUB);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);  // the raw stage may be refilled
+        if (lane_c == 0)  // the raw stage may be refilled
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_s + 8u * (uint32_t)stage) : "memory");
 
         if (any) {
-#pragma unroll
-            for (int r = 0; r < RMAX; ++r) {
-                if (r < n12) {
-                    const uint32_t a0 = planes_s + (dx[r] & 0xFFFFu);
-                    uint32_t cnt = 0;
-                    if (r < n1) {
-#pragma unroll
-                        for (int v = 0; v < V; ++v) cnt += popc4(lds128(a0 + 16 * v));
-                    } else {
-                        const uint32_t a1 = planes_s + (dx[r] >> 16);
-#pragma unroll
-                        for (int v = 0; v < V; ++v)
-                            cnt += popc4(xor4(lds128(a0 + 16 * v), lds128(a1 + 16 * v)));
-                    }
-                    acc[r] += cnt;
-                }
+#define ACES_W2(SL)                                                                          \
+    {                                                                                        \
+        const uint32_t b0 = planes_s + (dx[SL] & 0xFFFFu), b1 = planes_s + (dx[SL] >> 16);   \
+        uint32_t cnt = 0;                                                                    \
+        _Pragma("unroll") for (int v = 0; v < V; ++v)                                        \
+            cnt += popc4(xor4(lds128(b0 + 16 * v), lds128(b1 + 16 * v)));                    \
+        acc[SL] += cnt;                                                                      \
+    }
+#define ACES_W1(SL)                                                                          \
+    {                                                                                        \
+        uint32_t cnt = 0;                                                                    \
+        _Pragma("unroll") for (int v = 0; v < V; ++v) cnt += popc4(lds128(dx[SL] + 16 * v)); \
+        acc[SL] += cnt;                                                                      \
+    }
+#define ACES_C2(K) case K: if constexpr (RMAX >= K) ACES_W2(K - 1) [[fallthrough]];
+#define ACES_C1(K) case K: if constexpr (RMAX >= K) ACES_W1(RMAX - K) [[fallthrough]];
+            switch (n2) {
+                ACES_C2(32) ACES_C2(31) ACES_C2(30) ACES_C2(29) ACES_C2(28) ACES_C2(27) ACES_C2(26) ACES_C2(25)
+                ACES_C2(24) ACES_C2(23) ACES_C2(22) ACES_C2(21) ACES_C2(20) ACES_C2(19) ACES_C2(18) ACES_C2(17)
+                ACES_C2(16) ACES_C2(15) ACES_C2(14) ACES_C2(13) ACES_C2(12) ACES_C2(11) ACES_C2(10) ACES_C2(9)
+                ACES_C2(8) ACES_C2(7) ACES_C2(6) ACES_C2(5) ACES_C2(4) ACES_C2(3) ACES_C2(2) ACES_C2(1)
+                default: break;
             }
-            if (n12 < R) {
+            switch (n1) {
+                ACES_C1(32) ACES_C1(31) ACES_C1(30) ACES_C1(29) ACES_C1(28) ACES_C1(27) ACES_C1(26) ACES_C1(25)
+                ACES_C1(24) ACES_C1(23) ACES_C1(22) ACES_C1(21) ACES_C1(20) ACES_C1(19) ACES_C1(18) ACES_C1(17)
+                ACES_C1(16) ACES_C1(15) ACES_C1(14) ACES_C1(13) ACES_C1(12) ACES_C1(11) ACES_C1(10) ACES_C1(9)
+                ACES_C1(8) ACES_C1(7) ACES_C1(6) ACES_C1(5) ACES_C1(4) ACES_C1(3) ACES_C1(2) ACES_C1(1)
+                default: break;
+            }
+#undef ACES_C1
+#undef ACES_C2
+#undef ACES_W1
+#undef ACES_W2
+            if (ng > 0) {
                 // supports wider than two bits: table-driven
 #pragma unroll
-                for (int r = 0; r < RMAX; ++r) {
+                for (int sl = 0; sl < RMAX; ++sl) {
+                    const int r = n1 + sl;
                     const int p = r * 32 + lane;
-                    if (r >= n12 && r < R && p < E) {
+                    if (sl >= n2 && sl < n2 + ng && p < E) {
                         const PauliDesc* pd = &P.pauli[cur_poff + p];
                         const int w = pd->w;
                         const int ext = pd->ext;
@@ -292,7 +349,7 @@ __global__ void __launch_bounds__((NW + 1) * 32) parity_kernel_v2(const ParityPa
                             }
                             cnt += popc4(x);
                         }
-                        acc[r] += cnt;
+                        acc[sl] += cnt;
                     }
                 }
             }
@@ -317,7 +374,8 @@ inline bool v2_pick(int B, int max_E, int smem_optin, V2Cfg* cfg) {
     else if (B <= 25) { SUB = 128; BMAX = 25; }
     else if (B <= 41) { SUB = 128; BMAX = 41; }
     else return false;
-    const int NW = 8;
+    int NW = 8;
+    if (getenv("ACES_K1_NW4") && BMAX == 25) { NW = 4; SUB = 256; }  // experiment: wider warp tiles
     if ((8 * BMAX + 1) * (SUB / 8) >= 65536) return false;  // plane-row offsets are packed in 16 bits
     const int RMAX = max_E <= 256 ? 8 : (max_E <= 512 ? 16 : 32);
     const size_t planes = (size_t)NW * (8 * BMAX + 1) * (SUB / 8);
@@ -369,6 +427,7 @@ inline int v2_launch(aces_ctx* ctx, const ParityParams& P, const V2Cfg& cfg) {
     (cfg.RMAX == 8 ? v2_launch_t<8, SUBV, BMV, 8>(ctx, P, cfg)                           \
                    : cfg.RMAX == 16 ? v2_launch_t<8, SUBV, BMV, 16>(ctx, P, cfg)         \
                                     : v2_launch_t<8, SUBV, BMV, 32>(ctx, P, cfg))
+    if (cfg.NW == 4) return cfg.RMAX == 8 ? v2_launch_t<4, 256, 25, 8>(ctx, P, cfg) : cfg.RMAX == 16 ? v2_launch_t<4, 256, 25, 16>(ctx, P, cfg) : v2_launch_t<4, 256, 25, 32>(ctx, P, cfg);
     if (cfg.SUB == 128 && cfg.BMAX == 25) return ACES_V2_R(128, 25);
     if (cfg.SUB == 128) return ACES_V2_R(128, 41);
     if (cfg.SUB == 256) return ACES_V2_R(256, 13);
