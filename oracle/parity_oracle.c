@@ -129,3 +129,13 @@ int32_t oracle_num_threads(void) {
     return 1;
 #endif
 }
+
+/* Lets the harness use every host core even when the launcher exported OMP_NUM_THREADS=1
+ * (torchrun does): the reference runs with JULIA_NUM_THREADS = nproc. */
+void oracle_set_num_threads(int32_t n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

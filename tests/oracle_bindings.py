@@ -27,6 +27,8 @@ def lib():
         L.oracle_batch_shots.restype = i64
         L.oracle_batch_shots.argtypes = [i64, i64, i64, vp, i64]
         L.oracle_num_threads.restype = i32
+        L.oracle_set_num_threads.restype = None
+        L.oracle_set_num_threads.argtypes = [i32]
         _lib = L
     return _lib
 
@@ -92,6 +94,10 @@ def batch_shots(shots, measurements, max_samples):
 
 def num_threads():
     return int(lib().oracle_num_threads())
+
+
+def set_num_threads(n):
+    lib().oracle_set_num_threads(int(n))
 
 
 def table_supports(est, e):
