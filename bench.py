@@ -225,12 +225,9 @@ def fit_leg(ctx, torch, dist, world, rank, steps, warmup, with_cpu):
         ks.append(ctx.last_kernel_ms())
     ctx.set_timing(False)
     k_ms = sorted(ks)[1]
-    Np = -(-fd.matrix.shape[1] // 128) * 128
-    Mp = int(sum(-(-int(m) // 128) * 128 for m in fd.mapping_lengths))
-    tiles = (Np // 128) * (Np // 128 + 1) // 2
-    flops = 2.0 * tiles * 128 * 128 * Mp
+    flops = dd.gram_flops()
     peak = dgemm_peak_tflops(torch)
-    out["roofline"] = {"bound": "tensor", "kernel": "dense::gemm_kernel<TN> (Gram, DMMA m8n8k4 f64)",
+    out["roofline"] = {"bound": "tensor", "kernel": "dense::gemm_batched_kernel<TN> (Gram over the column windows of the tuple blocks, DMMA m8n8k4 f64)",
                        "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                        "frac": flops / (k_ms * 1e-3) / 1e12 / peak, "kernel_ms": k_ms,
                        "executed_flops_per_launch": flops,

@@ -222,6 +222,10 @@ int32_t aces_design_inv_factor(aces_ctx* ctx, aces_design* design, const double*
                                const int64_t* kept_rows, int64_t n_kept, int32_t index_base,
                                double fallback_epsilon, double* factor_blocks, int64_t* block_lengths);
 int32_t aces_design_fallback_count(const aces_design* design);
+/* Dense FP64 flops the GLS Gram matrix of this design executes on the tensor pipe per fit (the
+ * lower 128 x 128 tiles of sum_t At_t' At_t over the column window of every tuple block, or of the
+ * full At' At when the windows do not pay).  Bookkeeping for the roofline figure. */
+double aces_design_gram_flops(const aces_design* design);
 
 /* K2-K5 fused: the gate eigenvalues of one estimator from the circuit-eigenvalue estimates, as
  * estimate_gate_noise computes them (src/estimate.jl:711-743, 820-831): covariance of the

@@ -26,6 +26,8 @@ struct aces_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;  // stream in use (own_stream or caller's)
     cudaEvent_t ev = nullptr;
+    cudaStream_t aux_stream = nullptr;            // low-priority side stream (look-ahead updates)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t t0 = nullptr, t1 = nullptr;  // bracket the dominant kernel when timing is on
     int timing = 0;
     int timed = 0;
@@ -40,6 +42,7 @@ struct aces_ctx {
     DevBuf h_stage;    // pinned staging for the small per-call tables / outputs
     // fit workspaces are added by fit.cu through this generic pool
     DevBuf d_work[8];
+    DevBuf d_flags;    // inter-CTA flags of the persistent triangular solves
 };
 
 int aces_fail(aces_ctx* ctx, int code, const char* fmt, ...);

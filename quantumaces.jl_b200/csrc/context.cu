@@ -106,8 +106,13 @@ int32_t aces_init(int32_t device, aces_ctx** out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
-    e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    e = cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_lo);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->t0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->t1);
     if (e != cudaSuccess) {
@@ -124,7 +129,8 @@ int32_t aces_destroy(aces_ctx* ctx) {
     if (!ctx) return ACES_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* dev[] = {&ctx->d_arena, &ctx->d_streams, &ctx->d_seg, &ctx->d_odd};
+    if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+    DevBuf* dev[] = {&ctx->d_arena, &ctx->d_streams, &ctx->d_seg, &ctx->d_odd, &ctx->d_flags};
     for (DevBuf* b : dev)
         if (b->ptr) cudaFree(b->ptr);
     for (DevBuf& b : ctx->d_work)
@@ -133,6 +139,9 @@ int32_t aces_destroy(aces_ctx* ctx) {
     if (ctx->ev) cudaEventDestroy(ctx->ev);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return ACES_OK;

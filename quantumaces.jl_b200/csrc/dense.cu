@@ -361,50 +361,8 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) diag_kernel(const DiagDesc* _
     diag_block(d, rel_tol, sh);
 }
 
-// ---- blocked triangular solves with one right-hand side ------------------------------------------
+// ---- triangular solves with one right-hand side -------------------------------------------------
 constexpr int TRSV_THREADS = 256;
-
-// Step k of y = inv(L) b: every CTA recomputes y_k = inv(L_kk) b_k (the block inverse is in L2);
-// CTA 0 publishes y_k, CTA q >= 1 updates b_{k+q} -= L[k+q, k] y_k.
-__global__ void __launch_bounds__(TRSV_THREADS) trsv_fwd_kernel(const double* __restrict__ L, int64_t ldl,
-                                                                const double* __restrict__ dinv,
-                                                                double* __restrict__ b,
-                                                                double* __restrict__ y, int k) {
-    __shared__ double bk[DB], yk[DB], part[TRSV_THREADS];
-    const int tid = threadIdx.x, i = tid & (DB - 1), h = tid >> 7;
-    if (tid < DB) bk[tid] = b[(int64_t)k * DB + tid];
-    __syncthreads();
-    const double* X = dinv + (int64_t)k * DB * DB;
-    double s = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 4
-    for (int j = h * 64; j < h * 64 + 64; j += 4) {  // X is zero above the diagonal
-        s += X[i + j * DB] * bk[j];
-        s1 += X[i + (j + 1) * DB] * bk[j + 1];
-        s2 += X[i + (j + 2) * DB] * bk[j + 2];
-        s3 += X[i + (j + 3) * DB] * bk[j + 3];
-    }
-    part[tid] = (s + s1) + (s2 + s3);
-    __syncthreads();
-    if (tid < DB) yk[tid] = part[tid] + part[tid + DB];
-    __syncthreads();
-    if (blockIdx.x == 0) {
-        if (tid < DB) y[(int64_t)k * DB + tid] = yk[tid];
-        return;
-    }
-    const int64_t r = k + blockIdx.x;
-    const double* T = L + r * DB + (int64_t)k * DB * ldl;
-    s = s1 = s2 = s3 = 0.0;
-#pragma unroll 4
-    for (int j = h * 64; j < h * 64 + 64; j += 4) {
-        s += T[i + (int64_t)j * ldl] * yk[j];
-        s1 += T[i + (int64_t)(j + 1) * ldl] * yk[j + 1];
-        s2 += T[i + (int64_t)(j + 2) * ldl] * yk[j + 2];
-        s3 += T[i + (int64_t)(j + 3) * ldl] * yk[j + 3];
-    }
-    part[tid] = (s + s1) + (s2 + s3);
-    __syncthreads();
-    if (tid < DB) b[r * DB + tid] -= part[tid] + part[tid + DB];
-}
 
 // out[c] = sum_r T[r + c*ld] * v[r] for one 128 x 128 tile; warp w handles columns w, w+8, ...
 // All 64 loads of a lane are issued before the reductions (the tile comes from L2 / HBM).
@@ -426,28 +384,167 @@ __device__ __forceinline__ void tile_t_times_vec(const double* __restrict__ T, i
     }
 }
 
-// Step k (descending) of x = inv(L') y: x_k = inv(L_kk)' y_k; CTA q >= 1 updates
-// y_{q-1} -= L[k, q-1]' x_k.
-__global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_kernel(const double* __restrict__ L, int64_t ldl,
-                                                                const double* __restrict__ dinv,
-                                                                double* __restrict__ y,
-                                                                double* __restrict__ x, int k) {
-    __shared__ double yk[DB], xk[DB];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < DB) yk[tid] = y[(int64_t)k * DB + tid];
-    __syncthreads();
-    const double* X = dinv + (int64_t)k * DB * DB;
-    tile_t_times_vec(X, DB, yk, xk, lane, warp);
-    __syncthreads();
-    if (blockIdx.x == 0) {
-        if (tid < DB) x[(int64_t)k * DB + tid] = xk[tid];
-        return;
+
+// ---- persistent triangular solves --------------------------------------------------------------
+// One launch per solve.  CTA c owns the 128-row blocks c, c + G, ... and runs them in dependency
+// order; a block publishes its solution block and raises a flag, the blocks that depend on it
+// spin on that flag (all CTAs are co-resident: cooperative launch, grid <= SM count) and fold the
+// corresponding 128 x 128 tile of L into their right-hand side.  The chain of 128-blocks is
+// inherently sequential; what this removes is one launch (and its drain / fill) per block.
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// out[i] = sum_j T[i + j*ld] * v[j] for a 128 x 128 tile, 256 threads (two column halves)
+__device__ __forceinline__ void tile_times_vec(const double* __restrict__ T, int64_t ld, const double* v,
+                                               double* part, int tid) {
+    const int i = tid & (DB - 1), h = tid >> 7;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const double* Tp = T + i + (int64_t)(h * 64) * ld;
+    const double* vp = v + h * 64;
+#pragma unroll
+    for (int j0 = 0; j0 < 64; j0 += 16) {
+        double t[16];  // 16 independent loads in flight per thread (the tile streams from L2 / HBM)
+#pragma unroll
+        for (int q = 0; q < 16; ++q) t[q] = Tp[(int64_t)(j0 + q) * ld];
+#pragma unroll
+        for (int q = 0; q < 16; q += 4) {
+            s0 += t[q] * vp[j0 + q];
+            s1 += t[q + 1] * vp[j0 + q + 1];
+            s2 += t[q + 2] * vp[j0 + q + 2];
+            s3 += t[q + 3] * vp[j0 + q + 3];
+        }
     }
-    const int64_t j = blockIdx.x - 1;
-    const double* T = L + (int64_t)k * DB + j * DB * ldl;
-    tile_t_times_vec(T, ldl, xk, yk, lane, warp);  // yk is free now: reuse it for the product
-    __syncthreads();
-    if (tid < DB) y[j * DB + tid] -= yk[tid];
+    part[tid] = (s0 + s1) + (s2 + s3);
+}
+
+// The last dependency of a block is on the critical path of the whole solve (block r can only
+// finish after y_{r-1} arrives), so its tile of L is preloaded into registers and the block
+// inverse into shared memory BEFORE the wait: once the flag is up only one 1 KB vector load and
+// on-chip arithmetic remain.
+constexpr size_t TRSV_SMEM = (size_t)DB * DB * sizeof(double);
+
+__global__ void __launch_bounds__(TRSV_THREADS, 1) trsv_fwd_persistent(const double* __restrict__ L, int64_t ldl,
+                                                                       const double* __restrict__ dinv,
+                                                                       const double* __restrict__ b, double* y,
+                                                                       int nb, int* flags) {
+    extern __shared__ __align__(16) double sX[];  // inv(L_rr), column-major 128 x 128
+    __shared__ double acc[DB], vk[DB], part[TRSV_THREADS];
+    const int tid = threadIdx.x, i = tid & (DB - 1), h = tid >> 7;
+    for (int r = blockIdx.x; r < nb; r += gridDim.x) {
+        __syncthreads();  // the previous block of this CTA is done with sX
+        if (tid < DB) acc[tid] = b[(int64_t)r * DB + tid];
+        {
+            const double* X = dinv + (int64_t)r * DB * DB;
+            for (int e = tid; e < DB * DB; e += TRSV_THREADS) sX[e] = X[e];
+        }
+        __syncthreads();
+        for (int k = 0; k + 1 < r; ++k) {
+            if (tid == 0)
+                while (ld_acquire(flags + k) == 0) {}
+            __syncthreads();
+            if (tid < DB) vk[tid] = __ldcg(y + (int64_t)k * DB + tid);
+            __syncthreads();
+            tile_times_vec(L + (int64_t)r * DB + (int64_t)k * DB * ldl, ldl, vk, part, tid);
+            __syncthreads();
+            if (tid < DB) acc[tid] -= part[tid] + part[tid + DB];
+            __syncthreads();
+        }
+        if (r > 0) {
+            const int k = r - 1;
+            double t[64];  // this thread's half row of L[r, r-1]
+            const double* Tp = L + (int64_t)r * DB + i + ((int64_t)k * DB + h * 64) * ldl;
+#pragma unroll
+            for (int q = 0; q < 64; ++q) t[q] = Tp[(int64_t)q * ldl];
+            if (tid == 0)
+                while (ld_acquire(flags + k) == 0) {}
+            __syncthreads();
+            if (tid < DB) vk[tid] = __ldcg(y + (int64_t)k * DB + tid);
+            __syncthreads();
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int q = 0; q < 64; q += 4) {
+                s0 += t[q] * vk[h * 64 + q];
+                s1 += t[q + 1] * vk[h * 64 + q + 1];
+                s2 += t[q + 2] * vk[h * 64 + q + 2];
+                s3 += t[q + 3] * vk[h * 64 + q + 3];
+            }
+            part[tid] = (s0 + s1) + (s2 + s3);
+            __syncthreads();
+            if (tid < DB) acc[tid] -= part[tid] + part[tid + DB];
+            __syncthreads();
+        }
+        tile_times_vec(sX, DB, acc, part, tid);  // the block inverse is lower triangular (zeros above)
+        __syncthreads();
+        if (tid < DB) y[(int64_t)r * DB + tid] = part[tid] + part[tid + DB];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release(flags + r, 1);
+    }
+}
+
+__global__ void __launch_bounds__(TRSV_THREADS, 1) trsv_bwd_persistent(const double* __restrict__ L, int64_t ldl,
+                                                                       const double* __restrict__ dinv,
+                                                                       const double* __restrict__ yin, double* x,
+                                                                       int nb, int* flags) {
+    extern __shared__ __align__(16) double sX[];
+    __shared__ double acc[DB], vk[DB], out[DB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int q = blockIdx.x; q < nb; q += gridDim.x) {
+        const int k = nb - 1 - q;  // blocks in descending order
+        __syncthreads();
+        if (tid < DB) acc[tid] = yin[(int64_t)k * DB + tid];
+        {
+            const double* X = dinv + (int64_t)k * DB * DB;
+            for (int e = tid; e < DB * DB; e += TRSV_THREADS) sX[e] = X[e];
+        }
+        __syncthreads();
+        for (int r = nb - 1; r > k + 1; --r) {
+            if (tid == 0)
+                while (ld_acquire(flags + r) == 0) {}
+            __syncthreads();
+            if (tid < DB) vk[tid] = __ldcg(x + (int64_t)r * DB + tid);
+            __syncthreads();
+            tile_t_times_vec(L + (int64_t)r * DB + (int64_t)k * DB * ldl, ldl, vk, out, lane, warp);
+            __syncthreads();
+            if (tid < DB) acc[tid] -= out[tid];
+            __syncthreads();
+        }
+        if (k + 1 < nb) {
+            const int r = k + 1;
+            double t[16][4];  // columns warp, warp + 8, ... of L[k+1, k], four row chunks per lane
+            const double* T = L + (int64_t)r * DB + (int64_t)k * DB * ldl;
+#pragma unroll
+            for (int cc = 0; cc < 16; ++cc)
+#pragma unroll
+                for (int m = 0; m < 4; ++m) t[cc][m] = T[lane + 32 * m + (int64_t)(warp + 8 * cc) * ldl];
+            if (tid == 0)
+                while (ld_acquire(flags + r) == 0) {}
+            __syncthreads();
+            if (tid < DB) vk[tid] = __ldcg(x + (int64_t)r * DB + tid);
+            __syncthreads();
+#pragma unroll
+            for (int cc = 0; cc < 16; ++cc) {
+                double sum = (t[cc][0] * vk[lane] + t[cc][1] * vk[lane + 32]) + (t[cc][2] * vk[lane + 64] + t[cc][3] * vk[lane + 96]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                if (lane == 0) out[warp + 8 * cc] = sum;
+            }
+            __syncthreads();
+            if (tid < DB) acc[tid] -= out[tid];
+            __syncthreads();
+        }
+        tile_t_times_vec(sX, DB, acc, out, lane, warp);
+        __syncthreads();
+        if (tid < DB) x[(int64_t)k * DB + tid] = out[tid];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release(flags + k, 1);
+    }
 }
 
 __global__ void set_identity_kernel(int64_t n, double* A, int64_t lda) {
@@ -514,6 +611,8 @@ int configure(aces_ctx* ctx) {
     ACES_TRY(set_smem(ctx, gemm_batched_kernel<false, true>, GEMM_SMEM));
     ACES_TRY(set_smem(ctx, gemm_batched_kernel<true, true>, GEMM_SMEM));
     ACES_TRY(set_smem(ctx, diag_kernel, DIAG_SMEM));
+    ACES_TRY(set_smem(ctx, trsv_fwd_persistent, TRSV_SMEM));
+    ACES_TRY(set_smem(ctx, trsv_bwd_persistent, TRSV_SMEM));
     done = true;
     return ACES_OK;
 }
@@ -576,6 +675,8 @@ int potrf(aces_ctx* ctx, int64_t n, double* A, int64_t lda, double* dinv, int* f
     ACES_CHECK(ctx, n % DB == 0, "dense::potrf: n=%lld is not padded", (long long)n);
     ACES_TRY(configure(ctx));
     constexpr int64_t NB2 = 4 * DB;  // outer panel: the bulk of the flops runs as K = 512 updates
+    const cudaStream_t main_stream = ctx->stream;
+    bool side_pending = false;
     for (int64_t K0 = 0; K0 < n; K0 += NB2) {
         const int64_t kb = std::min(NB2, n - K0);
         for (int64_t k = K0; k < K0 + kb; k += DB) {
@@ -598,36 +699,69 @@ int potrf(aces_ctx* ctx, int64_t n, double* A, int64_t lda, double* dinv, int* f
         }
         const int64_t rows = n - (K0 + kb);
         if (rows > 0) {
+            // Trailing update with look-ahead: the columns of the NEXT panel are updated on the main
+            // stream (the next panel's factorisation needs nothing else), the rest on the side
+            // stream, where it overlaps the launch-latency-bound chain of diagonal-block kernels.
             const double* P = A + (K0 + kb) + K0 * lda;  // rows below the panel, its kb columns
-            ACES_TRY(gemm(ctx, GEMM_NT, rows, rows, kb, -1.0, P, lda, P, lda, 1.0,
-                          A + (K0 + kb) * (lda + 1), lda, 1));
+            const int64_t next = std::min(NB2, rows);
+            ACES_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main_stream));  // the panel is final
+            if (side_pending) ACES_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
+            ACES_TRY(gemm(ctx, GEMM_NT, rows, next, kb, -1.0, P, lda, P, lda, 1.0, A + (K0 + kb) * (lda + 1), lda, 1));
+            const int64_t rest = rows - next;
+            if (rest > 0) {
+                ACES_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+                ctx->stream = ctx->aux_stream;
+                const int rc = gemm(ctx, GEMM_NT, rest, rest, kb, -1.0, P + next, lda, P + next, lda, 1.0,
+                                    A + (K0 + kb + next) * (lda + 1), lda, 1);
+                ctx->stream = main_stream;
+                ACES_TRY(rc);
+                ACES_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+                side_pending = true;
+            }
         }
     }
+    if (side_pending) ACES_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
     return ACES_OK;
 }
+
+namespace {
+// flags of the persistent solves: one int per 128-block, zeroed before every launch
+int solve_flags(aces_ctx* ctx, int nb, int** flags) {
+    ACES_TRY(aces_reserve_dev(ctx, ctx->d_flags, sizeof(int) * (size_t)nb));
+    *flags = (int*)ctx->d_flags.ptr;
+    ACES_CUDA(ctx, cudaMemsetAsync(*flags, 0, sizeof(int) * (size_t)nb, ctx->stream));
+    return ACES_OK;
+}
+template <typename K>
+int launch_persistent(aces_ctx* ctx, K kern, int nb, const double* L, int64_t ldl, const double* dinv,
+                      const double* in, double* out, int* flags) {
+    const int grid = std::min(nb, ctx->sm_count);
+    void* args[] = {(void*)&L, (void*)&ldl, (void*)&dinv, (void*)&in, (void*)&out, (void*)&nb, (void*)&flags};
+    ACES_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(TRSV_THREADS), args,
+                                               TRSV_SMEM, ctx->stream));
+    ctx->launches += 1;
+    return ACES_OK;
+}
+}  // namespace
 
 int trsv_lower(aces_ctx* ctx, int64_t n, const double* L, int64_t ldl, const double* dinv, double* b,
                double* y) {
     ACES_CHECK(ctx, n % DB == 0, "dense::trsv_lower: not padded");
     const int nb = (int)(n / DB);
-    for (int k = 0; k < nb; ++k) {
-        trsv_fwd_kernel<<<(unsigned)(nb - k), TRSV_THREADS, 0, ctx->stream>>>(L, ldl, dinv, b, y, k);
-        ctx->launches += 1;
-    }
-    ACES_CUDA(ctx, cudaGetLastError());
-    return ACES_OK;
+    int* flags = nullptr;
+    ACES_TRY(configure(ctx));
+    ACES_TRY(solve_flags(ctx, nb, &flags));
+    return launch_persistent(ctx, trsv_fwd_persistent, nb, L, ldl, dinv, b, y, flags);
 }
 
 int trsv_lower_t(aces_ctx* ctx, int64_t n, const double* L, int64_t ldl, const double* dinv, double* y,
                  double* x) {
     ACES_CHECK(ctx, n % DB == 0, "dense::trsv_lower_t: not padded");
     const int nb = (int)(n / DB);
-    for (int k = nb - 1; k >= 0; --k) {
-        trsv_bwd_kernel<<<(unsigned)(k + 1), TRSV_THREADS, 0, ctx->stream>>>(L, ldl, dinv, y, x, k);
-        ctx->launches += 1;
-    }
-    ACES_CUDA(ctx, cudaGetLastError());
-    return ACES_OK;
+    int* flags = nullptr;
+    ACES_TRY(configure(ctx));
+    ACES_TRY(solve_flags(ctx, nb, &flags));
+    return launch_persistent(ctx, trsv_bwd_persistent, nb, L, ldl, dinv, y, x, flags);
 }
 
 int trsm_lower(aces_ctx* ctx, int64_t n, int64_t nrhs, const double* L, int64_t ldl,

@@ -75,9 +75,10 @@ int get_diag(aces_ctx* ctx, int64_t n, const double* A, int64_t lda, double* d);
 int trtri(aces_ctx* ctx, int64_t n, const double* L, int64_t ldl, const double* dinv, double* X,
           int64_t ldx);
 
-// Blocked triangular solves with one right-hand side, one launch per 128-block:
-//   trsv_lower:   y = inv(L)  * b   (b is destroyed)
-//   trsv_lower_t: x = inv(L') * y   (y is destroyed)
+// Triangular solves with one right-hand side, one persistent cooperative launch each (the
+// 128-blocks hand their solution to the dependent blocks through flags in global memory):
+//   trsv_lower:   y = inv(L)  * b
+//   trsv_lower_t: x = inv(L') * y
 int trsv_lower(aces_ctx* ctx, int64_t n, const double* L, int64_t ldl, const double* dinv, double* b,
                double* y);
 int trsv_lower_t(aces_ctx* ctx, int64_t n, const double* L, int64_t ldl, const double* dinv, double* y,

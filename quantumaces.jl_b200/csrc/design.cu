@@ -17,6 +17,7 @@
 // the launch sequence does not depend on what was clipped.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "dense.cuh"
@@ -57,6 +58,19 @@ struct aces_design {
     int32_t *row_map = nullptr;    // [M] compacted local row or -1
     int32_t *flags = nullptr;      // [T + 1] not-PD flags (blocks, then the Gram matrix)
     int fallback_blocks = 0;       // blocks that needed the not-PD fallback in the last call
+    // --- column windows of the tuple blocks (GLS Gram): block t only touches the columns cols_t ---
+    bool windowed = false;         // the windowed Gram does at most half the flops of the dense one
+    int max_ct = 0;                // max cp_t / 128
+    int64_t n_wcols = 0;           // sum of c_t
+    std::vector<int64_t> ct, cpt, cols_off, atc_off, gt_off;
+    int32_t *w_blk = nullptr;      // [n_wcols] block of each compact column
+    int64_t *w_ptr = nullptr;      // [n_wcols + 1] entries of each compact column
+    int32_t *w_row = nullptr;      // global row of each entry
+    double *w_val = nullptr;
+    int64_t *w_cols = nullptr;     // [n_wcols] global column of each compact column
+    int64_t *d_cols_off = nullptr, *d_atc_off = nullptr;
+    double *Atc = nullptr, *Gt = nullptr;
+    GemmDesc* g_gram = nullptr;    // [T]
     std::vector<void*> owned;
 };
 
@@ -299,6 +313,31 @@ __global__ void exp_neg_kernel(int64_t n, const double* __restrict__ x, double* 
     }
 }
 
+// out[0] = max |x_i|, out[1] = max |d_i| (one CTA): the convergence test of the refinement
+__global__ void max_abs_pair_kernel(int64_t n, const double* __restrict__ x, const double* __restrict__ dlt,
+                                    double* __restrict__ out) {
+    __shared__ double sx[256], sd[256];
+    double mx = 0.0, md = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        mx = fmax(mx, fabs(x[i]));
+        md = fmax(md, fabs(dlt[i]));
+    }
+    sx[threadIdx.x] = mx;
+    sd[threadIdx.x] = md;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            sx[threadIdx.x] = fmax(sx[threadIdx.x], sx[threadIdx.x + o]);
+            sd[threadIdx.x] = fmax(sd[threadIdx.x], sd[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[0] = sx[0];
+        out[1] = sd[0];
+    }
+}
+
 // ---- whitened design matrix (GLS) --------------------------------------------------------------------
 // At[:, j] = sum over the entries (r, a) of column j of A of a * X_t[:, lr]  (one CTA per column j;
 // row i of a block is always handled by thread i % blockDim, so no two threads touch one entry).
@@ -325,6 +364,42 @@ __global__ void whiten_tiles_kernel(int64_t N, const int64_t* __restrict__ colpt
         if (i < lr) i += bd;
         for (; i < n; i += bd) out[i] += a * X[i];
     }
+}
+
+// Compact whitened blocks for the windowed Gram: compact column jc of block t (global column
+// w_cols[jc]) = sum over its entries (r, a) of a * X_t[:, lr].  One CTA per compact column.
+__global__ void whiten_compact_kernel(int64_t n_wcols, const int32_t* __restrict__ w_blk,
+                                      const int64_t* __restrict__ w_ptr, const int32_t* __restrict__ w_row,
+                                      const double* __restrict__ w_val, const int64_t* __restrict__ cols_off,
+                                      const int64_t* __restrict__ atc_off, const int64_t* __restrict__ row0,
+                                      const int64_t* __restrict__ tile_off, const int64_t* __restrict__ mp,
+                                      const int32_t* __restrict__ row_map, const double* __restrict__ tiles,
+                                      double* __restrict__ Atc) {
+    const int64_t jc = blockIdx.x;
+    if (jc >= n_wcols) return;
+    const int t = w_blk[jc];
+    const int64_t n = mp[t];
+    double* out = Atc + atc_off[t] + (jc - cols_off[t]) * n;
+    const int bd = blockDim.x, tid = threadIdx.x;
+    for (int64_t e = w_ptr[jc]; e < w_ptr[jc + 1]; ++e) {
+        const int64_t r = w_row[e];
+        const int64_t lr = row_map ? row_map[r] : r - row0[t];
+        if (lr < 0) continue;
+        const double a = w_val[e];
+        const double* X = tiles + tile_off[t] + lr * n;
+        int64_t i = lr - (lr % bd) + tid;
+        if (i < lr) i += bd;
+        for (; i < n; i += bd) out[i] += a * X[i];
+    }
+}
+// G[cols[i], cols[j]] += Gt[i, j] for i >= j (cols ascending, so the target stays in the lower triangle)
+__global__ void gram_scatter_kernel(int64_t c, int64_t cp, const int64_t* __restrict__ cols,
+                                    const double* __restrict__ Gt, double* __restrict__ G, int64_t ldg) {
+    const int64_t j = blockIdx.y;
+    if (j >= c) return;
+    const int64_t gj = cols[j];
+    for (int64_t i = j + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < c; i += (int64_t)gridDim.x * blockDim.x)
+        G[cols[i] + gj * ldg] += Gt[i + j * cp];
 }
 
 // ---- sparse sandwich C = A' diag(w) S diag(w) A (lower triangle of C only) --------------------------
@@ -407,6 +482,34 @@ __global__ void moments_final_kernel(int nparts, double* __restrict__ out) {
     }
 }
 
+
+// Development aid (ACES_FIT_TRACE=1): CUDA-event timing of the phases of a fit, printed to stderr.
+struct PhaseTimer {
+    aces_ctx* ctx;
+    bool on;
+    std::vector<cudaEvent_t> ev;
+    std::vector<const char*> names;
+    explicit PhaseTimer(aces_ctx* c) : ctx(c), on(getenv("ACES_FIT_TRACE") != nullptr) { mark("start"); }
+    void mark(const char* name) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, ctx->stream);
+        ev.push_back(e);
+        names.push_back(name);
+    }
+    ~PhaseTimer() {
+        if (!on) return;
+        cudaEventSynchronize(ev.back());
+        for (size_t i = 1; i < ev.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            fprintf(stderr, "[aces fit] %-18s %8.3f ms\n", names[i], ms);
+        }
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    }
+};
+
 inline unsigned grid_for(int64_t n, int threads, int64_t cap = 148 * 16) {
     return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, cap));
 }
@@ -420,7 +523,19 @@ int ensure_workspaces(aces_ctx* ctx, aces_design* d, bool need_tiles, bool need_
         ACES_TRY(dev_alloc(ctx, d, &d->tilesX, tiles));
         ACES_TRY(dev_alloc(ctx, d, &d->dinvT, (size_t)d->dinv_off.back()));
     }
-    if (need_at && !d->At) ACES_TRY(dev_alloc(ctx, d, &d->At, (size_t)d->Mp * d->Np));
+    if (need_at && d->windowed && !d->Atc) {
+        ACES_TRY(dev_alloc(ctx, d, &d->Atc, (size_t)d->atc_off.back()));
+        ACES_TRY(dev_alloc(ctx, d, &d->Gt, (size_t)d->gt_off.back()));
+        std::vector<GemmDesc> gg((size_t)d->T);
+        for (int t = 0; t < d->T; ++t) {
+            const double* A = d->Atc + d->atc_off[t];
+            const int tiles = (int)(d->cpt[t] / DB);
+            gg[(size_t)t] = GemmDesc{A, A, d->Gt + d->gt_off[t], d->mp[t], d->mp[t], d->cpt[t], (int32_t)d->mp[t], tiles, tiles,
+                                     1, 1.0, 0.0};
+        }
+        ACES_TRY(dev_upload(ctx, d, &d->g_gram, gg));
+    }
+    if (need_at && !d->windowed && !d->At) ACES_TRY(dev_alloc(ctx, d, &d->At, (size_t)d->Mp * d->Np));
     if (!d->G) {
         ACES_TRY(dev_alloc(ctx, d, &d->G, (size_t)d->Np * d->Np));
         ACES_TRY(dev_alloc(ctx, d, &d->dinvG, (size_t)d->Np * DB));
@@ -550,7 +665,30 @@ int apply_F(aces_ctx* ctx, aces_design* d, int ls_type, const FitVectors& fv, co
 // for OLS / WLS, tilesX the block factors for GLS.
 int build_gram(aces_ctx* ctx, aces_design* d, int ls_type, const FitVectors& fv, const int32_t* row_map) {
     const int64_t Np = d->Np, Mp = d->Mp;
-    if (ls_type == 2) {
+    if (ls_type == 2 && d->windowed) {
+        // G = sum_t P_t' (At_t' At_t) P_t with At_t = X_t A_t restricted to the columns block t touches
+        ACES_CUDA(ctx, cudaMemsetAsync(d->Atc, 0, sizeof(double) * (size_t)d->atc_off.back(), ctx->stream));
+        ACES_CUDA(ctx, cudaMemsetAsync(d->G, 0, sizeof(double) * (size_t)Np * Np, ctx->stream));
+        whiten_compact_kernel<<<(unsigned)d->n_wcols, 256, 0, ctx->stream>>>(
+            d->n_wcols, d->w_blk, d->w_ptr, d->w_row, d->w_val, d->d_cols_off, d->d_atc_off, d->d_row0, d->d_tile_off,
+            d->d_mp, row_map, d->tilesX, d->Atc);
+        ACES_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+        if (ctx->timing) ACES_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
+        ACES_TRY(dense::gemm_batched(ctx, dense::GEMM_TN, d->g_gram, d->T, d->max_ct, d->max_ct));
+        if (ctx->timing) {
+            ACES_CUDA(ctx, cudaEventRecord(ctx->t1, ctx->stream));
+            ctx->timed = 1;
+        }
+        for (int t = 0; t < d->T; ++t) {  // one launch per block: the order of the additions is fixed
+            if (d->ct[t] == 0) continue;
+            dim3 grid((unsigned)std::min<int64_t>((d->ct[t] + 255) / 256, 8), (unsigned)d->ct[t]);
+            gram_scatter_kernel<<<grid, 256, 0, ctx->stream>>>(d->ct[t], d->cpt[t], d->w_cols + d->cols_off[t],
+                                                              d->Gt + d->gt_off[t], d->G, Np);
+            ctx->launches += 1;
+        }
+        ACES_CUDA(ctx, cudaGetLastError());
+    } else if (ls_type == 2) {
         ACES_CUDA(ctx, cudaMemsetAsync(d->At, 0, sizeof(double) * (size_t)Mp * Np, ctx->stream));
         whiten_tiles_kernel<<<(unsigned)d->N, 256, 0, ctx->stream>>>(d->N, d->a_colptr, d->a_rowval, d->a_nzval,
                                                                     d->blk_of_row, d->d_row0, d->d_prow0, d->d_tile_off,
@@ -659,7 +797,7 @@ int check_flags(aces_ctx* ctx, aces_design* d, const char* what) {
 // Prepares the estimator: covariance values (from eigenvalue estimates, or given), factor (GLS) or
 // diagonal weights (OLS / WLS), Gram matrix and its Cholesky factor.
 int prepare_estimator(aces_ctx* ctx, aces_design* d, int ls_type, const double* val_dev, const int32_t* row_map,
-                      const std::vector<int64_t>& kept_count, const FitVectors& fv) {
+                      const std::vector<int64_t>& kept_count, const FitVectors& fv, PhaseTimer* pt = nullptr) {
     d->fallback_blocks = 0;
     ACES_CUDA(ctx, cudaMemsetAsync(d->flags, 0, sizeof(int32_t) * ((size_t)d->T + 2), ctx->stream));
     ACES_CUDA(ctx, cudaMemsetAsync(d->vec, 0, sizeof(double) * (size_t)(8 * std::max(d->Mp, d->Np)), ctx->stream));
@@ -667,6 +805,7 @@ int prepare_estimator(aces_ctx* ctx, aces_design* d, int ls_type, const double* 
         ACES_TRY(build_and_factor_tiles(ctx, d, val_dev, row_map, kept_count));
         // sparse_covariance_inv_factor's default epsilon (src/merit.jl:381)
         ACES_TRY(fallback_tiles(ctx, d, val_dev, row_map, kept_count, 1e-12));
+        if (pt) pt->mark("block factor");
     } else {
         diag_factor_kernel<<<grid_for(d->M, 256), 256, 0, ctx->stream>>>(d->M, d->cov_colptr, d->cov_rowval, val_dev,
                                                                         d->blk_of_row, d->d_row0, d->d_prow0, row_map,
@@ -675,9 +814,11 @@ int prepare_estimator(aces_ctx* ctx, aces_design* d, int ls_type, const double* 
         ctx->launches += 1;
     }
     ACES_TRY(build_gram(ctx, d, ls_type, fv, row_map));
+    if (pt) pt->mark("gram");
     ACES_TRY(dense::get_diag(ctx, d->Np, d->G, d->Np, fv.t2));
     ACES_CUDA(ctx, cudaMemcpyAsync(fv.t1, fv.t2, sizeof(double) * (size_t)d->Np, cudaMemcpyDeviceToDevice, ctx->stream));
     ACES_TRY(dense::potrf(ctx, d->Np, d->G, d->Np, d->dinvG, d->flags + d->T, fv.t1, 1e-13));
+    if (pt) pt->mark("potrf");
     return ACES_OK;
 }
 
@@ -803,6 +944,56 @@ int32_t aces_design_create(aces_ctx* ctx, int32_t T, const int64_t* mapping_leng
     d->h_cov_colptr = cov_colptr;
     d->h_cov_rowval = cov_rowval;
 
+    // ---- column windows of the blocks (for the GLS Gram) -----------------------------------------
+    {
+        d->ct.assign(T, 0); d->cpt.assign(T, 0);
+        d->cols_off.assign(T + 1, 0); d->atc_off.assign(T + 1, 0); d->gt_off.assign(T + 1, 0);
+        std::vector<int64_t> w_cols, w_ptr(1, 0);
+        std::vector<int32_t> w_blk, w_row;
+        std::vector<double> w_val;
+        // entries of A grouped by (block, column): CSC order already groups rows of a column by block
+        std::vector<std::vector<int64_t>> cols_of((size_t)T);
+        for (int64_t j = 0; j < N; ++j) {
+            int last = -1;
+            for (int64_t e = colptr[(size_t)j]; e < colptr[(size_t)j + 1]; ++e) {
+                const int t = d->h_blk_of_row[(size_t)rowval[(size_t)e]];
+                if (t != last) { cols_of[(size_t)t].push_back(j); last = t; }  // rows are sorted within a column
+            }
+        }
+        double flops_w = 0.0;
+        for (int t = 0; t < T; ++t) {
+            auto& cs = cols_of[(size_t)t];
+            std::sort(cs.begin(), cs.end());
+            cs.erase(std::unique(cs.begin(), cs.end()), cs.end());
+            d->ct[t] = (int64_t)cs.size();
+            d->cpt[t] = std::max<int64_t>(pad_up(d->ct[t]), DB);
+            d->cols_off[t + 1] = d->cols_off[t] + d->ct[t];
+            d->atc_off[t + 1] = d->atc_off[t] + d->mp[t] * d->cpt[t];
+            d->gt_off[t + 1] = d->gt_off[t] + d->cpt[t] * d->cpt[t];
+            d->max_ct = std::max<int>(d->max_ct, (int)(d->cpt[t] / DB));
+            flops_w += (double)d->mp[t] * (double)d->cpt[t] * (double)d->cpt[t];
+            for (int64_t j : cs) {
+                w_cols.push_back(j);
+                w_blk.push_back(t);
+                for (int64_t e = colptr[(size_t)j]; e < colptr[(size_t)j + 1]; ++e) {
+                    const int64_t r = rowval[(size_t)e];
+                    if (d->h_blk_of_row[(size_t)r] != t) continue;
+                    w_row.push_back((int32_t)r);
+                    w_val.push_back(nzval[(size_t)e]);
+                }
+                w_ptr.push_back((int64_t)w_row.size());
+            }
+        }
+        d->n_wcols = (int64_t)w_cols.size();
+        d->windowed = flops_w < 0.5 * (double)d->Mp * (double)d->Np * (double)d->Np;
+        if (d->windowed) {
+            int rcw;
+#define UPW(field, vecname) if ((rcw = dev_upload(ctx, d, &d->field, vecname)) != ACES_OK) return fail(rcw)
+            UPW(w_blk, w_blk); UPW(w_ptr, w_ptr); UPW(w_row, w_row); UPW(w_val, w_val); UPW(w_cols, w_cols);
+            UPW(d_cols_off, d->cols_off); UPW(d_atc_off, d->atc_off);
+#undef UPW
+        }
+    }
     int rc;
 #define UP(field, vecname) if ((rc = dev_upload(ctx, d, &d->field, vecname)) != ACES_OK) return fail(rc)
     UP(a_colptr, colptr); UP(a_rowval, rowval); UP(a_nzval, nzval);
@@ -827,6 +1018,20 @@ int32_t aces_design_destroy(aces_ctx* ctx, aces_design* d) {
 
 int64_t aces_design_covariance_nnz(const aces_design* d) { return d ? d->nnz_cov : -1; }
 int32_t aces_design_fallback_count(const aces_design* d) { return d ? d->fallback_blocks : -1; }
+double aces_design_gram_flops(const aces_design* d) {
+    if (!d) return -1.0;
+    double tiles_k = 0.0;  // sum over 128 x 128 output tiles of their inner dimension
+    if (d->windowed) {
+        for (int t = 0; t < d->T; ++t) {
+            const double ct = (double)(d->cpt[t] / DB);
+            tiles_k += 0.5 * ct * (ct + 1.0) * (double)d->mp[t];
+        }
+    } else {
+        const double nt = (double)(d->Np / DB);
+        tiles_k = 0.5 * nt * (nt + 1.0) * (double)d->Mp;
+    }
+    return 2.0 * DB * DB * tiles_k;
+}
 
 int32_t aces_design_covariance_pattern(const aces_design* d, int64_t* colptr, int64_t* rowval) {
     if (!d || !colptr || !rowval) return ACES_E_INVALID;
@@ -973,9 +1178,11 @@ int32_t aces_design_fit(aces_ctx* ctx, aces_design* d, int32_t ls_type, const do
     double *lam, *lamcov;
     ACES_TRY(upload_eigenvalues(ctx, d, est_eigenvalues, est_covariance_eigenvalues, &lam, &lamcov));
     FitVectors fv = fit_vectors(d);
+    PhaseTimer pt(ctx);
     // K2: log-covariance of the estimates, weight_time = false (src/estimate.jl:713-720)
     if (ls_type != 0) ACES_TRY(launch_cov_values(ctx, d, lam, lamcov, epsilon, 0, 1, d->covval));
-    ACES_TRY(prepare_estimator(ctx, d, ls_type, d->covval, row_map, kept, fv));
+    pt.mark("covariance");
+    ACES_TRY(prepare_estimator(ctx, d, ls_type, d->covval, row_map, kept, fv, &pt));
     // right-hand side: g = A' F' F b
     const unsigned gm = grid_for(d->M, 128), gn = grid_for(d->N, 128);
     auto normal_rhs = [&](const double* x_or_null) -> int {
@@ -993,6 +1200,7 @@ int32_t aces_design_fit(aces_ctx* ctx, aces_design* d, int32_t ls_type, const do
     ACES_TRY(normal_rhs(nullptr));
     ACES_TRY(dense::trsv_lower(ctx, d->Np, d->G, d->Np, d->dinvG, fv.g, fv.t1));
     ACES_TRY(dense::trsv_lower_t(ctx, d->Np, d->G, d->Np, d->dinvG, fv.t1, fv.x));
+    pt.mark("first solve");
     for (int it = 0; it < 2; ++it) {
         // corrected semi-normal equations: r = F (b - A x) in FP64, x += inv(G) A' F' r
         ACES_TRY(normal_rhs(fv.x));
@@ -1000,7 +1208,18 @@ int32_t aces_design_fit(aces_ctx* ctx, aces_design* d, int32_t ls_type, const do
         ACES_TRY(dense::trsv_lower_t(ctx, d->Np, d->G, d->Np, d->dinvG, fv.t1, fv.t2));
         axpy_kernel<<<gn, 128, 0, ctx->stream>>>(d->N, 1.0, fv.t2, fv.x);
         ctx->launches += 1;
+        if (it == 0) {
+            // The correction contracts the error by about |delta| / |x| per step: when the first
+            // one is already below 1e-7 relative, a second step would change x by < 1e-14.
+            max_abs_pair_kernel<<<1, 256, 0, ctx->stream>>>(d->N, fv.x, fv.t2, d->mom);
+            ctx->launches += 1;
+            double h[2] = {0.0, 0.0};
+            ACES_CUDA(ctx, cudaMemcpyAsync(h, d->mom, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (h[1] <= 1e-7 * h[0]) break;
+        }
     }
+    pt.mark("refinement");
     exp_neg_kernel<<<gn, 128, 0, ctx->stream>>>(d->N, fv.x, fv.t1, constrain);
     ACES_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;

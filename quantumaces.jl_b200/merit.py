@@ -211,6 +211,10 @@ class DeviceDesign:
         """Blocks that took the not-positive-definite fallback (src/merit.jl:403-424) in the last call."""
         return int(self.ctx.lib.aces_design_fallback_count(self.handle))
 
+    def gram_flops(self) -> float:
+        """Dense FP64 flops of the GLS Gram matrix per fit (aces_design_gram_flops)."""
+        return float(self.ctx.lib.aces_design_gram_flops(self.handle))
+
     def sparse_covariance_inv_factor(self, covariance_log, clipped_indices=None, epsilon: float = 1e-12,
                                      fallback: bool = True):
         """sparse_covariance_inv_factor(covariance_log[clipped, clipped], clipped_mapping_lengths)

@@ -19,7 +19,7 @@ def main():
     d = int(args[0]) if len(args) > 0 else 9
     kind = args[1] if len(args) > 1 else "rotated"
     fd = aces_b200.synthetic_design(kind, d, full_covariance=True, with_matrix=True)
-    eig, cov = noisy_ensembles(fd, seed=3)
+    eig, cov = noisy_ensembles(fd, seed=11)
     lam = np.concatenate(aces_b200.mean_ensemble(eig))
     lc = np.concatenate(aces_b200.mean_ensemble(cov))
     with aces_b200.Context(0) as ctx:
