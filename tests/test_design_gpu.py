@@ -197,3 +197,45 @@ def test_design_create_rejects_bad_input(ctx):
     fd.cov_counts[0] = np.concatenate([fd.cov_counts[0], fd.cov_counts[0][:1]])
     with pytest.raises(aces_b200.AcesError):
         aces_b200.DeviceDesign(ctx, fd)
+
+
+@pytest.mark.parametrize("kind,d", [("rotated", 9), ("unrotated", 7)])
+def test_full_size_fit_properties(ctx, kind, d):
+    """BASELINE configs 3 / 4 shapes (rotated d=9: M = 12912, N = 6779; unrotated d=7): properties that
+    do not need the oracle at this size."""
+    import aces_b200
+
+    fd = aces_b200.synthetic_design(kind, d, full_covariance=True, with_matrix=True)
+    dd = aces_b200.DeviceDesign(ctx, fd)
+    try:
+        N = fd.matrix.shape[1]
+        # (1) noiseless records: every gate eigenvalue exactly 1.0 (test/device_tests.jl:144-155)
+        ones, c1 = np.ones(fd.M), np.ones(dd.C)
+        for k in ("ols", "wls", "gls"):
+            assert np.all(dd.fit(k, ones, c1) == 1.0), k
+        # (2) exact recovery from noiseless circuit eigenvalues
+        lam = np.exp(fd.matrix.astype(np.float64) @ np.log(fd.gate_eigenvalues))
+        lc = np.concatenate([np.exp(r.astype(np.float64) @ np.log(fd.gate_eigenvalues)) for r in fd.cov_rows])
+        for k in ("ols", "wls", "gls"):
+            assert np.max(np.abs(dd.fit(k, lam, lc) - fd.gate_eigenvalues)) < 1e-11, k
+        # (3) noisy estimates: the three estimators agree with the truth to shot noise and with each
+        #     other to a few standard errors; GLS == WLS when the off-diagonal covariance vanishes
+        #     (test/design_tests.jl:243-246), here by making lambda_pq = lambda_p * lambda_q exactly
+        eig, cov = aces_b200.synthetic_estimates(fd, shots=10**8, seed=11)
+        est = np.concatenate(aces_b200.mean_ensemble(eig))
+        off = np.concatenate([[0], np.cumsum(fd.mapping_lengths)])
+        cprod = np.concatenate([est[off[t] + fd.cov_keys[t][:, 0]] * est[off[t] + fd.cov_keys[t][:, 1]]
+                                for t in range(fd.tuple_number)])
+        wls = dd.fit("wls", est, cprod)
+        gls = dd.fit("gls", est, cprod)
+        assert rel(gls, wls) < RTOL
+        assert np.max(np.abs(wls - fd.gate_eigenvalues)) < 1e-3
+        # (4) covariance moments: GLS is at least as good as WLS, which beats OLS (Gauss-Markov)
+        lam_ens = [lam[off[t]:off[t + 1]] for t in range(fd.tuple_number)]
+        cov_ens = [lc[dd._keep["ptr"][t]:dd._keep["ptr"][t + 1]] for t in range(fd.tuple_number)]
+        cl = dd.calc_covariance(lam_ens, cov_ens, log_form=True)
+        tr = {k: dd.calc_ls_covariance(k, cl, want_matrix=False)[1] for k in ("gls", "wls", "ols")}
+        assert 0 < tr["gls"] <= tr["wls"] * (1 + 1e-9) <= tr["ols"] * (1 + 1e-9)
+        assert N == len(wls)
+    finally:
+        dd.close()

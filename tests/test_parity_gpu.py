@@ -308,3 +308,94 @@ def test_full_size_properties(ctx):
         d.zero_()
     torch.cuda.synchronize()
     assert not run().any()
+
+
+def test_d17_shot_shard_properties(ctx):
+    """BASELINE config 5 (rotated d=17, 1e9 shots, 73 GB) is sharded by shot ranges over 8 GPUs:
+    this runs the 9.1 GB shard of rank 3 (B = 73 byte columns: the wide-record kernel) and checks
+    size-independent properties; the shards' counts add up to the whole (test_shard.py)."""
+    import torch
+
+    import aces_b200
+    from aces_b200 import shard
+
+    fd = aces_b200.synthetic_design("rotated", 17)
+    est = aces_b200.DesignEstimator(ctx, fd)
+    shots_set = [10**7, 10**8, 10**9]
+    shots_divided, shots_max = aces_b200.shots_divide(fd, shots_set)
+    n_exp, B = fd.experiment_number, fd.n_bytes
+    assert B == 73
+    rows, prefix = [], []
+    for e in range(n_exp):
+        t = int(est.tuple_of_experiment[e])
+        lo, hi, local = shard.shard_shots(int(shots_max[t]), shots_divided[t], 8, 3)
+        rows.append(hi - lo)
+        prefix.append(local)
+    prefix = np.asarray(prefix, dtype=np.int64)
+    ld = [(r + 127) // 128 * 128 for r in rows]
+    assert 8.5e9 < sum(r * B for r in rows) < 9.5e9
+    g = torch.Generator(device="cuda").manual_seed(17)
+    dev = [torch.randint(0, 256, (B, ld[e]), dtype=torch.uint8, device="cuda", generator=g) for e in range(n_exp)]
+    total = int(np.sum(est.experiment_sizes()) * 3)
+    out = torch.zeros(total, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+
+    def run():
+        est.odd_counts([d.data_ptr() for d in dev], rows, ld, prefix, out=out.data_ptr(), asynchronous=True)
+        ctx.synchronize()
+        return out.cpu().numpy().copy()
+
+    got = run()
+    off = np.concatenate([[0], np.cumsum(est.experiment_sizes() * 3)])
+    rng = np.random.default_rng(5)
+    for e in rng.choice(n_exp, size=4, replace=False):
+        E = est.tables.experiment_size(int(e))
+        sup = ob.table_supports(est, int(e))
+        for p in rng.choice(E, size=4, replace=False):
+            acc = torch.zeros(rows[e], dtype=torch.uint8, device="cuda")
+            for q in sup[p]:
+                acc ^= (dev[e][(q - 1) // 8, :rows[e]] >> ((q - 1) % 8)) & 1
+            csum = torch.cumsum(acc.to(torch.int64), 0)
+            for k in range(3):
+                S = int(prefix[e, k])
+                assert got[off[e] + k * E + p] == (int(csum[S - 1]) if S > 0 else 0)
+    for d in dev:
+        d.bitwise_not_()
+    torch.cuda.synchronize()
+    flipped = run()
+    for e in range(n_exp):
+        E = est.tables.experiment_size(e)
+        w = np.array([len(s) for s in ob.table_supports(est, e)])
+        a = got[off[e]:off[e + 1]].reshape(3, E)
+        b = flipped[off[e]:off[e + 1]].reshape(3, E)
+        S = prefix[e][:, None]
+        assert np.array_equal(np.where(w % 2 == 1, S - a, a), b)
+
+
+def test_shot_sharded_counts_add_up(ctx):
+    """Two emulated ranks on one GPU: shot-range shards of every sample matrix reduce to counts that
+    add up to the unsharded counts (the all_reduce(sum) of a multi-GPU run; exact in integers)."""
+    import aces_b200
+    from aces_b200 import shard
+
+    fd = aces_b200.synthetic_design("rotated", 5, full_covariance=True)
+    est = aces_b200.DesignEstimator(ctx, fd)
+    shots_divided, shots_max = aces_b200.shots_divide(fd, [2_000, 33_333, 150_001])
+    rng = np.random.default_rng(9)
+    mats, prefix = [], []
+    for e in range(fd.experiment_number):
+        t = int(est.tuple_of_experiment[e])
+        mats.append(np.asfortranarray(rng.integers(0, 256, size=(int(shots_max[t]), fd.n_bytes), dtype=np.uint8)))
+        prefix.append(shots_divided[t])
+    prefix = np.asarray(prefix, dtype=np.int64)
+    whole = est.odd_counts(mats, [m.shape[0] for m in mats], [m.shape[0] for m in mats], prefix)
+    total = np.zeros_like(whole)
+    for rank in range(2):
+        sub, rows, pre = [], [], []
+        for e, m in enumerate(mats):
+            lo, hi, local = shard.shard_shots(m.shape[0], prefix[e], 2, rank)
+            sub.append(np.asfortranarray(m[lo:hi]))
+            rows.append(hi - lo)
+            pre.append(local)
+        total += est.odd_counts(sub, rows, [max(r, 1) for r in rows], np.asarray(pre, dtype=np.int64))
+    assert np.array_equal(total, whole)
