@@ -56,28 +56,52 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks and throttle reasons during the timed region (NVML in-process: forking
+    nvidia-smi from a CUDA process stalls the launching thread; nvidia-smi is the fallback)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
-        self.index = index
-        self.samples = []
+    def __init__(self, index, period=0.02):
+        self.index, self.period = index, period
+        self.samples = []  # (sm_mhz, sm_max_mhz, set of reasons)
         self.stop = threading.Event()
         self.th = threading.Thread(target=self.run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            masks = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            self.samples.append((sm, self.sm_max, {k for k, m in masks.items() if bits & m}))
+            return
+        out = subprocess.run(
+            ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+            capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            f = [x.strip() for x in out.split(",")]
+            self.samples.append((float(f[0]), float(f[1]),
+                                 {n for n, v in zip(self.NAMES, f[2:6]) if v.lower().startswith("active")}))
 
     def run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                    capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self.sample()
             except Exception:
                 pass
-            self.stop.wait(0.1)
+            self.stop.wait(self.period if self.nvml is not None else 0.2)
 
     def __enter__(self):
         self.th.start()
@@ -88,20 +112,12 @@ class ClockSampler:
         self.th.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sm = sorted(s[0] for s in self.samples)
+        reasons = set()
         for s in self.samples:
-            try:
-                sm.append(float(s[0]))
-                mx = max(mx, float(s[1]))
-                for n, v in zip(names, s[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                continue
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            reasons |= s[2]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((s[1] for s in self.samples), default=None),
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def build_design():
@@ -318,7 +334,11 @@ def main():
     fd = build_design()
     ctx = aces_b200.Context(local)
     est = aces_b200.DesignEstimator(ctx, fd)
-    stream = torch.cuda.current_stream()
+    # A real (non-default) stream: handle 0 would select the library's own stream and the events
+    # below would not bracket its kernels.
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
     shots_divided, shots_max = aces_b200.shots_divide(fd, SHOTS_SET)
@@ -337,8 +357,10 @@ def main():
     shot_parities = int(sum(rows[e] * int(sizes[e]) for e in range(n_exp)))
     shots = int(sum(rows))
 
+    batch = est.prepare(ptrs, rows, ld, prefix, out.data_ptr(), asynchronous=True)
+
     def step():
-        est.odd_counts(ptrs, rows, ld, prefix, out=out.data_ptr(), asynchronous=True)
+        batch.launch()  # aces_parity_counts_async: memset + parity kernel + prefix kernel on the stream
         if world > 1:
             dist.all_gather_into_tensor(gathered, out)
 
@@ -384,9 +406,11 @@ def main():
     hptrs = [h.data_ptr() for h in host]
     host_out = np.zeros(n_counts, dtype=np.int64)
 
+    e2e_batch = est.prepare(hptrs, rows, ld, prefix, host_out)
+
     def e2e_step():
         # host matrices in, host counts out: H2D of every sample matrix and D2H of the counts
-        est.odd_counts(hptrs, rows, ld, prefix, out=host_out)
+        e2e_batch.launch()
 
     e2e_step()
     ref_counts = out.cpu().numpy()

@@ -115,9 +115,10 @@ int32_t aces_parity_counts(aces_ctx* ctx, const aces_tables* tables, int32_t n_i
                            const int64_t* prefix_shots, int64_t* odd_counts,
                            int32_t accumulate);
 
-/* Same launch as aces_parity_counts but asynchronous on the context's stream, device
- * matrices only, odd_counts must be a device pointer.  Used to time the kernel with CUDA
- * events and to feed NCCL without a host round trip. */
+/* Same launch as aces_parity_counts but asynchronous on the context's stream.  By contract every
+ * matrix and odd_counts are DEVICE pointers (not checked: the per-pointer query would dominate the
+ * host cost of a call; a host pointer here faults in the kernel).  Used to time the kernel with
+ * CUDA events and to feed NCCL without a host round trip. */
 int32_t aces_parity_counts_async(aces_ctx* ctx, const aces_tables* tables, int32_t n_items,
                                  const int32_t* experiment_ids, const uint8_t* const* counts,
                                  const int64_t* rows, const int64_t* ld, int32_t K,

@@ -249,6 +249,36 @@ def parity_counts(
     return ret
 
 
+class PreparedBatch:
+    """The argument arrays of one aces_parity_counts[_async] call, marshalled once: repeated launches
+    over the same buffers (the repetition loop re-fills the same sample matrices) then cost one
+    foreign call each."""
+
+    def __init__(self, ctx: Context, tables: PauliTables, experiment_ids, matrices, rows, ld, prefix_shots, out,
+                 accumulate: bool = False, asynchronous: bool = False):
+        n = len(experiment_ids)
+        self.ctx, self.tables, self.n = ctx, tables, n
+        self.eid = np.ascontiguousarray(experiment_ids, dtype=np.int32)
+        self.rows = np.ascontiguousarray(rows, dtype=np.int64)
+        self.ld = np.ascontiguousarray(ld, dtype=np.int64)
+        self.pre = np.ascontiguousarray(prefix_shots, dtype=np.int64).reshape(n, -1)
+        self.K = self.pre.shape[1]
+        self.ptrs = (C.c_void_p * max(n, 1))()
+        self.keep = list(matrices)  # keeps numpy-backed matrices alive
+        for i, m in enumerate(matrices):
+            self.ptrs[i] = _ptr(m)
+        self.out = out
+        self.fn = ctx.lib.aces_parity_counts_async if asynchronous else ctx.lib.aces_parity_counts
+        self.args = (ctx.handle, tables.handle, n, _ptr(self.eid), C.cast(self.ptrs, C.c_void_p), _ptr(self.rows),
+                     _ptr(self.ld), self.K, _ptr(self.pre), _ptr(out), 1 if accumulate else 0)
+
+    def launch(self):
+        rc = self.fn(*self.args)
+        if rc != ACES_OK:
+            self.ctx.check(rc)
+        return self.out
+
+
 def estimate_experiment_raw(ctx: Context, counts: np.ndarray, meas_ptr, meas_indices, signs, shots_value: int):
     """aces_estimate_experiment on a Fortran-ordered uint8 matrix."""
     assert counts.dtype == np.uint8 and counts.ndim == 2

@@ -39,7 +39,13 @@ struct aces_ctx {
     DevBuf d_streams;  // stream table + item prefix
     DevBuf d_seg;      // per-segment odd counts (uint64)
     DevBuf d_odd;      // cumulative odd counts when the caller's output is on the host
-    DevBuf h_stage;    // pinned staging for the small per-call tables / outputs
+    DevBuf h_stage;    // pinned staging for the small per-call tables (two slots, used alternately so
+    DevBuf h_stage2;   // that the host can prepare call i+1 while call i's copy is still queued)
+    cudaEvent_t ev2 = nullptr;
+    int stage_slot = 0;
+    std::vector<uint8_t> tbl_scratch, tbl_uploaded;  // K1 tables: last upload (skipped when unchanged)
+    const void* tbl_dev = nullptr;
+    bool seg_clean = false;
     // fit workspaces are added by fit.cu through this generic pool
     DevBuf d_work[8];
     DevBuf d_flags;    // inter-CTA flags of the persistent triangular solves

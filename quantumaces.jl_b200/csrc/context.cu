@@ -111,6 +111,7 @@ int32_t aces_init(int32_t device, aces_ctx** out) {
     e = cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_lo);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev2, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->t0);
@@ -136,6 +137,8 @@ int32_t aces_destroy(aces_ctx* ctx) {
     for (DevBuf& b : ctx->d_work)
         if (b.ptr) cudaFree(b.ptr);
     if (ctx->h_stage.ptr) cudaFreeHost(ctx->h_stage.ptr);
+    if (ctx->h_stage2.ptr) cudaFreeHost(ctx->h_stage2.ptr);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->ev) cudaEventDestroy(ctx->ev);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);

@@ -97,9 +97,9 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
         item_E[i] = E;
         max_E = std::max(max_E, E);
         item_off[i + 1] = item_off[i] + (int64_t)E * K;
-        const bool dev = rows[i] > 0 && aces_is_device_ptr(counts[i]);
-        if (async_only)
-            ACES_CHECK(ctx, rows[i] == 0 || dev, "parity_counts_async: item %d is not a device matrix", i);
+        // The asynchronous entry point takes device matrices by contract: the per-item pointer query
+        // (about a microsecond each, times ~100 experiments per call) is skipped there.
+        const bool dev = rows[i] > 0 && (async_only || aces_is_device_ptr(counts[i]));
         in_place[i] = dev && (((uintptr_t)counts[i]) % 16 == 0) && (ld[i] % 16 == 0);
         if (!in_place[i] && rows[i] > 0) {
             const size_t pitch = ((size_t)rows[i] + 127) & ~(size_t)127;
@@ -109,8 +109,7 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
     }
     const int64_t total_out = item_off[n_items];
     if (total_out == 0) return ACES_OK;
-    const bool out_dev = aces_is_device_ptr(odd_counts);
-    if (async_only) ACES_CHECK(ctx, out_dev, "parity_counts_async: odd_counts must be a device pointer");
+    const bool out_dev = async_only || aces_is_device_ptr(odd_counts);
 
     // ---- stream table: one entry per (item, non-empty budget segment, Pauli slice) -------------
     // Paulis one pass can hold in registers (v2: 32 per lane; v1: 4 per thread)
@@ -169,22 +168,43 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t o_streams = 0, o_istart = al(sz_streams), o_ioff = o_istart + al(sz_istart),
                  o_iE = o_ioff + al(sz_ioff), tbl_bytes = o_iE + al(sz_iE);
-    // The pinned staging buffer is reused across calls: wait for earlier async work first.
-    ACES_CUDA(ctx, cudaEventSynchronize(ctx->ev));
-    ACES_TRY(aces_reserve_host(ctx, ctx->h_stage, tbl_bytes));
+    // The tables are assembled in a host vector and uploaded only when they differ from what the
+    // device already holds (a repetition loop re-fills the same sample buffers: identical tables).
+    // Two pinned staging slots are used alternately: before a slot is refilled the copy that last
+    // read it must have executed; the device-side table is ordered by the stream.
     ACES_TRY(aces_reserve_dev(ctx, ctx->d_streams, tbl_bytes));
-    uint8_t* hs = (uint8_t*)ctx->h_stage.ptr;
-    if (n_streams) memcpy(hs + o_streams, streams.data(), sizeof(StreamDesc) * n_streams);
-    memcpy(hs + o_istart, item_start.data(), sz_istart);
-    memcpy(hs + o_ioff, item_off.data(), sz_ioff);
-    memcpy(hs + o_iE, item_E.data(), sz_iE);
     uint8_t* ds = (uint8_t*)ctx->d_streams.ptr;
-    ACES_CUDA(ctx, cudaMemcpyAsync(ds, hs, tbl_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    ACES_CUDA(ctx, cudaEventRecord(ctx->ev, ctx->stream));
+    std::vector<uint8_t>& tb = ctx->tbl_scratch;
+    tb.assign(tbl_bytes, 0);
+    if (n_streams) memcpy(tb.data() + o_streams, streams.data(), sizeof(StreamDesc) * n_streams);
+    memcpy(tb.data() + o_istart, item_start.data(), sz_istart);
+    memcpy(tb.data() + o_ioff, item_off.data(), sz_ioff);
+    memcpy(tb.data() + o_iE, item_E.data(), sz_iE);
+    const bool tables_cached = ctx->tbl_dev == ds && ctx->tbl_uploaded == tb;
+    if (!tables_cached) {
+        ctx->stage_slot ^= 1;
+        DevBuf& hbuf = ctx->stage_slot ? ctx->h_stage2 : ctx->h_stage;
+        cudaEvent_t hev = ctx->stage_slot ? ctx->ev2 : ctx->ev;
+        ACES_CUDA(ctx, cudaEventSynchronize(hev));
+        ACES_TRY(aces_reserve_host(ctx, hbuf, tbl_bytes));
+        memcpy(hbuf.ptr, tb.data(), tbl_bytes);
+        ACES_CUDA(ctx, cudaMemcpyAsync(ds, hbuf.ptr, tbl_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        ACES_CUDA(ctx, cudaEventRecord(hev, ctx->stream));
+        ctx->tbl_uploaded.swap(tb);
+        ctx->tbl_dev = ds;
+    }
 
-    ACES_TRY(aces_reserve_dev(ctx, ctx->d_seg, sizeof(unsigned long long) * (size_t)total_out));
-    ACES_CUDA(ctx, cudaMemsetAsync(ctx->d_seg.ptr, 0, sizeof(unsigned long long) * (size_t)total_out,
-                                   ctx->stream));
+    // Per-segment counters: zeroed when (re)allocated; the prefix kernel clears what it has read,
+    // so that a call leaves them clean for the next one (no memset per call).
+    {
+        const size_t need = sizeof(unsigned long long) * (size_t)total_out;
+        const void* before = ctx->d_seg.ptr;
+        const size_t cap_before = ctx->d_seg.cap;
+        ACES_TRY(aces_reserve_dev(ctx, ctx->d_seg, need));
+        if (ctx->d_seg.ptr != before || ctx->d_seg.cap != cap_before || !ctx->seg_clean)
+            ACES_CUDA(ctx, cudaMemsetAsync(ctx->d_seg.ptr, 0, ctx->d_seg.cap, ctx->stream));
+        ctx->seg_clean = false;
+    }
 
     if (total_items > 0) {
         ParityParams P;
@@ -229,11 +249,12 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
     }
     {
         dim3 grid((unsigned)std::min<int64_t>(((int64_t)max_E + 255) / 256, 64), (unsigned)std::min(n_items, 16384));
-        prefix_kernel<<<grid, 256, 0, ctx->stream>>>((const unsigned long long*)ctx->d_seg.ptr, d_out,
+        prefix_kernel<<<grid, 256, 0, ctx->stream>>>((unsigned long long*)ctx->d_seg.ptr, d_out,
                                                     (const int64_t*)(ds + o_ioff),
                                                     (const int32_t*)(ds + o_iE), n_items, K, acc_dev);
         ACES_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
+        ctx->seg_clean = true;
     }
     if (async_only) return ACES_OK;
     if (out_dev) {

@@ -144,8 +144,9 @@ __device__ __forceinline__ uint4 xor4(uint4 x, const uint4 y) {
     x.x ^= y.x; x.y ^= y.y; x.z ^= y.z; x.w ^= y.w;
     return x;
 }
-// Per-segment counts -> per-prefix (cumulative) counts; optionally added to the output.
-__global__ void prefix_kernel(const unsigned long long* __restrict__ seg,
+// Per-segment counts -> per-prefix (cumulative) counts; optionally added to the output.  Clears the
+// segment counters it has consumed.
+__global__ void prefix_kernel(unsigned long long* __restrict__ seg,
                               long long* __restrict__ out, const int64_t* __restrict__ item_off,
                               const int32_t* __restrict__ item_E, int n_items, int K,
                               int accumulate) {
@@ -157,6 +158,7 @@ __global__ void prefix_kernel(const unsigned long long* __restrict__ seg,
             for (int k = 0; k < K; ++k) {
                 const int64_t idx = off + (int64_t)k * E + p;
                 run += (long long)seg[idx];
+                seg[idx] = 0ull;  // leave the counters clean for the next call
                 out[idx] = accumulate ? out[idx] + run : run;
             }
         }

@@ -77,6 +77,14 @@ class DesignEstimator:
                                   prefix_shots, out=out, accumulate=accumulate,
                                   asynchronous=asynchronous)
 
+    def prepare(self, matrices, rows, ld, prefix_shots, out, experiment_ids=None, accumulate=False,
+                asynchronous=False) -> "_lib.PreparedBatch":
+        """Marshals the arguments of odd_counts once; `.launch()` repeats the call."""
+        if experiment_ids is None:
+            experiment_ids = np.arange(self.fd.experiment_number, dtype=np.int32)
+        return _lib.PreparedBatch(self.ctx, self.tables, experiment_ids, matrices, rows, ld, prefix_shots, out,
+                                  accumulate=accumulate, asynchronous=asynchronous)
+
     def simulate_estimate(self, samples: Sequence[np.ndarray], shots_set: Sequence[int]):
         """The estimation half of simulate_stim_estimate (src/simulate.jl:195-234): given one
         sample matrix per experiment (tuple-major order, shots_maximum[t] rows each), returns
