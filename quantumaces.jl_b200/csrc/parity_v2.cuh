@@ -40,21 +40,22 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
 // private planes.  Plane row of record bit q = 8c + k is row (k * BMAX + c) (k-major: lanes of a
 // warp then store to consecutive words; the compile-time row stride keeps the eight stores of a
 // unit on immediate offsets), SUB/8 bytes per row.
+// Lane l handles units l, l + 32, ...; a step of 32 units moves 32 / UPS columns forward and keeps
+// the position inside the column, so both the source and the plane address advance by constants:
+// col_s = stage column address of the lane's first unit, pl_s = its plane word.
 template <int SUB, int BMAX, bool MASKED>
-__device__ __forceinline__ void v2_phase_a(uint32_t stage_s, uint32_t planes_s, int B, int CS,
-                                           int lane, int lo, int hi) {
+__device__ __forceinline__ void v2_phase_a(uint32_t col_s, uint32_t pl_s, int nunits, int CS, int lane, int lo,
+                                           int hi) {
     constexpr int UPS = SUB / 32;  // 32-shot units per byte column
-    const int nunits = B * UPS;
     constexpr uint32_t kstride = (uint32_t)(BMAX * UPS * 4);
-    for (int unit = lane; unit < nunits; unit += 32) {
-        const int c = unit / UPS;
-        const int u = unit - c * UPS;
-        const uint32_t col = stage_s + (uint32_t)(c * CS + 16 * u);
-        uint4 a = lds128(col);
-        uint4 b = lds128(col + SUB / 2);
+    const uint32_t col_step = (uint32_t)((32 / UPS) * CS);
+    const int row0 = 16 * (lane & (UPS - 1));  // first row of the unit inside the warp's sub-tile
+    for (int unit = lane; unit < nunits; unit += 32, col_s += col_step, pl_s += 128u) {
+        uint4 a = lds128(col_s);
+        uint4 b = lds128(col_s + SUB / 2);
         if (MASKED) {
-            a = mask_rows(a, 16 * u, lo, hi);
-            b = mask_rows(b, SUB / 2 + 16 * u, lo, hi);
+            a = mask_rows(a, row0, lo, hi);
+            b = mask_rows(b, SUB / 2 + row0, lo, hi);
         }
         uint32_t w0 = a.x, w1 = a.y, w2 = a.z, w3 = a.w;
         uint32_t w4 = b.x, w5 = b.y, w6 = b.z, w7 = b.w;
@@ -64,17 +65,16 @@ __device__ __forceinline__ void v2_phase_a(uint32_t stage_s, uint32_t planes_s, 
         ACES_BFLY(w4, w6, 0x33333333u, 2) ACES_BFLY(w5, w7, 0x33333333u, 2)
         ACES_BFLY(w0, w4, 0x0F0F0F0Fu, 4) ACES_BFLY(w1, w5, 0x0F0F0F0Fu, 4)
         ACES_BFLY(w2, w6, 0x0F0F0F0Fu, 4) ACES_BFLY(w3, w7, 0x0F0F0F0Fu, 4)
-        const uint32_t pl = planes_s + (uint32_t)((c * UPS + u) * 4);
-        sts32(pl + 0 * kstride, w0); sts32(pl + 1 * kstride, w1);
-        sts32(pl + 2 * kstride, w2); sts32(pl + 3 * kstride, w3);
-        sts32(pl + 4 * kstride, w4); sts32(pl + 5 * kstride, w5);
-        sts32(pl + 6 * kstride, w6); sts32(pl + 7 * kstride, w7);
+        sts32(pl_s + 0 * kstride, w0); sts32(pl_s + 1 * kstride, w1);
+        sts32(pl_s + 2 * kstride, w2); sts32(pl_s + 3 * kstride, w3);
+        sts32(pl_s + 4 * kstride, w4); sts32(pl_s + 5 * kstride, w5);
+        sts32(pl_s + 6 * kstride, w6); sts32(pl_s + 7 * kstride, w7);
     }
 }
 
 // BMAX = byte columns the plane layout is dimensioned for (B <= BMAX).
 template <int NW, int SUB, int BMAX, int RMAX>
-__global__ void __launch_bounds__((NW + 1) * 32) parity_kernel_v2(const ParityParams P) {
+__global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 16 ? 3 : 1) parity_kernel_v2(const ParityParams P) {
     constexpr int TS = NW * SUB;
     constexpr int CS = TS + 64;     // raw column stride: +64 B keeps quarter-warp LDS.128 conflict-free
     constexpr int V = SUB / 128;    // 128-shot vectors per plane row
@@ -171,10 +171,14 @@ __global__ void __launch_bounds__((NW + 1) * 32) parity_kernel_v2(const ParityPa
     // ================================== consumer warps =========================================
     uint32_t planes_s = smem_s + planes_off + (uint32_t)warp * planes_bytes;
     uint32_t empty_s = smem_u32(&empty[0]), full_s = smem_u32(&full[0]);
-    uint32_t raw_s = smem_s + raw_off + (uint32_t)(warp * SUB), lane_r = (uint32_t)lane;
+    // per-lane addresses of phase A: the lane's first unit in a raw stage and its plane word
+    constexpr int UPS_ = SUB / 32;
+    uint32_t raw_s = smem_s + raw_off + (uint32_t)(warp * SUB) + (uint32_t)((lane / UPS_) * CS + 16 * (lane % UPS_));
+    uint32_t pl_lane = planes_s + 4u * (uint32_t)lane, lane_r = (uint32_t)lane;
+    const int nunits = B * UPS_;
     // keep the loop invariants in registers (the compiler would otherwise rematerialise them from
     // the special registers every tile)
-    asm volatile("" : "+r"(planes_s), "+r"(empty_s), "+r"(full_s), "+r"(raw_s), "+r"(lane_r));
+    asm volatile("" : "+r"(planes_s), "+r"(empty_s), "+r"(full_s), "+r"(raw_s), "+r"(lane_r), "+r"(pl_lane));
     const int lane_c = (int)lane_r;
     uint32_t acc[RMAX];
     // per register slot: weight-1 slots hold the shared-memory address of their plane row;
@@ -284,12 +288,12 @@ __global__ void __launch_bounds__((NW + 1) * 32) parity_kernel_v2(const ParityPa
             any = (hi > 0) && (lo < SUB);
             if (any) {
                 if (lo > 0 || hi < SUB)
-                    v2_phase_a<SUB, BMAX, true>(stage_s, planes_s, B, CS, lane_c, lo, hi);
+                    v2_phase_a<SUB, BMAX, true>(stage_s, pl_lane, nunits, CS, lane_c, lo, hi);
                 else
-                    v2_phase_a<SUB, BMAX, false>(stage_s, planes_s, B, CS, lane_c, 0, SUB);
+                    v2_phase_a<SUB, BMAX, false>(stage_s, pl_lane, nunits, CS, lane_c, 0, SUB);
             }
         } else {
-            v2_phase_a<SUB, BMAX, false>(stage_s, planes_s, B, CS, lane_c, 0, SUB);
+            v2_phase_a<SUB, BMAX, false>(stage_s, pl_lane, nunits, CS, lane_c, 0, SUB);
         }
         __syncwarp();
         if (lane_c == 0)  // the raw stage may be refilled
