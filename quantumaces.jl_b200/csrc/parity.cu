@@ -24,6 +24,7 @@
 // odd count).  A second tiny kernel turns per-segment counts into per-prefix counts.
 // Counts are exact integers: the result is bit-identical to the reference by construction.
 #include <algorithm>
+#include <climits>
 #include <cstring>
 
 #include "aces_common.h"
@@ -319,7 +320,9 @@ int32_t aces_tables_create(aces_ctx* ctx, int32_t n_qubits, int32_t n_experiment
                 if ((j - i) & 1) red.push_back(sup[i]);
                 i = j;
             }
-            order.push_back({(int32_t)red.size(), p});
+            // identity Paulis (empty support: their odd count is 0) sort last, so that the weight-1
+            // prefix of the device order is not broken by them
+            order.push_back({red.empty() ? INT32_MAX : (int32_t)red.size(), p});
         }
         // device order: by weight, so that the lanes of a warp run the same number of plane loads
         std::stable_sort(order.begin(), order.end(),

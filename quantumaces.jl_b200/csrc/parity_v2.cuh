@@ -24,12 +24,29 @@ constexpr int V2_OFF_EMPTY = 64;
 constexpr int V2_OFF_DESC = 128;
 constexpr int V2_OFF_SACC = V2_OFF_DESC + V2_MAX_STAGES * 64;  // 640
 
+// after the shared counters: the table of the third / fourth plane row of weight-3/4 Paulis
+__host__ __device__ constexpr uint32_t v2_s4_off(int rmax) { return (uint32_t)(V2_OFF_SACC + 4 * 32 * rmax); }
 __host__ __device__ constexpr uint32_t v2_planes_off(int rmax) {
-    return (uint32_t)((V2_OFF_SACC + 4 * 32 * rmax + 127) & ~127);
+    return (uint32_t)((V2_OFF_SACC + 2 * 4 * 32 * rmax + 127) & ~127);
 }
+
+// Byte pitch of a plane row: the SUB / 8 data bytes plus, for rows longer than one 16-byte vector,
+// one vector of padding, so that the pitch is an odd number of vectors and the 128-bit loads of a
+// quarter warp (eight different rows) fall into eight different bank groups.
+__host__ __device__ constexpr int v2_row_pitch(int sub) { return sub / 8 + (sub / 8 > 16 ? 16 : 0); }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -47,10 +64,11 @@ template <int SUB, int BMAX, bool MASKED>
 __device__ __forceinline__ void v2_phase_a(uint32_t col_s, uint32_t pl_s, int nunits, int CS, int lane, int lo,
                                            int hi) {
     constexpr int UPS = SUB / 32;  // 32-shot units per byte column
-    constexpr uint32_t kstride = (uint32_t)(BMAX * UPS * 4);
+    constexpr uint32_t kstride = (uint32_t)(BMAX * v2_row_pitch(SUB));
+    constexpr uint32_t pl_step = (uint32_t)((32 / UPS) * v2_row_pitch(SUB));
     const uint32_t col_step = (uint32_t)((32 / UPS) * CS);
     const int row0 = 16 * (lane & (UPS - 1));  // first row of the unit inside the warp's sub-tile
-    for (int unit = lane; unit < nunits; unit += 32, col_s += col_step, pl_s += 128u) {
+    for (int unit = lane; unit < nunits; unit += 32, col_s += col_step, pl_s += pl_step) {
         uint4 a = lds128(col_s);
         uint4 b = lds128(col_s + SUB / 2);
         if (MASKED) {
@@ -74,11 +92,12 @@ __device__ __forceinline__ void v2_phase_a(uint32_t col_s, uint32_t pl_s, int nu
 
 // BMAX = byte columns the plane layout is dimensioned for (B <= BMAX).
 template <int NW, int SUB, int BMAX, int RMAX>
-__global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 16 ? 3 : 1) parity_kernel_v2(const ParityParams P) {
+__global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 8 ? 3 : (RMAX <= 16 ? 2 : 1)) parity_kernel_v2(const ParityParams P) {
     constexpr int TS = NW * SUB;
     constexpr int CS = TS + 64;     // raw column stride: +64 B keeps quarter-warp LDS.128 conflict-free
     constexpr int V = SUB / 128;    // 128-shot vectors per plane row
-    constexpr int ROWB = SUB / 8;   // bytes per plane row
+    constexpr int ROWB = SUB / 8;   // data bytes per plane row
+    constexpr int RSTR = v2_row_pitch(SUB);  // byte pitch of a plane row
     constexpr int NCT = NW * 32;    // consumer threads
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -87,7 +106,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 16 ? 3 : 1) parity_kern
     uint32_t* sacc = reinterpret_cast<uint32_t*>(smem + V2_OFF_SACC);
     const int B = P.B;
     const int NS = P.NS;
-    constexpr uint32_t planes_bytes = (uint32_t)((8 * BMAX + 1) * ROWB);  // + one all-zero row
+    constexpr uint32_t planes_bytes = (uint32_t)((8 * BMAX + 1) * RSTR);  // + one all-zero row
     const uint32_t planes_off = v2_planes_off(RMAX);
     const uint32_t raw_off = (planes_off + NW * planes_bytes + 127u) & ~127u;
     const uint32_t stage_bytes = (uint32_t)(B * CS);
@@ -174,7 +193,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 16 ? 3 : 1) parity_kern
     // per-lane addresses of phase A: the lane's first unit in a raw stage and its plane word
     constexpr int UPS_ = SUB / 32;
     uint32_t raw_s = smem_s + raw_off + (uint32_t)(warp * SUB) + (uint32_t)((lane / UPS_) * CS + 16 * (lane % UPS_));
-    uint32_t pl_lane = planes_s + 4u * (uint32_t)lane, lane_r = (uint32_t)lane;
+    uint32_t pl_lane = planes_s + (uint32_t)((lane / UPS_) * RSTR + 4 * (lane % UPS_)), lane_r = (uint32_t)lane;
     const int nunits = B * UPS_;
     // keep the loop invariants in registers (the compiler would otherwise rematerialise them from
     // the special registers every tile)
@@ -184,7 +203,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 16 ? 3 : 1) parity_kern
     // per register slot: weight-1 slots hold the shared-memory address of their plane row;
     // weight-2 slots hold the two plane-row offsets packed as a0 | a1 << 16
     uint32_t dx[RMAX];
-    constexpr uint32_t zero_row = (uint32_t)(8 * BMAX * ROWB);
+    constexpr uint32_t zero_row = (uint32_t)(8 * BMAX * RSTR);
     for (int i = lane; i < ROWB / 4; i += 32) sts32(planes_s + zero_row + 4 * i, 0u);
     __syncwarp();
 #pragma unroll
@@ -195,20 +214,22 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 16 ? 3 : 1) parity_kern
     // [n12,R) are table-driven.  The classes live in fixed register slots so that each class runs
     // as straight-line code entered through one computed jump (no per-round branches):
     //   weight-2 rounds  -> slots [0, n2),  n2 = n12 - n1          round = n1 + slot
-    //   table rounds     -> slots [n2, n2 + ng), ng = R - n12       round = n12 + (slot - n2)
+    //   weight<=4 rounds -> slots [n2, n2 + n4)                     round = n1 + slot   (third and
+    //                       fourth plane row in the shared table s4; predicated per slot)
+    //   table rounds     -> slots [n2 + n4, n2 + n4 + ng)           round = n1 + slot
     //   weight-1 rounds  -> slots [RMAX - n1, RMAX)                 round = slot - (RMAX - n1)
-    int n1 = 0, n2 = 0, ng = 0;
+    int n1 = 0, n2 = 0, n4 = 0, ng = 0;
+    const uint32_t s4_s = smem_s + v2_s4_off(RMAX) + 4u * (uint32_t)lane;
     int R = 0;                        // rounds in use
     int E = 0;
     int cur_stream = -1;
     int64_t cur_out = 0, cur_poff = 0;
 
     auto row_off = [&](uint32_t q) -> uint32_t {  // plane-row byte offset of record bit q
-        return ((q & 7u) * (uint32_t)BMAX + (q >> 3)) * (uint32_t)ROWB;
+        return ((q & 7u) * (uint32_t)BMAX + (q >> 3)) * (uint32_t)RSTR;
     };
     auto round_of_slot = [&](int slot) -> int {  // -1: slot not in use
-        if (slot < n2) return n1 + slot;
-        if (slot < n2 + ng) return n1 + slot;  // n12 + (slot - n2) == n1 + slot
+        if (slot < n2 + n4 + ng) return n1 + slot;
         if (slot >= RMAX - n1) return slot - (RMAX - n1);
         return -1;
     };
@@ -244,7 +265,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 16 ? 3 : 1) parity_kern
         E = sd->E;
         R = (E + 31) >> 5;
         // pass 1: classify the rounds (the table is sorted by weight: classes are prefixes)
-        int c1 = 0, c12 = 0;
+        int c1 = 0, c12 = 0, c14 = 0;
 #pragma unroll
         for (int r = 0; r < RMAX; ++r) {
             const int p = r * 32 + lane;
@@ -252,25 +273,32 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 16 ? 3 : 1) parity_kern
             if (r < R && p < E) w = (int)__ldg(&P.pauli[cur_poff + p].w);
             const bool all1 = __all_sync(0xffffffffu, w == 1);
             const bool all2 = __all_sync(0xffffffffu, w <= 2);
+            const bool all4 = __all_sync(0xffffffffu, w <= 4);
             if (all1 && c1 == r) c1 = r + 1;
             if (all2 && c12 == r && r < R) c12 = r + 1;
+            if (all4 && c14 == r && r < R) c14 = r + 1;
         }
         n1 = c1;
         n2 = c12 - c1;
-        ng = R - c12;
+        n4 = c14 - c12;
+        ng = R - c14;
         // pass 2: plane rows of every slot
 #pragma unroll
         for (int sl = 0; sl < RMAX; ++sl) {
             const int r = round_of_slot(sl);
             const int p = r * 32 + lane;
-            uint32_t a0 = zero_row, a1 = zero_row;
+            uint32_t a0 = zero_row, a1 = zero_row, a2 = zero_row, a3 = zero_row;
             if (r >= 0 && p < E) {
                 const PauliDesc* pd = &P.pauli[cur_poff + p];
                 const int w = (int)__ldg(&pd->w);
                 if (w >= 1) a0 = row_off((uint32_t)__ldg(&pd->q[0]));
                 if (w >= 2) a1 = row_off((uint32_t)__ldg(&pd->q[1]));
+                if (w >= 3) a2 = row_off((uint32_t)__ldg(&pd->q[2]));
+                if (w >= 4) a3 = row_off((uint32_t)__ldg(&pd->q[3]));
             }
             dx[sl] = (sl >= RMAX - n1) ? planes_s + a0 : (a0 | (a1 << 16));
+            // every consumer warp writes the same table (same lane <-> Pauli assignment)
+            if (sl >= n2 && sl < n2 + n4) sts32(s4_s + 128u * (uint32_t)sl, a2 | (a3 << 16));
         }
     };
 
@@ -334,13 +362,34 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 16 ? 3 : 1) parity_kern
 #undef ACES_C2
 #undef ACES_W1
 #undef ACES_W2
+            if (n4 > 0) {
+                // supports of three or four bits (products of two measured Paulis: the covariance
+                // Paulis of a full-covariance design)
+#pragma unroll
+                for (int sl = 0; sl < RMAX; ++sl) {
+                    if (sl >= n2 && sl < n2 + n4) {
+                        const uint32_t hi2 = lds32(s4_s + 128u * (uint32_t)sl);
+                        const uint32_t b0 = planes_s + (dx[sl] & 0xFFFFu), b1 = planes_s + (dx[sl] >> 16);
+                        const uint32_t b2 = planes_s + (hi2 & 0xFFFFu), b3 = planes_s + (hi2 >> 16);
+                        uint32_t cnt = 0;
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            const uint4 x0 = lds128(b0 + 16 * v), x1 = lds128(b1 + 16 * v);
+                            const uint4 x2 = lds128(b2 + 16 * v), x3 = lds128(b3 + 16 * v);
+                            cnt += (__popc(xor3(x0.x, x1.x, x2.x) ^ x3.x) + __popc(xor3(x0.y, x1.y, x2.y) ^ x3.y)) +
+                                   (__popc(xor3(x0.z, x1.z, x2.z) ^ x3.z) + __popc(xor3(x0.w, x1.w, x2.w) ^ x3.w));
+                        }
+                        acc[sl] += cnt;
+                    }
+                }
+            }
             if (ng > 0) {
-                // supports wider than two bits: table-driven
+                // wider supports: table-driven
 #pragma unroll
                 for (int sl = 0; sl < RMAX; ++sl) {
                     const int r = n1 + sl;
                     const int p = r * 32 + lane;
-                    if (sl >= n2 && sl < n2 + ng && p < E) {
+                    if (sl >= n2 + n4 && sl < n2 + n4 + ng && p < E) {
                         const PauliDesc* pd = &P.pauli[cur_poff + p];
                         const int w = pd->w;
                         const int ext = pd->ext;
@@ -373,21 +422,26 @@ struct V2Cfg {
 // the shape is outside what v2 covers (the caller falls back to the v1 kernel).
 inline bool v2_pick(int B, int max_E, int smem_optin, V2Cfg* cfg) {
     int SUB, BMAX;
-    if (B <= 7) { SUB = 512; BMAX = 7; }
-    else if (B <= 13) { SUB = 256; BMAX = 13; }
+    // sub-tile rows per warp: as large as three resident CTAs per SM (planes + two or more raw
+    // stages each) allow -- more rows amortise the per-tile overhead, fewer CTAs lose more
+    if (B <= 3) { SUB = 512; BMAX = 7; }
+    else if (B <= 7) { SUB = 256; BMAX = 7; }
+    else if (B <= 13) { SUB = 128; BMAX = 13; }
     else if (B <= 25) { SUB = 128; BMAX = 25; }
     else if (B <= 41) { SUB = 128; BMAX = 41; }
     else return false;
     int NW = 8;
     if (getenv("ACES_K1_NW4") && BMAX == 25) { NW = 4; SUB = 256; }  // experiment: wider warp tiles
-    if ((8 * BMAX + 1) * (SUB / 8) >= 65536) return false;  // plane-row offsets are packed in 16 bits
+    if (getenv("ACES_K1_WIDE") && BMAX <= 13) SUB *= 2;                 // experiment: the previous choice
+    if ((8 * BMAX + 1) * v2_row_pitch(SUB) >= 65536) return false;  // plane-row offsets are packed in 16 bits
     const int RMAX = max_E <= 256 ? 8 : (max_E <= 512 ? 16 : 32);
-    const size_t planes = (size_t)NW * (8 * BMAX + 1) * (SUB / 8);
+    const size_t planes = (size_t)NW * (8 * BMAX + 1) * v2_row_pitch(SUB);
     const size_t raw_off = (v2_planes_off(RMAX) + planes + 127) & ~(size_t)127;
     const size_t stage = (size_t)B * (NW * SUB + 64);
     const char* env_ns = getenv("ACES_K1_NS");
     const char* env_cta = getenv("ACES_K1_CTAS");
-    const int want_ctas = env_cta ? atoi(env_cta) : 3;
+    // resident CTAs per SM the register budget of the variant allows (launch bounds of the kernel)
+    const int want_ctas = env_cta ? atoi(env_cta) : (RMAX <= 8 ? 3 : (RMAX <= 16 ? 2 : 1));
     const size_t budget = ((size_t)smem_optin + 1024) / (size_t)(want_ctas > 0 ? want_ctas : 1) - 1024;
     int ns = 0;
     for (int s = (env_ns ? atoi(env_ns) : 4); s >= 2; --s)
@@ -433,8 +487,10 @@ inline int v2_launch(aces_ctx* ctx, const ParityParams& P, const V2Cfg& cfg) {
                                     : v2_launch_t<8, SUBV, BMV, 32>(ctx, P, cfg))
     if (cfg.NW == 4) return cfg.RMAX == 8 ? v2_launch_t<4, 256, 25, 8>(ctx, P, cfg) : cfg.RMAX == 16 ? v2_launch_t<4, 256, 25, 16>(ctx, P, cfg) : v2_launch_t<4, 256, 25, 32>(ctx, P, cfg);
     if (cfg.SUB == 128 && cfg.BMAX == 25) return ACES_V2_R(128, 25);
-    if (cfg.SUB == 128) return ACES_V2_R(128, 41);
-    if (cfg.SUB == 256) return ACES_V2_R(256, 13);
+    if (cfg.SUB == 128 && cfg.BMAX == 41) return ACES_V2_R(128, 41);
+    if (cfg.SUB == 128) return ACES_V2_R(128, 13);
+    if (cfg.SUB == 256 && cfg.BMAX == 13) return ACES_V2_R(256, 13);
+    if (cfg.SUB == 256) return ACES_V2_R(256, 7);
     return ACES_V2_R(512, 7);
 #undef ACES_V2_R
 }
