@@ -235,12 +235,20 @@ def fit_leg(ctx, torch, dist, world, rank, steps, warmup, with_cpu):
     out["max_abs_error_vs_truth"] = float(np.max(np.abs(res["gls"][1] - fd.gate_eigenvalues)))
     # Gram kernel of the GLS fit on the FP64 tensor pipe (lower tiles of At' At)
     ctx.set_timing(True)
-    ks = []
-    for _ in range(3):
-        dd.fit("gls", lam, lc)
-        ks.append(ctx.last_kernel_ms())
+    ks, phases = [], {}
+    for name in ("wls", "gls", "gls", "gls"):
+        dd.fit(name, lam, lc)
+        phases[name] = dd.phase_ms()
+        if name == "gls":
+            ks.append(ctx.last_kernel_ms())
     ctx.set_timing(False)
     k_ms = sorted(ks)[1]
+    out["phases_ms"] = phases  # CUDA events inside the library, one fit each
+    n = fd.matrix.shape[1]
+    n_pad = -(-n // 128) * 128
+    out["cholesky"] = {"kernel": "dense::potrf (DMMA trailing updates + 128-block factor/inverse kernel, look-ahead)",
+                       "ms": phases["gls"].get("potrf"), "flops": n_pad ** 3 / 3.0,
+                       "tflops": n_pad ** 3 / 3.0 / (phases["gls"].get("potrf", float("nan")) * 1e-3) / 1e12}
     flops = dd.gram_flops()
     peak = dgemm_peak_tflops(torch)
     out["roofline"] = {"bound": "tensor", "kernel": "dense::gemm_batched_kernel<TN> (Gram over the column windows of the tuple blocks, DMMA m8n8k4 f64)",

@@ -227,6 +227,9 @@ int32_t aces_design_fallback_count(const aces_design* design);
  * lower 128 x 128 tiles of sum_t At_t' At_t over the column window of every tuple block, or of the
  * full At' At when the windows do not pay).  Bookkeeping for the roofline figure. */
 double aces_design_gram_flops(const aces_design* design);
+/* Phases of the last aces_design_fit when timing was on (aces_set_timing): index 0, 1, ... until
+ * ACES_E_INVALID; name (e.g. "gram", "potrf", "first solve") and CUDA-event milliseconds. */
+int32_t aces_design_phase_ms(const aces_design* design, int32_t index, char* name, int32_t name_len, float* ms);
 
 /* K2-K5 fused: the gate eigenvalues of one estimator from the circuit-eigenvalue estimates, as
  * estimate_gate_noise computes them (src/estimate.jl:711-743, 820-831): covariance of the

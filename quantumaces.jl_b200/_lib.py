@@ -66,6 +66,7 @@ SIGNATURES = {
     "aces_design_inv_factor": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, C.c_double, _vp, _vp]),
     "aces_design_fallback_count": (_i32, [_vp]),
     "aces_design_gram_flops": (C.c_double, [_vp]),
+    "aces_design_phase_ms": (_i32, [_vp, _i32, C.c_char_p, _i32, _p(C.c_float)]),
     "aces_design_fit": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, C.c_double, _i32, _vp]),
     "aces_design_ls_covariance": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
 }

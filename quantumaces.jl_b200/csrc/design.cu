@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "dense.cuh"
@@ -58,6 +59,7 @@ struct aces_design {
     int32_t *row_map = nullptr;    // [M] compacted local row or -1
     int32_t *flags = nullptr;      // [T + 1] not-PD flags (blocks, then the Gram matrix)
     int fallback_blocks = 0;       // blocks that needed the not-PD fallback in the last call
+    std::vector<std::pair<std::string, float>> phase_ms;  // phases of the last fit (timing on)
     // --- column windows of the tuple blocks (GLS Gram): block t only touches the columns cols_t ---
     bool windowed = false;         // the windowed Gram does at most half the flops of the dense one
     int max_ct = 0;                // max cp_t / 128
@@ -483,13 +485,19 @@ __global__ void moments_final_kernel(int nparts, double* __restrict__ out) {
 }
 
 
-// Development aid (ACES_FIT_TRACE=1): CUDA-event timing of the phases of a fit, printed to stderr.
+// CUDA-event timing of the phases of a fit: recorded when timing is on (aces_set_timing) and read
+// back with aces_design_phase_ms; ACES_FIT_TRACE=1 also prints them to stderr.
 struct PhaseTimer {
     aces_ctx* ctx;
-    bool on;
+    aces_design* d;
+    bool on, print;
     std::vector<cudaEvent_t> ev;
     std::vector<const char*> names;
-    explicit PhaseTimer(aces_ctx* c) : ctx(c), on(getenv("ACES_FIT_TRACE") != nullptr) { mark("start"); }
+    PhaseTimer(aces_ctx* c, aces_design* dd)
+        : ctx(c), d(dd), on(false), print(getenv("ACES_FIT_TRACE") != nullptr) {
+        on = print || c->timing;
+        mark("start");
+    }
     void mark(const char* name) {
         if (!on) return;
         cudaEvent_t e;
@@ -501,10 +509,12 @@ struct PhaseTimer {
     ~PhaseTimer() {
         if (!on) return;
         cudaEventSynchronize(ev.back());
+        d->phase_ms.clear();
         for (size_t i = 1; i < ev.size(); ++i) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
-            fprintf(stderr, "[aces fit] %-18s %8.3f ms\n", names[i], ms);
+            d->phase_ms.push_back({names[i], ms});
+            if (print) fprintf(stderr, "[aces fit] %-18s %8.3f ms\n", names[i], ms);
         }
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
     }
@@ -1018,6 +1028,12 @@ int32_t aces_design_destroy(aces_ctx* ctx, aces_design* d) {
 
 int64_t aces_design_covariance_nnz(const aces_design* d) { return d ? d->nnz_cov : -1; }
 int32_t aces_design_fallback_count(const aces_design* d) { return d ? d->fallback_blocks : -1; }
+int32_t aces_design_phase_ms(const aces_design* d, int32_t index, char* name, int32_t name_len, float* ms) {
+    if (!d || index < 0 || (size_t)index >= d->phase_ms.size()) return ACES_E_INVALID;
+    if (name && name_len > 0) snprintf(name, (size_t)name_len, "%s", d->phase_ms[(size_t)index].first.c_str());
+    if (ms) *ms = d->phase_ms[(size_t)index].second;
+    return ACES_OK;
+}
 double aces_design_gram_flops(const aces_design* d) {
     if (!d) return -1.0;
     double tiles_k = 0.0;  // sum over 128 x 128 output tiles of their inner dimension
@@ -1178,7 +1194,7 @@ int32_t aces_design_fit(aces_ctx* ctx, aces_design* d, int32_t ls_type, const do
     double *lam, *lamcov;
     ACES_TRY(upload_eigenvalues(ctx, d, est_eigenvalues, est_covariance_eigenvalues, &lam, &lamcov));
     FitVectors fv = fit_vectors(d);
-    PhaseTimer pt(ctx);
+    PhaseTimer pt(ctx, d);
     // K2: log-covariance of the estimates, weight_time = false (src/estimate.jl:713-720)
     if (ls_type != 0) ACES_TRY(launch_cov_values(ctx, d, lam, lamcov, epsilon, 0, 1, d->covval));
     pt.mark("covariance");

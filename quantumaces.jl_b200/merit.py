@@ -211,6 +211,16 @@ class DeviceDesign:
         """Blocks that took the not-positive-definite fallback (src/merit.jl:403-424) in the last call."""
         return int(self.ctx.lib.aces_design_fallback_count(self.handle))
 
+    def phase_ms(self) -> dict:
+        """CUDA-event milliseconds of the phases of the last fit (needs ctx.set_timing(True))."""
+        out, i = {}, 0
+        buf = C.create_string_buffer(64)
+        ms = C.c_float()
+        while self.ctx.lib.aces_design_phase_ms(self.handle, i, buf, 64, C.byref(ms)) == 0:
+            out[buf.value.decode()] = float(ms.value)
+            i += 1
+        return out
+
     def gram_flops(self) -> float:
         """Dense FP64 flops of the GLS Gram matrix per fit (aces_design_gram_flops)."""
         return float(self.ctx.lib.aces_design_gram_flops(self.handle))
