@@ -43,6 +43,9 @@ struct aces_tables {
     int32_t n_experiments = 0;
     int32_t max_E = 0;
     std::vector<int64_t> exp_ptr;  // host copy: Paulis of experiment e
+    std::vector<int32_t> dev_E;    // Paulis of experiment e the kernel evaluates (identity Paulis,
+                                   // sorted last in the device order, always count 0 and are skipped)
+    int32_t max_dev_E = 0;
     PauliDesc* d_pauli = nullptr;
     int32_t* d_bits = nullptr;
 };
@@ -66,7 +69,7 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
     const char* env_impl = getenv("ACES_K1_IMPL");
     const int slice_v2 = 1024;
     const bool use_v2 = !(env_impl && atoi(env_impl) == 1) &&
-                        v2_pick(B, std::min(t->max_E, slice_v2), ctx->smem_optin, &cfg2);
+                        v2_pick(B, std::min(t->max_dev_E, slice_v2), ctx->smem_optin, &cfg2);
     if (!use_v2 && !pick_tile(B, ctx->smem_optin, &cfg))
         return aces_fail(ctx, ACES_E_UNSUPPORTED,
                          "parity_counts: %d byte columns per shot exceed the shared-memory tiling", B);
@@ -119,8 +122,9 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
     std::vector<int64_t> item_start(1, 0);
     if (arena_bytes > 0) ACES_TRY(aces_reserve_dev(ctx, ctx->d_arena, arena_bytes));
     for (int i = 0; i < n_items; ++i) {
-        if (rows[i] == 0 || item_E[i] == 0) continue;
         const int e = experiment_ids[i];
+        const int dev_E = t->dev_E[(size_t)e];
+        if (rows[i] == 0 || dev_E == 0) continue;
         const uint8_t* base;
         int64_t ldd;
         if (in_place[i]) {
@@ -138,7 +142,7 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
         for (int k = 0; k < K; ++k) {
             const int64_t s = prefix_shots[(int64_t)i * K + k];
             if (s > prev) {
-                for (int p0 = 0; p0 < item_E[i]; p0 += slice) {
+                for (int p0 = 0; p0 < dev_E; p0 += slice) {
                     StreamDesc sd;
                     sd.base = base;
                     sd.ld = ldd;
@@ -148,7 +152,7 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
                     sd.tile_first = prev / TS;
                     sd.out_off = item_off[i] + (int64_t)k * item_E[i];
                     sd.pauli_off = t->exp_ptr[e] + p0;
-                    sd.E = std::min(slice, item_E[i] - p0);
+                    sd.E = std::min(slice, dev_E - p0);
                     sd.pad = 0;
                     const int64_t ntiles = (s - 1) / TS - prev / TS + 1;
                     streams.push_back(sd);
@@ -293,7 +297,8 @@ int32_t aces_tables_create(aces_ctx* ctx, int32_t n_qubits, int32_t n_experiment
     std::vector<PauliDesc> descs((size_t)P);
     std::vector<int32_t> bits;
     bits.reserve((size_t)pauli_ptr[P] + 4);
-    int max_E = 0;
+    int max_E = 0, max_dev_E = 0;
+    std::vector<int32_t> dev_E;
     std::vector<int32_t> sup;
     std::vector<std::pair<int32_t, int32_t>> order;  // (weight, original index)
     std::vector<std::vector<int32_t>> sups;
@@ -329,9 +334,11 @@ int32_t aces_tables_create(aces_ctx* ctx, int32_t n_qubits, int32_t n_experiment
                          [](const std::pair<int32_t, int32_t>& a, const std::pair<int32_t, int32_t>& b) {
                              return a.first < b.first;
                          });
+        int n_dev = 0;
         for (int r = 0; r < E; ++r) {
             const int p = order[(size_t)r].second;
             const std::vector<int32_t>& red = sups[(size_t)p];
+            if (!red.empty()) n_dev = r + 1;
             PauliDesc& d = descs[(size_t)(p0 + r)];
             d.w = (int32_t)red.size();
             d.ext = (int32_t)bits.size();
@@ -341,8 +348,12 @@ int32_t aces_tables_create(aces_ctx* ctx, int32_t n_qubits, int32_t n_experiment
             ACES_CHECK(ctx, bits.size() + red.size() < ((size_t)1 << 31), "tables_create: table too large");
             bits.insert(bits.end(), red.begin(), red.end());
         }
+        dev_E.push_back(n_dev);
+        max_dev_E = std::max(max_dev_E, n_dev);
     }
     aces_tables* t = new aces_tables();
+    t->dev_E = dev_E;
+    t->max_dev_E = max_dev_E;
     t->n_qubits = n_qubits;
     t->B = (n_qubits + 7) / 8;
     t->n_experiments = n_experiments;

@@ -26,8 +26,11 @@ constexpr int V2_OFF_SACC = V2_OFF_DESC + V2_MAX_STAGES * 64;  // 640
 
 // after the shared counters: the table of the third / fourth plane row of weight-3/4 Paulis
 __host__ __device__ constexpr uint32_t v2_s4_off(int rmax) { return (uint32_t)(V2_OFF_SACC + 4 * 32 * rmax); }
+// third table: the first two plane rows of every slot, for the variants whose round count does not
+// leave registers for them (RMAX > 8)
+__host__ __device__ constexpr uint32_t v2_dx_off(int rmax) { return (uint32_t)(V2_OFF_SACC + 2 * 4 * 32 * rmax); }
 __host__ __device__ constexpr uint32_t v2_planes_off(int rmax) {
-    return (uint32_t)((V2_OFF_SACC + 2 * 4 * 32 * rmax + 127) & ~127);
+    return (uint32_t)((V2_OFF_SACC + 3 * 4 * 32 * rmax + 127) & ~127);
 }
 
 // Byte pitch of a plane row: the SUB / 8 data bytes plus, for rows longer than one 16-byte vector,
@@ -92,7 +95,7 @@ __device__ __forceinline__ void v2_phase_a(uint32_t col_s, uint32_t pl_s, int nu
 
 // BMAX = byte columns the plane layout is dimensioned for (B <= BMAX).
 template <int NW, int SUB, int BMAX, int RMAX>
-__global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 8 ? 3 : (RMAX <= 16 ? 2 : 1)) parity_kernel_v2(const ParityParams P) {
+__global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 8 ? 3 : 2) parity_kernel_v2(const ParityParams P) {
     constexpr int TS = NW * SUB;
     constexpr int CS = TS + 64;     // raw column stride: +64 B keeps quarter-warp LDS.128 conflict-free
     constexpr int V = SUB / 128;    // 128-shot vectors per plane row
@@ -202,12 +205,16 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 8 ? 3 : (RMAX <= 16 ? 2
     uint32_t acc[RMAX];
     // per register slot: weight-1 slots hold the shared-memory address of their plane row;
     // weight-2 slots hold the two plane-row offsets packed as a0 | a1 << 16
-    uint32_t dx[RMAX];
+    constexpr bool DXS = RMAX > 16;  // slot descriptors in shared memory instead of registers
+    uint32_t dx[DXS ? 1 : RMAX];
     constexpr uint32_t zero_row = (uint32_t)(8 * BMAX * RSTR);
     for (int i = lane; i < ROWB / 4; i += 32) sts32(planes_s + zero_row + 4 * i, 0u);
     __syncwarp();
 #pragma unroll
-    for (int r = 0; r < RMAX; ++r) { acc[r] = 0; dx[r] = 0; }
+    for (int r = 0; r < RMAX; ++r) {
+        acc[r] = 0;
+        if (!DXS) dx[r] = 0;
+    }
     // The Paulis of a slice are sorted by weight; lane l owns Paulis l, l+32, ... ("rounds").
     // Rounds [0,n1) hold only weight-1 Paulis, [n1,n12) only weight <= 2 (a missing second bit,
     // an identity Pauli or a lane past the end of the table points at the all-zero row),
@@ -220,6 +227,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 8 ? 3 : (RMAX <= 16 ? 2
     //   weight-1 rounds  -> slots [RMAX - n1, RMAX)                 round = slot - (RMAX - n1)
     int n1 = 0, n2 = 0, n4 = 0, ng = 0;
     const uint32_t s4_s = smem_s + v2_s4_off(RMAX) + 4u * (uint32_t)lane;
+    const uint32_t dx_s = smem_s + v2_dx_off(RMAX) + 4u * (uint32_t)lane;
     int R = 0;                        // rounds in use
     int E = 0;
     int cur_stream = -1;
@@ -296,7 +304,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 8 ? 3 : (RMAX <= 16 ? 2
                 if (w >= 3) a2 = row_off((uint32_t)__ldg(&pd->q[2]));
                 if (w >= 4) a3 = row_off((uint32_t)__ldg(&pd->q[3]));
             }
-            dx[sl] = (sl >= RMAX - n1) ? planes_s + a0 : (a0 | (a1 << 16));
+            if (DXS)  // every consumer warp writes the same table; weight-1 slots hold the row offset
+                sts32(dx_s + 128u * (uint32_t)sl, (sl >= RMAX - n1) ? a0 : (a0 | (a1 << 16)));
+            else
+                dx[sl] = (sl >= RMAX - n1) ? planes_s + a0 : (a0 | (a1 << 16));
             // every consumer warp writes the same table (same lane <-> Pauli assignment)
             if (sl >= n2 && sl < n2 + n4) sts32(s4_s + 128u * (uint32_t)sl, a2 | (a3 << 16));
         }
@@ -328,9 +339,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 8 ? 3 : (RMAX <= 16 ? 2
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_s + 8u * (uint32_t)stage) : "memory");
 
         if (any) {
+#define ACES_DX(SL) (DXS ? lds32(dx_s + 128u * (uint32_t)(SL)) : dx[DXS ? 0 : (SL)])
 #define ACES_W2(SL)                                                                          \
     {                                                                                        \
-        const uint32_t b0 = planes_s + (dx[SL] & 0xFFFFu), b1 = planes_s + (dx[SL] >> 16);   \
+        const uint32_t dxv = ACES_DX(SL);                                                    \
+        const uint32_t b0 = planes_s + (dxv & 0xFFFFu), b1 = planes_s + (dxv >> 16);         \
         uint32_t cnt = 0;                                                                    \
         _Pragma("unroll") for (int v = 0; v < V; ++v)                                        \
             cnt += popc4(xor4(lds128(b0 + 16 * v), lds128(b1 + 16 * v)));                    \
@@ -338,8 +351,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 8 ? 3 : (RMAX <= 16 ? 2
     }
 #define ACES_W1(SL)                                                                          \
     {                                                                                        \
+        const uint32_t b0 = DXS ? planes_s + ACES_DX(SL) : ACES_DX(SL);                      \
         uint32_t cnt = 0;                                                                    \
-        _Pragma("unroll") for (int v = 0; v < V; ++v) cnt += popc4(lds128(dx[SL] + 16 * v)); \
+        _Pragma("unroll") for (int v = 0; v < V; ++v) cnt += popc4(lds128(b0 + 16 * v));     \
         acc[SL] += cnt;                                                                      \
     }
 #define ACES_C2(K) case K: if constexpr (RMAX >= K) ACES_W2(K - 1) [[fallthrough]];
@@ -369,7 +383,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 8 ? 3 : (RMAX <= 16 ? 2
                 for (int sl = 0; sl < RMAX; ++sl) {
                     if (sl >= n2 && sl < n2 + n4) {
                         const uint32_t hi2 = lds32(s4_s + 128u * (uint32_t)sl);
-                        const uint32_t b0 = planes_s + (dx[sl] & 0xFFFFu), b1 = planes_s + (dx[sl] >> 16);
+                        const uint32_t dxv = ACES_DX(sl);
+                        const uint32_t b0 = planes_s + (dxv & 0xFFFFu), b1 = planes_s + (dxv >> 16);
                         const uint32_t b2 = planes_s + (hi2 & 0xFFFFu), b3 = planes_s + (hi2 >> 16);
                         uint32_t cnt = 0;
 #pragma unroll
@@ -411,6 +426,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 8 ? 3 : (RMAX <= 16 ? 2
         if (++stage == NS) { stage = 0; parity ^= 1u; }
     }
     change_stream(-1);
+#undef ACES_DX
 }
 
 struct V2Cfg {
@@ -440,15 +456,14 @@ inline bool v2_pick(int B, int max_E, int smem_optin, V2Cfg* cfg) {
     const size_t stage = (size_t)B * (NW * SUB + 64);
     const char* env_ns = getenv("ACES_K1_NS");
     const char* env_cta = getenv("ACES_K1_CTAS");
-    // resident CTAs per SM the register budget of the variant allows (launch bounds of the kernel)
-    const int want_ctas = env_cta ? atoi(env_cta) : (RMAX <= 8 ? 3 : (RMAX <= 16 ? 2 : 1));
-    const size_t budget = ((size_t)smem_optin + 1024) / (size_t)(want_ctas > 0 ? want_ctas : 1) - 1024;
+    // Resident CTAs per SM: what the register budget of the variant allows (launch bounds of the
+    // kernel), fewer when the shared memory of that many CTAs does not hold two stages each.
     int ns = 0;
-    for (int s = (env_ns ? atoi(env_ns) : 4); s >= 2; --s)
-        if (raw_off + s * stage <= budget) { ns = s; break; }
-    if (ns == 0)
-        for (int s = 4; s >= 2; --s)
-            if (raw_off + s * stage <= (size_t)smem_optin) { ns = s; break; }
+    for (int ctas = env_cta ? atoi(env_cta) : (RMAX <= 8 ? 3 : 2); ctas >= 1 && ns == 0; --ctas) {
+        const size_t budget = ((size_t)smem_optin + 1024) / (size_t)ctas - 1024;
+        for (int s = (env_ns ? atoi(env_ns) : 4); s >= 2; --s)
+            if (raw_off + s * stage <= budget) { ns = s; break; }
+    }
     if (ns == 0) return false;
     cfg->NW = NW;
     cfg->SUB = SUB;
