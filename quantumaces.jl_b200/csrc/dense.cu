@@ -46,15 +46,18 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-// One CTA computes the 128x128 tile (bm, bn) of C.  8 warps as 2 (m) x 4 (n), warp tile 64x32 =
-// 8x4 DMMA tiles; operands staged by cp.async in a 3-stage ring.
-template <bool A_KC, bool B_KC>
+// One CTA computes the BMT x 128 tile (bm, bn) of C (BMT = 128 or 64).  8 warps as 2 (m) x 4 (n),
+// warp tile (BMT/2) x 32 = (BMT/16) x 4 DMMA tiles; operands staged by cp.async in a 3-stage ring.
+// The 64-row variant doubles the number of CTAs of a launch: the skinny, short-K updates on the
+// critical path of the Cholesky (a 128-row tile with K = 128 occupies one SM for >= 15 us).
+template <bool A_KC, bool B_KC, int BMT>
 __device__ __forceinline__ void gemm_tile(const GemmP& p, const int bm, const int bn, double* sm) {
+    constexpr int MI = BMT / 16;  // DMMA tiles per warp along m
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+    const int wm = (warp & 1) * (BMT / 2), wn = (warp >> 1) * 32;
     // A_KC: op(A)(i,k) = A[k + i*lda]; else A[i + k*lda].  Same for B with (j,k).
-    const double* Ag = A_KC ? p.A + (int64_t)bm * BM * p.lda : p.A + (int64_t)bm * BM;
+    const double* Ag = A_KC ? p.A + (int64_t)bm * BMT * p.lda : p.A + (int64_t)bm * BMT;
     const double* Bg = B_KC ? p.B + (int64_t)bn * BN * p.ldb : p.B + (int64_t)bn * BN;
     const int nk = p.k / BK;
 
@@ -63,14 +66,17 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const int bm, const in
         double* sB = sA + OPER_DOUBLES;
         const int k0 = kt * BK;
 #pragma unroll
-        for (int c = tid; c < 1024; c += GT) {
+        for (int c = tid; c < BMT * 8; c += GT) {
             if (!A_KC) {
-                const int kk = c >> 6, ci = c & 63;
+                const int kk = c / (BMT / 2), ci = c % (BMT / 2);
                 cp_async16(sA + kk * LD_MC + 2 * ci, Ag + 2 * ci + (int64_t)(k0 + kk) * p.lda);
             } else {
                 const int i = c >> 3, ck = c & 7;
                 cp_async16(sA + i * LD_KC + 2 * ck, Ag + (k0 + 2 * ck) + (int64_t)i * p.lda);
             }
+        }
+#pragma unroll
+        for (int c = tid; c < 1024; c += GT) {
             if (!B_KC) {
                 const int kk = c >> 6, ci = c & 63;
                 cp_async16(sB + kk * LD_MC + 2 * ci, Bg + 2 * ci + (int64_t)(k0 + kk) * p.ldb);
@@ -81,9 +87,9 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const int bm, const in
         }
     };
 
-    double acc[8][4][2];
+    double acc[MI][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
@@ -102,9 +108,9 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const int bm, const in
         const double* sB = sA + OPER_DOUBLES;
 #pragma unroll
         for (int k4 = 0; k4 < BK / 4; ++k4) {
-            double a[8], b[4];
+            double a[MI], b[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < MI; ++i)
                 a[i] = A_KC ? sA[(wm + i * 8 + g) * LD_KC + k4 * 4 + t]
                             : sA[(k4 * 4 + t) * LD_MC + wm + i * 8 + g];
 #pragma unroll
@@ -112,7 +118,7 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const int bm, const in
                 b[j] = B_KC ? sB[(wn + j * 8 + g) * LD_KC + k4 * 4 + t]
                             : sB[(k4 * 4 + t) * LD_MC + wn + j * 8 + g];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < MI; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
@@ -120,9 +126,9 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const int bm, const in
     cp_async_wait<0>();
 
     // epilogue: thread holds C[g][2t], C[g][2t+1] of every 8x8 tile
-    double* Cg = p.C + (int64_t)bm * BM + (int64_t)bn * BN * p.ldc;
+    double* Cg = p.C + (int64_t)bm * BMT + (int64_t)bn * BN * p.ldc;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int r = wm + i * 8 + g;
@@ -139,11 +145,12 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const int bm, const in
         }
 }
 
-template <bool A_KC, bool B_KC>
+template <bool A_KC, bool B_KC, int BMT>
 __global__ void __launch_bounds__(GT, 1) gemm_kernel(const GemmP p, const int lower_only) {
-    if (lower_only && blockIdx.y > blockIdx.x) return;
+    // lower_only: skip the tiles that lie entirely above the block diagonal
+    if (lower_only && (int)blockIdx.y * BN >= ((int)blockIdx.x + 1) * BMT) return;
     extern __shared__ __align__(16) double sm[];
-    gemm_tile<A_KC, B_KC>(p, blockIdx.x, blockIdx.y, sm);
+    gemm_tile<A_KC, B_KC, BMT>(p, blockIdx.x, blockIdx.y, sm);
 }
 
 template <bool A_KC, bool B_KC>
@@ -153,7 +160,7 @@ __global__ void __launch_bounds__(GT, 1) gemm_batched_kernel(const GemmDesc* __r
     if (d.k == 0 || bm >= d.tiles_m || bn >= d.tiles_n || (d.lower_only && bn > bm)) return;
     GemmP p{d.A, d.B, d.C, d.lda, d.ldb, d.ldc, d.k, d.alpha, d.beta};
     extern __shared__ __align__(16) double sm[];
-    gemm_tile<A_KC, B_KC>(p, bm, bn, sm);
+    gemm_tile<A_KC, B_KC, BM>(p, bm, bn, sm);
 }
 
 // ---- 128 x 128 diagonal block: Cholesky factor and its inverse, one CTA of 512 threads ---------
@@ -232,13 +239,14 @@ __device__ __forceinline__ void diag_block(const DiagDesc& d, const double rel_t
     }
     if (tid < DB) pfloor[tid] = d.diag0 ? rel_tol * fabs(d.diag0[tid]) : 0.0;
     __syncthreads();
-    for (int k0 = 0; k0 < DB; k0 += PW) {
-        // (a) 16 x 16 diagonal piece, one warp, rows in registers (lane i holds row i; lanes
-        //     16..31 mirror 0..15 so that every shuffle source is defined)
-        if (warp == 0 && diag16(s, rdiag, pfloor, k0, lane) && lane == 0 && d.flag) atomicCAS(d.flag, 0, d.code);
+    // Right-looking factorisation with look-ahead inside the CTA: after the panel rows of panel p
+    // are solved, all warps update the 16 columns of panel p+1 (c1); then warp 0 factorises the
+    // next 16 x 16 diagonal piece while warps 1..15 update the remaining trailing columns (c2).
+    bool bad = false;
+    if (warp == 0) bad = diag16(s, rdiag, pfloor, 0, lane);
+    for (int k0 = 0; k0 < DB - PW; k0 += PW) {
         __syncthreads();
         const int r0 = k0 + PW;  // first trailing row / column
-        if (r0 >= DB) break;
         // (b) panel rows: x * L_dd' = a, one thread per row
         if (tid < DB - r0) {
             const int i = r0 + tid;
@@ -256,37 +264,59 @@ __device__ __forceinline__ void diag_block(const DiagDesc& d, const double rel_t
             for (int c = 0; c < PW; ++c) s[(k0 + c) * PLD + i] = a[c];
         }
         __syncthreads();
-        // (c) trailing update: thread (tx, ty) owns rows tx + 32a, columns ty + 16b
+        // (c1) the columns of the next panel: thread t owns column r0 + (t & 15), rows r0 + (t >> 4) + 32a
         {
-            const int tx = lane, ty = warp;
+            const int j = r0 + (tid & (PW - 1)), ib = r0 + (tid >> 4);
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+            for (int k = 0; k < PW; ++k) {
+                const double* col = s + (k0 + k) * PLD;
+                const double cj = col[j];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+                    if (ib + 32 * a < DB) acc[a] += col[ib + 32 * a] * cj;
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int i = ib + 32 * a;
+                if (i < DB && i >= j) s[j * PLD + i] -= acc[a];
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            bad |= diag16(s, rdiag, pfloor, r0, lane);
+        } else if (r0 + PW < DB) {
+            // (c2) the columns behind the next panel: warp w owns columns c0 + 15 b, rows lane + 32 a
+            const int c0 = r0 + PW + (warp - 1);
             double acc[4][8];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+                for (int bq = 0; bq < 8; ++bq) acc[a][bq] = 0.0;
 #pragma unroll 4
             for (int k = 0; k < PW; ++k) {
                 const double* col = s + (k0 + k) * PLD;
                 double ra[4], cb[8];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) ra[a] = (32 * a + 31 >= r0) ? col[tx + 32 * a] : 0.0;
+                for (int a = 0; a < 4; ++a) ra[a] = (32 * a + 31 >= r0) ? col[lane + 32 * a] : 0.0;
 #pragma unroll
-                for (int b = 0; b < 8; ++b) cb[b] = (ty + 16 * b >= r0) ? col[ty + 16 * b] : 0.0;
+                for (int bq = 0; bq < 8; ++bq) cb[bq] = (c0 + 15 * bq < DB) ? col[c0 + 15 * bq] : 0.0;
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 8; ++b) acc[a][b] += ra[a] * cb[b];
+                    for (int bq = 0; bq < 8; ++bq) acc[a][bq] += ra[a] * cb[bq];
             }
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    const int i = tx + 32 * a, j = ty + 16 * b;
-                    if (j >= r0 && i >= j) s[j * PLD + i] -= acc[a][b];
+                for (int bq = 0; bq < 8; ++bq) {
+                    const int i = lane + 32 * a, j = c0 + 15 * bq;
+                    if (j < DB && i >= j) s[j * PLD + i] -= acc[a][bq];
                 }
         }
-        __syncthreads();
     }
+    if (warp == 0 && bad && lane == 0 && d.flag) atomicCAS(d.flag, 0, d.code);
+    __syncthreads();
     // L -> global (strict upper triangle zeroed)
     for (int e = tid; e < DB * DB; e += DIAG_THREADS) {
         const int i = e & (DB - 1), j = e >> 7;
@@ -604,9 +634,12 @@ int set_smem(aces_ctx* ctx, K kern, size_t bytes) {
 int configure(aces_ctx* ctx) {
     static bool done = false;
     if (done) return ACES_OK;
-    ACES_TRY(set_smem(ctx, gemm_kernel<false, false>, GEMM_SMEM));
-    ACES_TRY(set_smem(ctx, gemm_kernel<false, true>, GEMM_SMEM));
-    ACES_TRY(set_smem(ctx, gemm_kernel<true, true>, GEMM_SMEM));
+    ACES_TRY(set_smem(ctx, gemm_kernel<false, false, 128>, GEMM_SMEM));
+    ACES_TRY(set_smem(ctx, gemm_kernel<false, true, 128>, GEMM_SMEM));
+    ACES_TRY(set_smem(ctx, gemm_kernel<true, true, 128>, GEMM_SMEM));
+    ACES_TRY(set_smem(ctx, gemm_kernel<false, false, 64>, GEMM_SMEM));
+    ACES_TRY(set_smem(ctx, gemm_kernel<false, true, 64>, GEMM_SMEM));
+    ACES_TRY(set_smem(ctx, gemm_kernel<true, true, 64>, GEMM_SMEM));
     ACES_TRY(set_smem(ctx, gemm_batched_kernel<false, false>, GEMM_SMEM));
     ACES_TRY(set_smem(ctx, gemm_batched_kernel<false, true>, GEMM_SMEM));
     ACES_TRY(set_smem(ctx, gemm_batched_kernel<true, true>, GEMM_SMEM));
@@ -619,8 +652,16 @@ int configure(aces_ctx* ctx) {
 
 template <bool A_KC, bool B_KC>
 int launch_gemm(aces_ctx* ctx, const GemmP& p, int64_t m, int64_t n, int lower_only) {
-    dim3 grid((unsigned)(m / BM), (unsigned)(n / BN));
-    gemm_kernel<A_KC, B_KC><<<grid, GT, GEMM_SMEM, ctx->stream>>>(p, lower_only);
+    // 64-row tiles when 128-row tiles would leave most SMs idle or give a ragged second wave
+    const int64_t tiles128 = lower_only ? ((m / BM) * (n / BN) + std::min(m / BM, n / BN)) / 2 : (m / BM) * (n / BN);
+    // (not when C aliases B: an in-place B operand is only safe while one CTA owns all its rows)
+    if (tiles128 < 2 * (int64_t)ctx->sm_count && (const double*)p.C != p.B) {
+        dim3 grid((unsigned)(m / 64), (unsigned)(n / BN));
+        gemm_kernel<A_KC, B_KC, 64><<<grid, GT, GEMM_SMEM, ctx->stream>>>(p, lower_only);
+    } else {
+        dim3 grid((unsigned)(m / BM), (unsigned)(n / BN));
+        gemm_kernel<A_KC, B_KC, 128><<<grid, GT, GEMM_SMEM, ctx->stream>>>(p, lower_only);
+    }
     ACES_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return ACES_OK;
