@@ -222,10 +222,6 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
         P.n_streams = n_streams;
         P.B = B;
         P.NS = use_v2 ? cfg2.NS : cfg.NS;
-        {
-            const char* env_dbg = getenv("ACES_K1_DBG");
-            P.dbg = env_dbg ? atoi(env_dbg) : 0;
-        }
         const int ppt = max_E <= NT ? 1 : (max_E <= 2 * NT ? 2 : 4);
         int rc;
         if (use_v2) {

@@ -53,7 +53,6 @@ struct ParityParams {
     int32_t n_streams;
     int32_t B;
     int32_t NS;
-    int32_t dbg;  // development only: bit 0 skips phase A, bit 1 skips phase B
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -446,9 +446,7 @@ inline bool v2_pick(int B, int max_E, int smem_optin, V2Cfg* cfg) {
     else if (B <= 25) { SUB = 128; BMAX = 25; }
     else if (B <= 41) { SUB = 128; BMAX = 41; }
     else return false;
-    int NW = 8;
-    if (getenv("ACES_K1_NW4") && BMAX == 25) { NW = 4; SUB = 256; }  // experiment: wider warp tiles
-    if (getenv("ACES_K1_WIDE") && BMAX <= 13) SUB *= 2;                 // experiment: the previous choice
+    const int NW = 8;
     if ((8 * BMAX + 1) * v2_row_pitch(SUB) >= 65536) return false;  // plane-row offsets are packed in 16 bits
     const int RMAX = max_E <= 256 ? 8 : (max_E <= 512 ? 16 : 32);
     const size_t planes = (size_t)NW * (8 * BMAX + 1) * v2_row_pitch(SUB);
@@ -500,11 +498,9 @@ inline int v2_launch(aces_ctx* ctx, const ParityParams& P, const V2Cfg& cfg) {
     (cfg.RMAX == 8 ? v2_launch_t<8, SUBV, BMV, 8>(ctx, P, cfg)                           \
                    : cfg.RMAX == 16 ? v2_launch_t<8, SUBV, BMV, 16>(ctx, P, cfg)         \
                                     : v2_launch_t<8, SUBV, BMV, 32>(ctx, P, cfg))
-    if (cfg.NW == 4) return cfg.RMAX == 8 ? v2_launch_t<4, 256, 25, 8>(ctx, P, cfg) : cfg.RMAX == 16 ? v2_launch_t<4, 256, 25, 16>(ctx, P, cfg) : v2_launch_t<4, 256, 25, 32>(ctx, P, cfg);
     if (cfg.SUB == 128 && cfg.BMAX == 25) return ACES_V2_R(128, 25);
     if (cfg.SUB == 128 && cfg.BMAX == 41) return ACES_V2_R(128, 41);
     if (cfg.SUB == 128) return ACES_V2_R(128, 13);
-    if (cfg.SUB == 256 && cfg.BMAX == 13) return ACES_V2_R(256, 13);
     if (cfg.SUB == 256) return ACES_V2_R(256, 7);
     return ACES_V2_R(512, 7);
 #undef ACES_V2_R
