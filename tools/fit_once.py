@@ -8,7 +8,7 @@ import aces_b200
 from fit_util import fo, noisy_ensembles
 d = int(sys.argv[1]) if len(sys.argv) > 1 else 9
 fd = aces_b200.synthetic_design("rotated", d, full_covariance=True, with_matrix=True)
-eig, cov = noisy_ensembles(fd, seed=3)
+eig, cov = noisy_ensembles(fd, seed=11)
 lam = np.concatenate(fo.mean_ensemble(eig))
 cl = fo.calc_covariance_log(fo.calc_covariance_from_experiments(fd, eig, cov, weight_time=False), lam)
 F = fo.sparse_covariance_inv_factor(cl, fd.mapping_lengths)
