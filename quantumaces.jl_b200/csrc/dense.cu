@@ -175,6 +175,17 @@ constexpr int PW = 16;
 constexpr int DIAG_THREADS = 512;
 constexpr size_t DIAG_SMEM = (size_t)(DB * PLD + PW * PLD + 2 * DB) * sizeof(double);
 
+// 1 / d to full precision without the division subroutine: hardware seed (about 20 bits) and two
+// Newton steps.  d is a pivot that already passed the positivity test.
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    return fma(r, e, r);
+}
+
 // Cholesky of the 16 x 16 piece at (k0, k0) of the shared-memory block by ONE warp, rows in
 // registers (lane i holds row i; lanes 16..31 mirror 0..15 so that every shuffle source is
 // defined).  Kept out of line so that its registers are allocated separately from the caller's
@@ -197,7 +208,7 @@ __device__ __noinline__ bool diag16(double* s, double* rdiag, const double* pflo
             dkk = 1.0;
         }
         if (li == k) dmine = dkk;
-        const double tk = a[k] * (1.0 / dkk);  // a_ik / d_k
+        const double tk = a[k] * fast_rcp(dkk);  // a_ik / d_k
 #pragma unroll
         for (int j = k + 1; j < PW; ++j) {
             const double ajk = __shfl_sync(0xffffffffu, a[k], j);
