@@ -37,17 +37,34 @@
 using namespace k1;
 
 
+// A column group: the Paulis of one experiment whose supports lie in a set of at most
+// GROUP_COLS byte columns, at most GROUP_PAULIS of them.  One group = one kernel stream that
+// reads only its columns (the producer issues one bulk copy per column anyway) and evaluates its
+// Paulis on LOCAL record bits 8 * (local column) + bit.  Narrow experiments are one group over
+// all columns; wide records (d = 17: 73 byte columns) and large experiments split into several,
+// so that every stream runs the best-tuned kernel variant (<= 25 columns, 8 rounds of 32 Paulis).
+constexpr int GROUP_COLS = 25;
+constexpr int GROUP_PAULIS = 256;
+
+struct ColGroup {
+    int64_t pauli_off;  // first PauliDesc (device order: by weight)
+    int32_t E;
+    int32_t cols_off, ncols;
+};
+
 struct aces_tables {
     int32_t n_qubits = 0;
     int32_t B = 0;
     int32_t n_experiments = 0;
     int32_t max_E = 0;
-    std::vector<int64_t> exp_ptr;  // host copy: Paulis of experiment e
-    std::vector<int32_t> dev_E;    // Paulis of experiment e the kernel evaluates (identity Paulis,
-                                   // sorted last in the device order, always count 0 and are skipped)
-    int32_t max_dev_E = 0;
+    std::vector<int64_t> exp_ptr;    // host copy: Paulis of experiment e (caller order; sizes the outputs)
+    std::vector<int32_t> grp_ptr;    // groups of experiment e: groups[grp_ptr[e] .. grp_ptr[e+1])
+    std::vector<ColGroup> groups;    // identity Paulis (odd count always 0) belong to no group
+    int32_t max_group_E = 0, max_group_cols = 0;
+    bool grouped = false;            // false: one group per experiment over all columns, global bits
     PauliDesc* d_pauli = nullptr;
     int32_t* d_bits = nullptr;
+    int32_t* d_cols = nullptr;
 };
 
 static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
@@ -67,9 +84,9 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
     TileCfg cfg;
     V2Cfg cfg2;
     const char* env_impl = getenv("ACES_K1_IMPL");
-    const int slice_v2 = 1024;
-    const bool use_v2 = !(env_impl && atoi(env_impl) == 1) &&
-                        v2_pick(B, std::min(t->max_dev_E, slice_v2), ctx->smem_optin, &cfg2);
+    // the v2 kernel sizes its stages and planes for the widest column group of the tables
+    const bool use_v2 = !(env_impl && atoi(env_impl) == 1) && t->max_group_E <= 1024 &&
+                        v2_pick(std::max(t->max_group_cols, 1), std::max(t->max_group_E, 1), ctx->smem_optin, &cfg2);
     if (!use_v2 && !pick_tile(B, ctx->smem_optin, &cfg))
         return aces_fail(ctx, ACES_E_UNSUPPORTED,
                          "parity_counts: %d byte columns per shot exceed the shared-memory tiling", B);
@@ -116,15 +133,16 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
     const bool out_dev = async_only || aces_is_device_ptr(odd_counts);
 
     // ---- stream table: one entry per (item, non-empty budget segment, Pauli slice) -------------
-    // Paulis one pass can hold in registers (v2: 32 per lane; v1: 4 per thread)
-    const int slice = use_v2 ? slice_v2 : NT * 4;
+    // v1 (records wider than the v2 tiling, ungrouped tables only) holds 4 Paulis per thread
+    const int slice = use_v2 ? 1024 : NT * 4;
+    ACES_CHECK(ctx, use_v2 || !t->grouped, "parity_counts: grouped tables need the v2 kernel");
     std::vector<StreamDesc> streams;
     std::vector<int64_t> item_start(1, 0);
     if (arena_bytes > 0) ACES_TRY(aces_reserve_dev(ctx, ctx->d_arena, arena_bytes));
     for (int i = 0; i < n_items; ++i) {
         const int e = experiment_ids[i];
-        const int dev_E = t->dev_E[(size_t)e];
-        if (rows[i] == 0 || dev_E == 0) continue;
+        const int g0 = t->grp_ptr[(size_t)e], g1 = t->grp_ptr[(size_t)e + 1];
+        if (rows[i] == 0 || g0 == g1) continue;
         const uint8_t* base;
         int64_t ldd;
         if (in_place[i]) {
@@ -142,21 +160,26 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
         for (int k = 0; k < K; ++k) {
             const int64_t s = prefix_shots[(int64_t)i * K + k];
             if (s > prev) {
-                for (int p0 = 0; p0 < dev_E; p0 += slice) {
-                    StreamDesc sd;
-                    sd.base = base;
-                    sd.ld = ldd;
-                    sd.lo = prev;
-                    sd.hi = s;
-                    sd.copy_rows = (rows[i] + 15) & ~(int64_t)15;
-                    sd.tile_first = prev / TS;
-                    sd.out_off = item_off[i] + (int64_t)k * item_E[i];
-                    sd.pauli_off = t->exp_ptr[e] + p0;
-                    sd.E = std::min(slice, dev_E - p0);
-                    sd.pad = 0;
-                    const int64_t ntiles = (s - 1) / TS - prev / TS + 1;
-                    streams.push_back(sd);
-                    item_start.push_back(item_start.back() + ntiles);
+                for (int g = g0; g < g1; ++g) {
+                    const ColGroup& cg = t->groups[(size_t)g];
+                    for (int p0 = 0; p0 < cg.E; p0 += slice) {
+                        StreamDesc sd;
+                        sd.base = base;
+                        sd.ld = ldd;
+                        sd.lo = prev;
+                        sd.hi = s;
+                        sd.copy_rows = (rows[i] + 15) & ~(int64_t)15;
+                        sd.tile_first = prev / TS;
+                        sd.out_off = item_off[i] + (int64_t)k * item_E[i];
+                        sd.pauli_off = cg.pauli_off + p0;
+                        sd.E = std::min(slice, cg.E - p0);
+                        sd.ncols = cg.ncols;
+                        sd.cols_off = cg.cols_off;
+                        sd.pad = 0;
+                        const int64_t ntiles = (s - 1) / TS - prev / TS + 1;
+                        streams.push_back(sd);
+                        item_start.push_back(item_start.back() + ntiles);
+                    }
                 }
             }
             prev = s;
@@ -217,10 +240,11 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
         P.item_start = (const int64_t*)(ds + o_istart);
         P.pauli = t->d_pauli;
         P.bits = t->d_bits;
+        P.cols = t->d_cols;
         P.seg = (unsigned long long*)ctx->d_seg.ptr;
         P.total_items = total_items;
         P.n_streams = n_streams;
-        P.B = B;
+        P.B = use_v2 ? std::max(t->max_group_cols, 1) : B;
         P.NS = use_v2 ? cfg2.NS : cfg.NS;
         const int ppt = max_E <= NT ? 1 : (max_E <= 2 * NT ? 2 : 4);
         int rc;
@@ -290,22 +314,29 @@ int32_t aces_tables_create(aces_ctx* ctx, int32_t n_qubits, int32_t n_experiment
     ACES_CHECK(ctx, exp_ptr[0] == 0 && pauli_ptr[0] == 0, "tables_create: offsets must start at 0");
     ACES_CUDA(ctx, cudaSetDevice(ctx->device));
     const int64_t P = exp_ptr[n_experiments];
-    std::vector<PauliDesc> descs((size_t)P);
-    std::vector<int32_t> bits;
+    const int B = (n_qubits + 7) / 8;
+    std::vector<PauliDesc> descs;
+    descs.reserve((size_t)P);
+    std::vector<int32_t> bits, cols_all;
     bits.reserve((size_t)pauli_ptr[P] + 4);
-    int max_E = 0, max_dev_E = 0;
-    std::vector<int32_t> dev_E;
+    std::vector<ColGroup> groups;
+    std::vector<int32_t> grp_ptr(1, 0);
+    int max_E = 0, max_group_E = 0, max_group_cols = 0;
+
+    // ---- pass 1: supports reduced mod 2 (a bit listed twice cancels: the per-shot sum is reduced
+    // mod 2, src/estimate.jl:251) and the decision whether the tables are grouped ----------------
+    std::vector<std::vector<std::vector<int32_t>>> sups((size_t)n_experiments);
     std::vector<int32_t> sup;
-    std::vector<std::pair<int32_t, int32_t>> order;  // (weight, original index)
-    std::vector<std::vector<int32_t>> sups;
+    bool need_groups = B > 41;  // wider than the widest single-group kernel variant
+    bool groupable = true;      // every Pauli fits one group of GROUP_COLS columns
     for (int e = 0; e < n_experiments; ++e) {
         ACES_CHECK(ctx, exp_ptr[e + 1] >= exp_ptr[e], "tables_create: exp_ptr not monotone at %d", e);
         const int64_t p0 = exp_ptr[e], p1 = exp_ptr[e + 1];
         ACES_CHECK(ctx, p1 - p0 < (int64_t)1 << 30, "tables_create: experiment %d too large", e);
         const int E = (int)(p1 - p0);
         max_E = std::max(max_E, E);
-        order.clear();
-        sups.assign((size_t)E, std::vector<int32_t>());
+        sups[(size_t)e].assign((size_t)E, std::vector<int32_t>());
+        int n_dev = 0;
         for (int p = 0; p < E; ++p) {
             const int64_t b0 = pauli_ptr[p0 + p], b1 = pauli_ptr[p0 + p + 1];
             ACES_CHECK(ctx, b1 >= b0, "tables_create: pauli_ptr not monotone at %lld", (long long)(p0 + p));
@@ -313,54 +344,124 @@ int32_t aces_tables_create(aces_ctx* ctx, int32_t n_qubits, int32_t n_experiment
             for (int32_t b : sup)
                 ACES_CHECK(ctx, b >= 0 && b < n_qubits, "tables_create: record bit %d out of range [0,%d)", b, n_qubits);
             std::sort(sup.begin(), sup.end());
-            // a bit listed twice cancels: the per-shot sum is reduced mod 2 (src/estimate.jl:251)
-            std::vector<int32_t>& red = sups[(size_t)p];
+            std::vector<int32_t>& red = sups[(size_t)e][(size_t)p];
             for (size_t i = 0; i < sup.size();) {
                 size_t j = i;
                 while (j < sup.size() && sup[j] == sup[i]) ++j;
                 if ((j - i) & 1) red.push_back(sup[i]);
                 i = j;
             }
-            // identity Paulis (empty support: their odd count is 0) sort last, so that the weight-1
-            // prefix of the device order is not broken by them
-            order.push_back({red.empty() ? INT32_MAX : (int32_t)red.size(), p});
+            if (!red.empty()) {
+                ++n_dev;
+                int ncol = 1;
+                for (size_t i = 1; i < red.size(); ++i) ncol += (red[i] >> 3) != (red[i - 1] >> 3);
+                if (ncol > GROUP_COLS) groupable = false;
+            }
         }
-        // device order: by weight, so that the lanes of a warp run the same number of plane loads
-        std::stable_sort(order.begin(), order.end(),
-                         [](const std::pair<int32_t, int32_t>& a, const std::pair<int32_t, int32_t>& b) {
-                             return a.first < b.first;
-                         });
-        int n_dev = 0;
-        for (int r = 0; r < E; ++r) {
-            const int p = order[(size_t)r].second;
-            const std::vector<int32_t>& red = sups[(size_t)p];
-            if (!red.empty()) n_dev = r + 1;
-            PauliDesc& d = descs[(size_t)(p0 + r)];
+        if (n_dev > GROUP_PAULIS) need_groups = true;
+    }
+    const bool grouped = need_groups && groupable;
+
+    // ---- pass 2: groups, device order (by weight inside a group), local bits -------------------
+    std::vector<int> members, local_col((size_t)B, -1);
+    std::vector<std::pair<int32_t, int32_t>> order;  // (sort key, original index)
+    auto emit_group = [&](int e, const std::vector<int>& mem, const std::vector<int32_t>& gcols) -> int {
+        (void)e;
+        ColGroup cg;
+        cg.pauli_off = (int64_t)descs.size();
+        cg.E = (int32_t)mem.size();
+        cg.cols_off = (int32_t)cols_all.size();
+        cg.ncols = (int32_t)gcols.size();
+        for (size_t c = 0; c < gcols.size(); ++c) local_col[(size_t)gcols[c]] = (int)c;
+        cols_all.insert(cols_all.end(), gcols.begin(), gcols.end());
+        std::vector<std::pair<int32_t, int32_t>> byw;
+        for (int p : mem) byw.push_back({(int32_t)sups[(size_t)e][(size_t)p].size(), p});
+        // by weight, so that the lanes of a warp run the same number of plane loads
+        std::stable_sort(byw.begin(), byw.end(),
+                         [](const std::pair<int32_t, int32_t>& x, const std::pair<int32_t, int32_t>& y) { return x.first < y.first; });
+        for (const auto& wp : byw) {
+            const std::vector<int32_t>& red = sups[(size_t)e][(size_t)wp.second];
+            PauliDesc d;
             d.w = (int32_t)red.size();
             d.ext = (int32_t)bits.size();
-            d.orig = p;
+            d.orig = wp.second;
             d.pad = 0;
-            for (int i = 0; i < 4; ++i) d.q[i] = i < d.w ? red[(size_t)i] : 0;
-            ACES_CHECK(ctx, bits.size() + red.size() < ((size_t)1 << 31), "tables_create: table too large");
-            bits.insert(bits.end(), red.begin(), red.end());
+            for (int i = 0; i < 4; ++i) d.q[i] = 0;
+            for (size_t i = 0; i < red.size(); ++i) {
+                const int32_t lb = 8 * local_col[(size_t)(red[i] >> 3)] + (red[i] & 7);
+                if (i < 4) d.q[i] = lb;
+                bits.push_back(lb);
+            }
+            if (bits.size() >= ((size_t)1 << 31)) return ACES_E_INVALID;
+            descs.push_back(d);
         }
-        dev_E.push_back(n_dev);
-        max_dev_E = std::max(max_dev_E, n_dev);
+        max_group_E = std::max(max_group_E, cg.E);
+        max_group_cols = std::max(max_group_cols, cg.ncols);
+        groups.push_back(cg);
+        return ACES_OK;
+    };
+    for (int e = 0; e < n_experiments; ++e) {
+        const int E = (int)sups[(size_t)e].size();
+        members.clear();
+        for (int p = 0; p < E; ++p)
+            if (!sups[(size_t)e][(size_t)p].empty()) members.push_back(p);
+        if (!members.empty()) {
+            if (!grouped) {
+                // one group over all byte columns: local bits are the record bits
+                std::vector<int32_t> all((size_t)B);
+                for (int c = 0; c < B; ++c) all[(size_t)c] = c;
+                ACES_CHECK(ctx, emit_group(e, members, all) == ACES_OK, "tables_create: table too large");
+            } else {
+                // Paulis in the order of their first column; a group closes when the next Pauli would
+                // push it past GROUP_COLS columns or past its share of the Paulis (equal shares, so
+                // that no group is left with a handful of Paulis)
+                std::stable_sort(members.begin(), members.end(), [&](int x, int y) {
+                    return sups[(size_t)e][(size_t)x].front() < sups[(size_t)e][(size_t)y].front();
+                });
+                const int n_by_count = ((int)members.size() + GROUP_PAULIS - 1) / GROUP_PAULIS;
+                const int share = ((int)members.size() + n_by_count - 1) / n_by_count;
+                std::vector<int> cur;
+                std::vector<int32_t> gcols;
+                for (int p : members) {
+                    std::vector<int32_t> merged = gcols;
+                    for (int32_t q : sups[(size_t)e][(size_t)p]) merged.push_back(q >> 3);
+                    std::sort(merged.begin(), merged.end());
+                    merged.erase(std::unique(merged.begin(), merged.end()), merged.end());
+                    if (!cur.empty() && ((int)merged.size() > GROUP_COLS || (int)cur.size() >= share)) {
+                        ACES_CHECK(ctx, emit_group(e, cur, gcols) == ACES_OK, "tables_create: table too large");
+                        cur.clear();
+                        merged.clear();
+                        for (int32_t q : sups[(size_t)e][(size_t)p]) merged.push_back(q >> 3);
+                        std::sort(merged.begin(), merged.end());
+                        merged.erase(std::unique(merged.begin(), merged.end()), merged.end());
+                    }
+                    cur.push_back(p);
+                    gcols.swap(merged);
+                }
+                if (!cur.empty()) ACES_CHECK(ctx, emit_group(e, cur, gcols) == ACES_OK, "tables_create: table too large");
+            }
+        }
+        grp_ptr.push_back((int32_t)groups.size());
     }
     aces_tables* t = new aces_tables();
-    t->dev_E = dev_E;
-    t->max_dev_E = max_dev_E;
     t->n_qubits = n_qubits;
-    t->B = (n_qubits + 7) / 8;
+    t->B = B;
     t->n_experiments = n_experiments;
     t->max_E = max_E;
     t->exp_ptr.assign(exp_ptr, exp_ptr + n_experiments + 1);
+    t->grp_ptr = grp_ptr;
+    t->groups = groups;
+    t->max_group_E = max_group_E;
+    t->max_group_cols = max_group_cols;
+    t->grouped = grouped;
     cudaError_t e1 = cudaMalloc(&t->d_pauli, sizeof(PauliDesc) * std::max<size_t>(descs.size(), 1));
     cudaError_t e2 = cudaMalloc(&t->d_bits, sizeof(int32_t) * std::max<size_t>(bits.size(), 1));
-    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    cudaError_t e3 = cudaMalloc(&t->d_cols, sizeof(int32_t) * std::max<size_t>(cols_all.size(), 1));
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
         cudaGetLastError();
         if (t->d_pauli) cudaFree(t->d_pauli);
         if (t->d_bits) cudaFree(t->d_bits);
+        if (t->d_cols) cudaFree(t->d_cols);
         delete t;
         return aces_fail(ctx, ACES_E_NOMEM, "tables_create: cudaMalloc failed");
     }
@@ -369,6 +470,9 @@ int32_t aces_tables_create(aces_ctx* ctx, int32_t n_qubits, int32_t n_experiment
                                   cudaMemcpyHostToDevice));
     if (!bits.empty())
         ACES_CUDA(ctx, cudaMemcpy(t->d_bits, bits.data(), sizeof(int32_t) * bits.size(),
+                                  cudaMemcpyHostToDevice));
+    if (!cols_all.empty())
+        ACES_CUDA(ctx, cudaMemcpy(t->d_cols, cols_all.data(), sizeof(int32_t) * cols_all.size(),
                                   cudaMemcpyHostToDevice));
     *out = t;
     return ACES_OK;
@@ -381,6 +485,7 @@ int32_t aces_tables_destroy(aces_ctx* ctx, aces_tables* t) {
     ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (t->d_pauli) cudaFree(t->d_pauli);
     if (t->d_bits) cudaFree(t->d_bits);
+    if (t->d_cols) cudaFree(t->d_cols);
     delete t;
     return ACES_OK;
 }

@@ -25,8 +25,10 @@ struct StreamDesc {
     int64_t copy_rows;    // rows rounded up to 16: limit for bulk-copy sizes
     int64_t tile_first;   // lo / TS
     int64_t out_off;      // seg[out_off + orig] accumulates this stream's counts
-    int64_t pauli_off;    // first PauliDesc of this slice
-    int32_t E;            // Paulis in this slice
+    int64_t pauli_off;    // first PauliDesc of this column group
+    int32_t E;            // Paulis in this group
+    int32_t ncols;        // byte columns the group reads (the kernel's local column 0 .. ncols-1)
+    int32_t cols_off;     // their global column numbers: ParityParams::cols[cols_off .. cols_off+ncols)
     int32_t pad;
 };
 
@@ -39,7 +41,8 @@ struct ItemDesc {  // lives in shared memory, one per pipeline stage
     const uint8_t* src;
     int64_t ld;
     uint32_t bytes;
-    uint32_t pad[7];
+    int32_t ncols, cols_off;
+    uint32_t pad[5];
 };
 static_assert(sizeof(ItemDesc) == 64, "ItemDesc must fill its 64-byte slot (128-bit shared loads)");
 
@@ -48,10 +51,11 @@ struct ParityParams {
     const int64_t* item_start;  // [n_streams + 1]
     const PauliDesc* pauli;
     const int32_t* bits;
+    const int32_t* cols;        // column lists of the column groups
     unsigned long long* seg;
     int64_t total_items;
     int32_t n_streams;
-    int32_t B;
+    int32_t B;                  // most byte columns any stream reads (sizes the raw stages)
     int32_t NS;
 };
 

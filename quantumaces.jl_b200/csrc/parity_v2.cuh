@@ -176,15 +176,21 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 8 ? 3 : 2) parity_kerne
                 d->src = sd.base + r0;
                 d->ld = sd.ld;
                 d->bytes = bytes;
-                mbar_arrive_expect_tx(&full[stage], bytes * (uint32_t)B);
+                d->ncols = sd.ncols;
+                d->cols_off = sd.cols_off;
+                mbar_arrive_expect_tx(&full[stage], bytes * (uint32_t)sd.ncols);
             }
             __syncwarp();
             const uint8_t* src = d->src;
             const int64_t ld = d->ld;
             const uint32_t bytes = d->bytes;
+            const int ncols = d->ncols;
+            const int32_t* cols = P.cols + d->cols_off;
             uint8_t* dst = smem + raw_off + (size_t)stage * stage_bytes;
-            for (int c = lane; c < B; c += 32)
-                bulk_g2s(dst + c * CS, src + (int64_t)c * ld, bytes, &full[stage], policy);
+            // one bulk copy per byte column of the stream's column group (local column c holds
+            // global column cols[c] of the sample matrix)
+            for (int c = lane; c < ncols; c += 32)
+                bulk_g2s(dst + c * CS, src + (int64_t)__ldg(cols + c) * ld, bytes, &full[stage], policy);
             if (++stage == NS) { stage = 0; parity ^= 1u; }
         }
         return;
@@ -197,7 +203,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 8 ? 3 : 2) parity_kerne
     constexpr int UPS_ = SUB / 32;
     uint32_t raw_s = smem_s + raw_off + (uint32_t)(warp * SUB) + (uint32_t)((lane / UPS_) * CS + 16 * (lane % UPS_));
     uint32_t pl_lane = planes_s + (uint32_t)((lane / UPS_) * RSTR + 4 * (lane % UPS_)), lane_r = (uint32_t)lane;
-    const int nunits = B * UPS_;
+    int nunits = 0;  // 32-shot units per sub-tile of the current stream: its columns x UPS
     // keep the loop invariants in registers (the compiler would otherwise rematerialise them from
     // the special registers every tile)
     asm volatile("" : "+r"(planes_s), "+r"(empty_s), "+r"(full_s), "+r"(raw_s), "+r"(lane_r), "+r"(pl_lane));
@@ -271,6 +277,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 8 ? 3 : 2) parity_kerne
         cur_out = sd->out_off;
         cur_poff = sd->pauli_off;
         E = sd->E;
+        nunits = sd->ncols * UPS_;
         R = (E + 31) >> 5;
         // pass 1: classify the rounds (the table is sorted by weight: classes are prefixes)
         int c1 = 0, c12 = 0, c14 = 0;
