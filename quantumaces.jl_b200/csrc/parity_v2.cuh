@@ -272,9 +272,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 8 ? 3 : 2) parity_kerne
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
         if (ns < 0 || ns == cur_stream) return;
-        cur_stream = ns;
         const StreamDesc* sd = &P.streams[ns];
         cur_out = sd->out_off;
+        // the next budget segment of the same matrix and column group keeps the Pauli slots: only
+        // the output block changes
+        const bool same_paulis = cur_stream >= 0 && sd->pauli_off == cur_poff && sd->E == E &&
+                                 sd->ncols * UPS_ == nunits;
+        cur_stream = ns;
+        if (same_paulis) return;
         cur_poff = sd->pauli_off;
         E = sd->E;
         nunits = sd->ncols * UPS_;
