@@ -91,6 +91,11 @@ int32_t aces_tables_create(aces_ctx* ctx, int32_t n_qubits, int32_t n_experiment
                            const int64_t* exp_ptr, const int64_t* pauli_ptr,
                            const int32_t* pauli_bits, aces_tables** out);
 int32_t aces_tables_destroy(aces_ctx* ctx, aces_tables* tables);
+/* Byte columns the kernel reads per shot of `experiment`: the sum over its column groups (an
+ * experiment whose Paulis fit one kernel pass is one group over all ceil(n_qubits / 8) columns;
+ * wide records and large experiments are split into groups that read only the columns their
+ * Paulis touch, a column shared by two groups being read twice).  Bookkeeping for the roofline. */
+int64_t aces_tables_group_columns(const aces_tables* tables, int32_t experiment);
 
 /* Odd-parity counts of a batch of sample matrices in ONE kernel launch.
  *

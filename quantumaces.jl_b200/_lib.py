@@ -53,6 +53,7 @@ SIGNATURES = {
     "aces_last_kernel_ms": (_i32, [_vp, _p(C.c_float)]),
     "aces_tables_create": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _p(_vp)]),
     "aces_tables_destroy": (_i32, [_vp, _vp]),
+    "aces_tables_group_columns": (_i64, [_vp, _i32]),
     "aces_parity_counts": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32]),
     "aces_parity_counts_async": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32]),
     "aces_estimate_experiment": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
@@ -192,6 +193,10 @@ class PauliTables:
 
     def experiment_size(self, e: int) -> int:
         return int(self.exp_ptr[e + 1] - self.exp_ptr[e])
+
+    def columns_read(self, e: int) -> int:
+        """Byte columns the kernel reads per shot of experiment e (aces_tables_group_columns)."""
+        return int(self.ctx.lib.aces_tables_group_columns(self.handle, int(e)))
 
     def close(self) -> None:
         if getattr(self, "handle", None) and self.ctx.handle:

@@ -374,11 +374,18 @@ int32_t aces_tables_create(aces_ctx* ctx, int32_t n_qubits, int32_t n_experiment
         cg.ncols = (int32_t)gcols.size();
         for (size_t c = 0; c < gcols.size(); ++c) local_col[(size_t)gcols[c]] = (int)c;
         cols_all.insert(cols_all.end(), gcols.begin(), gcols.end());
-        std::vector<std::pair<int32_t, int32_t>> byw;
-        for (int p : mem) byw.push_back({(int32_t)sups[(size_t)e][(size_t)p].size(), p});
-        // by weight, so that the lanes of a warp run the same number of plane loads
-        std::stable_sort(byw.begin(), byw.end(),
-                         [](const std::pair<int32_t, int32_t>& x, const std::pair<int32_t, int32_t>& y) { return x.first < y.first; });
+        // Device order: by weight, so that the lanes of a warp run the same number of plane loads,
+        // and inside a weight class by the plane row of the first bit (bit-major rows, see
+        // parity_v2.cuh): eight neighbouring lanes then load eight consecutive plane rows, which
+        // the odd row pitch spreads over all shared-memory banks.
+        std::vector<std::pair<int64_t, int32_t>> byw;
+        for (int p : mem) {
+            const std::vector<int32_t>& red = sups[(size_t)e][(size_t)p];
+            const int32_t lb = 8 * local_col[(size_t)(red.front() >> 3)] + (red.front() & 7);
+            const int64_t row = (int64_t)(lb & 7) * 64 + (lb >> 3);  // 64 >= any BMAX: same order
+            byw.push_back({((int64_t)red.size() << 32) | row, p});
+        }
+        std::sort(byw.begin(), byw.end());
         for (const auto& wp : byw) {
             const std::vector<int32_t>& red = sups[(size_t)e][(size_t)wp.second];
             PauliDesc d;
@@ -476,6 +483,13 @@ int32_t aces_tables_create(aces_ctx* ctx, int32_t n_qubits, int32_t n_experiment
                                   cudaMemcpyHostToDevice));
     *out = t;
     return ACES_OK;
+}
+
+int64_t aces_tables_group_columns(const aces_tables* t, int32_t experiment) {
+    if (!t || experiment < 0 || experiment >= t->n_experiments) return -1;
+    int64_t n = 0;
+    for (int g = t->grp_ptr[(size_t)experiment]; g < t->grp_ptr[(size_t)experiment + 1]; ++g) n += t->groups[(size_t)g].ncols;
+    return n;
 }
 
 int32_t aces_tables_destroy(aces_ctx* ctx, aces_tables* t) {

@@ -197,8 +197,12 @@ def synthetic_design(
     meas_indices, signs, experiments = [], [], []
     for t in range(T):
         sup_t = []
+        cls_len = max(int(m_t[t]) // int(X[t]), 1)
         for p in range(int(m_t[t])):
-            r = p // int(X[t])
+            # Position of the Pauli on the qubit line: class c = p mod X_t starts where class c-1
+            # ends, so that an experiment (its own class plus the start of the next one) walks
+            # over every qubit: weight 1 on each qubit, weight 2 on the disjoint neighbour pairs.
+            r = (p // int(X[t]) + (p % int(X[t])) * cls_len) % E_target
             if r % 3 == 2:
                 k = (r // 3) % max(n // 2, 1)
                 sup = [2 * k + 1, min(2 * k + 2, n)]
@@ -212,12 +216,23 @@ def synthetic_design(
             sup_t.append(np.asarray(sup, dtype=np.int64))
         meas_indices.append(sup_t)
         signs.append(rng.integers(0, 2, size=int(m_t[t])).astype(bool))
+        # Experiment j measures its own class and, like the reference's greedy packing that re-adds
+        # compatible Paulis of other experiments (src/design.jl:745-767), Paulis of the other classes
+        # at the line positions its own class does not reach: E_target Paulis, every qubit touched.
+        pos = (np.arange(int(m_t[t])) // int(X[t]) + (np.arange(int(m_t[t])) % int(X[t])) * cls_len) % E_target
         exps = []
         for j in range(int(X[t])):
-            own = np.arange(j, int(m_t[t]), int(X[t]), dtype=np.int64)
-            nxt = np.arange((j + 1) % int(X[t]), int(m_t[t]), int(X[t]), dtype=np.int64)
-            extra = nxt[: max(E_target - len(own), 0)]
-            exps.append(np.sort(np.concatenate([own[:E_target], extra])))
+            own = np.arange(j, int(m_t[t]), int(X[t]), dtype=np.int64)[:E_target]
+            have = np.zeros(E_target, dtype=bool)
+            have[pos[own]] = True
+            extra = []
+            for p in range(int(m_t[t])):
+                if len(own) + len(extra) >= E_target:
+                    break
+                if p % int(X[t]) != j and not have[pos[p]]:
+                    have[pos[p]] = True
+                    extra.append(p)
+            exps.append(np.sort(np.concatenate([own, np.asarray(extra, dtype=np.int64)])))
         experiments.append(exps)
     w_t = X / X.sum()
     fd = FlatDesign(
@@ -244,12 +259,16 @@ def synthetic_design(
         fd.cov_keys, fd.cov_meas_indices, fd.cov_signs, fd.cov_counts = [], [], [], []
         for t in range(T):
             keyset = {}
+            cls_len_t = max(int(m_t[t]) // int(X[t]), 1)
             for exp in experiments[t]:
-                # pairs of Paulis measured together: neighbours in the sorted experiment
-                picks = rng.choice(len(exp) - 1, size=min(n_cov, len(exp) - 1), replace=False)
+                # pairs of Paulis measured together whose product is also estimated: neighbours on
+                # the qubit line (products of Paulis on adjacent qubits, as in a real design)
+                line = (exp // int(X[t]) + (exp % int(X[t])) * cls_len_t) % E_target
+                byline = exp[np.argsort(line, kind="stable")]
+                picks = rng.choice(len(byline) - 1, size=min(n_cov, len(byline) - 1), replace=False)
                 for i in np.sort(picks):
-                    a, b = int(exp[i]), int(exp[i + 1])
-                    keyset[(a, b)] = 0
+                    a, b = int(byline[i]), int(byline[i + 1])
+                    keyset[(min(a, b), max(a, b))] = 0
             keys = np.asarray(sorted(keyset.keys()), dtype=np.int64).reshape(-1, 2)
             fd.cov_keys.append(keys)
             cm, cs = [], []
@@ -335,11 +354,11 @@ def _attach_synthetic_matrix(fd: FlatDesign, N: int, rng) -> None:
             if len(keys):
                 Rp = Acsr[row0 + keys[:, 0]]
                 Rq = Acsr[row0 + keys[:, 1]]
-                # The extra gate of a pair is one whose error is at most a tenth of the smaller
+                # The extra gate of a pair is one whose error is at most a fiftieth of the smaller
                 # of the two variances 1 - lambda^2 (none if no gate is that clean): every
                 # covariance block is then diagonally dominant, hence positive definite.
                 var = 1.0 - lam[row0:row0 + int(m_t[t])] ** 2
-                thr = 0.1 * np.minimum(var[keys[:, 0]], var[keys[:, 1]])
+                thr = 0.02 * np.minimum(var[keys[:, 0]], var[keys[:, 1]])
                 n_ok = np.searchsorted(err_sorted, thr, side="right")
                 has = n_ok > 0
                 pick = np.maximum(n_ok - 1 - rng.integers(0, 50, size=len(keys)), 0)

@@ -34,6 +34,7 @@ for case in cases:
     sizes = est.experiment_sizes()
     out = torch.zeros(int(np.sum(sizes) * 3), dtype=torch.int64, device="cuda")
     nbytes = sum(rows[e] * B for e in range(n_exp))
+    rbytes = sum(rows[e] * est.tables.columns_read(e) for e in range(n_exp))  # what the kernel reads
     for _ in range(3):
         est.odd_counts(ptrs, rows, ld, prefix, out=out.data_ptr(), asynchronous=True)
     torch.cuda.synchronize()
@@ -45,7 +46,8 @@ for case in cases:
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    print(f"{case:24s} n={fd.n_qubits:4d} B={B:3d} E={int(sizes.max()):4d} bytes={nbytes / 1e9:6.2f} GB  {ms:8.3f} ms/step  "
-          f"{nbytes / ms / 1e6:8.1f} GB/s  ({100 * nbytes / ms / 1e6 / 6547.2:5.1f}% of measured HBM peak)", flush=True)
+    print(f"{case:24s} n={fd.n_qubits:4d} B={B:3d} E={int(sizes.max()):4d} matrix {nbytes / 1e9:6.2f} GB, read {rbytes / 1e9:6.2f} GB  "
+          f"{ms:8.3f} ms/step  {rbytes / ms / 1e6:8.1f} GB/s read ({100 * rbytes / ms / 1e6 / 6547.2:5.1f}% of measured HBM peak), "
+          f"{nbytes / ms / 1e6:8.1f} GB/s of matrix", flush=True)
     del dev, out, est
     torch.cuda.empty_cache()
