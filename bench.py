@@ -233,6 +233,38 @@ def fit_leg(ctx, torch, dist, world, rank, steps, warmup, with_cpu):
         out[f"{name}_fits_per_s"] = res[name][0]
         out[f"{name}_ms_per_fit"] = 1e3 * float(t.item()) / steps
     out["max_abs_error_vs_truth"] = float(np.max(np.abs(res["gls"][1] - fd.gate_eigenvalues)))
+    # Throughput with several fit contexts on this GPU: fits are independent per budget and repetition
+    # (src/simulate.jl:393) and one fit leaves most SMs idle (its Cholesky is a latency-bound chain),
+    # so concurrent contexts (own stream and workspaces each, one host thread each) overlap.
+    n_conc = 4
+    ctxs = [aces_b200.Context(ctx.device) for _ in range(n_conc - 1)]
+    dds = [dd] + [aces_b200.DeviceDesign(c, fd) for c in ctxs]
+    for name in ("gls", "wls"):
+        outs = [None] * n_conc
+
+        def work(i, n, name=name, outs=outs):
+            for _ in range(n):
+                outs[i] = dds[i].fit(name, lam, lc)
+
+        for n in (warmup, steps):
+            ths = [threading.Thread(target=work, args=(i, n)) for i in range(n_conc)]
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert all(np.array_equal(o, res[name][1]) for o in outs), "concurrent fits differ from the single-context fit"
+        out[f"{name}_fits_per_s_concurrent{n_conc}"] = world * n_conc * steps / float(t.item())
+    for x in dds[1:]:
+        x.close()
+    for c in ctxs:
+        c.close()
     # Gram kernel of the GLS fit on the FP64 tensor pipe (lower tiles of At' At)
     ctx.set_timing(True)
     ks, phases = [], {}
