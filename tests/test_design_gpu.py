@@ -239,3 +239,20 @@ def test_full_size_fit_properties(ctx, kind, d):
         assert N == len(wls)
     finally:
         dd.close()
+
+
+def test_phase_timings_are_reported(ctx):
+    import aces_b200
+
+    fd = aces_b200.synthetic_design("rotated", 3, full_covariance=True, with_matrix=True)
+    dd = aces_b200.DeviceDesign(ctx, fd)
+    eig, cov = noisy_ensembles(fd, seed=11)
+    lam = np.concatenate(aces_b200.mean_ensemble(eig))
+    lc = np.concatenate(aces_b200.mean_ensemble(cov))
+    ctx.set_timing(True)
+    dd.fit("gls", lam, lc)
+    ph = dd.phase_ms()
+    ctx.set_timing(False)
+    assert {"covariance", "block factor", "gram", "potrf", "first solve", "refinement"} <= set(ph)
+    assert all(v >= 0.0 for v in ph.values()) and dd.gram_flops() > 0
+    dd.close()

@@ -399,3 +399,18 @@ def test_shot_sharded_counts_add_up(ctx):
             pre.append(local)
         total += est.odd_counts(sub, rows, [max(r, 1) for r in rows], np.asarray(pre, dtype=np.int64))
     assert np.array_equal(total, whole)
+
+
+def test_column_groups_bookkeeping(ctx):
+    """Narrow experiments are one group over all byte columns; wide records (d = 17: 73 columns) are
+    split into groups that together read every column at least once."""
+    import aces_b200
+
+    for d, single in ((9, True), (17, False)):
+        fd = aces_b200.synthetic_design("rotated", d)
+        est = aces_b200.DesignEstimator(ctx, fd)
+        cols = [est.tables.columns_read(e) for e in range(fd.experiment_number)]
+        if single:
+            assert all(c == fd.n_bytes for c in cols)
+        else:
+            assert all(fd.n_bytes <= c <= 1.25 * fd.n_bytes for c in cols)
