@@ -414,3 +414,22 @@ def test_column_groups_bookkeeping(ctx):
             assert all(c == fd.n_bytes for c in cols)
         else:
             assert all(fd.n_bytes <= c <= 1.25 * fd.n_bytes for c in cols)
+
+
+def test_wide_record_with_ungroupable_pauli_uses_fallback_kernel(ctx):
+    """A Pauli whose support spans more than 25 byte columns of a record wider than 41 bytes cannot
+    be put into a column group: the tables stay ungrouped and the CTA-synchronous kernel runs."""
+    import aces_b200
+
+    n, rows = 577, 20_011
+    rng = np.random.default_rng(77)
+    B = (n + 7) // 8
+    counts = np.asfortranarray(rng.integers(0, 256, size=(rows, B), dtype=np.uint8))
+    sup = rand_supports(rng, n, 60)
+    sup[7] = sorted(int(8 * c + rng.integers(0, 8)) + 1 for c in range(0, 70, 2))  # 35 columns
+    sup[7] = [q for q in sup[7] if q <= n]
+    signs = rng.integers(0, 2, size=len(sup))
+    for S in (1, rows // 2, rows):
+        got = aces_b200.estimate_experiment(ctx, counts, sup, signs, S)
+        want, _ = ob.estimate_experiment(counts, sup, signs, S)
+        assert np.array_equal(got, want)
