@@ -8,6 +8,8 @@ from ._lib import AcesError, Context, NotPositiveDefinite, PauliTables  # noqa: 
 from .design import (  # noqa: F401
     FlatDesign, build_pauli_tables, shots_divide, synthetic_design, synthetic_estimates,
 )
+from . import circuit_design  # noqa: F401
+from .circuit_design import example_design, rotated_design, unrotated_design  # noqa: F401
 from .estimate import DesignEstimator, estimate_experiment  # noqa: F401
 from . import merit  # noqa: F401
 from . import shard  # noqa: F401

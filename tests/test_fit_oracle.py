@@ -13,8 +13,12 @@ def approx(x, y, rtol=np.sqrt(np.finfo(float).eps)):
     return np.linalg.norm(x - y) <= rtol * max(np.linalg.norm(x), np.linalg.norm(y))
 
 
-@pytest.fixture(scope="module")
-def design():
+@pytest.fixture(scope="module", params=["synthetic", "real"])
+def design(request):
+    """The synthetic look-alike and the real rotated d=3 design (circuit_design.py: the array
+    restatement of generate_design); both have M = 1248, N = 659."""
+    if request.param == "real":
+        return aces_b200.rotated_design(3, full_covariance=True)
     return aces_b200.synthetic_design("rotated", 3, full_covariance=True, with_matrix=True)
 
 
@@ -35,10 +39,13 @@ def test_covariance_closed_forms(design):
     assert cov[0, 0] == (1 / w) * (X / cd[0]) * 1e-10
     assert cov[1, 1] == (1 / w) * (X / cd[1]) * 1e-10
     assert cov[2, 2] == (1 / w) * (X / cd[2]) * max(1 - 0.9 ** 2, 1e-10)
-    p, q = fd.cov_keys[0][-1]
-    c = fd.cov_counts[0][-1]
+    t = next(t for t in range(fd.tuple_number) if len(fd.cov_keys[t]))   # first tuple with off-diagonal keys
+    off = int(np.sum(fd.mapping_lengths[:t]))
+    X, w, cd = fd.experiment_numbers[t], fd.shot_weights[t], fd.diag_counts[t]
+    p, q = fd.cov_keys[t][-1]
+    c = fd.cov_counts[t][-1]
     want = (1 / w) * ((X * c) / (cd[p] * cd[q])) * (0.83 - 0.9 * 0.9)
-    assert cov[p, q] == want and cov[q, p] == want
+    assert cov[off + p, off + q] == want and cov[off + q, off + p] == want
     tf = float(np.sum(fd.shot_weights * fd.tuple_times))
     assert np.allclose(fo.calc_covariance(fd, lam, lam12, weight_time=True).toarray(), tf * cov, rtol=1e-15)
 
