@@ -36,11 +36,18 @@ SHOTS_SET = [10**6, 10**7, 10**8]
 WORKLOAD = "rotated_d9_wls_1e8shots"
 
 
-def workload_config(n_gpus):
+DESIGN_SOURCE = "real"   # "real": circuit_design.rotated_design(9) (the reference's own tables); "synthetic": look-alike
+
+
+def workload_config(n_gpus, fd=None, sizes=None):
+    n_exp = int(fd.experiment_number) if fd is not None else 96
+    mean_paulis = float(sum(int(x) for x in sizes)) / n_exp if sizes is not None else None
     return {
         "workload": WORKLOAD,
         "baseline_config": "configs[2]: rotated surface code d=9, full_covariance=false WLS, 1e8 shots",
-        "n_qubits": 161, "bytes_per_shot": 21, "experiments": 96, "paulis_per_experiment": 241,
+        "design": ("generate_design of the rotated planar d=9 circuit restated in numpy (circuit_design.py): real Pauli "
+                   "tables, experiment packing and shot weights" if DESIGN_SOURCE == "real" else "synthetic look-alike tables"),
+        "n_qubits": 161, "bytes_per_shot": 21, "experiments": n_exp, "paulis_per_experiment_mean": mean_paulis,
         "budgets": SHOTS_SET, "repetitions_per_step": n_gpus,
         "l2": "inputs (2.1 GB per GPU) exceed the 126 MB L2; no flush needed",
         "parallelism": f"repetitions x{n_gpus}" if n_gpus > 1 else "single GPU",
@@ -123,12 +130,14 @@ class ClockSampler:
 def build_design():
     import aces_b200
 
+    if DESIGN_SOURCE == "real":
+        return aces_b200.rotated_design(9, full_covariance=False)
     return aces_b200.synthetic_design("rotated", 9, full_covariance=False)
 
 
 def cpu_sample(fd, est_sizes, seconds_target=12.0):
     """Times the CPU restatement of the reference on a bounded sample of the workload: one
-    experiment (241 Paulis, 3 budget passes as in src/simulate.jl:206-213) over `rows` shots."""
+    experiment at a time (its measured Paulis, 3 budget passes as in src/simulate.jl:206-213) over `rows` shots."""
     import numpy as np
     import oracle_bindings as ob
 
@@ -195,7 +204,10 @@ def fit_inputs():
 
     import aces_b200
 
-    fd = aces_b200.synthetic_design("rotated", 9, full_covariance=True, with_matrix=True)
+    if DESIGN_SOURCE == "real":
+        fd = aces_b200.rotated_design(9, full_covariance=True, noise="lognormal", seed=9)
+    else:
+        fd = aces_b200.synthetic_design("rotated", 9, full_covariance=True, with_matrix=True)
     eig, cov = aces_b200.synthetic_estimates(fd, shots=10**8, seed=11)
     lam = np.concatenate(aces_b200.mean_ensemble(eig))
     lc = np.concatenate(aces_b200.mean_ensemble(cov))
@@ -210,7 +222,7 @@ def fit_leg(ctx, torch, dist, world, rank, steps, warmup, with_cpu):
 
     fd, eig, cov, lam, lc = fit_inputs()
     dd = aces_b200.DeviceDesign(ctx, fd)
-    out = {"workload": "rotated_d9 GLS (full covariance pattern)", "M": int(fd.M), "N": int(fd.matrix.shape[1]),
+    out = {"workload": "rotated_d9 GLS (full covariance pattern)", "design": DESIGN_SOURCE, "M": int(fd.M), "N": int(fd.matrix.shape[1]),
            "tuples": int(fd.tuple_number), "covariance_keys": int(dd.C),
            "api": "aces_design_fit: host estimate vectors in, host gate eigenvalues out (H2D + D2H inside)"}
     res = {}
@@ -326,13 +338,15 @@ def run_reference(args):
         if i >= args.warmup:
             vals.append(base["value"])
     value = sum(vals) / len(vals)
-    step_units = 96 * 241 * 1_041_667
+    _, shots_max = aces_b200.shots_divide(fd, SHOTS_SET)
+    sizes = [len(e) for t in range(fd.tuple_number) for e in fd.experiment_ensemble[t]]
+    step_units = sum(len(e) * int(shots_max[t]) for t in range(fd.tuple_number) for e in fd.experiment_ensemble[t])
     base["value"] = value
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * step_units / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-        "data": "synthetic", "config": workload_config(args.gpus), "cpu_baseline": base,
+        "data": "synthetic", "config": workload_config(args.gpus, fd, sizes), "cpu_baseline": base,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -352,7 +366,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-fit", action="store_true")
     ap.add_argument("--fit-steps", type=int, default=5)
+    ap.add_argument("--design", default="real", choices=["real", "synthetic"])
     args = ap.parse_args()
+    global DESIGN_SOURCE
+    DESIGN_SOURCE = args.design
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
@@ -492,7 +509,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(world),
+            "config": workload_config(world, fd, sizes),
             "shots_per_s": world * shots / (ms_per_step * 1e-3),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT,

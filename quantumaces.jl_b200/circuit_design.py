@@ -599,33 +599,38 @@ def calc_experiment_set(ms: MappingSet, consistent: np.ndarray) -> List[np.ndarr
     L = sup.shape[0]
     weight = sup.sum(axis=1)
     total = np.argsort(-weight, kind="stable")
+    sup_t = sup[total].astype(np.int32)          # everything below is indexed by position in `total`
+    cons_t = consistent[np.ix_(total, total)]
     unadded = np.ones(L, dtype=bool)
     experiments = []
-    for first in total:
+    for first in range(L):
         if not unadded[first]:
             continue
         # `first` is the first unadded Pauli in the order `total`
-        experiment = [int(first)]
+        experiment = [first]
         unadded[first] = False
-        set_sup = sup[first].copy()
         in_exp = np.zeros(L, dtype=bool)
         in_exp[first] = True
+        set_sup = sup_t[first] > 0
+        overlap = sup_t[:, set_sup].sum(axis=1)   # |final support of candidate  n  support of the set|
+        compatible = cons_t[first].copy()         # consistent with every Pauli of the experiment
         for phase in (0, 1):
             # phase 0: unadded Paulis; phase 1: all Paulis not in the experiment
-            cand_mask = (unadded if phase == 0 else ~in_exp).copy()
-            for p in experiment:
-                cand_mask &= consistent[p]
-            cand = total[cand_mask[total]]
-            while len(cand):
-                overlap = (sup[cand] & set_sup).sum(axis=1)
-                best = cand[int(np.argmax(overlap))]
-                experiment.append(int(best))
+            while True:
+                cand = compatible & (unadded if phase == 0 else ~in_exp)
+                if not cand.any():
+                    break
+                best = int(np.argmax(np.where(cand, overlap, -1)))   # most overlap, first in order on ties
+                experiment.append(best)
                 in_exp[best] = True
                 if phase == 0:
                     unadded[best] = False
-                set_sup |= sup[best]
-                cand = cand[(cand != best) & consistent[best][cand]]
-        experiments.append(np.array(sorted(experiment), dtype=np.int64))
+                new = (sup_t[best] > 0) & ~set_sup
+                if new.any():
+                    overlap += sup_t[:, new].sum(axis=1)
+                    set_sup |= new
+                compatible &= cons_t[best]
+        experiments.append(np.sort(total[np.array(experiment, dtype=np.int64)]).astype(np.int64))
     return experiments
 
 
@@ -733,16 +738,26 @@ def generate_design(c: Circuit, tuple_set: Optional[List[List[int]]] = None, ful
     return fd
 
 
-def rotated_design(d: int, full_covariance: bool = True, **kw) -> FlatDesign:
+def _with_noise(c: Circuit, noise: str, seed: int, kw) -> Dict:
+    if noise == "lognormal":
+        kw = dict(kw, gate_eigenvalues=lognormal_gate_eigenvalues(c, seed=seed))
+    elif noise != "depolarising":
+        raise ValueError(f"unknown noise model {noise!r}")
+    return kw
+
+
+def rotated_design(d: int, full_covariance: bool = True, noise: str = "depolarising", seed: int = 0, **kw) -> FlatDesign:
+    """`generate_design(get_circuit(get_rotated_param(d), noise_param))` with the default tuple set."""
     circuit, layer_types, n, params = rotated_planar_circuit(d)
-    return generate_design(get_circuit(circuit, layer_types, n, params, name=f"rotated_planar_{d}_{d}"),
-                           full_covariance=full_covariance, **kw)
+    c = get_circuit(circuit, layer_types, n, params, name=f"rotated_planar_{d}_{d}")
+    return generate_design(c, full_covariance=full_covariance, **_with_noise(c, noise, seed, kw))
 
 
-def unrotated_design(d: int, full_covariance: bool = True, **kw) -> FlatDesign:
+def unrotated_design(d: int, full_covariance: bool = True, noise: str = "depolarising", seed: int = 0, **kw) -> FlatDesign:
+    """`generate_design(get_circuit(get_unrotated_param(d), noise_param))` with the default tuple set."""
     circuit, layer_types, n, params = unrotated_planar_circuit(d)
-    return generate_design(get_circuit(circuit, layer_types, n, params, name=f"unrotated_planar_{d}_{d}"),
-                           full_covariance=full_covariance, **kw)
+    c = get_circuit(circuit, layer_types, n, params, name=f"unrotated_planar_{d}_{d}")
+    return generate_design(c, full_covariance=full_covariance, **_with_noise(c, noise, seed, kw))
 
 
 def example_design(full_covariance: bool = True, **kw) -> FlatDesign:

@@ -22,12 +22,17 @@ def dense(m):
     return m.toarray() if sp.issparse(m) else np.asarray(m)
 
 
-@pytest.fixture(scope="module", params=[(3, True), (5, True), (3, False)], ids=["d3_gls", "d5_gls", "d3_diag"])
+@pytest.fixture(scope="module", params=[(3, True), (5, True), (3, False), ("real3", True), ("real5", True), ("unrot3", True)],
+                ids=["d3_gls", "d5_gls", "d3_diag", "real_d3_gls", "real_d5_gls", "real_unrotated_d3_gls"])
 def setup(request, ctx):
     import aces_b200
 
     d, full = request.param
-    fd = aces_b200.synthetic_design("rotated", d, full_covariance=full, with_matrix=True)
+    if isinstance(d, str):   # real designs (circuit_design.py): the reference's own A, keys and counts
+        kind, d = d.rstrip("0123456789"), int(d[-1])
+        fd = (aces_b200.rotated_design if kind == "real" else aces_b200.unrotated_design)(d, full_covariance=full)
+    else:
+        fd = aces_b200.synthetic_design("rotated", d, full_covariance=full, with_matrix=True)
     dd = aces_b200.DeviceDesign(ctx, fd)
     eig, cov = noisy_ensembles(fd, seed=7 + d)
     yield fd, dd, eig, cov
@@ -167,7 +172,9 @@ def test_not_positive_definite_block_is_reported(setup):
         pytest.skip("diagonal design")
     lam = np.concatenate(fo.mean_ensemble(eig))
     cl = sp.lil_matrix(fo.calc_covariance_log(fo.calc_covariance_from_experiments(fd, eig, cov, weight_time=False), lam))
-    p, q = (int(x) for x in fd.cov_keys[0][0])
+    t0 = next(t for t in range(fd.tuple_number) if len(fd.cov_keys[t]))   # first tuple with off-diagonal keys
+    r0 = int(np.sum(fd.mapping_lengths[:t0]))
+    p, q = (r0 + int(x) for x in fd.cov_keys[t0][0])
     big = 10.0 * max(cl[p, p], cl[q, q])
     cl[p, q] = big
     cl[q, p] = big
@@ -179,13 +186,14 @@ def test_not_positive_definite_block_is_reported(setup):
     F = dd.sparse_covariance_inv_factor(cl, epsilon=eps)
     assert dd.fallback_count() == 1
     Fo = fo.sparse_covariance_inv_factor(cl, fd.mapping_lengths, epsilon=eps)
-    m0 = int(fd.mapping_lengths[0])
+    r1 = r0 + int(fd.mapping_lengths[t0])
     inv_got, inv_want = dense(F.T @ F), dense(Fo.T @ Fo)
     # the shifted block has condition number ~ 1e7: compare the inverses loosely, the other blocks tightly
-    assert rel(inv_got[m0:, m0:], inv_want[m0:, m0:]) < RTOL
-    assert rel(inv_got[:m0, :m0], inv_want[:m0, :m0]) < 1e-4
-    shifted = np.abs(dense(cl)[:m0, :m0])
-    w = np.linalg.eigvalsh(np.linalg.inv(inv_got[:m0, :m0]))
+    rest = np.r_[0:r0, r1:inv_got.shape[0]]
+    assert rel(inv_got[np.ix_(rest, rest)], inv_want[np.ix_(rest, rest)]) < RTOL
+    assert rel(inv_got[r0:r1, r0:r1], inv_want[r0:r1, r0:r1]) < 1e-4
+    shifted = np.abs(dense(cl)[r0:r1, r0:r1])
+    w = np.linalg.eigvalsh(np.linalg.inv(inv_got[r0:r1, r0:r1]))
     assert abs(w[0] - eps) < 0.05 * eps, (w[0], np.linalg.norm(shifted, np.inf))
 
 
@@ -199,13 +207,19 @@ def test_design_create_rejects_bad_input(ctx):
         aces_b200.DeviceDesign(ctx, fd)
 
 
-@pytest.mark.parametrize("kind,d", [("rotated", 9), ("unrotated", 7)])
+@pytest.mark.parametrize("kind,d", [("rotated", 9), ("unrotated", 7), ("real_rotated", 9), ("real_unrotated", 7)])
 def test_full_size_fit_properties(ctx, kind, d):
     """BASELINE configs 3 / 4 shapes (rotated d=9: M = 12912, N = 6779; unrotated d=7): properties that
     do not need the oracle at this size."""
     import aces_b200
 
-    fd = aces_b200.synthetic_design(kind, d, full_covariance=True, with_matrix=True)
+    if kind == "real_rotated":
+        fd = aces_b200.rotated_design(d, full_covariance=True)
+        assert fd.matrix.shape == (12912, 6779)          # SURVEY section 8 table
+    elif kind == "real_unrotated":
+        fd = aces_b200.unrotated_design(d, full_covariance=True)
+    else:
+        fd = aces_b200.synthetic_design(kind, d, full_covariance=True, with_matrix=True)
     dd = aces_b200.DeviceDesign(ctx, fd)
     try:
         N = fd.matrix.shape[1]

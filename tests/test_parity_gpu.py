@@ -94,11 +94,17 @@ def make_batch(rng, est, fd, shots_set, pad_ld=0):
     return mats, rows, ld, np.asarray(prefix, dtype=np.int64)
 
 
-@pytest.mark.parametrize("d,gls,stress", [(3, False, False), (3, True, True), (5, True, False)])
+@pytest.mark.parametrize("d,gls,stress", [(3, False, False), (3, True, True), (5, True, False),
+                                          ("real3", True, False), ("real5", True, False), ("real5", False, False),
+                                          ("unrot3", True, False)])
 def test_design_batch_vs_oracle(ctx, d, gls, stress):
     import aces_b200
 
-    fd = aces_b200.synthetic_design("rotated", d, full_covariance=gls, stress_weights=stress)
+    if isinstance(d, str):   # real designs (circuit_design.py): the reference's own tables
+        kind, d = d.rstrip("0123456789"), int(d[-1])
+        fd = (aces_b200.rotated_design if kind == "real" else aces_b200.unrotated_design)(d, full_covariance=gls)
+    else:
+        fd = aces_b200.synthetic_design("rotated", d, full_covariance=gls, stress_weights=stress)
     est = aces_b200.DesignEstimator(ctx, fd)
     rng = np.random.default_rng(d)
     mats, rows, ld, prefix = make_batch(rng, est, fd, [3_000, 41_111, 200_003])
@@ -248,13 +254,14 @@ def test_device_resident_inputs(ctx):
         assert np.array_equal(got, want)
 
 
-def test_full_size_properties(ctx):
+@pytest.mark.parametrize("source", ["real", "synthetic"])
+def test_full_size_properties(ctx, source):
     """BASELINE config 3 size (rotated d=9, 1e8 shots, 2.1 GB): size-independent properties."""
     import torch
 
     import aces_b200
 
-    fd = aces_b200.synthetic_design("rotated", 9)
+    fd = aces_b200.rotated_design(9, full_covariance=False) if source == "real" else aces_b200.synthetic_design("rotated", 9)
     est = aces_b200.DesignEstimator(ctx, fd)
     shots_set = [10**6, 10**7, 10**8]
     shots_divided, shots_max = aces_b200.shots_divide(fd, shots_set)

@@ -11,7 +11,8 @@ sys.path.insert(0, ROOT)
 import aces_b200  # noqa: E402
 
 cases = sys.argv[1:] or ["rotated:3:6e8:0", "rotated:5:3e8:1", "rotated:9:1e8:0", "rotated:9:1e8:1",
-                         "unrotated:7:1e8:1", "rotated:17:1.25e8:0"]
+                         "unrotated:7:1e8:1", "rotated:17:1.25e8:0",
+                         "real:3:6e8:0", "real:5:3e8:1", "real:9:1e8:0", "real:9:1e8:1", "realun:7:1e8:1", "real:17:1.25e8:0"]
 ctx = aces_b200.Context(0)
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
@@ -20,7 +21,10 @@ ctx.set_stream(stream.cuda_stream)
 for case in cases:
     kind, d, shots, full = case.split(":")
     d, shots, full = int(d), int(float(shots)), bool(int(full))
-    fd = aces_b200.synthetic_design(kind, d, full_covariance=full)
+    if kind.startswith("real"):   # the reference's own tables (circuit_design.py)
+        fd = (aces_b200.unrotated_design if kind == "realun" else aces_b200.rotated_design)(d, full_covariance=full)
+    else:
+        fd = aces_b200.synthetic_design(kind, d, full_covariance=full)
     est = aces_b200.DesignEstimator(ctx, fd)
     shots_set = [shots // 100, shots // 10, shots]
     shots_divided, shots_max = aces_b200.shots_divide(fd, shots_set)
