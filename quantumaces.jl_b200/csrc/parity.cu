@@ -362,49 +362,133 @@ int32_t aces_tables_create(aces_ctx* ctx, int32_t n_qubits, int32_t n_experiment
     }
     const bool grouped = need_groups && groupable;
 
-    // ---- pass 2: groups, device order (by weight inside a group), local bits -------------------
+    // ---- pass 2: groups (membership and columns only; the device order needs the kernel variant,
+    // which depends on the widest group of the whole table) ---------------------------------------
+    struct PendingGroup {
+        int e;
+        std::vector<int> mem;
+        std::vector<int32_t> gcols;
+    };
+    std::vector<PendingGroup> pending;
     std::vector<int> members, local_col((size_t)B, -1);
-    std::vector<std::pair<int32_t, int32_t>> order;  // (sort key, original index)
     auto emit_group = [&](int e, const std::vector<int>& mem, const std::vector<int32_t>& gcols) -> int {
-        (void)e;
+        pending.push_back(PendingGroup{e, mem, gcols});
+        max_group_E = std::max(max_group_E, (int)mem.size());
+        max_group_cols = std::max(max_group_cols, (int)gcols.size());
+        groups.push_back(ColGroup{});  // filled in pass 3
+        return ACES_OK;
+    };
+    // Pass 3 (after the loop below).  Device order: by weight, so that the lanes of a warp run the
+    // same number of plane loads.  Inside the weight-1 and weight-2 classes the order is chosen
+    // against shared-memory bank conflicts: a 128-bit load is served a quarter warp at a time, and
+    // the plane row pitch is an odd number of 16-byte vectors, so eight lanes are conflict-free
+    // exactly when their plane rows differ mod 8.  Real designs pair distant qubits (a data qubit
+    // and its ancilla), so sorting by the first bit leaves the second operand's rows colliding;
+    // instead every aligned block of eight lanes is filled greedily with Paulis whose first rows
+    // are pairwise different mod 8 and whose second rows are too (the operands of a weight-2 Pauli
+    // may be swapped: XOR commutes).  BMAXV = plane rows per record-bit position of the kernel
+    // variant (parity_v2.cuh: row = (bit & 7) * BMAX + (bit >> 3)).
+    auto build_group = [&](size_t gi, int BMAXV) -> int {
+        const PendingGroup& pg = pending[gi];
+        const int e = pg.e;
         ColGroup cg;
         cg.pauli_off = (int64_t)descs.size();
-        cg.E = (int32_t)mem.size();
+        cg.E = (int32_t)pg.mem.size();
         cg.cols_off = (int32_t)cols_all.size();
-        cg.ncols = (int32_t)gcols.size();
-        for (size_t c = 0; c < gcols.size(); ++c) local_col[(size_t)gcols[c]] = (int)c;
-        cols_all.insert(cols_all.end(), gcols.begin(), gcols.end());
-        // Device order: by weight, so that the lanes of a warp run the same number of plane loads,
-        // and inside a weight class by the plane row of the first bit (bit-major rows, see
-        // parity_v2.cuh): eight neighbouring lanes then load eight consecutive plane rows, which
-        // the odd row pitch spreads over all shared-memory banks.
+        cg.ncols = (int32_t)pg.gcols.size();
+        for (size_t c = 0; c < pg.gcols.size(); ++c) local_col[(size_t)pg.gcols[c]] = (int)c;
+        cols_all.insert(cols_all.end(), pg.gcols.begin(), pg.gcols.end());
+        auto local_bit = [&](int32_t q) -> int32_t { return 8 * local_col[(size_t)(q >> 3)] + (q & 7); };
+        auto row_of = [&](int32_t lb) -> int { return (lb & 7) * BMAXV + (lb >> 3); };
         std::vector<std::pair<int64_t, int32_t>> byw;
-        for (int p : mem) {
+        for (int p : pg.mem) {
             const std::vector<int32_t>& red = sups[(size_t)e][(size_t)p];
-            const int32_t lb = 8 * local_col[(size_t)(red.front() >> 3)] + (red.front() & 7);
+            const int32_t lb = local_bit(red.front());
             const int64_t row = (int64_t)(lb & 7) * 64 + (lb >> 3);  // 64 >= any BMAX: same order
             byw.push_back({((int64_t)red.size() << 32) | row, p});
         }
         std::sort(byw.begin(), byw.end());
+        struct Slot { int32_t p; bool swap; };
+        std::vector<Slot> order;
+        order.reserve(byw.size());
+        size_t n_w1 = 0, n_w2 = 0;
         for (const auto& wp : byw) {
-            const std::vector<int32_t>& red = sups[(size_t)e][(size_t)wp.second];
+            const size_t w = sups[(size_t)e][(size_t)wp.second].size();
+            n_w1 += w == 1;
+            n_w2 += w == 2;
+        }
+        if (BMAXV > 0 && n_w1 + n_w2 > 8) {
+            // pools in sorted order; `taken` marks what has been placed
+            std::vector<int> ra(n_w1 + n_w2), rb(n_w1 + n_w2, -1);
+            for (size_t i = 0; i < n_w1 + n_w2; ++i) {
+                const std::vector<int32_t>& red = sups[(size_t)e][(size_t)byw[i].second];
+                ra[i] = row_of(local_bit(red[0])) & 7;
+                if (red.size() == 2) rb[i] = row_of(local_bit(red[1])) & 7;
+            }
+            std::vector<char> taken(n_w1 + n_w2, 0);
+            const int zero_res = (8 * BMAXV) & 7;  // the all-zero row that stands in for a missing operand
+            int cnt1[8] = {0}, cnt2[8][8] = {{0}};
+            for (size_t i = 0; i < n_w1; ++i) cnt1[ra[i]]++;
+            for (size_t i = n_w1; i < n_w1 + n_w2; ++i) cnt2[ra[i]][rb[i]]++;
+            unsigned used_a = 0, used_b = 0;
+            for (size_t pos = 0; pos < n_w1 + n_w2; ++pos) {
+                if ((pos & 7) == 0) {
+                    used_a = used_b = 0;
+                    // a block that mixes the two classes sits in a weight-2 round: its weight-1 lanes
+                    // load the zero row as their second operand
+                    if (pos < n_w1 && pos + 8 > n_w1 && n_w2 > 0) used_b = 1u << zero_res;
+                }
+                int best = -1, best_score = -1;
+                bool best_swap = false;
+                if (pos < n_w1) {
+                    for (size_t i = 0; i < n_w1; ++i) {
+                        if (taken[i]) continue;
+                        const int free_a = !(used_a >> ra[i] & 1);
+                        const int score = free_a * 1000 + cnt1[ra[i]];
+                        if (score > best_score) { best_score = score; best = (int)i; }
+                    }
+                    if (best >= 0) cnt1[ra[best]]--;
+                } else {
+                    for (size_t i = n_w1; i < n_w1 + n_w2; ++i) {
+                        if (taken[i]) continue;
+                        for (int sw = 0; sw < 2; ++sw) {
+                            const int a = sw ? rb[i] : ra[i], b = sw ? ra[i] : rb[i];
+                            const int free_a = !(used_a >> a & 1), free_b = !(used_b >> b & 1);
+                            const int score = (free_a + free_b) * 1000 + cnt2[ra[i]][rb[i]];
+                            if (score > best_score) { best_score = score; best = (int)i; best_swap = sw != 0; }
+                        }
+                    }
+                    if (best >= 0) cnt2[ra[best]][rb[best]]--;
+                }
+                if (best < 0) return ACES_E_INVALID;  // cannot happen: the pool of this class is not empty
+                taken[(size_t)best] = 1;
+                const int a = best_swap ? rb[best] : ra[best], b = best_swap ? ra[best] : rb[best];
+                used_a |= 1u << a;
+                if (b >= 0) used_b |= 1u << b;
+                order.push_back(Slot{byw[(size_t)best].second, best_swap});
+            }
+            for (size_t i = n_w1 + n_w2; i < byw.size(); ++i) order.push_back(Slot{byw[i].second, false});
+        } else {
+            for (const auto& wp : byw) order.push_back(Slot{wp.second, false});
+        }
+        for (const Slot& sl : order) {
+            const std::vector<int32_t>& red = sups[(size_t)e][(size_t)sl.p];
             PauliDesc d;
             d.w = (int32_t)red.size();
             d.ext = (int32_t)bits.size();
-            d.orig = wp.second;
+            d.orig = sl.p;
             d.pad = 0;
             for (int i = 0; i < 4; ++i) d.q[i] = 0;
             for (size_t i = 0; i < red.size(); ++i) {
-                const int32_t lb = 8 * local_col[(size_t)(red[i] >> 3)] + (red[i] & 7);
+                const int32_t lb = local_bit(red[i]);
                 if (i < 4) d.q[i] = lb;
                 bits.push_back(lb);
             }
+            if (sl.swap) std::swap(d.q[0], d.q[1]);
             if (bits.size() >= ((size_t)1 << 31)) return ACES_E_INVALID;
             descs.push_back(d);
         }
-        max_group_E = std::max(max_group_E, cg.E);
-        max_group_cols = std::max(max_group_cols, cg.ncols);
-        groups.push_back(cg);
+        groups[gi] = cg;
         return ACES_OK;
     };
     for (int e = 0; e < n_experiments; ++e) {
@@ -449,6 +533,13 @@ int32_t aces_tables_create(aces_ctx* ctx, int32_t n_qubits, int32_t n_experiment
             }
         }
         grp_ptr.push_back((int32_t)groups.size());
+    }
+    {
+        V2Cfg vc;
+        const bool v2 = max_group_E <= 1024 &&
+                        v2_pick(std::max(max_group_cols, 1), std::max(max_group_E, 1), ctx->smem_optin, &vc);
+        for (size_t gi = 0; gi < pending.size(); ++gi)
+            ACES_CHECK(ctx, build_group(gi, v2 ? vc.BMAX : 0) == ACES_OK, "tables_create: table too large");
     }
     aces_tables* t = new aces_tables();
     t->n_qubits = n_qubits;
