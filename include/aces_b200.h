@@ -247,6 +247,33 @@ int32_t aces_design_fit(aces_ctx* ctx, aces_design* design, int32_t ls_type,
                         const int64_t* kept_rows, int64_t n_kept, int32_t index_base, double epsilon,
                         int32_t constrain, double* gate_eigenvalues);
 
+/* Tuple-sharded fit ("one large Gram"): the covariance is block diagonal by
+ * tuple (src/merit.jl:284), so the Gram matrix A' Omega'^-1 A and the right-hand side are sums
+ * over the tuple blocks.  Every shard holds the whole design but only works on the tuples whose
+ * tuple_on byte is non-zero (NULL = all: the design is no shard).  aces_design_fit is these stages
+ * back to back; a sharded fit sums the two device buffers of aces_design_fit_buffers over the
+ * shards after _begin and the right-hand side again after every _refine_begin (ncclAllReduce,
+ * sum, double, in place).  The Cholesky factorisation and the triangular solves are replicated.
+ * No other call on the same context may come between _begin and _end.
+ *   begin        : K2 covariance, K3 block factors of the shard's tuples, partial Gram (lower
+ *                  triangle of an Np x Np column-major matrix, Np = N padded to 128) and partial
+ *                  rhs A' F' F b;
+ *   solve        : Cholesky of the summed Gram matrix, x = inv(G) rhs;
+ *   refine_begin : partial rhs of the correction, A' F' F (b - A x);
+ *   refine_end   : x += inv(G) rhs; returns max|x| and max|delta| (stop when delta <= 1e-7 |x|,
+ *                  at most two corrections, as aces_design_fit does);
+ *   end          : g = exp(-x) (clamped to <= 1 when constrain), copied to gate_eigenvalues. */
+int32_t aces_design_set_tuple_shard(aces_ctx* ctx, aces_design* design, const uint8_t* tuple_on /* [T] or NULL */);
+int32_t aces_design_fit_begin(aces_ctx* ctx, aces_design* design, int32_t ls_type,
+                              const double* est_eigenvalues, const double* est_covariance_eigenvalues,
+                              const int64_t* kept_rows, int64_t n_kept, int32_t index_base, double epsilon);
+int32_t aces_design_fit_buffers(aces_design* design, double** gram, int64_t* gram_elems,
+                                double** rhs, int64_t* rhs_elems);
+int32_t aces_design_fit_solve(aces_ctx* ctx, aces_design* design);
+int32_t aces_design_fit_refine_begin(aces_ctx* ctx, aces_design* design);
+int32_t aces_design_fit_refine_end(aces_ctx* ctx, aces_design* design, double* x_max, double* delta_max);
+int32_t aces_design_fit_end(aces_ctx* ctx, aces_design* design, int32_t constrain, double* gate_eigenvalues);
+
 /* K6.  calc_gls_covariance / calc_wls_covariance / calc_ols_covariance(d, covariance_log)
  * (src/merit.jl:556-629) for ls_type 2 / 1 / 0: gate_eigenvalues [N] = get_gate_eigenvalues(d),
  * covariance_log_nzval in the design's pattern.  sigma (N x N column-major, host or device) may be

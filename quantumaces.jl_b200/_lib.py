@@ -70,6 +70,13 @@ SIGNATURES = {
     "aces_design_phase_ms": (_i32, [_vp, _i32, C.c_char_p, _i32, _p(C.c_float)]),
     "aces_design_fit": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, C.c_double, _i32, _vp]),
     "aces_design_ls_covariance": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "aces_design_set_tuple_shard": (_i32, [_vp, _vp, _vp]),
+    "aces_design_fit_begin": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, C.c_double]),
+    "aces_design_fit_buffers": (_i32, [_vp, _p(_vp), _p(_i64), _p(_vp), _p(_i64)]),
+    "aces_design_fit_solve": (_i32, [_vp, _vp]),
+    "aces_design_fit_refine_begin": (_i32, [_vp, _vp]),
+    "aces_design_fit_refine_end": (_i32, [_vp, _vp, _p(C.c_double), _p(C.c_double)]),
+    "aces_design_fit_end": (_i32, [_vp, _vp, _i32, _vp]),
 }
 
 

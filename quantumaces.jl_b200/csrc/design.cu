@@ -73,6 +73,15 @@ struct aces_design {
     int64_t *d_cols_off = nullptr, *d_atc_off = nullptr;
     double *Atc = nullptr, *Gt = nullptr;
     GemmDesc* g_gram = nullptr;    // [T]
+    // --- tuple shard ("one large Gram"): this design works on the tuples that are on;
+    //     the host sums the partial Gram matrix and right-hand sides over the shards ---
+    std::vector<uint8_t> tuple_on;  // [T], all 1 by default
+    uint8_t* d_tuple_on = nullptr;
+    bool sharded = false;
+    // --- state of a fit split at its reduction points (aces_design_fit_begin .. _end) ---
+    int fs_stage = 0, fs_ls_type = 0;
+    bool fs_clipped = false;
+    double* fs_lam = nullptr;
     std::vector<void*> owned;
 };
 
@@ -251,22 +260,24 @@ __global__ void at_times_kernel(int64_t N, const int64_t* __restrict__ colptr, c
 // out = F u with F = blockdiag(X_t) (lower triangular tiles): one thread per padded row
 __global__ void apply_f_kernel(int T, const int64_t* __restrict__ prow0, const int64_t* __restrict__ tile_off,
                                const int64_t* __restrict__ mp, const double* __restrict__ tiles,
-                               const double* __restrict__ u, double* __restrict__ out) {
+                               const uint8_t* __restrict__ on, const double* __restrict__ u, double* __restrict__ out) {
     const int t = blockIdx.y;
     if (t >= T) return;
     const int64_t n = mp[t];
     const double* X = tiles + tile_off[t];
     const double* ut = u + prow0[t];
+    const bool act = on[t] != 0;  // a tuple of another shard contributes nothing here
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double s = 0.0;
-        for (int64_t c = 0; c <= i; ++c) s += X[i + c * n] * ut[c];
+        if (act)
+            for (int64_t c = 0; c <= i; ++c) s += X[i + c * n] * ut[c];
         out[prow0[t] + i] = s;
     }
 }
 // out = F' v: one warp per padded column
 __global__ void apply_ft_kernel(int T, const int64_t* __restrict__ prow0, const int64_t* __restrict__ tile_off,
                                 const int64_t* __restrict__ mp, const double* __restrict__ tiles,
-                                const double* __restrict__ v, double* __restrict__ out) {
+                                const uint8_t* __restrict__ on, const double* __restrict__ v, double* __restrict__ out) {
     const int t = blockIdx.y;
     if (t >= T) return;
     const int64_t n = mp[t];
@@ -275,9 +286,11 @@ __global__ void apply_ft_kernel(int T, const int64_t* __restrict__ prow0, const 
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool act = on[t] != 0;
     for (int64_t c = warp; c < n; c += nwarps) {
         double s = 0.0;
-        for (int64_t i = c + lane; i < n; i += 32) s += X[i + c * n] * vt[i];
+        if (act)
+            for (int64_t i = c + lane; i < n; i += 32) s += X[i + c * n] * vt[i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) out[prow0[t] + c] = s;
@@ -287,13 +300,16 @@ __global__ void apply_ft_kernel(int T, const int64_t* __restrict__ prow0, const 
 __global__ void diag_factor_kernel(int64_t M, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval,
                                    const double* __restrict__ val, const int32_t* __restrict__ blk_of_row,
                                    const int64_t* __restrict__ row0, const int64_t* __restrict__ prow0,
-                                   const int32_t* __restrict__ row_map, int unit, double* __restrict__ f) {
+                                   const int32_t* __restrict__ row_map, const uint8_t* __restrict__ on, int unit,
+                                   double* __restrict__ f) {
     for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < M; r += (int64_t)gridDim.x * blockDim.x) {
         const int t = blk_of_row[r];
         const int64_t lr = row_map ? row_map[r] : r - row0[t];
         if (lr < 0) continue;
         double d = 1.0;
-        if (!unit)
+        if (!on[t])
+            d = 0.0;  // rows of another shard's tuples: weight 0 (f is zeroed before, kept explicit)
+        else if (!unit)
             for (int64_t e = colptr[r]; e < colptr[r + 1]; ++e)
                 if (rowval[e] == r) d = pow(val[e], -0.5);
         f[prow0[t] + lr] = d;
@@ -348,7 +364,7 @@ __global__ void whiten_tiles_kernel(int64_t N, const int64_t* __restrict__ colpt
                                     const int64_t* __restrict__ row0, const int64_t* __restrict__ prow0,
                                     const int64_t* __restrict__ tile_off, const int64_t* __restrict__ mp,
                                     const int32_t* __restrict__ row_map, const double* __restrict__ tiles,
-                                    double* __restrict__ At, int64_t ld) {
+                                    const uint8_t* __restrict__ on, double* __restrict__ At, int64_t ld) {
     const int64_t j = blockIdx.x;
     if (j >= N) return;
     double* col = At + j * ld;
@@ -357,7 +373,7 @@ __global__ void whiten_tiles_kernel(int64_t N, const int64_t* __restrict__ colpt
         const int64_t r = rowval[e];
         const int t = blk_of_row[r];
         const int64_t lr = row_map ? row_map[r] : r - row0[t];
-        if (lr < 0) continue;
+        if (lr < 0 || !on[t]) continue;
         const double a = nzval[e];
         const int64_t n = mp[t];
         const double* X = tiles + tile_off[t] + lr * n;  // column lr of X_t: nonzero for rows >= lr
@@ -376,10 +392,11 @@ __global__ void whiten_compact_kernel(int64_t n_wcols, const int32_t* __restrict
                                       const int64_t* __restrict__ atc_off, const int64_t* __restrict__ row0,
                                       const int64_t* __restrict__ tile_off, const int64_t* __restrict__ mp,
                                       const int32_t* __restrict__ row_map, const double* __restrict__ tiles,
-                                      double* __restrict__ Atc) {
+                                      const uint8_t* __restrict__ on, double* __restrict__ Atc) {
     const int64_t jc = blockIdx.x;
     if (jc >= n_wcols) return;
     const int t = w_blk[jc];
+    if (!on[t]) return;
     const int64_t n = mp[t];
     double* out = Atc + atc_off[t] + (jc - cols_off[t]) * n;
     const int bd = blockDim.x, tid = threadIdx.x;
@@ -536,12 +553,15 @@ int ensure_workspaces(aces_ctx* ctx, aces_design* d, bool need_tiles, bool need_
     if (need_at && d->windowed && !d->Atc) {
         ACES_TRY(dev_alloc(ctx, d, &d->Atc, (size_t)d->atc_off.back()));
         ACES_TRY(dev_alloc(ctx, d, &d->Gt, (size_t)d->gt_off.back()));
+    }
+    if (need_at && d->windowed && !d->g_gram) {
         std::vector<GemmDesc> gg((size_t)d->T);
         for (int t = 0; t < d->T; ++t) {
             const double* A = d->Atc + d->atc_off[t];
             const int tiles = (int)(d->cpt[t] / DB);
             gg[(size_t)t] = GemmDesc{A, A, d->Gt + d->gt_off[t], d->mp[t], d->mp[t], d->cpt[t], (int32_t)d->mp[t], tiles, tiles,
                                      1, 1.0, 0.0};
+            if (!d->tuple_on[(size_t)t]) gg[(size_t)t] = GemmDesc{};  // k = 0: inactive entry
         }
         ACES_TRY(dev_upload(ctx, d, &d->g_gram, gg));
     }
@@ -660,9 +680,9 @@ int apply_F(aces_ctx* ctx, aces_design* d, int ls_type, const FitVectors& fv, co
     if (ls_type == 2) {
         dim3 grid(16, (unsigned)d->T);
         if (!transpose)
-            apply_f_kernel<<<grid, 128, 0, ctx->stream>>>(d->T, d->d_prow0, d->d_tile_off, d->d_mp, d->tilesX, u, out);
+            apply_f_kernel<<<grid, 128, 0, ctx->stream>>>(d->T, d->d_prow0, d->d_tile_off, d->d_mp, d->tilesX, d->d_tuple_on, u, out);
         else
-            apply_ft_kernel<<<grid, 256, 0, ctx->stream>>>(d->T, d->d_prow0, d->d_tile_off, d->d_mp, d->tilesX, u, out);
+            apply_ft_kernel<<<grid, 256, 0, ctx->stream>>>(d->T, d->d_prow0, d->d_tile_off, d->d_mp, d->tilesX, d->d_tuple_on, u, out);
     } else {
         mul_vec_kernel<<<grid_for(d->Mp, 256), 256, 0, ctx->stream>>>(d->Mp, fv.f, u, out);
     }
@@ -681,7 +701,7 @@ int build_gram(aces_ctx* ctx, aces_design* d, int ls_type, const FitVectors& fv,
         ACES_CUDA(ctx, cudaMemsetAsync(d->G, 0, sizeof(double) * (size_t)Np * Np, ctx->stream));
         whiten_compact_kernel<<<(unsigned)d->n_wcols, 256, 0, ctx->stream>>>(
             d->n_wcols, d->w_blk, d->w_ptr, d->w_row, d->w_val, d->d_cols_off, d->d_atc_off, d->d_row0, d->d_tile_off,
-            d->d_mp, row_map, d->tilesX, d->Atc);
+            d->d_mp, row_map, d->tilesX, d->d_tuple_on, d->Atc);
         ACES_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
         if (ctx->timing) ACES_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
@@ -691,7 +711,7 @@ int build_gram(aces_ctx* ctx, aces_design* d, int ls_type, const FitVectors& fv,
             ctx->timed = 1;
         }
         for (int t = 0; t < d->T; ++t) {  // one launch per block: the order of the additions is fixed
-            if (d->ct[t] == 0) continue;
+            if (d->ct[t] == 0 || !d->tuple_on[(size_t)t]) continue;
             dim3 grid((unsigned)std::min<int64_t>((d->ct[t] + 255) / 256, 8), (unsigned)d->ct[t]);
             gram_scatter_kernel<<<grid, 256, 0, ctx->stream>>>(d->ct[t], d->cpt[t], d->w_cols + d->cols_off[t],
                                                               d->Gt + d->gt_off[t], d->G, Np);
@@ -702,7 +722,7 @@ int build_gram(aces_ctx* ctx, aces_design* d, int ls_type, const FitVectors& fv,
         ACES_CUDA(ctx, cudaMemsetAsync(d->At, 0, sizeof(double) * (size_t)Mp * Np, ctx->stream));
         whiten_tiles_kernel<<<(unsigned)d->N, 256, 0, ctx->stream>>>(d->N, d->a_colptr, d->a_rowval, d->a_nzval,
                                                                     d->blk_of_row, d->d_row0, d->d_prow0, d->d_tile_off,
-                                                                    d->d_mp, row_map, d->tilesX, d->At, Mp);
+                                                                    d->d_mp, row_map, d->tilesX, d->d_tuple_on, d->At, Mp);
         ACES_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
         if (ctx->timing) ACES_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
@@ -806,8 +826,10 @@ int check_flags(aces_ctx* ctx, aces_design* d, const char* what) {
 
 // Prepares the estimator: covariance values (from eigenvalue estimates, or given), factor (GLS) or
 // diagonal weights (OLS / WLS), Gram matrix and its Cholesky factor.
+int factor_gram_matrix(aces_ctx* ctx, aces_design* d, const FitVectors& fv, PhaseTimer* pt);
 int prepare_estimator(aces_ctx* ctx, aces_design* d, int ls_type, const double* val_dev, const int32_t* row_map,
-                      const std::vector<int64_t>& kept_count, const FitVectors& fv, PhaseTimer* pt = nullptr) {
+                      const std::vector<int64_t>& kept_count, const FitVectors& fv, PhaseTimer* pt = nullptr,
+                      bool factor_gram = true) {
     d->fallback_blocks = 0;
     ACES_CUDA(ctx, cudaMemsetAsync(d->flags, 0, sizeof(int32_t) * ((size_t)d->T + 2), ctx->stream));
     ACES_CUDA(ctx, cudaMemsetAsync(d->vec, 0, sizeof(double) * (size_t)(8 * std::max(d->Mp, d->Np)), ctx->stream));
@@ -819,12 +841,19 @@ int prepare_estimator(aces_ctx* ctx, aces_design* d, int ls_type, const double* 
     } else {
         diag_factor_kernel<<<grid_for(d->M, 256), 256, 0, ctx->stream>>>(d->M, d->cov_colptr, d->cov_rowval, val_dev,
                                                                         d->blk_of_row, d->d_row0, d->d_prow0, row_map,
-                                                                        ls_type == 0 ? 1 : 0, fv.f);
+                                                                        d->d_tuple_on, ls_type == 0 ? 1 : 0, fv.f);
         ACES_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
     }
     ACES_TRY(build_gram(ctx, d, ls_type, fv, row_map));
     if (pt) pt->mark("gram");
+    if (!factor_gram) return ACES_OK;  // a shard: the host sums the partial Gram matrices first
+    return factor_gram_matrix(ctx, d, fv, pt);
+}
+
+// Cholesky factor of the Gram matrix (in place, lower) with the relative pivot test against the
+// original diagonal.
+int factor_gram_matrix(aces_ctx* ctx, aces_design* d, const FitVectors& fv, PhaseTimer* pt) {
     ACES_TRY(dense::get_diag(ctx, d->Np, d->G, d->Np, fv.t2));
     ACES_CUDA(ctx, cudaMemcpyAsync(fv.t1, fv.t2, sizeof(double) * (size_t)d->Np, cudaMemcpyDeviceToDevice, ctx->stream));
     ACES_TRY(dense::potrf(ctx, d->Np, d->G, d->Np, d->dinvG, d->flags + d->T, fv.t1, 1e-13));
@@ -1011,6 +1040,8 @@ int32_t aces_design_create(aces_ctx* ctx, int32_t T, const int64_t* mapping_leng
     UP(cov_colptr, cov_colptr); UP(cov_rowval, cov_rowval); UP(cov_src, cov_src);
     UP(blk_of_row, d->h_blk_of_row); UP(dfac, dfac); UP(kfac, kfac); UP(key_p, key_p); UP(key_q, key_q);
     UP(d_row0, d->row0); UP(d_prow0, d->prow0); UP(d_tile_off, d->tile_off); UP(d_mp, d->mp);
+    d->tuple_on.assign((size_t)T, 1);
+    UP(d_tuple_on, d->tuple_on);
 #undef UP
     *out = d;
     return ACES_OK;
@@ -1075,7 +1106,7 @@ int build_tile_descs(aces_ctx* ctx, aces_design* d) {
             GemmDesc z{};
             gp[idx] = gt[idx] = g1[idx] = g2[idx] = z;
             a = DiagDesc{};
-            if (k >= nb) continue;
+            if (k >= nb || !d->tuple_on[(size_t)t]) continue;  // inactive entry
             double* L = d->tilesL + d->tile_off[t];
             double* X = d->tilesX + d->tile_off[t];
             double* dk = d->dinvT + d->dinv_off[t] + (int64_t)k * DB * DB;
@@ -1146,6 +1177,7 @@ int32_t aces_design_inv_factor(aces_ctx* ctx, aces_design* d, const double* cova
                                const int64_t* kept_rows, int64_t n_kept, int32_t index_base,
                                double fallback_epsilon, double* factor_blocks, int64_t* block_lengths) {
     ACES_TRY(check_design(ctx, d, "design_inv_factor"));
+    ACES_CHECK(ctx, !d->sharded, "design_inv_factor: the design is a tuple shard");
     ACES_CHECK(ctx, covariance_log_nzval && factor_blocks, "design_inv_factor: NULL argument");
     ACES_TRY(ensure_workspaces(ctx, d, true, false, false, false));
     ACES_TRY(build_tile_descs(ctx, d));
@@ -1178,12 +1210,38 @@ int32_t aces_design_inv_factor(aces_ctx* ctx, aces_design* d, const double* cova
     return check_flags(ctx, d, "design_inv_factor");
 }
 
-int32_t aces_design_fit(aces_ctx* ctx, aces_design* d, int32_t ls_type, const double* est_eigenvalues,
-                        const double* est_covariance_eigenvalues, const int64_t* kept_rows, int64_t n_kept,
-                        int32_t index_base, double epsilon, int32_t constrain, double* gate_eigenvalues) {
-    ACES_TRY(check_design(ctx, d, "design_fit"));
+// ---- the fit, split at its reduction points -----------------------------------------------------------
+// aces_design_fit runs the stages back to back on one design.  A tuple-sharded fit (the
+// Gram matrix is a sum over the tuple blocks because the covariance is block diagonal by tuple,
+// src/merit.jl:284) runs them on every shard and sums the buffers of aces_design_fit_buffers over
+// the shards between the stages (ncclAllReduce on the device pointers); the Cholesky factorisation
+// and the triangular solves are replicated.
+
+namespace {
+
+// right-hand side of the (corrected semi-) normal equations: g = A' F' F (b - A x), x may be NULL
+int fit_normal_rhs(aces_ctx* ctx, aces_design* d, const double* x_or_null) {
+    FitVectors fv = fit_vectors(d);
+    const int32_t* row_map = d->fs_clipped ? d->row_map : nullptr;
+    const unsigned gm = grid_for(d->M, 128), gn = grid_for(d->N, 128);
+    residual_kernel<<<gm, 128, 0, ctx->stream>>>(d->M, d->a_rowptr, d->a_colidx, d->a_vals, d->blk_of_row, d->d_row0,
+                                                d->d_prow0, row_map, d->fs_lam, x_or_null, fv.u);
+    ctx->launches += 1;
+    ACES_TRY(apply_F(ctx, d, d->fs_ls_type, fv, fv.u, fv.v, false));
+    ACES_TRY(apply_F(ctx, d, d->fs_ls_type, fv, fv.v, fv.w, true));
+    at_times_kernel<<<gn, 128, 0, ctx->stream>>>(d->N, d->a_colptr, d->a_rowval, d->a_nzval, d->blk_of_row, d->d_row0,
+                                                d->d_prow0, row_map, fv.w, fv.g);
+    ACES_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return ACES_OK;
+}
+
+int fit_begin(aces_ctx* ctx, aces_design* d, int32_t ls_type, const double* est_eigenvalues,
+              const double* est_covariance_eigenvalues, const int64_t* kept_rows, int64_t n_kept,
+              int32_t index_base, double epsilon, PhaseTimer* pt, bool factor_gram) {
     ACES_CHECK(ctx, ls_type >= 0 && ls_type <= 2, "design_fit: ls_type must be 0 (OLS), 1 (WLS) or 2 (GLS)");
-    ACES_CHECK(ctx, est_eigenvalues && gate_eigenvalues, "design_fit: NULL argument");
+    ACES_CHECK(ctx, est_eigenvalues != nullptr, "design_fit: NULL argument");
+    d->fs_stage = 0;
     const bool gls = ls_type == 2;
     ACES_TRY(ensure_workspaces(ctx, d, gls, gls, false, false));
     if (gls) ACES_TRY(build_tile_descs(ctx, d));
@@ -1194,59 +1252,156 @@ int32_t aces_design_fit(aces_ctx* ctx, aces_design* d, int32_t ls_type, const do
     double *lam, *lamcov;
     ACES_TRY(upload_eigenvalues(ctx, d, est_eigenvalues, est_covariance_eigenvalues, &lam, &lamcov));
     FitVectors fv = fit_vectors(d);
-    PhaseTimer pt(ctx, d);
     // K2: log-covariance of the estimates, weight_time = false (src/estimate.jl:713-720)
     if (ls_type != 0) ACES_TRY(launch_cov_values(ctx, d, lam, lamcov, epsilon, 0, 1, d->covval));
-    pt.mark("covariance");
-    ACES_TRY(prepare_estimator(ctx, d, ls_type, d->covval, row_map, kept, fv, &pt));
-    // right-hand side: g = A' F' F b
-    const unsigned gm = grid_for(d->M, 128), gn = grid_for(d->N, 128);
-    auto normal_rhs = [&](const double* x_or_null) -> int {
-        residual_kernel<<<gm, 128, 0, ctx->stream>>>(d->M, d->a_rowptr, d->a_colidx, d->a_vals, d->blk_of_row, d->d_row0,
-                                                    d->d_prow0, row_map, lam, x_or_null, fv.u);
-        ctx->launches += 1;
-        ACES_TRY(apply_F(ctx, d, ls_type, fv, fv.u, fv.v, false));
-        ACES_TRY(apply_F(ctx, d, ls_type, fv, fv.v, fv.w, true));
-        at_times_kernel<<<gn, 128, 0, ctx->stream>>>(d->N, d->a_colptr, d->a_rowval, d->a_nzval, d->blk_of_row, d->d_row0,
-                                                    d->d_prow0, row_map, fv.w, fv.g);
-        ACES_CUDA(ctx, cudaGetLastError());
-        ctx->launches += 1;
-        return ACES_OK;
-    };
-    ACES_TRY(normal_rhs(nullptr));
+    if (pt) pt->mark("covariance");
+    d->fs_ls_type = ls_type;
+    d->fs_clipped = clipped;
+    d->fs_lam = lam;
+    ACES_TRY(prepare_estimator(ctx, d, ls_type, d->covval, row_map, kept, fv, pt, factor_gram));
+    ACES_TRY(fit_normal_rhs(ctx, d, nullptr));  // g = A' F' F b
+    d->fs_stage = 1;
+    return ACES_OK;
+}
+
+int fit_solve(aces_ctx* ctx, aces_design* d, bool factor_gram, PhaseTimer* pt) {
+    ACES_CHECK(ctx, d->fs_stage == 1, "design_fit_solve: call aces_design_fit_begin first");
+    FitVectors fv = fit_vectors(d);
+    if (factor_gram) {
+        // padding rows: the shards each wrote 1.0 on the padding diagonal, the sum is their number
+        ACES_TRY(factor_gram_matrix(ctx, d, fv, pt));
+    }
     ACES_TRY(dense::trsv_lower(ctx, d->Np, d->G, d->Np, d->dinvG, fv.g, fv.t1));
     ACES_TRY(dense::trsv_lower_t(ctx, d->Np, d->G, d->Np, d->dinvG, fv.t1, fv.x));
-    pt.mark("first solve");
-    for (int it = 0; it < 2; ++it) {
-        // corrected semi-normal equations: r = F (b - A x) in FP64, x += inv(G) A' F' r
-        ACES_TRY(normal_rhs(fv.x));
-        ACES_TRY(dense::trsv_lower(ctx, d->Np, d->G, d->Np, d->dinvG, fv.g, fv.t1));
-        ACES_TRY(dense::trsv_lower_t(ctx, d->Np, d->G, d->Np, d->dinvG, fv.t1, fv.t2));
-        axpy_kernel<<<gn, 128, 0, ctx->stream>>>(d->N, 1.0, fv.t2, fv.x);
+    if (pt) pt->mark("first solve");
+    d->fs_stage = 2;
+    return ACES_OK;
+}
+
+// x += inv(G) g; returns max|x| and max|delta| (host) for the stopping rule
+int fit_correct(aces_ctx* ctx, aces_design* d, double* x_max, double* delta_max) {
+    FitVectors fv = fit_vectors(d);
+    const unsigned gn = grid_for(d->N, 128);
+    ACES_TRY(dense::trsv_lower(ctx, d->Np, d->G, d->Np, d->dinvG, fv.g, fv.t1));
+    ACES_TRY(dense::trsv_lower_t(ctx, d->Np, d->G, d->Np, d->dinvG, fv.t1, fv.t2));
+    axpy_kernel<<<gn, 128, 0, ctx->stream>>>(d->N, 1.0, fv.t2, fv.x);
+    ctx->launches += 1;
+    if (x_max) {
+        max_abs_pair_kernel<<<1, 256, 0, ctx->stream>>>(d->N, fv.x, fv.t2, d->mom);
         ctx->launches += 1;
-        if (it == 0) {
-            // The correction contracts the error by about |delta| / |x| per step: when the first
-            // one is already below 1e-7 relative, a second step would change x by < 1e-14.
-            max_abs_pair_kernel<<<1, 256, 0, ctx->stream>>>(d->N, fv.x, fv.t2, d->mom);
-            ctx->launches += 1;
-            double h[2] = {0.0, 0.0};
-            ACES_CUDA(ctx, cudaMemcpyAsync(h, d->mom, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-            ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            if (h[1] <= 1e-7 * h[0]) break;
-        }
+        double h[2] = {0.0, 0.0};
+        ACES_CUDA(ctx, cudaMemcpyAsync(h, d->mom, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *x_max = h[0];
+        *delta_max = h[1];
     }
-    pt.mark("refinement");
-    exp_neg_kernel<<<gn, 128, 0, ctx->stream>>>(d->N, fv.x, fv.t1, constrain);
+    return ACES_OK;
+}
+
+int fit_end(aces_ctx* ctx, aces_design* d, int32_t constrain, double* gate_eigenvalues) {
+    ACES_CHECK(ctx, d->fs_stage == 2, "design_fit_end: call aces_design_fit_solve first");
+    ACES_CHECK(ctx, gate_eigenvalues != nullptr, "design_fit: NULL argument");
+    FitVectors fv = fit_vectors(d);
+    exp_neg_kernel<<<grid_for(d->N, 128), 128, 0, ctx->stream>>>(d->N, fv.x, fv.t1, constrain);
     ACES_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     ACES_CUDA(ctx, cudaMemcpyAsync(gate_eigenvalues, fv.t1, sizeof(double) * (size_t)d->N, cudaMemcpyDefault, ctx->stream));
+    d->fs_stage = 0;
     return check_flags(ctx, d, "design_fit");
+}
+
+}  // namespace
+
+int32_t aces_design_fit(aces_ctx* ctx, aces_design* d, int32_t ls_type, const double* est_eigenvalues,
+                        const double* est_covariance_eigenvalues, const int64_t* kept_rows, int64_t n_kept,
+                        int32_t index_base, double epsilon, int32_t constrain, double* gate_eigenvalues) {
+    ACES_TRY(check_design(ctx, d, "design_fit"));
+    ACES_CHECK(ctx, !d->sharded, "design_fit: the design is a tuple shard; use aces_design_fit_begin .. _end");
+    ACES_CHECK(ctx, gate_eigenvalues != nullptr, "design_fit: NULL argument");
+    PhaseTimer pt(ctx, d);
+    ACES_TRY(fit_begin(ctx, d, ls_type, est_eigenvalues, est_covariance_eigenvalues, kept_rows, n_kept, index_base,
+                       epsilon, &pt, true));
+    ACES_TRY(fit_solve(ctx, d, false, &pt));
+    for (int it = 0; it < 2; ++it) {
+        // corrected semi-normal equations: r = F (b - A x) in FP64, x += inv(G) A' F' r
+        ACES_TRY(fit_normal_rhs(ctx, d, fit_vectors(d).x));
+        double xm = 0.0, dm = 0.0;
+        ACES_TRY(fit_correct(ctx, d, it == 0 ? &xm : nullptr, &dm));
+        // The correction contracts the error by about |delta| / |x| per step: when the first one is
+        // already below 1e-7 relative, a second step would change x by < 1e-14.
+        if (it == 0 && dm <= 1e-7 * xm) break;
+    }
+    pt.mark("refinement");
+    return fit_end(ctx, d, constrain, gate_eigenvalues);
+}
+
+int32_t aces_design_set_tuple_shard(aces_ctx* ctx, aces_design* d, const uint8_t* tuple_on) {
+    ACES_TRY(check_design(ctx, d, "design_set_tuple_shard"));
+    std::vector<uint8_t> on((size_t)d->T, 1);
+    bool all = true;
+    if (tuple_on)
+        for (int t = 0; t < d->T; ++t) {
+            on[(size_t)t] = tuple_on[t] ? 1 : 0;
+            all = all && on[(size_t)t];
+        }
+    ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    d->tuple_on = on;
+    d->sharded = !all;
+    ACES_CUDA(ctx, cudaMemcpy(d->d_tuple_on, on.data(), (size_t)d->T, cudaMemcpyHostToDevice));
+    // the batched descriptor tables carry the mask (inactive entries): rebuilt on the next use
+    d->dd = nullptr;
+    d->g_panel = d->g_trail = d->g_tri1 = d->g_tri2 = nullptr;
+    d->g_gram = nullptr;
+    d->fs_stage = 0;
+    return ACES_OK;
+}
+
+int32_t aces_design_fit_begin(aces_ctx* ctx, aces_design* d, int32_t ls_type, const double* est_eigenvalues,
+                              const double* est_covariance_eigenvalues, const int64_t* kept_rows, int64_t n_kept,
+                              int32_t index_base, double epsilon) {
+    ACES_TRY(check_design(ctx, d, "design_fit_begin"));
+    ACES_TRY(fit_begin(ctx, d, ls_type, est_eigenvalues, est_covariance_eigenvalues, kept_rows, n_kept, index_base,
+                       epsilon, nullptr, false));
+    // a failed block factorisation must surface on the shard that owns the block, before the sum
+    return check_flags(ctx, d, "design_fit_begin");
+}
+
+int32_t aces_design_fit_buffers(aces_design* d, double** gram, int64_t* gram_elems, double** rhs, int64_t* rhs_elems) {
+    if (!d || !d->G) return ACES_E_INVALID;
+    if (gram) *gram = d->G;
+    if (gram_elems) *gram_elems = d->Np * d->Np;
+    if (rhs) *rhs = fit_vectors(d).g;
+    if (rhs_elems) *rhs_elems = d->Np;
+    return ACES_OK;
+}
+
+int32_t aces_design_fit_solve(aces_ctx* ctx, aces_design* d) {
+    ACES_TRY(check_design(ctx, d, "design_fit_solve"));
+    return fit_solve(ctx, d, true, nullptr);
+}
+
+int32_t aces_design_fit_refine_begin(aces_ctx* ctx, aces_design* d) {
+    ACES_TRY(check_design(ctx, d, "design_fit_refine_begin"));
+    ACES_CHECK(ctx, d->fs_stage == 2, "design_fit_refine_begin: call aces_design_fit_solve first");
+    return fit_normal_rhs(ctx, d, fit_vectors(d).x);
+}
+
+int32_t aces_design_fit_refine_end(aces_ctx* ctx, aces_design* d, double* x_max, double* delta_max) {
+    ACES_TRY(check_design(ctx, d, "design_fit_refine_end"));
+    ACES_CHECK(ctx, d->fs_stage == 2 && x_max && delta_max, "design_fit_refine_end: bad state or NULL argument");
+    return fit_correct(ctx, d, x_max, delta_max);
+}
+
+int32_t aces_design_fit_end(aces_ctx* ctx, aces_design* d, int32_t constrain, double* gate_eigenvalues) {
+    ACES_TRY(check_design(ctx, d, "design_fit_end"));
+    return fit_end(ctx, d, constrain, gate_eigenvalues);
 }
 
 int32_t aces_design_ls_covariance(aces_ctx* ctx, aces_design* d, int32_t ls_type, const double* gate_eigenvalues,
                                   const double* covariance_log_nzval, double* sigma, double* trace,
                                   double* trace_sq) {
     ACES_TRY(check_design(ctx, d, "design_ls_covariance"));
+    ACES_CHECK(ctx, !d->sharded, "design_ls_covariance: the design is a tuple shard");
     ACES_CHECK(ctx, ls_type >= 0 && ls_type <= 2, "design_ls_covariance: ls_type must be 0 (OLS), 1 (WLS) or 2 (GLS)");
     ACES_CHECK(ctx, gate_eigenvalues && covariance_log_nzval, "design_ls_covariance: NULL argument");
     const bool gls = ls_type == 2;

@@ -269,6 +269,50 @@ class DeviceDesign:
             0 if kept is None else len(kept), 0, float(epsilon), 1 if constrain else 0, _ptr(g)))
         return g
 
+    # -- tuple-sharded fit ("one large Gram") ------------------------------------------
+    def set_tuple_shard(self, tuple_on=None) -> None:
+        """This design only works on the tuples with a non-zero byte (None: all tuples, no shard)."""
+        on = None if tuple_on is None else np.ascontiguousarray(tuple_on, dtype=np.uint8)
+        assert on is None or on.shape == (self.fd.tuple_number,)
+        self.ctx.check(self.ctx.lib.aces_design_set_tuple_shard(self.ctx.handle, self.handle, _ptr(on)))
+
+    def fit_buffers(self):
+        """(device pointer, element count) of the partial Gram matrix and of the partial rhs."""
+        g, r = C.c_void_p(), C.c_void_p()
+        ng, nr = C.c_int64(), C.c_int64()
+        self.ctx.check(self.ctx.lib.aces_design_fit_buffers(self.handle, C.byref(g), C.byref(ng), C.byref(r), C.byref(nr)))
+        return (int(g.value), int(ng.value)), (int(r.value), int(nr.value))
+
+    def fit_sharded(self, ls_type: str, est_eigenvalues, est_covariance_eigenvalues, reduce, clipped_indices=None,
+                    epsilon: float = 1e-10, constrain: bool = False) -> np.ndarray:
+        """The stages of `fit` with `reduce(device_pointer, n_doubles)` (an in-place sum over the
+        shards, e.g. shard.all_reduce_device) at the reduction points.  Every shard returns the
+        same gate eigenvalues."""
+        lam = np.ascontiguousarray(est_eigenvalues, dtype=np.float64)
+        lc = None
+        if self.C:
+            lc = np.ascontiguousarray(est_covariance_eigenvalues, dtype=np.float64)
+        kept = None if clipped_indices is None else np.ascontiguousarray(clipped_indices, dtype=np.int64)
+        lib, h = self.ctx.lib, self.ctx.handle
+        self.ctx.check(lib.aces_design_fit_begin(h, self.handle, LS_TYPES[ls_type], _ptr(lam), _ptr(lc), _ptr(kept),
+                                                 0 if kept is None else len(kept), 0, float(epsilon)))
+        (gram, n_gram), (rhs, n_rhs) = self.fit_buffers()
+        self.ctx.synchronize()
+        reduce(gram, n_gram)
+        reduce(rhs, n_rhs)
+        self.ctx.check(lib.aces_design_fit_solve(h, self.handle))
+        for it in range(2):
+            self.ctx.check(lib.aces_design_fit_refine_begin(h, self.handle))
+            self.ctx.synchronize()
+            reduce(rhs, n_rhs)
+            xm, dm = C.c_double(), C.c_double()
+            self.ctx.check(lib.aces_design_fit_refine_end(h, self.handle, C.byref(xm), C.byref(dm)))
+            if it == 0 and dm.value <= 1e-7 * xm.value:
+                break
+        g = np.zeros(self.N, dtype=np.float64)
+        self.ctx.check(lib.aces_design_fit_end(h, self.handle, 1 if constrain else 0, _ptr(g)))
+        return g
+
     # -- K6 -------------------------------------------------------------------------------------
     def calc_ls_covariance(self, ls_type: str, covariance_log, gate_eigenvalues=None, want_matrix: bool = True):
         """calc_gls_covariance / calc_wls_covariance / calc_ols_covariance(d, covariance_log)

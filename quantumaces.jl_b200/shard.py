@@ -74,3 +74,51 @@ def all_gather_vectors(vec, group=None):
     out = torch.empty((world, vec.numel()), dtype=vec.dtype, device=vec.device)
     dist.all_gather_into_tensor(out.reshape(-1), vec.reshape(-1).contiguous(), group=group)
     return out
+
+
+def shard_tuples(mapping_lengths: Sequence[int], world: int) -> List[List[int]]:
+    """Tuple blocks of one fit over `world` shards ("one large Gram"): greedy by the
+    cubic cost of a block (its Cholesky factor, inverse and whitening), largest first."""
+    cost = [float(m) ** 3 for m in mapping_lengths]
+    order = sorted(range(len(cost)), key=lambda t: -cost[t])
+    load = [0.0] * world
+    out: List[List[int]] = [[] for _ in range(world)]
+    for t in order:
+        r = min(range(world), key=lambda k: load[k])
+        out[r].append(t)
+        load[r] += cost[t]
+    return [sorted(x) for x in out]
+
+
+class _DeviceBuffer:
+    """A raw device pointer as a __cuda_array_interface__ object (float64, 1-D)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+def all_reduce_device(ptr: int, n: int, group=None) -> None:
+    """In-place sum over the ranks of `n` doubles at device pointer `ptr` (NCCL over NVLink)."""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.as_tensor(_DeviceBuffer(ptr, n), device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    torch.cuda.current_stream().synchronize()
+
+
+def fit_tuple_sharded(dd, ls_type: str, est_eigenvalues, est_covariance_eigenvalues=None, group=None, **kw):
+    """One fit with the tuple blocks sharded over the ranks of `group`: block factors and partial
+    Gram matrices per rank, ncclAllReduce of the Gram matrix and the right-hand sides, replicated
+    Cholesky and solves.  `dd` is the rank's DeviceDesign; the shard is set here."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = shard_tuples(dd.fd.mapping_lengths, world)[rank]
+    on = [1 if t in mine else 0 for t in range(dd.fd.tuple_number)]
+    dd.set_tuple_shard(on)
+    try:
+        return dd.fit_sharded(ls_type, est_eigenvalues, est_covariance_eigenvalues,
+                              lambda p, n: all_reduce_device(p, n, group), **kw)
+    finally:
+        dd.set_tuple_shard(None)

@@ -270,3 +270,78 @@ def test_phase_timings_are_reported(ctx):
     assert {"covariance", "block factor", "gram", "potrf", "first solve", "refinement"} <= set(ph)
     assert all(v >= 0.0 for v in ph.values()) and dd.gram_flops() > 0
     dd.close()
+
+
+@pytest.mark.parametrize("shards,ls_type", [(2, "gls"), (3, "gls"), (2, "wls"), (2, "ols")])
+def test_tuple_sharded_fit_equals_unsharded(ctx, shards, ls_type):
+    """SURVEY 8e "one large Gram": the tuple blocks of one fit split over shards, the partial Gram
+    matrix and right-hand sides summed at the reduction points (here: shards are contexts on one GPU
+    and the sum is done by torch; across GPUs it is shard.all_reduce_device = ncclAllReduce)."""
+    import threading
+
+    import torch
+
+    import aces_b200
+    from aces_b200 import shard
+
+    fd = aces_b200.rotated_design(3, full_covariance=True, noise="lognormal", seed=4)
+    eig, cov = noisy_ensembles(fd, seed=21)
+    lam = np.concatenate(aces_b200.mean_ensemble(eig))
+    lc = np.concatenate(aces_b200.mean_ensemble(cov))
+    # clip rows of the repeated tuples only: a real design stays full rank without them
+    first_repeated = int(np.sum(fd.mapping_lengths[:9]))
+    rows = np.arange(fd.M)
+    kept = aces_b200.get_clipped_indices(np.where((rows % 17 == 3) & (rows >= first_repeated), 0.05, lam), warning=False)
+    assert len(kept) < fd.M
+    dd0 = aces_b200.DeviceDesign(ctx, fd)
+    want = dd0.fit(ls_type, lam, lc)
+    want_clipped = dd0.fit(ls_type, lam, lc, clipped_indices=kept)
+    dd0.close()
+    parts = shard.shard_tuples(fd.mapping_lengths, shards)
+    assert sorted(t for p in parts for t in p) == list(range(fd.tuple_number))
+    ctxs = [aces_b200.Context(0) for _ in range(shards)]
+    dds = [aces_b200.DeviceDesign(c, fd) for c in ctxs]
+    for dd, mine in zip(dds, parts):
+        dd.set_tuple_shard([1 if t in mine else 0 for t in range(fd.tuple_number)])
+    barrier = threading.Barrier(shards)
+    slots = [None] * shards
+
+    def reducer(i):
+        def reduce(ptr, n):
+            slots[i] = torch.as_tensor(shard._DeviceBuffer(ptr, n), device="cuda")
+            barrier.wait()
+            if i == 0:
+                torch.cuda.synchronize()
+                total = torch.stack(slots).sum(dim=0)
+                for s in slots:
+                    s.copy_(total)
+                torch.cuda.synchronize()
+            barrier.wait()
+        return reduce
+
+    for clipped, ref in ((None, want), (kept, want_clipped)):
+        outs, errs = [None] * shards, []
+
+        def work(i):
+            try:
+                outs[i] = dds[i].fit_sharded(ls_type, lam, lc, reducer(i), clipped_indices=clipped)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+                barrier.abort()
+
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(shards)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+        assert not errs, errs
+        for o in outs:
+            assert np.array_equal(o, outs[0])            # every shard ends with the same answer
+        assert rel(outs[0], ref) < 1e-12                 # and it is the unsharded fit (summation order differs)
+    # a sharded design refuses the unsharded entry points; clearing the shard restores them
+    with pytest.raises(aces_b200.AcesError):
+        dds[0].fit(ls_type, lam, lc)
+    dds[0].set_tuple_shard(None)
+    assert rel(dds[0].fit(ls_type, lam, lc), want) < 1e-15
+    for dd in dds:
+        dd.close()
+    for c in ctxs:
+        c.close()

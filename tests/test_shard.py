@@ -123,3 +123,14 @@ def test_shard_helpers():
     assert covered == rows and np.array_equal(total, pre)
     # more ranks than rows: empty shards are valid
     assert [shard.shard_shots(5, [5], 4, r)[:2] for r in range(4)] == [(0, 5), (5, 5), (5, 5), (5, 5)]
+
+
+def test_shard_tuples_partition_is_balanced():
+    from aces_b200 import shard
+
+    m = [483, 483, 1131, 483, 1131, 483, 1131, 1131, 483, 483, 483, 483, 1131, 1131, 1131, 1131]   # rotated d=9
+    for world in (1, 2, 3, 4, 8):
+        parts = shard.shard_tuples(m, world)
+        assert sorted(t for p in parts for t in p) == list(range(len(m)))
+        cost = [sum(float(m[t]) ** 3 for t in p) for p in parts]
+        assert max(cost) <= sum(cost) / world + max(float(x) ** 3 for x in m)
