@@ -328,6 +328,10 @@ int32_t aces_tables_create(aces_ctx* ctx, int32_t n_qubits, int32_t n_experiment
     std::vector<std::vector<std::vector<int32_t>>> sups((size_t)n_experiments);
     std::vector<int32_t> sup;
     bool need_groups = B > 41;  // wider than the widest single-group kernel variant
+    // Records of at most 21 byte columns (rotated d <= 9) run the 16-round kernel variant at three
+    // CTAs per SM, so an experiment of up to 512 Paulis (a full-covariance design: eigenvalue and
+    // covariance Paulis together) stays one group and its columns are transposed once.
+    const int group_paulis = B <= 21 ? 2 * GROUP_PAULIS : GROUP_PAULIS;
     bool groupable = true;      // every Pauli fits one group of GROUP_COLS columns
     for (int e = 0; e < n_experiments; ++e) {
         ACES_CHECK(ctx, exp_ptr[e + 1] >= exp_ptr[e], "tables_create: exp_ptr not monotone at %d", e);
@@ -358,7 +362,7 @@ int32_t aces_tables_create(aces_ctx* ctx, int32_t n_qubits, int32_t n_experiment
                 if (ncol > GROUP_COLS) groupable = false;
             }
         }
-        if (n_dev > GROUP_PAULIS) need_groups = true;
+        if (n_dev > group_paulis) need_groups = true;
     }
     const bool grouped = need_groups && groupable;
 
@@ -509,7 +513,7 @@ int32_t aces_tables_create(aces_ctx* ctx, int32_t n_qubits, int32_t n_experiment
                 std::stable_sort(members.begin(), members.end(), [&](int x, int y) {
                     return sups[(size_t)e][(size_t)x].front() < sups[(size_t)e][(size_t)y].front();
                 });
-                const int n_by_count = ((int)members.size() + GROUP_PAULIS - 1) / GROUP_PAULIS;
+                const int n_by_count = ((int)members.size() + group_paulis - 1) / group_paulis;
                 const int share = ((int)members.size() + n_by_count - 1) / n_by_count;
                 std::vector<int> cur;
                 std::vector<int32_t> gcols;

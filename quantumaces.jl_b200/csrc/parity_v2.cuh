@@ -95,7 +95,7 @@ __device__ __forceinline__ void v2_phase_a(uint32_t col_s, uint32_t pl_s, int nu
 
 // BMAX = byte columns the plane layout is dimensioned for (B <= BMAX).
 template <int NW, int SUB, int BMAX, int RMAX>
-__global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 8 ? 3 : 2) parity_kernel_v2(const ParityParams P) {
+__global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 16 ? 3 : 2) parity_kernel_v2(const ParityParams P) {
     constexpr int TS = NW * SUB;
     constexpr int CS = TS + 64;     // raw column stride: +64 B keeps quarter-warp LDS.128 conflict-free
     constexpr int V = SUB / 128;    // 128-shot vectors per plane row
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 8 ? 3 : 2) parity_kerne
     uint32_t acc[RMAX];
     // per register slot: weight-1 slots hold the shared-memory address of their plane row;
     // weight-2 slots hold the two plane-row offsets packed as a0 | a1 << 16
-    constexpr bool DXS = RMAX > 16;  // slot descriptors in shared memory instead of registers
+    constexpr bool DXS = RMAX > 8;   // slot descriptors in shared memory instead of registers
     uint32_t dx[DXS ? 1 : RMAX];
     constexpr uint32_t zero_row = (uint32_t)(8 * BMAX * RSTR);
     for (int i = lane; i < ROWB / 4; i += 32) sts32(planes_s + zero_row + 4 * i, 0u);
@@ -455,6 +455,7 @@ inline bool v2_pick(int B, int max_E, int smem_optin, V2Cfg* cfg) {
     if (B <= 3) { SUB = 512; BMAX = 7; }
     else if (B <= 7) { SUB = 256; BMAX = 7; }
     else if (B <= 13) { SUB = 128; BMAX = 13; }
+    else if (B <= 21) { SUB = 128; BMAX = 21; }  // d = 9 (B = 21): the smaller planes let the 16-round variant keep 3 CTAs/SM
     else if (B <= 25) { SUB = 128; BMAX = 25; }
     else if (B <= 41) { SUB = 128; BMAX = 41; }
     else return false;
@@ -469,7 +470,7 @@ inline bool v2_pick(int B, int max_E, int smem_optin, V2Cfg* cfg) {
     // Resident CTAs per SM: what the register budget of the variant allows (launch bounds of the
     // kernel), fewer when the shared memory of that many CTAs does not hold two stages each.
     int ns = 0;
-    for (int ctas = env_cta ? atoi(env_cta) : (RMAX <= 8 ? 3 : 2); ctas >= 1 && ns == 0; --ctas) {
+    for (int ctas = env_cta ? atoi(env_cta) : (RMAX <= 16 ? 3 : 2); ctas >= 1 && ns == 0; --ctas) {
         const size_t budget = ((size_t)smem_optin + 1024) / (size_t)ctas - 1024;
         for (int s = (env_ns ? atoi(env_ns) : 4); s >= 2; --s)
             if (raw_off + s * stage <= budget) { ns = s; break; }
@@ -510,6 +511,7 @@ inline int v2_launch(aces_ctx* ctx, const ParityParams& P, const V2Cfg& cfg) {
     (cfg.RMAX == 8 ? v2_launch_t<8, SUBV, BMV, 8>(ctx, P, cfg)                           \
                    : cfg.RMAX == 16 ? v2_launch_t<8, SUBV, BMV, 16>(ctx, P, cfg)         \
                                     : v2_launch_t<8, SUBV, BMV, 32>(ctx, P, cfg))
+    if (cfg.SUB == 128 && cfg.BMAX == 21) return ACES_V2_R(128, 21);
     if (cfg.SUB == 128 && cfg.BMAX == 25) return ACES_V2_R(128, 25);
     if (cfg.SUB == 128 && cfg.BMAX == 41) return ACES_V2_R(128, 41);
     if (cfg.SUB == 128) return ACES_V2_R(128, 13);
