@@ -520,7 +520,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k1::parity_kernel_v2<8,128,25,8>", "kernel_ms": k_ms,
+                         "kernel": "k1::parity_kernel_v2<8,128,21,8>", "kernel_ms": k_ms,
                          "kernel_ms_single_launch_events": k_iso,
                          "kernel_ms_source": "CUDA events over the timed region / steps (includes the memset and "
                                              "prefix helper kernels of each step)",

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 import aces_b200
 ctx = aces_b200.Context(0)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); assert stream.cuda_stream != 0; ctx.set_stream(stream.cuda_stream)
-fd = aces_b200.synthetic_design("rotated", 9)
+fd = aces_b200.rotated_design(9, full_covariance=False)
 est = aces_b200.DesignEstimator(ctx, fd)
 shots_divided, shots_max = aces_b200.shots_divide(fd, [10**6, 10**7, 10**8])
 n_exp, B = fd.experiment_number, fd.n_bytes
