@@ -352,6 +352,60 @@ function fit(dd::DeviceDesign, ls_type::Symbol, est_eigenvalues::Vector{Float64}
 end
 
 """
+    fit_tuple_sharded(dd, ls_type, est_eigenvalues, est_covariance_eigenvalues, tuple_on, allreduce!; ...)
+
+One fit with the tuple blocks split over several GPUs (one process per GPU, each with its own
+`DeviceDesign` of the same `Design`): this process works on the tuples with `tuple_on[t] == true`.
+`allreduce!(ptr::Ptr{Float64}, n::Int)` must sum `n` doubles at the DEVICE pointer `ptr` in place
+over the processes (NCCL.jl `Allreduce!` on an unsafe_wrap'd CuArray, or a CUDA-aware MPI.jl
+`Allreduce!`).  The Gram matrix and the right-hand sides are summed at the reduction points of
+include/aces_b200.h (`aces_design_fit_begin` .. `aces_design_fit_end`); every process returns the
+same gate eigenvalues.
+"""
+function fit_tuple_sharded(dd::DeviceDesign, ls_type::Symbol, est_eigenvalues::Vector{Float64},
+                           est_covariance_eigenvalues::Vector{Float64}, tuple_on::Vector{Bool}, allreduce!::Function;
+                           clipped_indices::Union{Vector{Int}, Nothing} = nothing, epsilon::Real = 1e-10,
+                           constrain::Bool = false)
+    kind = ls_type == :ols ? 0 : ls_type == :wls ? 1 : ls_type == :gls ? 2 :
+           throw(error("The least squares type $(ls_type) must be either :gls, :wls, or :ols."))
+    on = UInt8.(tuple_on)
+    g = Vector{Float64}(undef, dd.N)
+    kept = clipped_indices === nothing ? Int64[] : Int64.(clipped_indices)
+    gram = Ref{Ptr{Float64}}(C_NULL); rhs = Ref{Ptr{Float64}}(C_NULL)
+    n_gram = Ref{Int64}(0); n_rhs = Ref{Int64}(0)
+    GC.@preserve on est_eigenvalues est_covariance_eigenvalues kept g begin
+        check(ccall((:aces_design_set_tuple_shard, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{UInt8}), CTX[], dd.handle, on))
+        try
+            check(ccall((:aces_design_fit_begin, LIB[]), Int32,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Int64, Int32, Float64),
+                CTX[], dd.handle, Int32(kind), est_eigenvalues,
+                dd.C > 0 ? pointer(est_covariance_eigenvalues) : Ptr{Float64}(C_NULL),
+                clipped_indices === nothing ? Ptr{Int64}(C_NULL) : pointer(kept), length(kept), Int32(1), Float64(epsilon)))
+            check(ccall((:aces_design_fit_buffers, LIB[]), Int32,
+                (Ptr{Cvoid}, Ptr{Ptr{Float64}}, Ptr{Int64}, Ptr{Ptr{Float64}}, Ptr{Int64}), dd.handle, gram, n_gram, rhs, n_rhs))
+            check(ccall((:aces_synchronize, LIB[]), Int32, (Ptr{Cvoid},), CTX[]))
+            allreduce!(gram[], Int(n_gram[]))
+            allreduce!(rhs[], Int(n_rhs[]))
+            check(ccall((:aces_design_fit_solve, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), CTX[], dd.handle))
+            for it in 1:2
+                check(ccall((:aces_design_fit_refine_begin, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), CTX[], dd.handle))
+                check(ccall((:aces_synchronize, LIB[]), Int32, (Ptr{Cvoid},), CTX[]))
+                allreduce!(rhs[], Int(n_rhs[]))
+                xm = Ref{Float64}(0.0); dm = Ref{Float64}(0.0)
+                check(ccall((:aces_design_fit_refine_end, LIB[]), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), CTX[], dd.handle, xm, dm))
+                (it == 1 && dm[] <= 1e-7 * xm[]) && break
+            end
+            check(ccall((:aces_design_fit_end, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Float64}),
+                CTX[], dd.handle, Int32(constrain), g))
+        finally
+            ccall((:aces_design_set_tuple_shard, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{UInt8}), CTX[], dd.handle, C_NULL)
+        end
+    end
+    return g
+end
+
+"""
 S3: sparse_covariance_inv_factor(covariance_log, mapping_lengths; epsilon) (src/merit.jl:378-427) for
 a covariance_log in the design's pattern, optionally restricted to `clipped_indices`.
 """
