@@ -345,3 +345,28 @@ def test_tuple_sharded_fit_equals_unsharded(ctx, shards, ls_type):
         dd.close()
     for c in ctxs:
         c.close()
+
+
+def test_fit_matches_golden_fixture(ctx):
+    """The committed known answers (tests/golden/fit_golden.npz: a literal dense transcription of the
+    reference's formulas on the real example and rotated d=3 designs) through the CUDA path."""
+    import aces_b200
+    from test_fit_oracle import _golden_designs, _split
+
+    for name, fd, g in _golden_designs():
+        dd = aces_b200.DeviceDesign(ctx, fd)
+        try:
+            for k in ("ols", "wls", "gls"):
+                got = dd.fit(k, g["lam"], g["lam_cov"])
+                assert rel(got, g[k]) < RTOL, (name, k)
+            ge = fd.gate_eigenvalues
+            lam_true = np.exp(fd.matrix.astype(np.float64) @ np.log(ge))
+            lc_true = np.concatenate([np.exp(r.astype(np.float64) @ np.log(ge)) for r in fd.cov_rows])
+            lam_ens, cov_ens = _split(fd, lam_true, lc_true)
+            ct = dd.calc_covariance(lam_ens, cov_ens, log_form=True)
+            assert np.allclose(ct.diagonal(), g["true_covariance_log_diag"], rtol=1e-13)
+            for k in ("gls", "wls", "ols"):
+                _, tr, _ = dd.calc_ls_covariance(k, ct, want_matrix=False)
+                assert abs(tr - float(g[f"tr_{k}"])) <= RTOL * float(g[f"tr_{k}"]), (name, k)
+        finally:
+            dd.close()

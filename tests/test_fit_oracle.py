@@ -1,4 +1,7 @@
 """CPU tests: the numpy/scipy fit oracle against the reference's own identities."""
+import os
+import sys
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -140,3 +143,44 @@ def test_gate_noise_core_statistics(design):
     for k in ("ols", "wls", "gls"):
         err = np.linalg.norm(out[k] - fd.gate_eigenvalues) / np.sqrt(len(fd.gate_eigenvalues))
         assert err < 5e-4, (k, err)
+
+
+# ---- committed golden vectors (tests/golden/fit_golden.npz, made by a literal dense transcription) ----
+
+def _golden_designs():
+    import hashlib
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fit_golden.npz"))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_fit_golden import design_hash
+
+    for name, fd in (("example", aces_b200.example_design(full_covariance=True)),
+                     ("rotated_d3", aces_b200.rotated_design(3, full_covariance=True, noise="lognormal", seed=3))):
+        assert design_hash(fd) == str(z[f"{name}_hash"]), "the design generator changed: regenerate the fixture"
+        yield name, fd, {k[len(name) + 1:]: z[k] for k in z.files if k.startswith(name + "_")}
+    del hashlib
+
+
+def _split(fd, lam, lam_cov):
+    off = np.concatenate([[0], np.cumsum(fd.mapping_lengths)])
+    coff = np.concatenate([[0], np.cumsum([len(k) for k in fd.cov_keys])])
+    return ([lam[off[t]:off[t + 1]] for t in range(fd.tuple_number)],
+            [lam_cov[coff[t]:coff[t + 1]] for t in range(fd.tuple_number)])
+
+
+def test_oracle_matches_golden_fixture():
+    for name, fd, g in _golden_designs():
+        lam_ens, cov_ens = _split(fd, g["lam"], g["lam_cov"])
+        cl = fo.calc_covariance_log(fo.calc_covariance(fd, lam_ens, cov_ens, weight_time=False), g["lam"])
+        A = fd.matrix.astype(np.float64)
+        got = {"ols": fo.estimate_gate_eigenvalues(A, g["lam"]),
+               "wls": fo.estimate_gate_eigenvalues(A, g["lam"], sp.diags(cl.diagonal() ** -0.5)),
+               "gls": fo.estimate_gate_eigenvalues(A, g["lam"], fo.sparse_covariance_inv_factor(cl, fd.mapping_lengths))}
+        for k in ("ols", "wls", "gls"):
+            assert np.linalg.norm(got[k] - g[k]) <= 1e-9 * np.linalg.norm(g[k]), (name, k)
+        ge = fd.gate_eigenvalues
+        ct = fo.calc_covariance_log(fo.calc_covariance(fd, fo.get_eigenvalues_ensemble(fd, ge),
+                                                       fo.calc_covariance_eigenvalues(fd, ge)), fo.get_eigenvalues(fd, ge))
+        assert np.allclose(ct.diagonal(), g["true_covariance_log_diag"], rtol=1e-13)
+        for k, f in (("gls", fo.calc_gls_covariance), ("wls", fo.calc_wls_covariance), ("ols", fo.calc_ols_covariance)):
+            assert abs(np.trace(f(fd, ct)) - float(g[f"tr_{k}"])) <= 1e-9 * float(g[f"tr_{k}"]), (name, k)
