@@ -36,6 +36,7 @@ SHOTS_SET = [10**6, 10**7, 10**8]
 WORKLOAD = "rotated_d9_wls_1e8shots"
 
 
+FIT_CONTEXTS = 4         # concurrent fit contexts of the throughput line (--fit-contexts)
 DESIGN_SOURCE = "real"   # "real": circuit_design.rotated_design(9) (the reference's own tables); "synthetic": look-alike
 
 
@@ -248,7 +249,7 @@ def fit_leg(ctx, torch, dist, world, rank, steps, warmup, with_cpu):
     # Throughput with several fit contexts on this GPU: fits are independent per budget and repetition
     # (src/simulate.jl:393) and one fit leaves most SMs idle (its Cholesky is a latency-bound chain),
     # so concurrent contexts (own stream and workspaces each, one host thread each) overlap.
-    n_conc = 4
+    n_conc = FIT_CONTEXTS
     ctxs = [aces_b200.Context(ctx.device) for _ in range(n_conc - 1)]
     dds = [dd] + [aces_b200.DeviceDesign(c, fd) for c in ctxs]
     for name in ("gls", "wls"):
@@ -367,9 +368,11 @@ def main():
     ap.add_argument("--no-fit", action="store_true")
     ap.add_argument("--fit-steps", type=int, default=5)
     ap.add_argument("--design", default="real", choices=["real", "synthetic"])
+    ap.add_argument("--fit-contexts", type=int, default=4)
     args = ap.parse_args()
-    global DESIGN_SOURCE
+    global DESIGN_SOURCE, FIT_CONTEXTS
     DESIGN_SOURCE = args.design
+    FIT_CONTEXTS = args.fit_contexts
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
         return run_reference(args)

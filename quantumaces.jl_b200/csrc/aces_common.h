@@ -28,6 +28,8 @@ struct aces_ctx {
     cudaEvent_t ev = nullptr;
     cudaStream_t aux_stream = nullptr;            // low-priority side stream (look-ahead updates)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t aux2_stream = nullptr;           // medium priority: off-critical-path work of a Cholesky step
+    cudaEvent_t ev_crit = nullptr, ev_aux2 = nullptr;
     cudaEvent_t t0 = nullptr, t1 = nullptr;  // bracket the dominant kernel when timing is on
     int timing = 0;
     int timed = 0;

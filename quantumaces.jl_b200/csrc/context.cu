@@ -110,6 +110,10 @@ int32_t aces_init(int32_t device, aces_ctx** out) {
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     e = cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_lo);
+    if (e == cudaSuccess)
+        e = cudaStreamCreateWithPriority(&ctx->aux2_stream, cudaStreamNonBlocking, (prio_lo + prio_hi) / 2);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_crit, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_aux2, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev2, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
@@ -131,6 +135,7 @@ int32_t aces_destroy(aces_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+    if (ctx->aux2_stream) cudaStreamSynchronize(ctx->aux2_stream);
     DevBuf* dev[] = {&ctx->d_arena, &ctx->d_streams, &ctx->d_seg, &ctx->d_odd, &ctx->d_flags};
     for (DevBuf* b : dev)
         if (b->ptr) cudaFree(b->ptr);
@@ -145,6 +150,9 @@ int32_t aces_destroy(aces_ctx* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->ev_crit) cudaEventDestroy(ctx->ev_crit);
+    if (ctx->ev_aux2) cudaEventDestroy(ctx->ev_aux2);
+    if (ctx->aux2_stream) cudaStreamDestroy(ctx->aux2_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return ACES_OK;

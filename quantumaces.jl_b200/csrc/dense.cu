@@ -18,6 +18,11 @@ constexpr int LD_KC = BK + 4;  // row stride of a [BM][BK] tile (operand contigu
 constexpr int OPER_DOUBLES = BM * LD_KC;  // 2560 >= BK * LD_MC = 2112
 constexpr int STAGE_DOUBLES = 2 * OPER_DOUBLES;
 constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);
+// The 64-row variant keeps a compact A operand so that two of its CTAs fit one SM (92 KB each): the
+// prologue / epilogue of one tile then overlaps the main loop of another (short-K updates).
+__host__ __device__ constexpr int a_doubles(int bmt) { return bmt == BM ? OPER_DOUBLES : (bmt * LD_KC > BK * (bmt + 4) ? bmt * LD_KC : BK * (bmt + 4)); }
+__host__ __device__ constexpr int stage_doubles(int bmt) { return a_doubles(bmt) + OPER_DOUBLES; }
+constexpr size_t gemm_smem(int bmt) { return (size_t)STAGES * stage_doubles(bmt) * sizeof(double); }
 
 struct GemmP {
     const double* A;
@@ -60,16 +65,19 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const int bm, const in
     const double* Ag = A_KC ? p.A + (int64_t)bm * BMT * p.lda : p.A + (int64_t)bm * BMT;
     const double* Bg = B_KC ? p.B + (int64_t)bn * BN * p.ldb : p.B + (int64_t)bn * BN;
     const int nk = p.k / BK;
+    constexpr int LDA_MC = BMT + 4;            // row stride of the A tile in the [BK][BMT] layout
+    constexpr int SD = stage_doubles(BMT);     // doubles per pipeline stage
+    constexpr int AD = a_doubles(BMT);
 
     auto load = [&](int stage, int kt) {
-        double* sA = sm + stage * STAGE_DOUBLES;
-        double* sB = sA + OPER_DOUBLES;
+        double* sA = sm + stage * SD;
+        double* sB = sA + AD;
         const int k0 = kt * BK;
 #pragma unroll
         for (int c = tid; c < BMT * 8; c += GT) {
             if (!A_KC) {
                 const int kk = c / (BMT / 2), ci = c % (BMT / 2);
-                cp_async16(sA + kk * LD_MC + 2 * ci, Ag + 2 * ci + (int64_t)(k0 + kk) * p.lda);
+                cp_async16(sA + kk * LDA_MC + 2 * ci, Ag + 2 * ci + (int64_t)(k0 + kk) * p.lda);
             } else {
                 const int i = c >> 3, ck = c & 7;
                 cp_async16(sA + i * LD_KC + 2 * ck, Ag + (k0 + 2 * ck) + (int64_t)i * p.lda);
@@ -104,15 +112,15 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const int bm, const in
         const int nxt = kt + STAGES - 1;
         if (nxt < nk) load(nxt % STAGES, nxt);
         cp_async_commit();
-        const double* sA = sm + (kt % STAGES) * STAGE_DOUBLES;
-        const double* sB = sA + OPER_DOUBLES;
+        const double* sA = sm + (kt % STAGES) * SD;
+        const double* sB = sA + AD;
 #pragma unroll
         for (int k4 = 0; k4 < BK / 4; ++k4) {
             double a[MI], b[4];
 #pragma unroll
             for (int i = 0; i < MI; ++i)
                 a[i] = A_KC ? sA[(wm + i * 8 + g) * LD_KC + k4 * 4 + t]
-                            : sA[(k4 * 4 + t) * LD_MC + wm + i * 8 + g];
+                            : sA[(k4 * 4 + t) * LDA_MC + wm + i * 8 + g];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 b[j] = B_KC ? sB[(wn + j * 8 + g) * LD_KC + k4 * 4 + t]
@@ -146,7 +154,7 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const int bm, const in
 }
 
 template <bool A_KC, bool B_KC, int BMT>
-__global__ void __launch_bounds__(GT, 1) gemm_kernel(const GemmP p, const int lower_only) {
+__global__ void __launch_bounds__(GT, BMT == 64 ? 2 : 1) gemm_kernel(const GemmP p, const int lower_only) {
     // lower_only: skip the tiles that lie entirely above the block diagonal
     if (lower_only && (int)blockIdx.y * BN >= ((int)blockIdx.x + 1) * BMT) return;
     extern __shared__ __align__(16) double sm[];
@@ -648,9 +656,9 @@ int configure(aces_ctx* ctx) {
     ACES_TRY(set_smem(ctx, gemm_kernel<false, false, 128>, GEMM_SMEM));
     ACES_TRY(set_smem(ctx, gemm_kernel<false, true, 128>, GEMM_SMEM));
     ACES_TRY(set_smem(ctx, gemm_kernel<true, true, 128>, GEMM_SMEM));
-    ACES_TRY(set_smem(ctx, gemm_kernel<false, false, 64>, GEMM_SMEM));
-    ACES_TRY(set_smem(ctx, gemm_kernel<false, true, 64>, GEMM_SMEM));
-    ACES_TRY(set_smem(ctx, gemm_kernel<true, true, 64>, GEMM_SMEM));
+    ACES_TRY(set_smem(ctx, gemm_kernel<false, false, 64>, gemm_smem(64)));
+    ACES_TRY(set_smem(ctx, gemm_kernel<false, true, 64>, gemm_smem(64)));
+    ACES_TRY(set_smem(ctx, gemm_kernel<true, true, 64>, gemm_smem(64)));
     ACES_TRY(set_smem(ctx, gemm_batched_kernel<false, false>, GEMM_SMEM));
     ACES_TRY(set_smem(ctx, gemm_batched_kernel<false, true>, GEMM_SMEM));
     ACES_TRY(set_smem(ctx, gemm_batched_kernel<true, true>, GEMM_SMEM));
@@ -665,10 +673,12 @@ template <bool A_KC, bool B_KC>
 int launch_gemm(aces_ctx* ctx, const GemmP& p, int64_t m, int64_t n, int lower_only) {
     // 64-row tiles when 128-row tiles would leave most SMs idle or give a ragged second wave
     const int64_t tiles128 = lower_only ? ((m / BM) * (n / BN) + std::min(m / BM, n / BN)) / 2 : (m / BM) * (n / BN);
-    // (not when C aliases B: an in-place B operand is only safe while one CTA owns all its rows)
-    if (tiles128 < 2 * (int64_t)ctx->sm_count && (const double*)p.C != p.B) {
+    static const int force64 = [] { const char* e = getenv("ACES_GEMM_64"); return e ? atoi(e) : 1; }();
+    // force64: 1 = every launch whose K is at most 512 (the Cholesky updates), 2 = every launch
+    const bool want64 = tiles128 < 2 * (int64_t)ctx->sm_count || force64 == 2 || (force64 == 1 && p.k <= 512);
+    if (want64 && (const double*)p.C != p.B) {
         dim3 grid((unsigned)(m / 64), (unsigned)(n / BN));
-        gemm_kernel<A_KC, B_KC, 64><<<grid, GT, GEMM_SMEM, ctx->stream>>>(p, lower_only);
+        gemm_kernel<A_KC, B_KC, 64><<<grid, GT, gemm_smem(64), ctx->stream>>>(p, lower_only);
     } else {
         dim3 grid((unsigned)(m / BM), (unsigned)(n / BN));
         gemm_kernel<A_KC, B_KC, 128><<<grid, GT, GEMM_SMEM, ctx->stream>>>(p, lower_only);
@@ -727,28 +737,65 @@ int potrf(aces_ctx* ctx, int64_t n, double* A, int64_t lda, double* dinv, int* f
     ACES_CHECK(ctx, n % DB == 0, "dense::potrf: n=%lld is not padded", (long long)n);
     ACES_TRY(configure(ctx));
     constexpr int64_t NB2 = 4 * DB;  // outer panel: the bulk of the flops runs as K = 512 updates
+    // development probe: skip parts of the factorisation to time the others (results are then wrong)
+    const char* skip_env = getenv("ACES_POTRF_SKIP");
+    const int skip = skip_env ? atoi(skip_env) : 0;  // 1 diag, 2 critical tiles, 4 second stream, 8 look-ahead, 16 side
     const cudaStream_t main_stream = ctx->stream;
     bool side_pending = false;
+    // The chain diag(k) -> diag(k+1) is the critical path (one CTA at a time).  Only one tile of the
+    // panel and one tile of the update stand between two diagonal blocks: block row k+1 of the panel
+    // and the update of block (k+1, k+1).  They run on the main stream; the rest of step k (the
+    // panel rows below, the update of the other blocks of the outer panel) runs on a second stream
+    // while the next diagonal block is being factorised.
+    bool aux2_pending = false;
+    auto on_aux2 = [&](auto&& fn) -> int {
+        ctx->stream = ctx->aux2_stream;
+        const int rc = fn();
+        ctx->stream = main_stream;
+        return rc;
+    };
     for (int64_t K0 = 0; K0 < n; K0 += NB2) {
         const int64_t kb = std::min(NB2, n - K0);
         for (int64_t k = K0; k < K0 + kb; k += DB) {
             double* Akk = A + k * (lda + 1);
             double* dk = dinv + (k / DB) * DB * DB;
             DiagDesc one{Akk, lda, dk, diag0 ? diag0 + k : nullptr, flag, (int32_t)(k / DB) + 1, 0};
-            diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, ctx->stream>>>(nullptr, one, rel_tol);
+            if (!(skip & 1)) diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, ctx->stream>>>(nullptr, one, rel_tol);
             ACES_CUDA(ctx, cudaGetLastError());
             ctx->launches += 1;
             const int64_t rows = n - (k + DB);
             if (rows <= 0) continue;
             double* panel = Akk + DB;
-            // panel <- panel * inv(L_kk)'  (in place: a CTA reads exactly the tile it writes)
-            ACES_TRY(gemm(ctx, GEMM_NT, rows, DB, DB, 1.0, panel, lda, dk, DB, 0.0, panel, lda, 0));
-            // update the rest of the outer panel (columns k+128 .. K0+kb)
-            const int64_t cols = K0 + kb - (k + DB);
+            const int64_t cols = K0 + kb - (k + DB);  // columns of the outer panel behind block column k
+            // block column k below the diagonal got its last update from the second stream (step k-1)
+            if (aux2_pending) ACES_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_aux2, 0));
+            // critical tile: panel rows [k+128, k+256) <- panel * inv(L_kk)'  (in place), then block (k+1, k+1)
+            if (!(skip & 2)) {
+            ACES_TRY(gemm(ctx, GEMM_NT, DB, DB, DB, 1.0, panel, lda, dk, DB, 0.0, panel, lda, 0));
             if (cols > 0)
-                ACES_TRY(gemm(ctx, GEMM_NT, rows, cols, DB, -1.0, panel, lda, panel, lda, 1.0,
-                              Akk + DB * (lda + 1), lda, 1));
+                ACES_TRY(gemm(ctx, GEMM_NT, DB, DB, DB, -1.0, panel, lda, panel, lda, 1.0, Akk + DB * (lda + 1), lda, 1));
+            }
+            const int64_t rest = rows - DB;
+            if (rest > 0 && !(skip & 4)) {
+                ACES_CUDA(ctx, cudaEventRecord(ctx->ev_crit, main_stream));
+                ACES_CUDA(ctx, cudaStreamWaitEvent(ctx->aux2_stream, ctx->ev_crit, 0));
+                double* below = panel + DB;  // panel rows from k + 256 on
+                ACES_TRY(on_aux2([&] {
+                    ACES_TRY(gemm(ctx, GEMM_NT, rest, DB, DB, 1.0, below, lda, dk, DB, 0.0, below, lda, 0));
+                    if (cols > 0)  // block column k+1 below its diagonal block
+                        ACES_TRY(gemm(ctx, GEMM_NT, rest, DB, DB, -1.0, below, lda, panel, lda, 1.0,
+                                      Akk + DB * (lda + 1) + DB, lda, 0));
+                    if (cols > DB)  // the other columns of the outer panel (lower triangle from (k+2, k+2))
+                        ACES_TRY(gemm(ctx, GEMM_NT, rest, cols - DB, DB, -1.0, below, lda, below, lda, 1.0,
+                                      Akk + 2 * DB * (lda + 1), lda, 1));
+                    return (int)ACES_OK;
+                }));
+                ACES_CUDA(ctx, cudaEventRecord(ctx->ev_aux2, ctx->aux2_stream));
+                aux2_pending = true;
+            }
         }
+        // the outer panel is final once the second stream is done with it
+        if (aux2_pending) ACES_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_aux2, 0));
         const int64_t rows = n - (K0 + kb);
         if (rows > 0) {
             // Trailing update with look-ahead: the columns of the NEXT panel are updated on the main
@@ -758,9 +805,27 @@ int potrf(aces_ctx* ctx, int64_t n, double* A, int64_t lda, double* dinv, int* f
             const int64_t next = std::min(NB2, rows);
             ACES_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main_stream));  // the panel is final
             if (side_pending) ACES_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
-            ACES_TRY(gemm(ctx, GEMM_NT, rows, next, kb, -1.0, P, lda, P, lda, 1.0, A + (K0 + kb) * (lda + 1), lda, 1));
+            if (!(skip & 8)) {
+                // Only the first 128 columns of the next panel are needed by its first diagonal block
+                // and panel; the other column blocks are needed one step later each, so they are
+                // updated on the second stream (which also applies the in-panel updates to them: same
+                // stream, so the two accumulations into a block are ordered).
+                const int64_t first = std::min<int64_t>(DB, next);
+                ACES_TRY(gemm(ctx, GEMM_NT, rows, first, kb, -1.0, P, lda, P, lda, 1.0, A + (K0 + kb) * (lda + 1), lda, 1));
+                if (next > first) {
+                    ACES_CUDA(ctx, cudaEventRecord(ctx->ev_crit, main_stream));
+                    ACES_CUDA(ctx, cudaStreamWaitEvent(ctx->aux2_stream, ctx->ev_crit, 0));
+                    // rows from the second block row on (the first block row of these columns lies above the diagonal)
+                    ACES_TRY(on_aux2([&] {
+                        return gemm(ctx, GEMM_NT, rows - first, next - first, kb, -1.0, P + first, lda, P + first, lda, 1.0,
+                                    A + (K0 + kb + first) * (lda + 1), lda, 1);
+                    }));
+                    ACES_CUDA(ctx, cudaEventRecord(ctx->ev_aux2, ctx->aux2_stream));
+                    aux2_pending = true;
+                }
+            }
             const int64_t rest = rows - next;
-            if (rest > 0) {
+            if (rest > 0 && !(skip & 16)) {
                 ACES_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
                 ctx->stream = ctx->aux_stream;
                 const int rc = gemm(ctx, GEMM_NT, rest, rest, kb, -1.0, P + next, lda, P + next, lda, 1.0,
@@ -773,6 +838,7 @@ int potrf(aces_ctx* ctx, int64_t n, double* A, int64_t lda, double* dinv, int* f
         }
     }
     if (side_pending) ACES_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
+    if (aux2_pending) ACES_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_aux2, 0));
     return ACES_OK;
 }
 
