@@ -377,6 +377,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # Libraries print banners on stdout (NCCL: "NCCL version ..."): stdout carries exactly one JSON
+    # line, so everything else goes to stderr until the line is printed.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -533,7 +539,9 @@ def main():
             line["cpu_baseline"] = cpu_sample(fd, sizes)
         if fit is not None:
             line["fit"] = fit
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
