@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaces_b200.so")
+LIB_PATH = os.environ.get("ACES_B200_LIB") or os.path.join(_HERE, "libaces_b200.so")
 
 ACES_OK = 0
 ACES_E_INVALID = -1

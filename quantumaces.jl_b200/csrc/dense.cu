@@ -238,7 +238,43 @@ __device__ __noinline__ bool diag16(double* s, double* rdiag, const double* pflo
     return bad;
 }
 
+// Trailing update of one row (one lane) for NB columns c0, c0 + 15, ... of the shared-memory block:
+// s(row, j) -= sum_k s(row, k0 + k) * s(j, k0 + k) for the 16 columns k of the current panel.
+template <int NB>
+__device__ __forceinline__ void c2_rows(double* s, const int k0, const int c0, const int row) {
+    double acc[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc[b] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < PW; ++k) {
+        const double* col = s + (k0 + k) * PLD;
+        const double ra = col[row];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) acc[b] += ra * col[c0 + 15 * b];
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int j = c0 + 15 * b;
+        if (row >= j) s[j * PLD + row] -= acc[b];
+    }
+}
+
+#ifdef ACES_DIAG_PROFILE
+__device__ int g_diag_prof_count = 0;
+__device__ unsigned long long g_c2_cycles[2] = {0, 0};
+#define DPROF_DECL long long _t[12]; int _ti = 0; long long _acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define DPROF(slot) { if (threadIdx.x == 0) { long long _n = clock64(); _acc[slot] += _n - _last; _last = _n; } }
+#define DPROF_START long long _last = clock64();
+#define DPROF_WARP(slot, t0) { if (threadIdx.x == 0) _acc[slot] += clock64() - (t0); }
+#else
+#define DPROF_DECL
+#define DPROF(slot)
+#define DPROF_START
+#define DPROF_WARP(slot, t0)
+#endif
 __device__ __forceinline__ void diag_block(const DiagDesc& d, const double rel_tol, double* sh) {
+    DPROF_DECL
+    DPROF_START
     double* s = sh;                  // s[j*PLD + i] = A(i, j)
     double* tmp = sh + DB * PLD;     // [PW][PLD] scratch of the inverse
     double* rdiag = tmp + PW * PLD;  // reciprocals of the diagonal of L
@@ -258,6 +294,7 @@ __device__ __forceinline__ void diag_block(const DiagDesc& d, const double rel_t
     }
     if (tid < DB) pfloor[tid] = d.diag0 ? rel_tol * fabs(d.diag0[tid]) : 0.0;
     __syncthreads();
+    DPROF(0)  // load
     // Right-looking factorisation with look-ahead inside the CTA: after the panel rows of panel p
     // are solved, all warps update the 16 columns of panel p+1 (c1); then warp 0 factorises the
     // next 16 x 16 diagonal piece while warps 1..15 update the remaining trailing columns (c2).
@@ -265,6 +302,7 @@ __device__ __forceinline__ void diag_block(const DiagDesc& d, const double rel_t
     if (warp == 0) bad = diag16(s, rdiag, pfloor, 0, lane);
     for (int k0 = 0; k0 < DB - PW; k0 += PW) {
         __syncthreads();
+        DPROF(1)  // diag16 (warp 0) / c2 (other warps), whichever is longer
         const int r0 = k0 + PW;  // first trailing row / column
         // (b) panel rows: x * L_dd' = a, one thread per row
         if (tid < DB - r0) {
@@ -283,6 +321,7 @@ __device__ __forceinline__ void diag_block(const DiagDesc& d, const double rel_t
             for (int c = 0; c < PW; ++c) s[(k0 + c) * PLD + i] = a[c];
         }
         __syncthreads();
+        DPROF(2)  // panel rows
         // (c1) the columns of the next panel: thread t owns column r0 + (t & 15), rows r0 + (t >> 4) + 32a
         {
             const int j = r0 + (tid & (PW - 1)), ib = r0 + (tid >> 4);
@@ -302,46 +341,53 @@ __device__ __forceinline__ void diag_block(const DiagDesc& d, const double rel_t
             }
         }
         __syncthreads();
+        DPROF(3)  // c1
+#ifdef ACES_DIAG_PROFILE
+        const long long _tw = clock64();
+#endif
         if (warp == 0) {
             bad |= diag16(s, rdiag, pfloor, r0, lane);
+            DPROF_WARP(7, _tw)  // diag16 alone
         } else if (r0 + PW < DB) {
-            // (c2) the columns behind the next panel: warp w owns columns c0 + 15 b, rows lane + 32 a
+            // (c2) the columns behind the next panel: warp w owns columns j_b = c0 + 15 b (b = 0, 1, ...
+            // while j_b < 128); a group of 32 rows [32 a, 32 a + 31] only needs the columns up to its
+            // last row (lower triangle), a prefix of this warp's columns: the k loop runs once per row
+            // group with exactly that many accumulators (a fifth of the multiply-adds of the full
+            // 128 x 120 rectangle over the eight panels).
             const int c0 = r0 + PW + (warp - 1);
-            double acc[4][8];
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int bq = 0; bq < 8; ++bq) acc[a][bq] = 0.0;
-#pragma unroll 4
-            for (int k = 0; k < PW; ++k) {
-                const double* col = s + (k0 + k) * PLD;
-                double ra[4], cb[8];
-#pragma unroll
-                for (int a = 0; a < 4; ++a) ra[a] = (32 * a + 31 >= r0) ? col[lane + 32 * a] : 0.0;
-#pragma unroll
-                for (int bq = 0; bq < 8; ++bq) cb[bq] = (c0 + 15 * bq < DB) ? col[c0 + 15 * bq] : 0.0;
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int bq = 0; bq < 8; ++bq) acc[a][bq] += ra[a] * cb[bq];
-            }
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int bq = 0; bq < 8; ++bq) {
-                    const int i = lane + 32 * a, j = c0 + 15 * bq;
-                    if (j < DB && i >= j) s[j * PLD + i] -= acc[a][bq];
+#ifdef ACES_DIAG_PROFILE
+            const long long _tc = clock64();
+#endif
+            for (int a = (r0 + PW) >> 5; a < 4; ++a) {
+                const int last = 32 * a + 31;
+                if (last < c0) continue;
+                const int nb = (last - c0) / 15 + 1;  // <= 8
+                switch (nb) {
+                    case 1: c2_rows<1>(s, k0, c0, lane + 32 * a); break;
+                    case 2: c2_rows<2>(s, k0, c0, lane + 32 * a); break;
+                    case 3: c2_rows<3>(s, k0, c0, lane + 32 * a); break;
+                    case 4: c2_rows<4>(s, k0, c0, lane + 32 * a); break;
+                    case 5: c2_rows<5>(s, k0, c0, lane + 32 * a); break;
+                    case 6: c2_rows<6>(s, k0, c0, lane + 32 * a); break;
+                    case 7: c2_rows<7>(s, k0, c0, lane + 32 * a); break;
+                    default: c2_rows<8>(s, k0, c0, lane + 32 * a); break;
                 }
+            }
+#ifdef ACES_DIAG_PROFILE
+            if (blockIdx.x == 0 && (tid == 32 || tid == 15 * 32)) atomicAdd(&g_c2_cycles[tid == 32 ? 0 : 1], (unsigned long long)(clock64() - _tc));
+#endif
         }
     }
     if (warp == 0 && bad && lane == 0 && d.flag) atomicCAS(d.flag, 0, d.code);
     __syncthreads();
+    DPROF(1)
     // L -> global (strict upper triangle zeroed)
     for (int e = tid; e < DB * DB; e += DIAG_THREADS) {
         const int i = e & (DB - 1), j = e >> 7;
         d.A[i + (int64_t)j * d.lda] = (i >= j) ? s[j * PLD + i] : 0.0;
     }
     __syncthreads();
+    DPROF(4)  // store L
     // ---- in-place inverse ------------------------------------------------------------------
     if (warp < DB / PW) {
         const int b0 = warp * PW;
@@ -396,10 +442,18 @@ __device__ __forceinline__ void diag_block(const DiagDesc& d, const double rel_t
         }
         __syncthreads();
     }
+    DPROF(5)  // inverse
     for (int e = tid; e < DB * DB; e += DIAG_THREADS) {
         const int i = e & (DB - 1), j = e >> 7;
         d.dinv[i + j * DB] = (i >= j) ? s[j * PLD + i] : 0.0;
     }
+    DPROF(6)  // store inverse
+#ifdef ACES_DIAG_PROFILE
+    if (threadIdx.x == 0 && blockIdx.x == 0 && atomicAdd(&g_diag_prof_count, 1) % 40 == 5)
+        printf("[diag prof] cycles: load %lld | diag16-or-c2 wait %lld | panel rows %lld | c1 %lld | store L %lld | inverse %lld | "
+               "store inv %lld | diag16 alone (7 calls) %lld | c2 of warp 1 / warp 15, sum over all launches so far %llu / %llu (launch %d)\n",
+               _acc[0], _acc[1], _acc[2], _acc[3], _acc[4], _acc[5], _acc[6], _acc[7], g_c2_cycles[0], g_c2_cycles[1], g_diag_prof_count);
+#endif
 }
 
 __global__ void __launch_bounds__(DIAG_THREADS, 1) diag_kernel(const DiagDesc* __restrict__ descs,

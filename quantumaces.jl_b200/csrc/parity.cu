@@ -328,10 +328,11 @@ int32_t aces_tables_create(aces_ctx* ctx, int32_t n_qubits, int32_t n_experiment
     std::vector<std::vector<std::vector<int32_t>>> sups((size_t)n_experiments);
     std::vector<int32_t> sup;
     bool need_groups = B > 41;  // wider than the widest single-group kernel variant
-    // Records of at most 21 byte columns (rotated d <= 9) run the 16-round kernel variant at three
-    // CTAs per SM, so an experiment of up to 512 Paulis (a full-covariance design: eigenvalue and
-    // covariance Paulis together) stays one group and its columns are transposed once.
-    const int group_paulis = B <= 21 ? 2 * GROUP_PAULIS : GROUP_PAULIS;
+    // Records that fit one column group run the 16-round kernel variant (three CTAs per SM up to 21
+    // byte columns, two above), so an experiment of up to 512 Paulis (a full-covariance design:
+    // eigenvalue and covariance Paulis together) stays one group and its columns are transposed once.
+    const char* gp_env = getenv("ACES_K1_GROUP_PAULIS");  // development knob
+    const int group_paulis = gp_env ? atoi(gp_env) : (B <= GROUP_COLS ? 2 * GROUP_PAULIS : GROUP_PAULIS);
     bool groupable = true;      // every Pauli fits one group of GROUP_COLS columns
     for (int e = 0; e < n_experiments; ++e) {
         ACES_CHECK(ctx, exp_ptr[e + 1] >= exp_ptr[e], "tables_create: exp_ptr not monotone at %d", e);
