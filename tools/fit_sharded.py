@@ -28,7 +28,19 @@ os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
 os.environ.setdefault("MASTER_PORT", "29511")
 dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
 gen = aces_b200.rotated_design if kind == "rotated" else aces_b200.unrotated_design
-fd = gen(d, full_covariance=True, noise="lognormal", seed=9)
+# rank 0 generates the design (minutes at d = 17) and shares it through a file; the others wait
+import pickle  # noqa: E402
+
+path = f"/tmp/aces_design_{kind}_{d}.pkl"
+if rank == 0:
+    fd = gen(d, full_covariance=True, noise="lognormal", seed=9)
+    with open(path + ".tmp", "wb") as f:
+        pickle.dump(fd, f, protocol=4)
+    os.replace(path + ".tmp", path)
+dist.barrier()
+if rank != 0:
+    with open(path, "rb") as f:
+        fd = pickle.load(f)
 eig, cov = aces_b200.synthetic_estimates(fd, shots=10**8, seed=11)
 lam = np.concatenate(aces_b200.mean_ensemble(eig))
 lc = np.concatenate(aces_b200.mean_ensemble(cov))
