@@ -24,6 +24,8 @@
 // odd count).  A second tiny kernel turns per-segment counts into per-prefix counts.
 // Counts are exact integers: the result is bit-identical to the reference by construction.
 #include <algorithm>
+#include <array>
+#include <cstdio>
 #include <climits>
 #include <cstring>
 
@@ -194,8 +196,43 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
     const size_t sz_ioff = sizeof(int64_t) * (size_t)(n_items + 1);
     const size_t sz_iE = sizeof(int32_t) * (size_t)n_items;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    // ---- cost-balanced partition of the work items over the persistent CTAs (v2) ----------------
+    // A CTA takes a contiguous range of tiles (a stream change costs a counter flush), and a tile's
+    // cost depends on its stream: the transposition is proportional to the byte columns read, the
+    // parity evaluation to the rounds of 32 Paulis.  Weights in warp instructions per 1024-shot
+    // tile, from the ncu source view of the d = 9 kernel (profiles/k1_r01_ncu_full_summary.txt).
+    std::vector<int64_t> cta_start;
+    int grid = 0;
+    static const bool balance = [] { const char* e = getenv("ACES_K1_BALANCE"); return !e || atoi(e) != 0; }();
+    static const std::array<double, 3> cost_w = [] {
+        std::array<double, 3> w{1300.0, 114.0, 150.0};
+        if (const char* e = getenv("ACES_K1_COST")) sscanf(e, "%lf,%lf,%lf", &w[0], &w[1], &w[2]);  // development knob
+        return w;
+    }();
+    if (use_v2 && total_items > 0 && balance) {
+        grid = v2_grid(ctx, cfg2);
+        if (grid < 0) return grid;
+        if ((int64_t)grid > total_items) grid = (int)total_items;
+        std::vector<double> cum((size_t)n_streams + 1, 0.0), per((size_t)n_streams, 0.0);
+        for (int s = 0; s < n_streams; ++s) {
+            const int rounds = (streams[(size_t)s].E + 31) / 32;
+            per[(size_t)s] = cost_w[0] + cost_w[1] * streams[(size_t)s].ncols + cost_w[2] * rounds;
+            cum[(size_t)s + 1] = cum[(size_t)s] + per[(size_t)s] * (double)(item_start[(size_t)s + 1] - item_start[(size_t)s]);
+        }
+        cta_start.assign((size_t)grid + 1, 0);
+        int s = 0;
+        for (int b = 1; b < grid; ++b) {
+            const double target = cum[(size_t)n_streams] * (double)b / (double)grid;
+            while (s + 1 < n_streams && cum[(size_t)s + 1] <= target) ++s;
+            int64_t it = item_start[(size_t)s] + (int64_t)((target - cum[(size_t)s]) / per[(size_t)s]);
+            it = std::min(it, item_start[(size_t)s + 1]);
+            cta_start[(size_t)b] = std::max(it, cta_start[(size_t)b - 1]);
+        }
+        cta_start[(size_t)grid] = total_items;
+    }
+    const size_t sz_cta = sizeof(int64_t) * cta_start.size();
     const size_t o_streams = 0, o_istart = al(sz_streams), o_ioff = o_istart + al(sz_istart),
-                 o_iE = o_ioff + al(sz_ioff), tbl_bytes = o_iE + al(sz_iE);
+                 o_iE = o_ioff + al(sz_ioff), o_cta = o_iE + al(sz_iE), tbl_bytes = o_cta + al(sz_cta);
     // The tables are assembled in a host vector and uploaded only when they differ from what the
     // device already holds (a repetition loop re-fills the same sample buffers: identical tables).
     // Two pinned staging slots are used alternately: before a slot is refilled the copy that last
@@ -208,6 +245,7 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
     memcpy(tb.data() + o_istart, item_start.data(), sz_istart);
     memcpy(tb.data() + o_ioff, item_off.data(), sz_ioff);
     memcpy(tb.data() + o_iE, item_E.data(), sz_iE);
+    if (sz_cta) memcpy(tb.data() + o_cta, cta_start.data(), sz_cta);
     const bool tables_cached = ctx->tbl_dev == ds && ctx->tbl_uploaded == tb;
     if (!tables_cached) {
         ctx->stage_slot ^= 1;
@@ -246,6 +284,8 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
         P.n_streams = n_streams;
         P.B = use_v2 ? std::max(t->max_group_cols, 1) : B;
         P.NS = use_v2 ? cfg2.NS : cfg.NS;
+        P.cta_start = sz_cta ? (const int64_t*)(ds + o_cta) : nullptr;
+        P.grid = grid;
         const int ppt = max_E <= NT ? 1 : (max_E <= 2 * NT ? 2 : 4);
         int rc;
         if (use_v2) {

@@ -57,6 +57,8 @@ struct ParityParams {
     int32_t n_streams;
     int32_t B;                  // most byte columns any stream reads (sizes the raw stages)
     int32_t NS;
+    const int64_t* cta_start;   // [grid + 1] first work item of every CTA (cost-balanced), or NULL: equal counts
+    int32_t grid;               // CTAs the partition was made for
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

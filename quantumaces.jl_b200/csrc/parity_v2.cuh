@@ -119,8 +119,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 16 ? 3 : 2) parity_kern
     const int lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
 
-    const int64_t i0 = (P.total_items * (int64_t)blockIdx.x) / gridDim.x;
-    const int64_t i1 = (P.total_items * (int64_t)(blockIdx.x + 1)) / gridDim.x;
+    // contiguous work items per CTA: equal estimated cost when the host supplied a partition (tiles of
+    // experiments with more Paulis take longer), equal counts otherwise
+    const int64_t i0 = P.cta_start ? P.cta_start[blockIdx.x] : (P.total_items * (int64_t)blockIdx.x) / gridDim.x;
+    const int64_t i1 = P.cta_start ? P.cta_start[blockIdx.x + 1] : (P.total_items * (int64_t)(blockIdx.x + 1)) / gridDim.x;
     if (i0 >= i1) return;
     const int n_my = (int)(i1 - i0);
 
@@ -485,16 +487,28 @@ inline bool v2_pick(int B, int max_E, int smem_optin, V2Cfg* cfg) {
     return true;
 }
 
+// Resident CTAs of the variant on the whole GPU (the persistent grid), or an error code (< 0).
 template <int NW, int SUB, int BMAX, int RMAX>
-int v2_launch_t(aces_ctx* ctx, const ParityParams& P, const V2Cfg& cfg) {
+int v2_grid_t(aces_ctx* ctx, const V2Cfg& cfg) {
     auto kern = parity_kernel_v2<NW, SUB, BMAX, RMAX>;
     ACES_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
     int per_sm = 0;
     ACES_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (NW + 1) * 32, cfg.smem));
     if (per_sm < 1)
         return aces_fail(ctx, ACES_E_UNSUPPORTED, "parity kernel v2 does not fit on an SM (smem %zu)", cfg.smem);
-    int64_t grid = (int64_t)ctx->sm_count * per_sm;
-    if (grid > P.total_items) grid = P.total_items;
+    return ctx->sm_count * per_sm;
+}
+
+template <int NW, int SUB, int BMAX, int RMAX>
+int v2_launch_t(aces_ctx* ctx, const ParityParams& P, const V2Cfg& cfg) {
+    auto kern = parity_kernel_v2<NW, SUB, BMAX, RMAX>;
+    int64_t grid = P.grid;
+    if (grid < 1) {
+        const int g = v2_grid_t<NW, SUB, BMAX, RMAX>(ctx, cfg);
+        if (g < 0) return g;
+        grid = g;
+        if (grid > P.total_items) grid = P.total_items;
+    }
     if (ctx->timing) ACES_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
     kern<<<(unsigned)grid, (NW + 1) * 32, cfg.smem, ctx->stream>>>(P);
     ACES_CUDA(ctx, cudaGetLastError());
@@ -504,6 +518,20 @@ int v2_launch_t(aces_ctx* ctx, const ParityParams& P, const V2Cfg& cfg) {
     }
     ctx->launches += 1;
     return ACES_OK;
+}
+
+inline int v2_grid(aces_ctx* ctx, const V2Cfg& cfg) {
+#define ACES_V2_G(SUBV, BMV)                                                    \
+    (cfg.RMAX == 8 ? v2_grid_t<8, SUBV, BMV, 8>(ctx, cfg)                       \
+                   : cfg.RMAX == 16 ? v2_grid_t<8, SUBV, BMV, 16>(ctx, cfg)     \
+                                    : v2_grid_t<8, SUBV, BMV, 32>(ctx, cfg))
+    if (cfg.SUB == 128 && cfg.BMAX == 21) return ACES_V2_G(128, 21);
+    if (cfg.SUB == 128 && cfg.BMAX == 25) return ACES_V2_G(128, 25);
+    if (cfg.SUB == 128 && cfg.BMAX == 41) return ACES_V2_G(128, 41);
+    if (cfg.SUB == 128) return ACES_V2_G(128, 13);
+    if (cfg.SUB == 256) return ACES_V2_G(256, 7);
+    return ACES_V2_G(512, 7);
+#undef ACES_V2_G
 }
 
 inline int v2_launch(aces_ctx* ctx, const ParityParams& P, const V2Cfg& cfg) {
