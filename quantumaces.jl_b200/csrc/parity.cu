@@ -52,6 +52,7 @@ struct ColGroup {
     int64_t pauli_off;  // first PauliDesc (device order: by weight)
     int32_t E;
     int32_t cols_off, ncols;
+    int32_t r1 = 0, r2 = 0, r4 = 0, rg = 0;  // rounds of 32 Paulis by class (weight 1, <= 2, <= 4, wider), as the kernel classifies them
 };
 
 struct aces_tables {
@@ -138,7 +139,14 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
     // v1 (records wider than the v2 tiling, ungrouped tables only) holds 4 Paulis per thread
     const int slice = use_v2 ? 1024 : NT * 4;
     ACES_CHECK(ctx, use_v2 || !t->grouped, "parity_counts: grouped tables need the v2 kernel");
+    static const std::array<double, 5> cost_w = [] {
+        std::array<double, 5> w{1300.0, 114.0, 125.0, 210.0, 400.0};  // fixed, per column, per weight-1 / weight-2 / wider round
+        if (const char* e = getenv("ACES_K1_COST"))  // development knob
+            sscanf(e, "%lf,%lf,%lf,%lf,%lf", &w[0], &w[1], &w[2], &w[3], &w[4]);
+        return w;
+    }();
     std::vector<StreamDesc> streams;
+    std::vector<double> stream_cost;  // estimated warp instructions per tile (cost-balanced partition below)
     std::vector<int64_t> item_start(1, 0);
     if (arena_bytes > 0) ACES_TRY(aces_reserve_dev(ctx, ctx->d_arena, arena_bytes));
     for (int i = 0; i < n_items; ++i) {
@@ -180,6 +188,9 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
                         sd.pad = 0;
                         const int64_t ntiles = (s - 1) / TS - prev / TS + 1;
                         streams.push_back(sd);
+                        stream_cost.push_back(use_v2 ? cost_w[0] + cost_w[1] * cg.ncols + cost_w[2] * cg.r1 + cost_w[3] * cg.r2 +
+                                                           cost_w[4] * (cg.r4 + cg.rg)
+                                                     : 1.0);
                         item_start.push_back(item_start.back() + ntiles);
                     }
                 }
@@ -204,19 +215,13 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
     std::vector<int64_t> cta_start;
     int grid = 0;
     static const bool balance = [] { const char* e = getenv("ACES_K1_BALANCE"); return !e || atoi(e) != 0; }();
-    static const std::array<double, 3> cost_w = [] {
-        std::array<double, 3> w{1300.0, 114.0, 150.0};
-        if (const char* e = getenv("ACES_K1_COST")) sscanf(e, "%lf,%lf,%lf", &w[0], &w[1], &w[2]);  // development knob
-        return w;
-    }();
     if (use_v2 && total_items > 0 && balance) {
         grid = v2_grid(ctx, cfg2);
         if (grid < 0) return grid;
         if ((int64_t)grid > total_items) grid = (int)total_items;
         std::vector<double> cum((size_t)n_streams + 1, 0.0), per((size_t)n_streams, 0.0);
         for (int s = 0; s < n_streams; ++s) {
-            const int rounds = (streams[(size_t)s].E + 31) / 32;
-            per[(size_t)s] = cost_w[0] + cost_w[1] * streams[(size_t)s].ncols + cost_w[2] * rounds;
+            per[(size_t)s] = stream_cost[(size_t)s];
             cum[(size_t)s + 1] = cum[(size_t)s] + per[(size_t)s] * (double)(item_start[(size_t)s + 1] - item_start[(size_t)s]);
         }
         cta_start.assign((size_t)grid + 1, 0);
@@ -461,6 +466,22 @@ int32_t aces_tables_create(aces_ctx* ctx, int32_t n_qubits, int32_t n_experiment
             const size_t w = sups[(size_t)e][(size_t)wp.second].size();
             n_w1 += w == 1;
             n_w2 += w == 2;
+        }
+        {
+            // rounds by class, as parity_kernel_v2 classifies them (the table is sorted by weight)
+            size_t n_w4 = 0;
+            for (const auto& wp : byw) {
+                const size_t w = sups[(size_t)e][(size_t)wp.second].size();
+                n_w4 += (w == 3 || w == 4);
+            }
+            const int R = (int)((byw.size() + 31) / 32);
+            cg.r1 = (int)(n_w1 / 32);
+            if (n_w1 == byw.size()) cg.r1 = R;  // a last, partial round of weight-1 Paulis only
+            const int c12 = (n_w1 + n_w2 == byw.size()) ? R : (int)((n_w1 + n_w2) / 32);
+            const int c14 = (n_w1 + n_w2 + n_w4 == byw.size()) ? R : (int)((n_w1 + n_w2 + n_w4) / 32);
+            cg.r2 = std::max(c12 - cg.r1, 0);
+            cg.r4 = std::max(c14 - std::max(c12, cg.r1), 0);
+            cg.rg = std::max(R - std::max(c14, std::max(c12, cg.r1)), 0);
         }
         if (BMAXV > 0 && n_w1 + n_w2 > 8) {
             // pools in sorted order; `taken` marks what has been placed
