@@ -302,6 +302,14 @@ def fit_leg(ctx, torch, dist, world, rank, steps, warmup, with_cpu):
                        "executed_flops_per_launch": flops,
                        "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (burst, best of 5)",
                        "share_of_fit": k_ms / out["gls_ms_per_fit"], "traffic": None}
+    gpath = os.path.join(ROOT, "profiles", "fit_gram_traffic.json")
+    if DESIGN_SOURCE == "real" and os.path.exists(gpath):
+        try:  # one ncu --set full capture of this kernel (per launch), see profiles/fit_r01_gram_ncu_summary.txt
+            gj = json.load(open(gpath))
+            out["roofline"]["traffic"] = gj.get("dram_bytes_per_launch")
+            out["roofline"]["ncu_tensor_pipe_dmma_active_pct"] = gj.get("tensor_pipe_dmma_active_pct")
+        except Exception:
+            pass
     if with_cpu and rank == 0:
         out["cpu_baseline"] = cpu_fit_sample(fd, eig, cov)
     dd.close()
