@@ -177,10 +177,14 @@ def _circuit(kind):
         return cd.get_circuit(*cd.rotated_planar_circuit(3))
     if kind == "unrotated2x3":
         return cd.get_circuit(*cd.unrotated_planar_circuit(2, 3))
+    if kind == "rotated3_no_decoupling":
+        return cd.get_circuit(*cd.rotated_planar_circuit(3, dynamically_decouple=False))
+    if kind == "rotated3x4_standard_cx":
+        return cd.get_circuit(*cd.rotated_planar_circuit(3, 4, check_type="standard", gate_type="cx"))
     raise AssertionError(kind)
 
 
-@pytest.mark.parametrize("kind", ["example", "rotated3", "unrotated2x3"])
+@pytest.mark.parametrize("kind", ["example", "rotated3", "unrotated2x3", "rotated3_no_decoupling", "rotated3x4_standard_cx"])
 def test_batched_conjugation_matches_literal_tableau(kind):
     c = _circuit(kind)
     rng = np.random.default_rng(5)
@@ -331,3 +335,18 @@ def test_real_tables_through_the_parity_oracle():
     # pauli_estimate (src/estimate.jl:239-254) returns shots - 2 * odd, from 1-based qubit lists
     got = np.array([ob.pauli_estimate(rec, np.asarray(l) + 1, rows) for l in lists])
     assert np.array_equal(got, rows - 2 * want)
+
+
+@pytest.mark.parametrize("kind", ["rotated3_no_decoupling", "rotated3x4_standard_cx"])
+def test_other_circuit_variants_give_full_rank_designs(kind):
+    """The non-default circuit variants of src/circuits/rotated_planar.jl:306-343 (no dynamical
+    decoupling; standard checks with CX gates) go through the same generator."""
+    fd = cd.generate_design(_circuit(kind), full_covariance=True)
+    A = fd.matrix.toarray().astype(float)
+    assert np.linalg.matrix_rank(A) == A.shape[1]
+    assert abs(fd.shot_weights.sum() - 1.0) < 1e-12
+    for t in range(fd.tuple_number):
+        seen = np.zeros(int(fd.mapping_lengths[t]), dtype=int)
+        for exp in fd.experiment_ensemble[t]:
+            seen[exp] += 1
+        assert seen.min() >= 1
