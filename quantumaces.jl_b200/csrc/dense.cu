@@ -154,7 +154,7 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const int bm, const in
 }
 
 template <bool A_KC, bool B_KC, int BMT>
-__global__ void __launch_bounds__(GT, BMT == 64 ? 2 : 1) gemm_kernel(const GemmP p, const int lower_only) {
+__global__ void __launch_bounds__(GT, BMT <= 64 ? 2 : 1) gemm_kernel(const GemmP p, const int lower_only) {
     // lower_only: skip the tiles that lie entirely above the block diagonal
     if (lower_only && (int)blockIdx.y * BN >= ((int)blockIdx.x + 1) * BMT) return;
     extern __shared__ __align__(16) double sm[];
@@ -710,6 +710,9 @@ int configure(aces_ctx* ctx) {
     ACES_TRY(set_smem(ctx, gemm_kernel<false, false, 128>, GEMM_SMEM));
     ACES_TRY(set_smem(ctx, gemm_kernel<false, true, 128>, GEMM_SMEM));
     ACES_TRY(set_smem(ctx, gemm_kernel<true, true, 128>, GEMM_SMEM));
+    ACES_TRY(set_smem(ctx, gemm_kernel<false, false, 32>, gemm_smem(32)));
+    ACES_TRY(set_smem(ctx, gemm_kernel<false, true, 32>, gemm_smem(32)));
+    ACES_TRY(set_smem(ctx, gemm_kernel<true, true, 32>, gemm_smem(32)));
     ACES_TRY(set_smem(ctx, gemm_kernel<false, false, 64>, gemm_smem(64)));
     ACES_TRY(set_smem(ctx, gemm_kernel<false, true, 64>, gemm_smem(64)));
     ACES_TRY(set_smem(ctx, gemm_kernel<true, true, 64>, gemm_smem(64)));
@@ -730,7 +733,13 @@ int launch_gemm(aces_ctx* ctx, const GemmP& p, int64_t m, int64_t n, int lower_o
     static const int force64 = [] { const char* e = getenv("ACES_GEMM_64"); return e ? atoi(e) : 1; }();
     // force64: 1 = every launch whose K is at most 512 (the Cholesky updates), 2 = every launch
     const bool want64 = tiles128 < 2 * (int64_t)ctx->sm_count || force64 == 2 || (force64 == 1 && p.k <= 512);
-    if (want64 && (const double*)p.C != p.B) {
+    static const int tiny32 = [] { const char* e = getenv("ACES_GEMM_32"); return e ? atoi(e) : 1; }();
+    if (tiny32 && tiles128 <= 2 && (const double*)p.C != p.B) {
+        // a single 128 x 128 tile on the Cholesky's critical path: four CTAs of 32 rows finish it
+        // in a quarter of the time one CTA needs (the launch is latency, not throughput)
+        dim3 grid((unsigned)(m / 32), (unsigned)(n / BN));
+        gemm_kernel<A_KC, B_KC, 32><<<grid, GT, gemm_smem(32), ctx->stream>>>(p, lower_only);
+    } else if (want64 && (const double*)p.C != p.B) {
         dim3 grid((unsigned)(m / 64), (unsigned)(n / BN));
         gemm_kernel<A_KC, B_KC, 64><<<grid, GT, gemm_smem(64), ctx->stream>>>(p, lower_only);
     } else {
