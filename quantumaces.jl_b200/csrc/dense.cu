@@ -710,6 +710,9 @@ int configure(aces_ctx* ctx) {
     ACES_TRY(set_smem(ctx, gemm_kernel<false, false, 128>, GEMM_SMEM));
     ACES_TRY(set_smem(ctx, gemm_kernel<false, true, 128>, GEMM_SMEM));
     ACES_TRY(set_smem(ctx, gemm_kernel<true, true, 128>, GEMM_SMEM));
+    ACES_TRY(set_smem(ctx, gemm_kernel<false, false, 16>, gemm_smem(16)));
+    ACES_TRY(set_smem(ctx, gemm_kernel<false, true, 16>, gemm_smem(16)));
+    ACES_TRY(set_smem(ctx, gemm_kernel<true, true, 16>, gemm_smem(16)));
     ACES_TRY(set_smem(ctx, gemm_kernel<false, false, 32>, gemm_smem(32)));
     ACES_TRY(set_smem(ctx, gemm_kernel<false, true, 32>, gemm_smem(32)));
     ACES_TRY(set_smem(ctx, gemm_kernel<true, true, 32>, gemm_smem(32)));
@@ -733,12 +736,20 @@ int launch_gemm(aces_ctx* ctx, const GemmP& p, int64_t m, int64_t n, int lower_o
     static const int force64 = [] { const char* e = getenv("ACES_GEMM_64"); return e ? atoi(e) : 1; }();
     // force64: 1 = every launch whose K is at most 512 (the Cholesky updates), 2 = every launch
     const bool want64 = tiles128 < 2 * (int64_t)ctx->sm_count || force64 == 2 || (force64 == 1 && p.k <= 512);
-    static const int tiny32 = [] { const char* e = getenv("ACES_GEMM_32"); return e ? atoi(e) : 1; }();
-    if (tiny32 && tiles128 <= 2 && (const double*)p.C != p.B) {
-        // a single 128 x 128 tile on the Cholesky's critical path: four CTAs of 32 rows finish it
-        // in a quarter of the time one CTA needs (the launch is latency, not throughput)
-        dim3 grid((unsigned)(m / 32), (unsigned)(n / BN));
-        gemm_kernel<A_KC, B_KC, 32><<<grid, GT, gemm_smem(32), ctx->stream>>>(p, lower_only);
+    // Small launches are latency, not throughput: a single 128 x 128 tile on the Cholesky's critical
+    // path runs as eight CTAs of 16 rows (a seventh of the time one CTA needs), and launches that
+    // would fill less than half the SMs with 64-row tiles use 32-row tiles.
+    // ACES_GEMM_32 (development knob): 0 off, 1 = 32-row tiles only, 2 = both, 3 = 16-row for single tiles only
+    static const int tiny32 = [] { const char* e = getenv("ACES_GEMM_32"); return e ? atoi(e) : 2; }();
+    const bool single = tiles128 <= 2;
+    if (tiny32 && (const double*)p.C != p.B && (single || (tiny32 != 3 && 4 * tiles128 < (int64_t)ctx->sm_count))) {
+        if (single && tiny32 >= 2) {
+            dim3 grid((unsigned)(m / 16), (unsigned)(n / BN));
+            gemm_kernel<A_KC, B_KC, 16><<<grid, GT, gemm_smem(16), ctx->stream>>>(p, lower_only);
+        } else {
+            dim3 grid((unsigned)(m / 32), (unsigned)(n / BN));
+            gemm_kernel<A_KC, B_KC, 32><<<grid, GT, gemm_smem(32), ctx->stream>>>(p, lower_only);
+        }
     } else if (want64 && (const double*)p.C != p.B) {
         dim3 grid((unsigned)(m / 64), (unsigned)(n / BN));
         gemm_kernel<A_KC, B_KC, 64><<<grid, GT, gemm_smem(64), ctx->stream>>>(p, lower_only);
