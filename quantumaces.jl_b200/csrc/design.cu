@@ -257,21 +257,47 @@ __global__ void at_times_kernel(int64_t N, const int64_t* __restrict__ colptr, c
         g[j] = s;
     }
 }
-// out = F u with F = blockdiag(X_t) (lower triangular tiles): one thread per padded row
-__global__ void apply_f_kernel(int T, const int64_t* __restrict__ prow0, const int64_t* __restrict__ tile_off,
-                               const int64_t* __restrict__ mp, const double* __restrict__ tiles,
-                               const uint8_t* __restrict__ on, const double* __restrict__ u, double* __restrict__ out) {
+// out = F u with F = blockdiag(X_t) (lower triangular tiles).  A block of 256 threads owns 32 rows
+// of one tile: thread (r, q) sums the columns c = q, q + 8, ... <= row (for a fixed column the 32
+// rows are consecutive in memory), the eight partial sums of a row are added in a fixed order
+// (deterministic: concurrent fits stay bit-identical).
+__global__ void __launch_bounds__(256) apply_f_kernel(int T, const int64_t* __restrict__ prow0,
+                                                      const int64_t* __restrict__ tile_off, const int64_t* __restrict__ mp,
+                                                      const double* __restrict__ tiles, const uint8_t* __restrict__ on,
+                                                      const double* __restrict__ u, double* __restrict__ out) {
+    __shared__ double part[8][33];
     const int t = blockIdx.y;
     if (t >= T) return;
     const int64_t n = mp[t];
     const double* X = tiles + tile_off[t];
     const double* ut = u + prow0[t];
     const bool act = on[t] != 0;  // a tuple of another shard contributes nothing here
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = threadIdx.x & 31, q = threadIdx.x >> 5;
+    for (int64_t i0 = 32 * (int64_t)blockIdx.x; i0 < n; i0 += 32 * (int64_t)gridDim.x) {
+        const int64_t i = i0 + r;
         double s = 0.0;
-        if (act)
-            for (int64_t c = 0; c <= i; ++c) s += X[i + c * n] * ut[c];
-        out[prow0[t] + i] = s;
+        if (act) {
+            // four independent chains hide the load latency
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int64_t c = q;
+            for (; c + 24 <= i; c += 32) {
+                s0 += X[i + c * n] * ut[c];
+                s1 += X[i + (c + 8) * n] * ut[c + 8];
+                s2 += X[i + (c + 16) * n] * ut[c + 16];
+                s3 += X[i + (c + 24) * n] * ut[c + 24];
+            }
+            for (; c <= i; c += 8) s0 += X[i + c * n] * ut[c];
+            s = (s0 + s1) + (s2 + s3);
+        }
+        part[q][r] = s;
+        __syncthreads();
+        if (q == 0) {
+            double v = part[0][r];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) v += part[k][r];
+            out[prow0[t] + i] = v;
+        }
+        __syncthreads();
     }
 }
 // out = F' v: one warp per padded column
@@ -680,7 +706,7 @@ int apply_F(aces_ctx* ctx, aces_design* d, int ls_type, const FitVectors& fv, co
     if (ls_type == 2) {
         dim3 grid(16, (unsigned)d->T);
         if (!transpose)
-            apply_f_kernel<<<grid, 128, 0, ctx->stream>>>(d->T, d->d_prow0, d->d_tile_off, d->d_mp, d->tilesX, d->d_tuple_on, u, out);
+            apply_f_kernel<<<dim3(48, (unsigned)d->T), 256, 0, ctx->stream>>>(d->T, d->d_prow0, d->d_tile_off, d->d_mp, d->tilesX, d->d_tuple_on, u, out);
         else
             apply_ft_kernel<<<grid, 256, 0, ctx->stream>>>(d->T, d->d_prow0, d->d_tile_off, d->d_mp, d->tilesX, d->d_tuple_on, u, out);
     } else {
