@@ -350,3 +350,14 @@ def test_other_circuit_variants_give_full_rank_designs(kind):
         for exp in fd.experiment_ensemble[t]:
             seen[exp] += 1
         assert seen.min() >= 1
+
+
+@pytest.mark.parametrize("kind,d,shape,tuples", [("rotated", 9, (12912, 6779), 16), ("unrotated", 7, (11700, 6189), 12)])
+def test_headline_design_sizes(kind, d, shape, tuples):
+    """The BASELINE.json shapes from the generator, diagonal covariance only."""
+    fd = (aces_b200.rotated_design if kind == "rotated" else aces_b200.unrotated_design)(d, full_covariance=False)
+    assert fd.matrix.shape == shape and fd.tuple_number == tuples
+    assert fd.n_qubits == (2 * d * d - 1 if kind == "rotated" else (2 * d - 1) ** 2)
+    sizes = [len(e) for t in range(fd.tuple_number) for e in fd.experiment_ensemble[t]]
+    assert max(sizes) <= 256          # one 8-round column group per experiment in the K1 kernel
+    assert all(len(s) in (1, 2) for t in range(fd.tuple_number) for s in fd.meas_indices[t])
