@@ -741,8 +741,10 @@ int launch_gemm(aces_ctx* ctx, const GemmP& p, int64_t m, int64_t n, int lower_o
     // would fill less than half the SMs with 64-row tiles use 32-row tiles.
     // ACES_GEMM_32 (development knob): 0 off, 1 = 32-row tiles only, 2 = both, 3 = 16-row for single tiles only
     static const int tiny32 = [] { const char* e = getenv("ACES_GEMM_32"); return e ? atoi(e) : 2; }();
+    // 32-row tiles when 64-row tiles would give fewer than (8 / fill32) CTAs per SM ... fill32 = 16: less than half the SMs
+    static const int fill32 = [] { const char* e = getenv("ACES_GEMM_32_FILL"); return e ? atoi(e) : 16; }();
     const bool single = tiles128 <= 2;
-    if (tiny32 && (const double*)p.C != p.B && (single || (tiny32 != 3 && 4 * tiles128 < (int64_t)ctx->sm_count))) {
+    if (tiny32 && (const double*)p.C != p.B && (single || (tiny32 != 3 && fill32 * tiles128 < 4 * (int64_t)ctx->sm_count))) {
         if (single && tiny32 >= 2) {
             dim3 grid((unsigned)(m / 16), (unsigned)(n / BN));
             gemm_kernel<A_KC, B_KC, 16><<<grid, GT, gemm_smem(16), ctx->stream>>>(p, lower_only);
