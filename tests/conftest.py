@@ -11,6 +11,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "slow: headline-size cases whose CPU oracle takes tens of seconds (still part of -m gpu)")
 
 
 @pytest.fixture(scope="session")

@@ -207,6 +207,101 @@ def test_design_create_rejects_bad_input(ctx):
         aces_b200.DeviceDesign(ctx, fd)
 
 
+@pytest.fixture(scope="module", params=["real9", "unrot7"], ids=["real_rotated_d9_gls", "real_unrotated_d7_gls"])
+def setup_headline(request, ctx):
+    """The headline shapes of BASELINE.json (configs[2]/[3]: rotated d=9, M x N = 12912 x 6779; unrotated
+    d=7, 11700 x 6189) on the reference's own design tables, with log-normal noise and shot-noise-level
+    estimates.  The oracle's dense QR takes tens of seconds per estimator at this size."""
+    import aces_b200
+
+    if request.param == "real9":
+        fd = aces_b200.rotated_design(9, full_covariance=True, noise="lognormal", seed=9)
+        assert fd.matrix.shape == (12912, 6779)
+    else:
+        fd = aces_b200.unrotated_design(7, full_covariance=True, noise="lognormal", seed=7)
+        assert fd.matrix.shape == (11700, 6189)
+    dd = aces_b200.DeviceDesign(ctx, fd)
+    eig, cov = aces_b200.synthetic_estimates(fd, shots=10**8, seed=11)
+    yield fd, dd, eig, cov
+    dd.close()
+
+
+@pytest.mark.slow
+def test_headline_fit_vs_oracle(setup_headline):
+    """North star: OLS / WLS / GLS gate eigenvalues within 1e-9 (relative, fp64) of the reference's
+    estimate_gate_noise core (src/estimate.jl:492-524, 711-743) at rotated d=9 and unrotated d=7 --
+    noisy estimates, so the conditioning of the whitened system is what a real run sees."""
+    import aces_b200
+
+    fd, dd, eig, cov = setup_headline
+    want = fo.estimate_gate_noise_core(fd, eig, cov)
+    got = aces_b200.estimate_gate_noise_core(dd, eig, cov, clip_warning=False)
+    assert np.array_equal(got["est_eigenvalues"], want["est_eigenvalues"])
+    assert np.array_equal(got["clipped_indices"], want["clipped_indices"])
+    assert dd.fallback_count() == 0
+    for k in ("ols", "wls", "gls"):
+        assert rel(got[k], want[k]) < RTOL, (k, rel(got[k], want[k]))
+        assert np.max(np.abs(got[k] - want[k]) / np.abs(want[k])) < RTOL, k   # element-wise too
+    # the estimators differ from each other by far more than the tolerance (the test is not vacuous)
+    assert rel(got["gls"], got["ols"]) > 1e3 * RTOL
+
+
+@pytest.mark.slow
+def test_headline_fit_after_clipping_vs_oracle(setup_headline):
+    """Same with clipped rows (src/estimate.jl:435-484, 727-735): 40 circuit eigenvalues below 0.1."""
+    import aces_b200
+
+    fd, dd, eig, cov = setup_headline
+    eig = [[list(v) for v in t] for t in eig]
+    rng = np.random.default_rng(5)
+    multi = np.nonzero(np.diff(sp.csr_matrix(fd.matrix).indptr) >= 2)[0]
+    off = np.concatenate([[0], np.cumsum(fd.mapping_lengths)])
+    for r in rng.choice(multi, size=40, replace=False):
+        t = int(np.searchsorted(off, r, side="right") - 1)
+        eig[t][int(r - off[t])] = [0.05 for _ in eig[t][int(r - off[t])]]
+    want = fo.estimate_gate_noise_core(fd, eig, cov)
+    got = aces_b200.estimate_gate_noise_core(dd, eig, cov, clip_warning=False)
+    assert len(got["clipped_indices"]) == fd.M - 40
+    assert np.array_equal(got["clipped_indices"], want["clipped_indices"])
+    for k in ("ols", "wls", "gls"):
+        assert rel(got[k], want[k]) < RTOL, (k, rel(got[k], want[k]))
+
+
+@pytest.mark.slow
+def test_headline_covariances_vs_oracle(setup_headline):
+    """K2 / K3 / K6 at the headline shapes: covariance values (1e-15), F'F against the oracle's block
+    inverse (1e-9), GLS / WLS / OLS estimator covariances and their trace moments (1e-9)."""
+    import aces_b200
+
+    fd, dd, eig, cov = setup_headline
+    lam_ens, cov_ens = aces_b200.mean_ensemble(eig), aces_b200.mean_ensemble(cov)
+    got = dd.calc_covariance(lam_ens, cov_ens, weight_time=False)
+    want = fo.calc_covariance_from_experiments(fd, eig, cov, weight_time=False)
+    diff = sp.csc_matrix(got) - sp.csc_matrix(want)
+    assert (abs(diff).max() if diff.nnz else 0.0) <= 1e-15 * abs(want).max()
+    lam = np.concatenate(lam_ens)
+    cl = fo.calc_covariance_log(want, lam)
+    got_log = dd.calc_covariance(lam_ens, cov_ens, weight_time=False, log_form=True)
+    dl = sp.csc_matrix(got_log) - cl
+    assert np.sqrt(dl.multiply(dl).sum()) <= 1e-15 * np.sqrt(cl.multiply(cl).sum())
+    F = dd.sparse_covariance_inv_factor(cl)
+    Fo = fo.sparse_covariance_inv_factor(cl, fd.mapping_lengths)
+    P, Po = sp.csc_matrix(F.T @ F), sp.csc_matrix(Fo.T @ Fo)
+    dP = P - Po
+    assert np.sqrt(dP.multiply(dP).sum()) < RTOL * np.sqrt(Po.multiply(Po).sum())
+    # estimator covariances of the true gate eigenvalues (src/merit.jl:556-629)
+    g = fd.gate_eigenvalues
+    cov_eig = fo.calc_covariance_eigenvalues(fd, g)
+    clt = fo.calc_covariance_log(fo.calc_covariance(fd, fo.get_eigenvalues_ensemble(fd, g), cov_eig), fo.get_eigenvalues(fd, g))
+    for k, ref in (("gls", fo.calc_gls_covariance), ("wls", fo.calc_wls_covariance), ("ols", fo.calc_ols_covariance)):
+        w = ref(fd, clt)
+        sigma, tr, trsq = dd.calc_ls_covariance(k, clt)
+        assert rel(sigma, w) < RTOL, (k, rel(sigma, w))
+        assert abs(tr - np.trace(w)) < RTOL * np.trace(w), k
+        assert abs(trsq - np.sum(w * w.T)) < RTOL * np.sum(w * w.T), k
+        del sigma, w
+
+
 @pytest.mark.parametrize("kind,d", [("rotated", 9), ("unrotated", 7), ("real_rotated", 9), ("real_unrotated", 7)])
 def test_full_size_fit_properties(ctx, kind, d):
     """BASELINE configs 3 / 4 shapes (rotated d=9: M = 12912, N = 6779; unrotated d=7): properties that

@@ -96,18 +96,26 @@ def make_batch(rng, est, fd, shots_set, pad_ld=0):
 
 @pytest.mark.parametrize("d,gls,stress", [(3, False, False), (3, True, True), (5, True, False),
                                           ("real3", True, False), ("real5", True, False), ("real5", False, False),
-                                          ("unrot3", True, False)])
+                                          ("unrot3", True, False),
+                                          # the headline shapes on the reference's own tables: rotated d=9 WLS
+                                          # (RMAX=8 / BMAX=21), d=9 GLS (449 Paulis: RMAX=16 / BMAX=21), unrotated
+                                          # d=7 (22 byte columns: BMAX=25), rotated d=17 (73 columns: column groups)
+                                          ("real9", False, False), ("real9", True, False), ("unrot7", True, False),
+                                          ("unrot7", False, False), ("real17", False, False)])
 def test_design_batch_vs_oracle(ctx, d, gls, stress):
     import aces_b200
 
+    shots_set = [3_000, 41_111, 200_003]
     if isinstance(d, str):   # real designs (circuit_design.py): the reference's own tables
-        kind, d = d.rstrip("0123456789"), int(d[-1])
+        kind, d = d.rstrip("0123456789"), int(d[len(d.rstrip("0123456789")):])
         fd = (aces_b200.rotated_design if kind == "real" else aces_b200.unrotated_design)(d, full_covariance=gls)
+        if d >= 7:               # ~100 experiments: about 2e4 shots each (several tiles per stream)
+            shots_set = [30_000, 411_111, 2_000_003]
     else:
         fd = aces_b200.synthetic_design("rotated", d, full_covariance=gls, stress_weights=stress)
     est = aces_b200.DesignEstimator(ctx, fd)
     rng = np.random.default_rng(d)
-    mats, rows, ld, prefix = make_batch(rng, est, fd, [3_000, 41_111, 200_003])
+    mats, rows, ld, prefix = make_batch(rng, est, fd, shots_set)
     got = est.odd_counts([m.ctypes.data for m in mats], rows, ld, prefix)
     want = ob.oracle_odd_counts(est, mats, prefix)
     assert np.array_equal(got, want)
