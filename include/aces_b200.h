@@ -65,6 +65,17 @@ int32_t aces_host_free(aces_ctx* ctx, void* ptr);
 /* Number of kernels this context has launched since creation (bench bookkeeping). */
 int64_t aces_kernel_launches(const aces_ctx* ctx);
 
+/* Rank deficiency of the last fit on this context (aces_estimate_gate_eigenvalues, aces_design_fit,
+ * aces_design_fit_end): the number of gate eigenvalues whose column of the whitened design matrix was
+ * numerically dependent on the columns before it (pivot below 1e-13 of the Gram diagonal), e.g. after
+ * clipping (src/estimate.jl:435-460) removed every row that determines them.  Such a fit does not
+ * fail: like the reference's sparse-QR solve (src/estimate.jl:500-502) it returns a BASIC solution --
+ * the dependent columns get x = 0 (gate eigenvalue 1) and the others solve the reduced problem.
+ * Which columns a basic solution zeroes depends on the elimination order (SPQR's fill-reducing column
+ * ordering in the reference, left to right here), so for a rank-deficient fit only the fitted circuit
+ * eigenvalues exp(-A x) agree with the reference, not the individual gate eigenvalues. */
+int32_t aces_last_rank_deficiency(const aces_ctx* ctx);
+
 /* With timing on, the dominant kernel of each call (K1: the parity kernel) is bracketed by
  * CUDA events on the stream it is launched on; aces_last_kernel_ms waits for the last one
  * and returns its duration.  Used by bench.py for the roofline figure. */
@@ -149,8 +160,8 @@ int32_t aces_estimate_experiment(aces_ctx* ctx, const uint8_t* counts, int64_t r
  * A is M x N, F is M x M, both CSC exactly as Julia stores them (colptr [ncols+1], rowval,
  * nzval); index_base = 1 for Julia's 1-based colptr/rowval, 0 for C.  The whitened matrix F*A is
  * formed densely on the device, its Gram matrix accumulated on the FP64 tensor pipe, factorised
- * by a blocked Cholesky and the solution refined twice with FP64 residuals.  Returns
- * ACES_E_NOT_PD when F*A is numerically rank deficient. */
+ * by a blocked Cholesky and the solution refined twice with FP64 residuals.  A numerically rank
+ * deficient F*A gives a basic solution (see aces_last_rank_deficiency). */
 int32_t aces_estimate_gate_eigenvalues(aces_ctx* ctx, int64_t M, int64_t N, const int64_t* A_colptr,
                                        const int64_t* A_rowval, const double* A_nzval,
                                        const int64_t* F_colptr, const int64_t* F_rowval,
@@ -282,6 +293,32 @@ int32_t aces_design_fit_end(aces_ctx* ctx, aces_design* design, int32_t constrai
 int32_t aces_design_ls_covariance(aces_ctx* ctx, aces_design* design, int32_t ls_type,
                                   const double* gate_eigenvalues, const double* covariance_log_nzval,
                                   double* sigma, double* trace, double* trace_sq);
+
+/* ---- simplex projection of the fitted gate eigenvalues ----------------
+ *
+ * A gate is a group of 1 (SPAM / mid-circuit reset), 3 (one qubit) or 15 (two qubits) gate
+ * eigenvalues: group g owns group_idx[group_ptr[g] .. group_ptr[g+1]-1] (GateIndex.indices of
+ * src/noise.jl:16-24, in the Pauli order of the symplectic Walsh-Hadamard matrix, src/noise.jl:285-312).
+ * The padded vectors (identity entry first: GateIndex.pad_indices) are laid out gate after gate, so
+ * gate g starts at group_ptr[g] + g.
+ *
+ * aces_project_simplex: drop-in for simple_project_gate_eigenvalues (src/estimate.jl:635-663), i.e.
+ * per gate p = W^-1 [1; lambda], project_simplex(p) (src/utils.jl:36-50, sort based), lambda' = W p'.
+ * The arithmetic follows the reference's order of operations: the results are bit-identical.
+ *   gate_eigenvalues [N]; unproj_probabilities / probabilities [N + G] (may be NULL). */
+int32_t aces_project_simplex(aces_ctx* ctx, int64_t N, int32_t G, const int64_t* group_ptr, const int32_t* group_idx,
+                             int32_t index_base, const double* unproj_gate_eigenvalues, double* gate_eigenvalues,
+                             double* unproj_probabilities, double* probabilities);
+
+/* Batched drop-in for scs_project_nonnegative(vector, precision_matrix; precision) (src/utils.jl:57-97)
+ * as split_project_gate_eigenvalues calls it once per gate (src/estimate.jl:606-618):
+ *     y_p = argmin (y - v_p)' Q_p (y - v_p)  subject to  y >= 0,   then y_p[y_p < threshold] = 0.
+ * Problem p has n_p = ptr[p+1] - ptr[p] <= 15 variables; v and y are the concatenated vectors, Q the
+ * concatenated dense symmetric n_p x n_p blocks.  Solved exactly (active-set method) where the
+ * reference iterates SCS to eps = threshold = 1e-8: results agree to that tolerance.  A block that is
+ * not positive definite returns ACES_E_NOT_PD (their number in *n_failed). */
+int32_t aces_project_nonnegative_batched(aces_ctx* ctx, int32_t n_problems, const int64_t* ptr, const double* Q,
+                                         const double* v, double threshold, double* y, int32_t* n_failed);
 
 #ifdef __cplusplus
 }

@@ -49,6 +49,7 @@ SIGNATURES = {
     "aces_host_alloc": (_i32, [_vp, _i64, _p(_vp)]),
     "aces_host_free": (_i32, [_vp, _vp]),
     "aces_kernel_launches": (_i64, [_vp]),
+    "aces_last_rank_deficiency": (_i32, [_vp]),
     "aces_set_timing": (_i32, [_vp, _i32]),
     "aces_last_kernel_ms": (_i32, [_vp, _p(C.c_float)]),
     "aces_tables_create": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _p(_vp)]),
@@ -77,6 +78,8 @@ SIGNATURES = {
     "aces_design_fit_refine_begin": (_i32, [_vp, _vp]),
     "aces_design_fit_refine_end": (_i32, [_vp, _vp, _p(C.c_double), _p(C.c_double)]),
     "aces_design_fit_end": (_i32, [_vp, _vp, _i32, _vp]),
+    "aces_project_simplex": (_i32, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "aces_project_nonnegative_batched": (_i32, [_vp, _i32, _vp, _vp, _vp, C.c_double, _vp, _p(_i32)]),
 }
 
 
@@ -155,6 +158,10 @@ class Context:
 
     def kernel_launches(self) -> int:
         return int(self.lib.aces_kernel_launches(self.handle))
+
+    def last_rank_deficiency(self) -> int:
+        """Columns the last fit eliminated as numerically dependent (0 for a full-rank fit)."""
+        return int(self.lib.aces_last_rank_deficiency(self.handle))
 
     def set_timing(self, on: bool) -> None:
         self.check(self.lib.aces_set_timing(self.handle, 1 if on else 0))

@@ -34,6 +34,7 @@ struct aces_ctx {
     int timing = 0;
     int timed = 0;
     int64_t launches = 0;
+    int rank_deficiency = 0;  // columns eliminated by the last fit (aces_last_rank_deficiency)
     std::string err;
 
     // K1 workspaces

@@ -197,6 +197,7 @@ int32_t aces_host_free(aces_ctx* ctx, void* ptr) {
 }
 
 int64_t aces_kernel_launches(const aces_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int32_t aces_last_rank_deficiency(const aces_ctx* ctx) { return ctx ? ctx->rank_deficiency : -1; }
 
 int32_t aces_set_timing(aces_ctx* ctx, int32_t on) {
     if (!ctx) return ACES_E_INVALID;

@@ -8,6 +8,7 @@
 #include "dense.cuh"
 
 #include <algorithm>
+#include <mutex>
 
 namespace dense {
 namespace {
@@ -197,11 +198,15 @@ __device__ __forceinline__ double fast_rcp(double d) {
 // Cholesky of the 16 x 16 piece at (k0, k0) of the shared-memory block by ONE warp, rows in
 // registers (lane i holds row i; lanes 16..31 mirror 0..15 so that every shuffle source is
 // defined).  Kept out of line so that its registers are allocated separately from the caller's
-// tile accumulators.  Returns true when a pivot was not above its floor (and was replaced by 1).
-__device__ __noinline__ bool diag16(double* s, double* rdiag, const double* pfloor, int k0, int lane) {
+// tile accumulators.  Returns the number of pivots that were not above their floor; each was replaced
+// by `repl` (1: the caller reports a failed factorisation; DEAD_PIVOT: the column is eliminated --
+// its entries of L become ~1e-150 times the data, so the variable drops out of every later update
+// and solve: the basic solution of a rank-deficient least-squares problem).
+constexpr double DEAD_PIVOT = 1e300;
+__device__ __noinline__ int diag16(double* s, double* rdiag, const double* pfloor, int k0, int lane, double repl) {
     const int li = lane & (PW - 1);
     double a[PW];
-    bool bad = false;
+    int bad = 0;
 #pragma unroll
     for (int c = 0; c < PW; ++c) a[c] = s[(k0 + c) * PLD + k0 + li];
     // Square-root-free elimination: column k stays unscaled (a_ik) while the update uses
@@ -212,8 +217,8 @@ __device__ __noinline__ bool diag16(double* s, double* rdiag, const double* pflo
     for (int k = 0; k < PW; ++k) {
         double dkk = __shfl_sync(0xffffffffu, a[k], k);
         if (!(dkk > pfloor[k0 + k])) {
-            bad = true;
-            dkk = 1.0;
+            bad += 1;
+            dkk = repl;
         }
         if (li == k) dmine = dkk;
         const double tk = a[k] * fast_rcp(dkk);  // a_ik / d_k
@@ -298,8 +303,9 @@ __device__ __forceinline__ void diag_block(const DiagDesc& d, const double rel_t
     // Right-looking factorisation with look-ahead inside the CTA: after the panel rows of panel p
     // are solved, all warps update the 16 columns of panel p+1 (c1); then warp 0 factorises the
     // next 16 x 16 diagonal piece while warps 1..15 update the remaining trailing columns (c2).
-    bool bad = false;
-    if (warp == 0) bad = diag16(s, rdiag, pfloor, 0, lane);
+    int bad = 0;
+    const double repl = d.dead_mode ? DEAD_PIVOT : 1.0;
+    if (warp == 0) bad = diag16(s, rdiag, pfloor, 0, lane, repl);
     for (int k0 = 0; k0 < DB - PW; k0 += PW) {
         __syncthreads();
         DPROF(1)  // diag16 (warp 0) / c2 (other warps), whichever is longer
@@ -346,7 +352,7 @@ __device__ __forceinline__ void diag_block(const DiagDesc& d, const double rel_t
         const long long _tw = clock64();
 #endif
         if (warp == 0) {
-            bad |= diag16(s, rdiag, pfloor, r0, lane);
+            bad += diag16(s, rdiag, pfloor, r0, lane, repl);
             DPROF_WARP(7, _tw)  // diag16 alone
         } else if (r0 + PW < DB) {
             // (c2) the columns behind the next panel: warp w owns columns j_b = c0 + 15 b (b = 0, 1, ...
@@ -378,7 +384,10 @@ __device__ __forceinline__ void diag_block(const DiagDesc& d, const double rel_t
 #endif
         }
     }
-    if (warp == 0 && bad && lane == 0 && d.flag) atomicCAS(d.flag, 0, d.code);
+    if (warp == 0 && bad && lane == 0 && d.flag) {
+        if (d.dead_mode) atomicAdd(d.flag, bad);  // number of eliminated columns
+        else atomicCAS(d.flag, 0, d.code);
+    }
     __syncthreads();
     DPROF(1)
     // L -> global (strict upper triangle zeroed)
@@ -704,8 +713,13 @@ int set_smem(aces_ctx* ctx, K kern, size_t bytes) {
     return ACES_OK;
 }
 
+// Function attributes are per device: one flag per device, set under a lock (several contexts, one
+// host thread each, may make their first call at the same time).
 int configure(aces_ctx* ctx) {
-    static bool done = false;
+    static std::mutex mu;
+    static bool done_dev[64] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    bool& done = done_dev[ctx->device & 63];
     if (done) return ACES_OK;
     ACES_TRY(set_smem(ctx, gemm_kernel<false, false, 128>, GEMM_SMEM));
     ACES_TRY(set_smem(ctx, gemm_kernel<false, true, 128>, GEMM_SMEM));
@@ -809,13 +823,17 @@ int diag_blocks(aces_ctx* ctx, const DiagDesc* descs, int count, double rel_tol)
 }
 
 int potrf(aces_ctx* ctx, int64_t n, double* A, int64_t lda, double* dinv, int* flag, const double* diag0,
-          double rel_tol) {
+          double rel_tol, int dead_mode) {
     ACES_CHECK(ctx, n % DB == 0, "dense::potrf: n=%lld is not padded", (long long)n);
     ACES_TRY(configure(ctx));
     constexpr int64_t NB2 = 4 * DB;  // outer panel: the bulk of the flops runs as K = 512 updates
     // development probe: skip parts of the factorisation to time the others (results are then wrong)
+#ifdef ACES_POTRF_PROBE  // never in a production build: a stray environment variable must not corrupt results
     const char* skip_env = getenv("ACES_POTRF_SKIP");
     const int skip = skip_env ? atoi(skip_env) : 0;  // 1 diag, 2 critical tiles, 4 second stream, 8 look-ahead, 16 side
+#else
+    constexpr int skip = 0;
+#endif
     const cudaStream_t main_stream = ctx->stream;
     bool side_pending = false;
     // The chain diag(k) -> diag(k+1) is the critical path (one CTA at a time).  Only one tile of the
@@ -835,7 +853,7 @@ int potrf(aces_ctx* ctx, int64_t n, double* A, int64_t lda, double* dinv, int* f
         for (int64_t k = K0; k < K0 + kb; k += DB) {
             double* Akk = A + k * (lda + 1);
             double* dk = dinv + (k / DB) * DB * DB;
-            DiagDesc one{Akk, lda, dk, diag0 ? diag0 + k : nullptr, flag, (int32_t)(k / DB) + 1, 0};
+            DiagDesc one{Akk, lda, dk, diag0 ? diag0 + k : nullptr, flag, (int32_t)(k / DB) + 1, dead_mode};
             if (!(skip & 1)) diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, ctx->stream>>>(nullptr, one, rel_tol);
             ACES_CUDA(ctx, cudaGetLastError());
             ctx->launches += 1;

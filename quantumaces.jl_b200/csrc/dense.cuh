@@ -41,7 +41,7 @@ struct DiagDesc {
     const double* diag0; // original diagonal of the block (pivot test), may be NULL
     int32_t* flag;       // set to code when a pivot fails (must be 0 before), may be NULL
     int32_t code;
-    int32_t pad;
+    int32_t dead_mode;   // != 0: a failed pivot eliminates its column and *flag counts them (see potrf)
 };
 
 // C (m x n, ldc) = alpha * op(A) op(B) + beta * C.  m, n multiples of 128, k a multiple of 16.
@@ -66,8 +66,12 @@ int diag_blocks(aces_ctx* ctx, const DiagDesc* descs, int count, double rel_tol)
 // with diag0 (the diagonal of A before the call, device), not above rel_tol * |diag0|.
 // descs: device scratch for n/128 DiagDesc entries (filled here through `stage`, a pinned or
 // pageable host array of the same length that must stay alive until the stream has consumed it).
+// dead_mode != 0 (the Gram matrix of a least-squares fit): a pivot that fails the test is not an
+// error; its column is eliminated (pivot replaced by 1e300, so the column of L underflows to ~0 and
+// the variable gets the value 0 in every solve with this factor -- the basic solution of the
+// rank-deficient problem), and *flag receives the NUMBER of eliminated columns.
 int potrf(aces_ctx* ctx, int64_t n, double* A, int64_t lda, double* dinv, int* flag,
-          const double* diag0 = nullptr, double rel_tol = 0.0);
+          const double* diag0 = nullptr, double rel_tol = 0.0, int dead_mode = 0);
 int get_diag(aces_ctx* ctx, int64_t n, const double* A, int64_t lda, double* d);
 
 // X = inv(L) for the lower-triangular factor produced by potrf (needs its dinv).  X is n x n

@@ -57,6 +57,9 @@ struct aces_design {
     double *mom = nullptr;         // partial sums of the trace moments
     double *covval = nullptr;      // [nnz_cov]
     int32_t *row_map = nullptr;    // [M] compacted local row or -1
+    double *lam_buf = nullptr;     // [M + C + 2] eigenvalue estimates of the current call (owned: the staged
+                                   // fit API reads them again in later calls)
+    int64_t *kept_dev = nullptr;   // [2 T + 2] kept rows per tuple | export offsets
     int32_t *flags = nullptr;      // [T + 1] not-PD flags (blocks, then the Gram matrix)
     int fallback_blocks = 0;       // blocks that needed the not-PD fallback in the last call
     std::vector<std::pair<std::string, float>> phase_ms;  // phases of the last fit (timing on)
@@ -600,6 +603,8 @@ int ensure_workspaces(aces_ctx* ctx, aces_design* d, bool need_tiles, bool need_
         ACES_TRY(dev_alloc(ctx, d, &d->mom, (size_t)(2 + 2 * 148 * 4)));
         ACES_TRY(dev_alloc(ctx, d, &d->row_map, (size_t)d->M));
         ACES_TRY(dev_alloc(ctx, d, &d->flags, (size_t)d->T + 2));
+        ACES_TRY(dev_alloc(ctx, d, &d->lam_buf, (size_t)(d->M + d->C + 2)));
+        ACES_TRY(dev_alloc(ctx, d, &d->kept_dev, (size_t)(2 * d->T + 2)));
     }
     if (need_inverse && !d->Xn) ACES_TRY(dev_alloc(ctx, d, &d->Xn, (size_t)d->Np * d->Np));
     if (need_c && !d->Cn) ACES_TRY(dev_alloc(ctx, d, &d->Cn, (size_t)d->Np * d->Np));
@@ -677,9 +682,7 @@ int build_and_factor_tiles(aces_ctx* ctx, aces_design* d, const double* val_dev,
     tiles_scatter_kernel<<<grid_for(d->M, 128), 128, 0, ctx->stream>>>(d->M, d->cov_colptr, d->cov_rowval, val_dev,
                                                                       d->blk_of_row, d->d_row0, d->d_tile_off, d->d_mp,
                                                                       row_map, d->tilesL);
-    // kept counts -> device (small, reuse the tail of vec)
-    int64_t* kept_dev = (int64_t*)(d->vec + 8 * std::max(d->Mp, d->Np));
-    ACES_CHECK(ctx, T <= 60, "design: more than 60 tuples are not supported by the workspace layout");
+    int64_t* kept_dev = d->kept_dev;
     ACES_CUDA(ctx, cudaMemcpyAsync(kept_dev, kept_count.data(), sizeof(int64_t) * (size_t)T, cudaMemcpyHostToDevice,
                                    ctx->stream));
     dim3 gpad(4, (unsigned)T);
@@ -781,6 +784,7 @@ int fallback_tiles(aces_ctx* ctx, aces_design* d, const double* val_dev, const i
     ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     d->fallback_blocks = 0;
     std::vector<double> hval;
+    std::vector<int32_t> hmap;
     for (int t = 0; t < d->T; ++t) {
         if (!fl[(size_t)t]) continue;
         d->fallback_blocks += 1;
@@ -789,10 +793,19 @@ int fallback_tiles(aces_ctx* ctx, aces_design* d, const double* val_dev, const i
             ACES_CUDA(ctx, cudaMemcpy(hval.data(), val_dev, sizeof(double) * hval.size(), cudaMemcpyDeviceToHost));
         }
         // infinity norm of the block bounds every eigenvalue
+        // (kept rows and columns only: a clipped row can hold inf or huge values from 1 / lambda)
+        if (row_map && hmap.empty()) {
+            hmap.resize((size_t)d->M);
+            ACES_CUDA(ctx, cudaMemcpy(hmap.data(), row_map, sizeof(int32_t) * hmap.size(), cudaMemcpyDeviceToHost));
+        }
         double norm = 0.0;
         for (int64_t c = d->row0[t]; c < d->row0[t + 1]; ++c) {
+            if (row_map && hmap[(size_t)c] < 0) continue;
             double sum = 0.0;
-            for (int64_t e = d->h_cov_colptr[(size_t)c]; e < d->h_cov_colptr[(size_t)c + 1]; ++e) sum += std::fabs(hval[(size_t)e]);
+            for (int64_t e = d->h_cov_colptr[(size_t)c]; e < d->h_cov_colptr[(size_t)c + 1]; ++e) {
+                if (row_map && hmap[(size_t)d->h_cov_rowval[(size_t)e]] < 0) continue;
+                sum += std::fabs(hval[(size_t)e]);
+            }
             norm = std::max(norm, sum);
         }
         const int64_t n = d->mp[t];
@@ -836,13 +849,19 @@ int fallback_tiles(aces_ctx* ctx, aces_design* d, const double* val_dev, const i
     return ACES_OK;
 }
 
-int check_flags(aces_ctx* ctx, aces_design* d, const char* what) {
+// gram_dead_ok: the Gram matrix was factorised in dead-pivot mode (a fit): its flag counts the
+// eliminated columns and is reported through aces_last_rank_deficiency instead of failing.
+int check_flags(aces_ctx* ctx, aces_design* d, const char* what, bool gram_dead_ok = false) {
     std::vector<int32_t> fl((size_t)d->T + 1);
     ACES_CUDA(ctx, cudaMemcpyAsync(fl.data(), d->flags, sizeof(int32_t) * fl.size(), cudaMemcpyDeviceToHost, ctx->stream));
     ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (int t = 0; t < d->T; ++t)
         if (fl[(size_t)t])
             return aces_fail(ctx, ACES_E_NOT_PD, "%s: the covariance block of tuple %d is not positive definite", what, t);
+    if (gram_dead_ok) {
+        ctx->rank_deficiency = fl[(size_t)d->T];
+        return ACES_OK;
+    }
     if (fl[(size_t)d->T])
         return aces_fail(ctx, ACES_E_NOT_PD,
                          "%s: the Gram matrix is not positive definite (diagonal block %d): the whitened design "
@@ -852,10 +871,10 @@ int check_flags(aces_ctx* ctx, aces_design* d, const char* what) {
 
 // Prepares the estimator: covariance values (from eigenvalue estimates, or given), factor (GLS) or
 // diagonal weights (OLS / WLS), Gram matrix and its Cholesky factor.
-int factor_gram_matrix(aces_ctx* ctx, aces_design* d, const FitVectors& fv, PhaseTimer* pt);
+int factor_gram_matrix(aces_ctx* ctx, aces_design* d, const FitVectors& fv, PhaseTimer* pt, int dead_mode);
 int prepare_estimator(aces_ctx* ctx, aces_design* d, int ls_type, const double* val_dev, const int32_t* row_map,
                       const std::vector<int64_t>& kept_count, const FitVectors& fv, PhaseTimer* pt = nullptr,
-                      bool factor_gram = true) {
+                      bool factor_gram = true, int dead_mode = 0) {
     d->fallback_blocks = 0;
     ACES_CUDA(ctx, cudaMemsetAsync(d->flags, 0, sizeof(int32_t) * ((size_t)d->T + 2), ctx->stream));
     ACES_CUDA(ctx, cudaMemsetAsync(d->vec, 0, sizeof(double) * (size_t)(8 * std::max(d->Mp, d->Np)), ctx->stream));
@@ -874,15 +893,18 @@ int prepare_estimator(aces_ctx* ctx, aces_design* d, int ls_type, const double* 
     ACES_TRY(build_gram(ctx, d, ls_type, fv, row_map));
     if (pt) pt->mark("gram");
     if (!factor_gram) return ACES_OK;  // a shard: the host sums the partial Gram matrices first
-    return factor_gram_matrix(ctx, d, fv, pt);
+    return factor_gram_matrix(ctx, d, fv, pt, dead_mode);
 }
 
 // Cholesky factor of the Gram matrix (in place, lower) with the relative pivot test against the
-// original diagonal.
-int factor_gram_matrix(aces_ctx* ctx, aces_design* d, const FitVectors& fv, PhaseTimer* pt) {
+// original diagonal.  dead_mode (fits): a column that fails the test is eliminated, which gives the
+// basic solution of a rank-deficient problem (the reference's sparse QR also returns a basic
+// solution there, src/estimate.jl:500-502; WHICH columns it zeroes depends on SPQR's column
+// ordering, so only the fitted values A x are comparable in that case).
+int factor_gram_matrix(aces_ctx* ctx, aces_design* d, const FitVectors& fv, PhaseTimer* pt, int dead_mode) {
     ACES_TRY(dense::get_diag(ctx, d->Np, d->G, d->Np, fv.t2));
     ACES_CUDA(ctx, cudaMemcpyAsync(fv.t1, fv.t2, sizeof(double) * (size_t)d->Np, cudaMemcpyDeviceToDevice, ctx->stream));
-    ACES_TRY(dense::potrf(ctx, d->Np, d->G, d->Np, d->dinvG, d->flags + d->T, fv.t1, 1e-13));
+    ACES_TRY(dense::potrf(ctx, d->Np, d->G, d->Np, d->dinvG, d->flags + d->T, fv.t1, 1e-13, dead_mode));
     if (pt) pt->mark("potrf");
     return ACES_OK;
 }
@@ -1167,10 +1189,9 @@ int check_design(aces_ctx* ctx, const aces_design* d, const char* what) {
 // device copies of the eigenvalue vectors; returns pointers inside the vector workspace tail
 int upload_eigenvalues(aces_ctx* ctx, aces_design* d, const double* eig, const double* cov_eig, double** lam_dev,
                        double** lamcov_dev) {
-    // the covariance value buffer is followed by nothing else, so keep the inputs in their own buffers
-    static_assert(sizeof(double) == 8, "");
-    ACES_TRY(aces_reserve_dev(ctx, ctx->d_work[0], sizeof(double) * (size_t)(d->M + d->C + 2)));
-    double* base = (double*)ctx->d_work[0].ptr;
+    // a buffer of the design, not context scratch: fit_begin keeps the pointer for the later stages
+    // of a staged fit, and other calls on the same context may run in between
+    double* base = d->lam_buf;
     *lam_dev = base;
     *lamcov_dev = base + d->M;
     ACES_CUDA(ctx, cudaMemcpyAsync(*lam_dev, eig, sizeof(double) * (size_t)d->M, cudaMemcpyDefault, ctx->stream));
@@ -1220,7 +1241,7 @@ int32_t aces_design_inv_factor(aces_ctx* ctx, aces_design* d, const double* cova
     // export: blocks of kept[t] x kept[t], concatenated
     std::vector<int64_t> out_off((size_t)d->T + 1, 0);
     for (int t = 0; t < d->T; ++t) out_off[(size_t)t + 1] = out_off[(size_t)t] + kept[(size_t)t] * kept[(size_t)t];
-    int64_t* meta = (int64_t*)(d->vec + 8 * std::max(d->Mp, d->Np));  // [kept | out_off]
+    int64_t* meta = d->kept_dev;  // [kept | out_off]
     ACES_CUDA(ctx, cudaMemcpyAsync(meta, kept.data(), sizeof(int64_t) * (size_t)d->T, cudaMemcpyHostToDevice, ctx->stream));
     const size_t hdr = ((size_t)d->T + 2) & ~(size_t)1;  // int64 slots before the (8-byte aligned) blocks
     ACES_TRY(aces_reserve_dev(ctx, ctx->d_work[1], sizeof(int64_t) * hdr + sizeof(double) * (size_t)out_off.back()));
@@ -1284,7 +1305,7 @@ int fit_begin(aces_ctx* ctx, aces_design* d, int32_t ls_type, const double* est_
     d->fs_ls_type = ls_type;
     d->fs_clipped = clipped;
     d->fs_lam = lam;
-    ACES_TRY(prepare_estimator(ctx, d, ls_type, d->covval, row_map, kept, fv, pt, factor_gram));
+    ACES_TRY(prepare_estimator(ctx, d, ls_type, d->covval, row_map, kept, fv, pt, factor_gram, 1));
     ACES_TRY(fit_normal_rhs(ctx, d, nullptr));  // g = A' F' F b
     d->fs_stage = 1;
     return ACES_OK;
@@ -1295,7 +1316,7 @@ int fit_solve(aces_ctx* ctx, aces_design* d, bool factor_gram, PhaseTimer* pt) {
     FitVectors fv = fit_vectors(d);
     if (factor_gram) {
         // padding rows: the shards each wrote 1.0 on the padding diagonal, the sum is their number
-        ACES_TRY(factor_gram_matrix(ctx, d, fv, pt));
+        ACES_TRY(factor_gram_matrix(ctx, d, fv, pt, 1));
     }
     ACES_TRY(dense::trsv_lower(ctx, d->Np, d->G, d->Np, d->dinvG, fv.g, fv.t1));
     ACES_TRY(dense::trsv_lower_t(ctx, d->Np, d->G, d->Np, d->dinvG, fv.t1, fv.x));
@@ -1333,7 +1354,7 @@ int fit_end(aces_ctx* ctx, aces_design* d, int32_t constrain, double* gate_eigen
     ctx->launches += 1;
     ACES_CUDA(ctx, cudaMemcpyAsync(gate_eigenvalues, fv.t1, sizeof(double) * (size_t)d->N, cudaMemcpyDefault, ctx->stream));
     d->fs_stage = 0;
-    return check_flags(ctx, d, "design_fit");
+    return check_flags(ctx, d, "design_fit", true);
 }
 
 }  // namespace

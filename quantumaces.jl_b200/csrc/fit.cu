@@ -224,15 +224,20 @@ int lsq_setup(aces_ctx* ctx, int64_t M, int64_t N, const int64_t* A_colptr, cons
     ACES_TRY(dense::fill_diag_range(ctx, st->G, Np, N, Np, 1.0));
     ACES_TRY(gemv_t(ctx, Mp, Np, st->At, Mp, st->bt, st->g, 1.0, 0.0));
     ACES_TRY(dense::get_diag(ctx, Np, st->G, Np, st->t2));
-    ACES_TRY(dense::potrf(ctx, Np, st->G, Np, st->dinv, st->flag, st->t2, 1e-13));
-    int flag = 0;
-    ACES_CUDA(ctx, cudaMemcpyAsync(&flag, st->flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (flag != 0)
-        return aces_fail(ctx, ACES_E_NOT_PD,
-                         "lsq: the Gram matrix is not positive definite (diagonal block %d): the whitened "
-                         "design matrix is rank deficient", flag - 1);
-    if (with_inverse) ACES_TRY(dense::trtri(ctx, Np, st->G, Np, st->dinv, st->X, Np));
+    // A fit eliminates the columns that fail the pivot test (basic solution of a rank-deficient
+    // problem, as the reference's sparse QR returns; the count is read back with the result).  The
+    // inverse of a singular Gram matrix is an error, as inv(cholesky(.)) is in the reference.
+    ACES_TRY(dense::potrf(ctx, Np, st->G, Np, st->dinv, st->flag, st->t2, 1e-13, with_inverse ? 0 : 1));
+    if (with_inverse) {
+        int flag = 0;
+        ACES_CUDA(ctx, cudaMemcpyAsync(&flag, st->flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (flag != 0)
+            return aces_fail(ctx, ACES_E_NOT_PD,
+                             "lsq: the Gram matrix is not positive definite (diagonal block %d): the whitened "
+                             "design matrix is rank deficient", flag - 1);
+        ACES_TRY(dense::trtri(ctx, Np, st->G, Np, st->dinv, st->X, Np));
+    }
     return ACES_OK;
 }
 
@@ -281,7 +286,10 @@ int32_t aces_estimate_gate_eigenvalues(aces_ctx* ctx, int64_t M, int64_t N, cons
     ACES_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     ACES_CUDA(ctx, cudaMemcpyAsync(gate_eigenvalues, st.t1, sizeof(double) * (size_t)N, cudaMemcpyDefault, ctx->stream));
+    int dead = 0;
+    ACES_CUDA(ctx, cudaMemcpyAsync(&dead, st.flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->rank_deficiency = dead;
     return ACES_OK;
 }
 

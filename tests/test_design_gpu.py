@@ -207,6 +207,57 @@ def test_design_create_rejects_bad_input(ctx):
         aces_b200.DeviceDesign(ctx, fd)
 
 
+@pytest.mark.parametrize("mode", ["zero_column", "random_70pct"])
+def test_rank_deficient_fit_gives_basic_solution(ctx, mode):
+    """Clipping (src/estimate.jl:435-460) can remove every row that determines a gate eigenvalue.  The
+    reference's sparse-QR solve (src/estimate.jl:500-502) then returns a basic solution; so does the
+    fit here (dependent columns -> x = 0, i.e. gate eigenvalue 1) instead of failing.  Which columns a
+    basic solution zeroes depends on the elimination order, so the comparable quantities are the rank
+    and the fitted circuit eigenvalues A x -- checked against LAPACK's rank-revealing gelsy."""
+    import scipy.linalg as sla
+
+    import aces_b200
+
+    fd = aces_b200.rotated_design(3, full_covariance=True, noise="lognormal", seed=4)
+    A = sp.csr_matrix(fd.matrix).astype(np.float64)
+    M, N = A.shape
+    eig, cov = noisy_ensembles(fd, seed=3)
+    lam = np.concatenate(aces_b200.mean_ensemble(eig))
+    lc = np.concatenate(aces_b200.mean_ensemble(cov))
+    if mode == "zero_column":
+        rows = np.unique(sp.csc_matrix(A)[:, 100].nonzero()[0])
+        kept = np.setdiff1d(np.arange(M), rows)
+    else:
+        kept = np.sort(np.random.default_rng(5).choice(M, size=int(0.7 * M), replace=False))
+    Ak = A[kept].toarray()
+    rank = int(np.linalg.matrix_rank(Ak))
+    assert rank < N
+    dd = aces_b200.DeviceDesign(ctx, fd)
+    try:
+        cl = fo.calc_covariance_log(fo.calc_covariance_from_experiments(fd, eig, cov, weight_time=False), lam)
+        clk = sp.csc_matrix(cl)[kept, :][:, kept]
+        factors = {"ols": None, "wls": sp.diags(clk.diagonal() ** (-0.5)),
+                   "gls": fo.sparse_covariance_inv_factor(clk, fo.get_clipped_mapping_lengths(fd.mapping_lengths, kept))}
+        b = -np.log(lam[kept])
+        for k in ("ols", "wls", "gls"):
+            g = dd.fit(k, lam, lc, clipped_indices=kept)
+            assert ctx.last_rank_deficiency() == N - rank, (k, ctx.last_rank_deficiency(), N - rank)
+            x = -np.log(g)
+            assert int(np.sum(x == 0.0)) >= N - rank          # the eliminated columns sit at g = 1 exactly
+            F = factors[k]
+            FA, Fb = (Ak, b) if F is None else (F @ Ak, F @ b)
+            xo, *_ = sla.lstsq(FA, Fb, lapack_driver="gelsy", cond=1e-12)
+            # the whitened fitted values are unique even though x is not
+            assert rel(FA @ x, FA @ xo) < 1e-8, (k, rel(FA @ x, FA @ xo))
+        if mode == "zero_column":
+            assert dd.fit("gls", lam, lc, clipped_indices=kept)[100] == 1.0
+        # a full-rank fit on the same context reports zero again
+        dd.fit("wls", lam, lc)
+        assert ctx.last_rank_deficiency() == 0
+    finally:
+        dd.close()
+
+
 @pytest.fixture(scope="module", params=["real9", "unrot7"], ids=["real_rotated_d9_gls", "real_unrotated_d7_gls"])
 def setup_headline(request, ctx):
     """The headline shapes of BASELINE.json (configs[2]/[3]: rotated d=9, M x N = 12912 x 6779; unrotated

@@ -88,12 +88,21 @@ def test_fit_after_clipping(ctx, design, inputs):
         aces_b200.get_clipped_indices(np.array([0.5, 1.5]))
 
 
-def test_rank_deficient_reports_not_pd(ctx):
+def test_rank_deficient_gives_basic_solution(ctx):
+    """(F*A) \\ (F*b) with a rank-deficient matrix: the reference's sparse QR returns a basic solution
+    (src/estimate.jl:500-502); so does the CSC path (dependent column -> x = 0), reporting the rank
+    deficiency.  The inverse of the singular Gram matrix stays an error."""
     import aces_b200
 
     A = sp.csc_matrix(np.array([[1.0, 1.0], [2.0, 2.0], [3.0, 3.0]]))
+    y = np.array([0.9, 0.8, 0.7])
+    g = aces_b200.estimate_gate_eigenvalues(ctx, A, y)
+    assert ctx.last_rank_deficiency() == 1
+    assert g[1] == 1.0                                   # the second column is eliminated
+    x0 = np.linalg.lstsq(np.array([[1.0], [2.0], [3.0]]), -np.log(y), rcond=None)[0][0]
+    assert abs(-np.log(g[0]) - x0) < 1e-12
     with pytest.raises(aces_b200.NotPositiveDefinite):
-        aces_b200.estimate_gate_eigenvalues(ctx, A, np.array([0.9, 0.8, 0.7]))
+        aces_b200.calc_gls_covariance_from_factor(ctx, A, np.ones(2), None)
 
 
 def test_gls_covariance_and_precision(ctx, design):
