@@ -285,6 +285,17 @@ int32_t aces_design_fit_refine_begin(aces_ctx* ctx, aces_design* design);
 int32_t aces_design_fit_refine_end(aces_ctx* ctx, aces_design* design, double* x_max, double* delta_max);
 int32_t aces_design_fit_end(aces_ctx* ctx, aces_design* design, int32_t constrain, double* gate_eigenvalues);
 
+/* Per-gate diagonal blocks of calc_precision_matrix(design_matrix, gate_eigenvalues, covariance_log_inv)
+ * (src/merit.jl:754-770) = D^-1 A' Omega'^-1 A D^-1 -- all that split_project_gate_eigenvalues reads of
+ * it (src/estimate.jl:606-612: est_precision_matrix[indices, indices] per gate).  Must directly follow
+ * aces_design_fit of the same ls_type on this design: the blocks are those of that fit's Gram matrix
+ * (its clipping, weights and block factors), rebuilt on the device.  Group g owns
+ * group_idx[group_ptr[g] .. group_ptr[g+1]-1]; blocks receives the n_g x n_g blocks concatenated
+ * (symmetric).  gate_eigenvalues [N] = the unprojected estimate D is made of (NULL: D = I). */
+int32_t aces_design_precision_blocks(aces_ctx* ctx, aces_design* design, int32_t ls_type, int32_t G,
+                                     const int64_t* group_ptr, const int32_t* group_idx, int32_t index_base,
+                                     const double* gate_eigenvalues, double* blocks);
+
 /* K6.  calc_gls_covariance / calc_wls_covariance / calc_ols_covariance(d, covariance_log)
  * (src/merit.jl:556-629) for ls_type 2 / 1 / 0: gate_eigenvalues [N] = get_gate_eigenvalues(d),
  * covariance_log_nzval in the design's pattern.  sigma (N x N column-major, host or device) may be

@@ -32,7 +32,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import scipy.sparse as sp
 
-from .design import FlatDesign, get_covariance_experiment_ensemble
+from aces_b200.design import FlatDesign, get_covariance_experiment_ensemble
 
 Gate = Tuple[str, int, Tuple[int, ...]]   # (type, index, 1-based targets), src/tableau.jl:88-92
 
@@ -731,6 +731,9 @@ def generate_design(c: Circuit, tuple_set: Optional[List[List[int]]] = None, ful
         gate_eigenvalues=depolarising_gate_eigenvalues(c) if gate_eigenvalues is None else gate_eigenvalues,
         name=c.name + ("_gls" if full_covariance else ""),
     )
+    # gate index ranges in the order of get_gate_index_dict (src/noise.jl:271-277)
+    fd.gate_ptr = np.asarray([c.gate_offset[g] for g in c.total_gates] + [c.N], dtype=np.int64)
+    assert np.all(np.diff(fd.gate_ptr) == [c.gate_size[g] for g in c.total_gates])
     if full_covariance:
         fd.cov_keys, fd.cov_meas_indices, fd.cov_signs = cov_keys, cov_meas, cov_signs
         fd.cov_counts, fd.cov_rows = cov_counts, cov_rows

@@ -8,13 +8,12 @@ from ._lib import AcesError, Context, NotPositiveDefinite, PauliTables  # noqa: 
 from .design import (  # noqa: F401
     FlatDesign, build_pauli_tables, shots_divide, synthetic_design, synthetic_estimates,
 )
-from . import circuit_design  # noqa: F401
-from .circuit_design import example_design, rotated_design, unrotated_design  # noqa: F401
 from .estimate import DesignEstimator, estimate_experiment  # noqa: F401
 from . import merit  # noqa: F401
 from . import shard  # noqa: F401
+from . import project  # noqa: F401
 from .merit import (  # noqa: F401
     calc_gls_covariance_from_factor, calc_precision_matrix_from_factor, estimate_gate_eigenvalues,
     get_clipped_indices, get_clipped_mapping_lengths, DeviceDesign, estimate_gate_noise_core, mean_ensemble,
-    nrmse_moments,
+    nrmse_moments, estimate_gate_noise_projected,
 )

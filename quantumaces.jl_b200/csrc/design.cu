@@ -83,6 +83,7 @@ struct aces_design {
     bool sharded = false;
     // --- state of a fit split at its reduction points (aces_design_fit_begin .. _end) ---
     int fs_stage = 0, fs_ls_type = 0;
+    int est_ls_type = -1;          // estimator whose factors / weights / clipping the workspaces hold (-1: none)
     bool fs_clipped = false;
     double* fs_lam = nullptr;
     std::vector<void*> owned;
@@ -482,6 +483,25 @@ __global__ void sandwich_kernel(int64_t N, const int64_t* __restrict__ a_colptr,
                 }
             }
         }
+    }
+}
+
+// Per-gate diagonal blocks of the precision matrix D^-1 G D^-1 (src/merit.jl:754-770) from the lower
+// triangle of the Gram matrix: one CTA per gate, block (a, b) = (1 / g_a) * G[i_a, i_b] * (1 / g_b).
+__global__ void precision_blocks_kernel(int G, const int64_t* __restrict__ gptr, const int64_t* __restrict__ boff,
+                                        const int32_t* __restrict__ gidx, const double* __restrict__ Gm, int64_t ldg,
+                                        const double* __restrict__ scale, double* __restrict__ out) {
+    const int g = blockIdx.x;
+    if (g >= G) return;
+    const int64_t e0 = gptr[g];
+    const int n = (int)(gptr[g + 1] - e0);
+    double* o = out + boff[g];
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int a = e / n, b = e % n;
+        const int64_t ia = gidx[e0 + a], ib = gidx[e0 + b];
+        const double v = Gm[(ia > ib ? ia : ib) + (ia > ib ? ib : ia) * ldg];
+        const double da = scale ? __ddiv_rn(1.0, scale[ia]) : 1.0, db = scale ? __ddiv_rn(1.0, scale[ib]) : 1.0;
+        o[e] = __dmul_rn(__dmul_rn(da, v), db);
     }
 }
 
@@ -1226,6 +1246,7 @@ int32_t aces_design_inv_factor(aces_ctx* ctx, aces_design* d, const double* cova
     ACES_TRY(check_design(ctx, d, "design_inv_factor"));
     ACES_CHECK(ctx, !d->sharded, "design_inv_factor: the design is a tuple shard");
     ACES_CHECK(ctx, covariance_log_nzval && factor_blocks, "design_inv_factor: NULL argument");
+    d->est_ls_type = -1;
     ACES_TRY(ensure_workspaces(ctx, d, true, false, false, false));
     ACES_TRY(build_tile_descs(ctx, d));
     std::vector<int64_t> kept;
@@ -1305,7 +1326,9 @@ int fit_begin(aces_ctx* ctx, aces_design* d, int32_t ls_type, const double* est_
     d->fs_ls_type = ls_type;
     d->fs_clipped = clipped;
     d->fs_lam = lam;
+    d->est_ls_type = -1;
     ACES_TRY(prepare_estimator(ctx, d, ls_type, d->covval, row_map, kept, fv, pt, factor_gram, 1));
+    d->est_ls_type = ls_type;
     ACES_TRY(fit_normal_rhs(ctx, d, nullptr));  // g = A' F' F b
     d->fs_stage = 1;
     return ACES_OK;
@@ -1400,6 +1423,7 @@ int32_t aces_design_set_tuple_shard(aces_ctx* ctx, aces_design* d, const uint8_t
     d->g_panel = d->g_trail = d->g_tri1 = d->g_tri2 = nullptr;
     d->g_gram = nullptr;
     d->fs_stage = 0;
+    d->est_ls_type = -1;
     return ACES_OK;
 }
 
@@ -1444,6 +1468,56 @@ int32_t aces_design_fit_end(aces_ctx* ctx, aces_design* d, int32_t constrain, do
     return fit_end(ctx, d, constrain, gate_eigenvalues);
 }
 
+int32_t aces_design_precision_blocks(aces_ctx* ctx, aces_design* d, int32_t ls_type, int32_t G,
+                                     const int64_t* group_ptr, const int32_t* group_idx, int32_t index_base,
+                                     const double* gate_eigenvalues, double* blocks) {
+    ACES_TRY(check_design(ctx, d, "design_precision_blocks"));
+    ACES_CHECK(ctx, !d->sharded, "design_precision_blocks: the design is a tuple shard");
+    ACES_CHECK(ctx, G >= 1 && group_ptr && group_idx && blocks, "design_precision_blocks: bad argument");
+    ACES_CHECK(ctx, index_base == 0 || index_base == 1, "design_precision_blocks: index_base must be 0 or 1");
+    ACES_CHECK(ctx, d->est_ls_type == ls_type && d->fs_stage == 0,
+               "design_precision_blocks: call aces_design_fit with the same ls_type on this design first (the blocks "
+               "are those of the Gram matrix of that fit: its clipping, weights and block factors)");
+    ACES_CHECK(ctx, group_ptr[0] == 0, "design_precision_blocks: group_ptr must start at 0");
+    const int64_t nidx = group_ptr[G];
+    std::vector<int32_t> idx((size_t)nidx);
+    std::vector<int64_t> boff((size_t)G + 1, 0);
+    for (int g = 0; g < G; ++g) {
+        const int64_t n = group_ptr[g + 1] - group_ptr[g];
+        ACES_CHECK(ctx, n >= 0 && n <= 4096, "design_precision_blocks: bad group size");
+        boff[(size_t)g + 1] = boff[(size_t)g] + n * n;
+        for (int64_t e = group_ptr[g]; e < group_ptr[g + 1]; ++e) {
+            const int64_t i = (int64_t)group_idx[e] - index_base;
+            ACES_CHECK(ctx, i >= 0 && i < d->N, "design_precision_blocks: index %lld outside 0..N-1", (long long)i);
+            idx[(size_t)e] = (int32_t)i;
+        }
+    }
+    FitVectors fv = fit_vectors(d);
+    // the Gram matrix of the last fit again (its Cholesky factor overwrote it): same clipping and factors
+    ACES_TRY(build_gram(ctx, d, ls_type, fv, d->fs_clipped ? d->row_map : nullptr));
+    d->est_ls_type = ls_type;
+    const size_t b_ptr = sizeof(int64_t) * ((size_t)G + 1), b_idx = (sizeof(int32_t) * (size_t)nidx + 7) & ~(size_t)7;
+    ACES_TRY(aces_reserve_dev(ctx, ctx->d_work[6], 2 * b_ptr + b_idx + sizeof(double) * (size_t)(boff.back() + d->N) + 64));
+    uint8_t* base = (uint8_t*)ctx->d_work[6].ptr;
+    int64_t* d_ptr = (int64_t*)base;
+    int64_t* d_boff = (int64_t*)(base + b_ptr);
+    int32_t* d_idx = (int32_t*)(base + 2 * b_ptr);
+    double* d_scale = (double*)(base + 2 * b_ptr + b_idx);
+    double* d_out = d_scale + d->N;
+    ACES_CUDA(ctx, cudaMemcpyAsync(d_ptr, group_ptr, b_ptr, cudaMemcpyHostToDevice, ctx->stream));
+    ACES_CUDA(ctx, cudaMemcpyAsync(d_boff, boff.data(), b_ptr, cudaMemcpyHostToDevice, ctx->stream));
+    ACES_CUDA(ctx, cudaMemcpyAsync(d_idx, idx.data(), sizeof(int32_t) * (size_t)nidx, cudaMemcpyHostToDevice, ctx->stream));
+    if (gate_eigenvalues)
+        ACES_CUDA(ctx, cudaMemcpyAsync(d_scale, gate_eigenvalues, sizeof(double) * (size_t)d->N, cudaMemcpyDefault, ctx->stream));
+    precision_blocks_kernel<<<(unsigned)G, 64, 0, ctx->stream>>>(G, d_ptr, d_boff, d_idx, d->G, d->Np,
+                                                                gate_eigenvalues ? d_scale : nullptr, d_out);
+    ACES_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    ACES_CUDA(ctx, cudaMemcpyAsync(blocks, d_out, sizeof(double) * (size_t)boff.back(), cudaMemcpyDefault, ctx->stream));
+    ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ACES_OK;
+}
+
 int32_t aces_design_ls_covariance(aces_ctx* ctx, aces_design* d, int32_t ls_type, const double* gate_eigenvalues,
                                   const double* covariance_log_nzval, double* sigma, double* trace,
                                   double* trace_sq) {
@@ -1451,6 +1525,7 @@ int32_t aces_design_ls_covariance(aces_ctx* ctx, aces_design* d, int32_t ls_type
     ACES_CHECK(ctx, !d->sharded, "design_ls_covariance: the design is a tuple shard");
     ACES_CHECK(ctx, ls_type >= 0 && ls_type <= 2, "design_ls_covariance: ls_type must be 0 (OLS), 1 (WLS) or 2 (GLS)");
     ACES_CHECK(ctx, gate_eigenvalues && covariance_log_nzval, "design_ls_covariance: NULL argument");
+    d->est_ls_type = -1;
     const bool gls = ls_type == 2;
     ACES_TRY(ensure_workspaces(ctx, d, gls, gls, true, !gls));
     if (gls) ACES_TRY(build_tile_descs(ctx, d));

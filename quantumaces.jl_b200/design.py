@@ -45,6 +45,9 @@ class FlatDesign:
     gate_eigenvalues: Optional[np.ndarray] = None  # d.c.gate_eigenvalues (true values, synthetic)
     # design rows of the covariance Paulis (covariance_dict[key][1].design_row), CSR per tuple
     cov_rows: List = field(default_factory=list)
+    # gates as groups of consecutive gate eigenvalues (GateIndex.indices, src/noise.jl:16-24): gate g owns
+    # columns gate_ptr[g] .. gate_ptr[g+1]-1 of the design matrix (1, 3 or 15 of them)
+    gate_ptr: Optional[np.ndarray] = None
     name: str = ""
 
     @property

@@ -269,6 +269,23 @@ class DeviceDesign:
             0 if kept is None else len(kept), 0, float(epsilon), 1 if constrain else 0, _ptr(g)))
         return g
 
+    def precision_blocks(self, ls_type: str, gate_ptr, gate_eigenvalues=None, gate_idx=None):
+        """Per-gate diagonal blocks of calc_precision_matrix (src/merit.jl:754-770) for the estimator of
+        the LAST `fit` call on this design (same ls_type): list of n_g x n_g arrays."""
+        gp = np.ascontiguousarray(gate_ptr, dtype=np.int64)
+        gi = np.arange(self.N, dtype=np.int32) if gate_idx is None else np.ascontiguousarray(gate_idx, dtype=np.int32)
+        g = None if gate_eigenvalues is None else np.ascontiguousarray(gate_eigenvalues, dtype=np.float64)
+        sizes = np.diff(gp)
+        out = np.zeros(int(np.sum(sizes ** 2)), dtype=np.float64)
+        self.ctx.check(self.ctx.lib.aces_design_precision_blocks(
+            self.ctx.handle, self.handle, LS_TYPES[ls_type], len(gp) - 1, _ptr(gp), _ptr(gi), 0, _ptr(g), _ptr(out)))
+        blocks, off = [], 0
+        for n in sizes:
+            n = int(n)
+            blocks.append(out[off:off + n * n].reshape(n, n))
+            off += n * n
+        return blocks
+
     # -- tuple-sharded fit (SURVEY 8e, "one large Gram") ------------------------------------------
     def set_tuple_shard(self, tuple_on=None) -> None:
         """This design only works on the tuples with a non-zero byte (None: all tuples, no shard)."""
@@ -349,4 +366,48 @@ def estimate_gate_noise_core(dd: DeviceDesign, est_eigenvalues_experiment_ensemb
     out = {"est_eigenvalues": est, "clipped_indices": clipped,
            "ols": dd.fit("ols", est, cov, kept), "wls": dd.fit("wls", est, cov, kept)}
     out["gls"] = dd.fit("gls", est, cov, kept) if fd.full_covariance else out["wls"]
+    return out
+
+
+def isapprox(x, y) -> bool:
+    """Julia's x ≈ y for vectors (default rtol = sqrt(eps), atol = 0; src/estimate.jl:744)."""
+    x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    return bool(np.linalg.norm(x - y) <= np.sqrt(np.finfo(np.float64).eps) * max(np.linalg.norm(x), np.linalg.norm(y)))
+
+
+def estimate_gate_noise_projected(dd: DeviceDesign, est_eigenvalues_experiment_ensemble,
+                                  est_covariance_experiment_ensemble, min_eigenvalue: float = 0.1,
+                                  clip_warning: bool = True, precision: float = 1e-8):
+    """estimate_gate_noise (src/estimate.jl:703-831) up to the NoiseEstimate bookkeeping, with
+    split = true: unprojected OLS / WLS / GLS gate eigenvalues, the Euclidean projection of the OLS
+    estimate (simple_project_gate_eigenvalues), and -- when that projection moved it
+    (`precision_project`, :744) -- the per-gate Mahalanobis projection of WLS / GLS with the slices
+    of their precision matrices (split_project_gate_eigenvalues), else the Euclidean one.  The
+    simultaneous projection of all gates (full_project_gate_eigenvalues, the reference's default below
+    5000 gate eigenvalues) stays on the reference's SCS path."""
+    from . import project
+
+    fd, ctx = dd.fd, dd.ctx
+    assert fd.gate_ptr is not None, "the design carries no gate index ranges"
+    est = np.concatenate(mean_ensemble(est_eigenvalues_experiment_ensemble))
+    cov = np.concatenate(mean_ensemble(est_covariance_experiment_ensemble)) if dd.C else None
+    clipped = get_clipped_indices(est, min_eigenvalue=min_eigenvalue, warning=clip_warning)
+    kept = None if len(clipped) == dd.M else clipped
+    out = {"est_eigenvalues": est, "clipped_indices": clipped}
+    out["ols_unproj"] = dd.fit("ols", est, cov, kept)
+    out["ols"], out["ols_unproj_probabilities"], out["ols_probabilities"] = \
+        project.simple_project_gate_eigenvalues(ctx, out["ols_unproj"], fd.gate_ptr)
+    out["precision_project"] = not isapprox(out["ols"], out["ols_unproj"])
+    for k in (("wls", "gls") if fd.full_covariance else ("wls",)):
+        un = dd.fit(k, est, cov, kept)
+        out[k + "_unproj"] = un
+        if out["precision_project"]:
+            blocks = dd.precision_blocks(k, fd.gate_ptr, un)
+            res = project.split_project_gate_eigenvalues(ctx, un, blocks, fd.gate_ptr, precision=precision)
+        else:
+            res = project.simple_project_gate_eigenvalues(ctx, un, fd.gate_ptr)
+        out[k], out[k + "_unproj_probabilities"], out[k + "_probabilities"] = res
+    if not fd.full_covariance:
+        for suffix in ("", "_unproj", "_unproj_probabilities", "_probabilities"):
+            out["gls" + suffix] = out["wls" + suffix]
     return out
