@@ -141,6 +141,18 @@ int32_t aces_parity_counts_async(aces_ctx* ctx, const aces_tables* tables, int32
                                  const int64_t* prefix_shots, int64_t* odd_counts,
                                  int32_t accumulate);
 
+/* Ingest: the same counts from ROW-major records, i.e. the buffer Stim's
+ * sampler.sample(shots, bit_packed = true) returns before the reference's pyconvert(Matrix{UInt8}, ...)
+ * turns it into a column-major Julia matrix with a strided host copy (src/simulate.jl:57-63):
+ *   records[i]  uint8 [rows[i] x B], shot s at records[i] + s * row_pitch[i] (row_pitch >= B =
+ *               ceil(n_qubits / 8); numpy C order: row_pitch = B), host or device.
+ * One contiguous copy per item, a device-side byte transposition into the column-major arena, then
+ * the kernel of aces_parity_counts; every other argument as there. */
+int32_t aces_parity_counts_rowmajor(aces_ctx* ctx, const aces_tables* tables, int32_t n_items,
+                                    const int32_t* experiment_ids, const uint8_t* const* records,
+                                    const int64_t* rows, const int64_t* row_pitch, int32_t K,
+                                    const int64_t* prefix_shots, int64_t* odd_counts, int32_t accumulate);
+
 /* Drop-in for estimate_experiment(counts::Matrix{UInt8}, experiment_meas_indices,
  * experiment_pauli_signs, shots_value) (src/estimate.jl:284-301): meas_indices are the
  * reference's 1-based qubit indices in CSR form (meas_ptr [E+1]); est[p] =

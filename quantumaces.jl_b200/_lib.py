@@ -57,6 +57,7 @@ SIGNATURES = {
     "aces_tables_group_columns": (_i64, [_vp, _i32]),
     "aces_parity_counts": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32]),
     "aces_parity_counts_async": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32]),
+    "aces_parity_counts_rowmajor": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32]),
     "aces_estimate_experiment": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
     "aces_estimate_gate_eigenvalues": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp]),
     "aces_gram_inverse": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _vp]),
@@ -236,8 +237,10 @@ def parity_counts(
     out=None,
     accumulate: bool = False,
     asynchronous: bool = False,
+    rowmajor: bool = False,
 ):
-    """aces_parity_counts / aces_parity_counts_async.
+    """aces_parity_counts / aces_parity_counts_async / aces_parity_counts_rowmajor (`rowmajor`: the
+    matrices are C-ordered [rows x B] records and `ld` is the byte pitch between shots).
 
     `matrices` are numpy uint8 arrays (column-major, i.e. Fortran order [rows x cols]) or raw
     integer addresses (host or device).  `out` is None (a host int64 array is returned), a
@@ -261,6 +264,9 @@ def parity_counts(
         out_ptr = _ptr(out)
         ret = out
     fn = ctx.lib.aces_parity_counts_async if asynchronous else ctx.lib.aces_parity_counts
+    if rowmajor:
+        assert not asynchronous
+        fn = ctx.lib.aces_parity_counts_rowmajor
     ctx.check(
         fn(
             ctx.handle, tables.handle, n, _ptr(eid), C.cast(ptrs, C.c_void_p), _ptr(rows_a),
@@ -276,7 +282,7 @@ class PreparedBatch:
     foreign call each."""
 
     def __init__(self, ctx: Context, tables: PauliTables, experiment_ids, matrices, rows, ld, prefix_shots, out,
-                 accumulate: bool = False, asynchronous: bool = False):
+                 accumulate: bool = False, asynchronous: bool = False, rowmajor: bool = False):
         n = len(experiment_ids)
         self.ctx, self.tables, self.n = ctx, tables, n
         self.eid = np.ascontiguousarray(experiment_ids, dtype=np.int32)
@@ -290,6 +296,9 @@ class PreparedBatch:
             self.ptrs[i] = _ptr(m)
         self.out = out
         self.fn = ctx.lib.aces_parity_counts_async if asynchronous else ctx.lib.aces_parity_counts
+        if rowmajor:
+            assert not asynchronous
+            self.fn = ctx.lib.aces_parity_counts_rowmajor
         self.args = (ctx.handle, tables.handle, n, _ptr(self.eid), C.cast(self.ptrs, C.c_void_p), _ptr(self.rows),
                      _ptr(self.ld), self.K, _ptr(self.pre), _ptr(out), 1 if accumulate else 0)
 

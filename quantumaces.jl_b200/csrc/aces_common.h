@@ -39,6 +39,8 @@ struct aces_ctx {
 
     // K1 workspaces
     DevBuf d_arena;    // pitched copies of sample matrices that cannot be read in place
+    DevBuf d_raw;      // row-major records as they arrive from the host (ingest path), before the transposition
+    DevBuf d_tdesc;    // descriptor table of the batched transposition
     DevBuf d_streams;  // stream table + item prefix
     DevBuf d_seg;      // per-segment odd counts (uint64)
     DevBuf d_odd;      // cumulative odd counts when the caller's output is on the host

@@ -70,11 +70,65 @@ struct aces_tables {
     int32_t* d_cols = nullptr;
 };
 
+// ---- ingest of row-major records ----------------------------------------
+// Stim's sample(bit_packed = true) returns a ROW-major uint8 [shots x B] array; the reference turns it
+// into a column-major Julia matrix with a strided element-by-element copy on the host
+// (pyconvert(Matrix{UInt8}, ...), src/simulate.jl:60-63).  Here the row-major buffer is taken as it
+// is (one contiguous host-to-device copy) and transposed on the device into the pitched column-major
+// arena the parity kernel reads: an HBM-bound byte transposition, one CTA per tile of TR shots.
+struct TransDesc {
+    const uint8_t* src;  // row-major, `pitch` bytes between shots (device)
+    int64_t pitch, rows;
+    uint8_t* dst;        // column-major, `dst_ld` bytes between byte columns (a multiple of 128)
+    int64_t dst_ld;
+};
+constexpr int TR = 512;  // shots per tile
+
+__global__ void __launch_bounds__(256) rowmajor_to_colmajor_kernel(const TransDesc* __restrict__ descs, int B) {
+    extern __shared__ __align__(16) uint8_t tile[];  // [TR][B] as in the source
+    const TransDesc d = descs[blockIdx.y];
+    const int tid = threadIdx.x;
+    for (int64_t r0 = (int64_t)blockIdx.x * TR; r0 < d.rows; r0 += (int64_t)gridDim.x * TR) {
+        const int nr = (int)min((int64_t)TR, d.rows - r0);
+        const uint8_t* src = d.src + r0 * d.pitch;
+        if (d.pitch == B && (((uintptr_t)src) & 15) == 0) {
+            const int nbytes = nr * B, nvec = nbytes >> 4;
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            uint4* t4 = reinterpret_cast<uint4*>(tile);
+            for (int i = tid; i < nvec; i += 256) t4[i] = __ldcs(s4 + i);
+            for (int i = (nvec << 4) + tid; i < nbytes; i += 256) tile[i] = src[i];
+        } else {
+            for (int i = tid; i < nr * B; i += 256) {
+                const int sidx = i / B, c = i - sidx * B;
+                tile[i] = src[(int64_t)sidx * d.pitch + c];
+            }
+        }
+        __syncthreads();
+        // thread (c, q): four consecutive shots of byte column c -> one 32-bit store (the destination
+        // pitch is a multiple of 128 and r0 of 512: aligned).  Shots past `rows` are written as zero.
+        const int quads = TR / 4;
+        for (int i = tid; i < B * quads; i += 256) {
+            const int c = i / quads, q = i - c * quads;
+            uint32_t w = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int sidx = 4 * q + k;
+                if (sidx < nr) w |= (uint32_t)tile[sidx * B + c] << (8 * k);
+            }
+            if (4 * q < ((nr + 15) & ~15))  // up to the 16-shot copy granularity of the parity kernel
+                *reinterpret_cast<uint32_t*>(d.dst + (int64_t)c * d.dst_ld + r0 + 4 * q) = w;
+        }
+        __syncthreads();
+    }
+}
+
+// layout: 0 = column-major sample matrices (ld = bytes between byte columns); 1 = row-major records
+// (ld = bytes between shots, >= B)
 static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
                       const int32_t* experiment_ids, const uint8_t* const* counts,
                       const int64_t* rows, const int64_t* ld, int32_t K,
                       const int64_t* prefix_shots, int64_t* odd_counts, int32_t accumulate,
-                      bool async_only) {
+                      bool async_only, int layout = 0) {
     if (!ctx) return ACES_E_INVALID;
     ACES_CHECK(ctx, t != nullptr, "parity_counts: tables is NULL");
     ACES_CHECK(ctx, n_items >= 0 && K >= 1, "parity_counts: n_items=%d K=%d", n_items, K);
@@ -99,15 +153,20 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
     std::vector<int64_t> item_off(n_items + 1, 0);
     std::vector<int32_t> item_E(n_items);
     std::vector<char> in_place(n_items);
-    std::vector<size_t> arena_off(n_items, 0);
-    size_t arena_bytes = 0;
+    std::vector<size_t> arena_off(n_items, 0), raw_off(n_items, 0);
+    std::vector<char> src_dev(n_items, 0);
+    size_t arena_bytes = 0, raw_bytes = 0;
     int max_E = 0;
     for (int i = 0; i < n_items; ++i) {
         const int e = experiment_ids[i];
         ACES_CHECK(ctx, e >= 0 && e < t->n_experiments, "parity_counts: item %d: experiment %d out of range", i, e);
         ACES_CHECK(ctx, rows[i] >= 0, "parity_counts: item %d: rows=%lld", i, (long long)rows[i]);
-        ACES_CHECK(ctx, ld[i] >= rows[i], "parity_counts: item %d: ld=%lld < rows=%lld", i,
-                   (long long)ld[i], (long long)rows[i]);
+        if (layout == 0)
+            ACES_CHECK(ctx, ld[i] >= rows[i], "parity_counts: item %d: ld=%lld < rows=%lld", i,
+                       (long long)ld[i], (long long)rows[i]);
+        else
+            ACES_CHECK(ctx, ld[i] >= B, "parity_counts: item %d: row pitch %lld < %d bytes per shot", i,
+                       (long long)ld[i], B);
         ACES_CHECK(ctx, rows[i] == 0 || counts[i] != nullptr, "parity_counts: item %d: NULL matrix", i);
         int64_t prev = 0;
         for (int k = 0; k < K; ++k) {
@@ -124,11 +183,18 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
         // The asynchronous entry point takes device matrices by contract: the per-item pointer query
         // (about a microsecond each, times ~100 experiments per call) is skipped there.
         const bool dev = rows[i] > 0 && (async_only || aces_is_device_ptr(counts[i]));
-        in_place[i] = dev && (((uintptr_t)counts[i]) % 16 == 0) && (ld[i] % 16 == 0);
+        in_place[i] = layout == 0 && dev && (((uintptr_t)counts[i]) % 16 == 0) && (ld[i] % 16 == 0);
         if (!in_place[i] && rows[i] > 0) {
             const size_t pitch = ((size_t)rows[i] + 127) & ~(size_t)127;
             arena_off[i] = arena_bytes;
             arena_bytes += pitch * B;
+            if (layout == 1) {
+                src_dev[i] = dev;
+                if (!dev) {  // host records: staged contiguously, 16-byte aligned per item
+                    raw_off[i] = raw_bytes;
+                    raw_bytes += ((size_t)rows[i] * (size_t)ld[i] + 255) & ~(size_t)255;
+                }
+            }
         }
     }
     const int64_t total_out = item_off[n_items];
@@ -149,6 +215,40 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
     std::vector<double> stream_cost;  // estimated warp instructions per tile (cost-balanced partition below)
     std::vector<int64_t> item_start(1, 0);
     if (arena_bytes > 0) ACES_TRY(aces_reserve_dev(ctx, ctx->d_arena, arena_bytes));
+    if (layout == 1 && arena_bytes > 0) {
+        // row-major records: contiguous copies into the raw staging area, then ONE batched transposition
+        if (raw_bytes > 0) ACES_TRY(aces_reserve_dev(ctx, ctx->d_raw, raw_bytes));
+        std::vector<TransDesc> td;
+        int64_t max_rows = 0;
+        for (int i = 0; i < n_items; ++i) {
+            if (rows[i] == 0) continue;
+            const uint8_t* src = counts[i];
+            if (!src_dev[i]) {
+                uint8_t* raw = (uint8_t*)ctx->d_raw.ptr + raw_off[i];
+                ACES_CUDA(ctx, cudaMemcpyAsync(raw, counts[i], (size_t)rows[i] * (size_t)ld[i], cudaMemcpyHostToDevice,
+                                               ctx->stream));
+                src = raw;
+            }
+            const size_t pitch = ((size_t)rows[i] + 127) & ~(size_t)127;
+            td.push_back(TransDesc{src, ld[i], rows[i], (uint8_t*)ctx->d_arena.ptr + arena_off[i], (int64_t)pitch});
+            max_rows = std::max(max_rows, rows[i]);
+        }
+        if (!td.empty()) {
+            ACES_TRY(aces_reserve_dev(ctx, ctx->d_tdesc, sizeof(TransDesc) * td.size()));
+            // pageable source: the runtime stages it before returning, `td` may die afterwards
+            ACES_CUDA(ctx, cudaMemcpyAsync(ctx->d_tdesc.ptr, td.data(), sizeof(TransDesc) * td.size(), cudaMemcpyHostToDevice,
+                                           ctx->stream));
+            const size_t smem = (size_t)TR * (size_t)B;
+            ACES_CHECK(ctx, smem <= (size_t)ctx->smem_optin, "parity_counts: %d bytes per shot exceed the transposition tile", B);
+            ACES_CUDA(ctx, cudaFuncSetAttribute(rowmajor_to_colmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int64_t tiles = (max_rows + TR - 1) / TR;
+            const int64_t want = std::max<int64_t>(1, (int64_t)ctx->sm_count * 8 / (int64_t)td.size());
+            dim3 grid((unsigned)std::min<int64_t>(tiles, want), (unsigned)td.size());
+            rowmajor_to_colmajor_kernel<<<grid, 256, smem, ctx->stream>>>((const TransDesc*)ctx->d_tdesc.ptr, B);
+            ACES_CUDA(ctx, cudaGetLastError());
+            ctx->launches += 1;
+        }
+    }
     for (int i = 0; i < n_items; ++i) {
         const int e = experiment_ids[i];
         const int g0 = t->grp_ptr[(size_t)e], g1 = t->grp_ptr[(size_t)e + 1];
@@ -161,8 +261,9 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
         } else {
             const size_t pitch = ((size_t)rows[i] + 127) & ~(size_t)127;
             uint8_t* dst = (uint8_t*)ctx->d_arena.ptr + arena_off[i];
-            ACES_CUDA(ctx, cudaMemcpy2DAsync(dst, pitch, counts[i], (size_t)ld[i], (size_t)rows[i],
-                                             (size_t)B, cudaMemcpyDefault, ctx->stream));
+            if (layout == 0)
+                ACES_CUDA(ctx, cudaMemcpy2DAsync(dst, pitch, counts[i], (size_t)ld[i], (size_t)rows[i],
+                                                 (size_t)B, cudaMemcpyDefault, ctx->stream));
             base = dst;
             ldd = (int64_t)pitch;
         }
@@ -676,6 +777,14 @@ int32_t aces_parity_counts_async(aces_ctx* ctx, const aces_tables* tables, int32
                                  int32_t accumulate) {
     return parity_run(ctx, tables, n_items, experiment_ids, counts, rows, ld, K, prefix_shots,
                       odd_counts, accumulate, true);
+}
+
+int32_t aces_parity_counts_rowmajor(aces_ctx* ctx, const aces_tables* tables, int32_t n_items,
+                                    const int32_t* experiment_ids, const uint8_t* const* records,
+                                    const int64_t* rows, const int64_t* row_pitch, int32_t K,
+                                    const int64_t* prefix_shots, int64_t* odd_counts, int32_t accumulate) {
+    return parity_run(ctx, tables, n_items, experiment_ids, records, rows, row_pitch, K, prefix_shots,
+                      odd_counts, accumulate, false, 1);
 }
 
 int32_t aces_estimate_experiment(aces_ctx* ctx, const uint8_t* counts, int64_t rows, int64_t ld,

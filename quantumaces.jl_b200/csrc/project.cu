@@ -139,7 +139,7 @@ __global__ void nnqp_kernel(int n_problems, const int64_t* __restrict__ ptr, con
     const double* Q = Qall + qoff[pidx];  // n x n, symmetric (either triangle order reads the same)
     const double* v = vall + ptr[pidx];
     double* yout = yall + ptr[pidx];
-    double y[QMAX], r[QMAX], w[QMAX], z[QMAX];
+    double y[QMAX], r[QMAX], z[QMAX];
     int passive[QMAX], in_set[QMAX];
     int m = 0;
     double scale = 0.0;
@@ -152,7 +152,9 @@ __global__ void nnqp_kernel(int n_problems, const int64_t* __restrict__ ptr, con
         scale = fmax(scale, fabs(s));
     }
     const double tol = 1e-13 * scale;
-    int ok = 1;
+    // the whole block must be positive definite (the reference hands it to SCS as a convex objective)
+    for (int i = 0; i < n; ++i) passive[i] = i;
+    int ok = solve_passive(Q, n, passive, n, r, z) ? 1 : 0;
     for (int outer = 0; outer < 4 * QMAX && ok; ++outer) {
         // w = r - Q y: the negative gradient
         int best = -1;
@@ -160,7 +162,6 @@ __global__ void nnqp_kernel(int n_problems, const int64_t* __restrict__ ptr, con
         for (int i = 0; i < n; ++i) {
             double s = r[i];
             for (int j = 0; j < n; ++j) s -= Q[i * n + j] * y[j];
-            w[i] = s;
             if (!in_set[i] && s > wbest) {
                 wbest = s;
                 best = i;

@@ -69,21 +69,22 @@ class DesignEstimator:
         return np.diff(self.exp_ptr)
 
     def odd_counts(self, matrices, rows, ld, prefix_shots, experiment_ids=None, out=None,
-                   accumulate=False, asynchronous=False):
-        """One launch over a batch of sample matrices (aces_parity_counts)."""
+                   accumulate=False, asynchronous=False, rowmajor=False):
+        """One launch over a batch of sample matrices (aces_parity_counts; `rowmajor`: Stim's C-ordered
+        [shots x bytes] records through aces_parity_counts_rowmajor, `ld` = bytes between shots)."""
         if experiment_ids is None:
             experiment_ids = np.arange(self.fd.experiment_number, dtype=np.int32)
         return _lib.parity_counts(self.ctx, self.tables, experiment_ids, matrices, rows, ld,
                                   prefix_shots, out=out, accumulate=accumulate,
-                                  asynchronous=asynchronous)
+                                  asynchronous=asynchronous, rowmajor=rowmajor)
 
     def prepare(self, matrices, rows, ld, prefix_shots, out, experiment_ids=None, accumulate=False,
-                asynchronous=False) -> "_lib.PreparedBatch":
+                asynchronous=False, rowmajor=False) -> "_lib.PreparedBatch":
         """Marshals the arguments of odd_counts once; `.launch()` repeats the call."""
         if experiment_ids is None:
             experiment_ids = np.arange(self.fd.experiment_number, dtype=np.int32)
         return _lib.PreparedBatch(self.ctx, self.tables, experiment_ids, matrices, rows, ld, prefix_shots, out,
-                                  accumulate=accumulate, asynchronous=asynchronous)
+                                  accumulate=accumulate, asynchronous=asynchronous, rowmajor=rowmajor)
 
     def simulate_estimate(self, samples: Sequence[np.ndarray], shots_set: Sequence[int]):
         """The estimation half of simulate_stim_estimate (src/simulate.jl:195-234): given one
@@ -96,18 +97,21 @@ class DesignEstimator:
         n_exp = fd.experiment_number
         assert len(samples) == n_exp
         rows, ld, mats, prefix = [], [], [], np.zeros((n_exp, K), dtype=np.int64)
+        # Stim hands back C-ordered records: taken as they are (row-major ingest) when every sample is
+        # C-contiguous; Fortran-ordered matrices (the reference's Matrix{UInt8}) go in place as well
+        rowmajor = all(sm.flags.c_contiguous and not sm.flags.f_contiguous for sm in samples)
         for e, sm in enumerate(samples):
             t = int(self.tuple_of_experiment[e])
-            if not sm.flags.f_contiguous:
+            if not rowmajor and not sm.flags.f_contiguous:
                 sm = np.asfortranarray(sm)
             assert sm.shape[0] >= shots_maximum[t], "sample matrix has fewer rows than shots_maximum"
             mats.append(sm)
             rows.append(sm.shape[0])
-            ld.append(max(sm.shape[0], 1))
+            ld.append(sm.shape[1] if rowmajor else max(sm.shape[0], 1))
             prefix[e, :] = shots_divided[t, :]
         # budgets need not be sorted in the reference; the kernel wants nested prefixes
         order = np.argsort(np.asarray(shots_set), kind="stable")
-        odd = self.odd_counts(mats, rows, ld, prefix[:, order])
+        odd = self.odd_counts(mats, rows, ld, prefix[:, order], rowmajor=rowmajor)
         return self.scatter(odd, prefix[:, order], order)
 
     def scatter(self, odd: np.ndarray, prefix_sorted: np.ndarray, order: np.ndarray):

@@ -448,3 +448,57 @@ def test_wide_record_with_ungroupable_pauli_uses_fallback_kernel(ctx):
         got = aces_b200.estimate_experiment(ctx, counts, sup, signs, S)
         want, _ = ob.estimate_experiment(counts, sup, signs, S)
         assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("n,rows,pad", [(17, 1, 0), (17, 511, 0), (49, 513, 0), (49, 70001, 3), (161, 33333, 0), (161, 4096, 11),
+                                        (169, 20000, 0), (577, 5000, 0)])
+def test_rowmajor_ingest_vs_oracle(ctx, n, rows, pad):
+    """Stim's row-major bit-packed records (shots x bytes, C order) taken as they are --
+    bit-exact against the oracle on the transposed (column-major) input; a row pitch larger than the
+    record and device-resident records as well."""
+    import torch
+
+    import aces_b200
+
+    rng = np.random.default_rng(n + rows)
+    B = (n + 7) // 8
+    rec = rng.integers(0, 256, size=(rows, B + pad), dtype=np.uint8)       # C order, pitch B + pad
+    sup = rand_supports(rng, n, 120)
+    ptr, flat = ob._csr(sup)
+    tables = aces_b200.PauliTables(ctx, n, [0, 120], ptr, flat - 1)
+    prefixes = sorted({1, max(1, rows // 3), rows})
+    K = len(prefixes)
+    want = np.zeros((K, 120), dtype=np.int64)
+    colmajor = np.asfortranarray(rec[:, :B])
+    for k, S in enumerate(prefixes):
+        _, ps = ob.estimate_experiment(colmajor, sup, [0] * 120, S)
+        want[k] = (S - ps) // 2
+    got = aces_b200._lib.parity_counts(ctx, tables, [0], [rec], [rows], [B + pad], [prefixes], rowmajor=True)
+    assert np.array_equal(got.reshape(K, 120), want)
+    dev = torch.from_numpy(rec).cuda()
+    got_dev = aces_b200._lib.parity_counts(ctx, tables, [0], [dev.data_ptr()], [rows], [B + pad], [prefixes], rowmajor=True)
+    assert np.array_equal(got_dev.reshape(K, 120), want)
+    # accumulating two row-major batches == the concatenated records (src/simulate.jl:174-186)
+    if rows > 2:
+        cut = rows // 2
+        acc = aces_b200._lib.parity_counts(ctx, tables, [0], [rec[:cut]], [cut], [B + pad], [[cut]], rowmajor=True)
+        acc = aces_b200._lib.parity_counts(ctx, tables, [0], [rec[cut:]], [rows - cut], [B + pad], [[rows - cut]], out=acc,
+                                           accumulate=True, rowmajor=True)
+        assert np.array_equal(acc, want[-1])
+
+
+def test_rowmajor_design_batch_equals_colmajor(ctx):
+    """A whole repetition of the real rotated d=9 design through the row-major entry point (the ingest
+    path of simulate_estimate) equals the column-major path on the same records."""
+    import aces_b200
+
+    fd = aces_b200.rotated_design(9, full_covariance=True)
+    est = aces_b200.DesignEstimator(ctx, fd)
+    rng = np.random.default_rng(2)
+    shots_set = [20_000, 300_000, 1_000_003]
+    _, shots_max = aces_b200.shots_divide(fd, shots_set)
+    recs = [rng.integers(0, 256, size=(int(shots_max[int(est.tuple_of_experiment[e])]), fd.n_bytes), dtype=np.uint8)
+            for e in range(fd.experiment_number)]
+    eig_r, cov_r = est.simulate_estimate(recs, shots_set)                           # C order -> row-major ingest
+    eig_c, cov_c = est.simulate_estimate([np.asfortranarray(r) for r in recs], shots_set)
+    assert eig_r == eig_c and cov_r == cov_c
