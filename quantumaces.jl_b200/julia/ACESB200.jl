@@ -2,27 +2,41 @@
 # into QuantumACES.jl's estimation hot path without changing user code.
 #
 # STATUS: written against the C ABI and the reference's Julia signatures, NOT executed: there is
-# no `julia` binary in the build image or on the GPU box (DESIGN.md section 1).  The Python/ctypes
-# twin (quantumaces.jl_b200/_lib.py, merit.py, estimate.py) binds the same entry points with the
-# same argument meaning and is what the test-suite exercises.
+# no `julia` binary in the build image or on the GPU box (DESIGN.md section 1).  What IS checked
+# without Julia: every `ccall` type tuple in this file against the prototypes of
+# include/aces_b200.h (tools/check_ccall.py, part of the CPU test-suite), and the same call
+# sequences with Julia-style 1-based index arrays and pageable host buffers from plain C
+# (tests/abi_host.c).  The Python/ctypes twin (quantumaces.jl_b200/_lib.py, merit.py, estimate.py,
+# project.py) binds the same entry points with the same argument meaning and is what the
+# test-suite exercises on the GPU.
 #
 # Usage
 #     using QuantumACES
 #     include("ACESB200.jl"); using .ACESB200
 #     ACESB200.init!(; device = 0, lib = "/path/to/libaces_b200.so")
-#     ACESB200.install!()        # overwrite the hot-path methods inside QuantumACES (seams S1-S3)
+#     ACESB200.install!()        # overwrite the hot-path methods inside QuantumACES
 #     aces_data = simulate_aces(d, budget_set; repetitions = 20)      # unchanged user code
 #
-# What is replaced (file:line of the reference):
-#   S1  estimate_experiment(::Matrix{UInt8}, ...)          src/estimate.jl:284-301
-#   S2  estimate_gate_eigenvalues(A, F, est; constrain)     src/estimate.jl:492-524 (and the OLS form)
-#   S3  sparse_covariance_inv_factor(cov_log, lengths)      src/merit.jl:378-427
-# plus a design-resident fast path (`DeviceDesign`, `fit`, `calc_ls_covariance_moments`) for callers
-# that fit the same Design many times (simulate_aces repetitions, calc_merit, scaling sweeps).
-# Everything else (Stim sampling, projections, NoiseEstimate bookkeeping, I/O) stays in QuantumACES.
+# What install!() replaces (file:line of the reference):
+#   simulate_stim_estimate(d, shots_set; ...)                src/simulate.jl:84-252   sampling loop kept, the
+#        estimation inner loop (:195-234) replaced by ONE aces_parity_counts_rowmajor call per sampled
+#        batch: Stim's row-major buffer goes through pinned staging, all budgets and both Pauli sets
+#        in one pass, batches accumulated instead of vcat'ed
+#   estimate_gate_noise(d, ens, cov_ens, shot_budget; ...)    src/estimate.jl:691-941  numeric core on the
+#        device-resident Design (covariance, clipping, block factors, OLS / WLS / GLS fits, precision
+#        slices, split projection); NoiseEstimate bookkeeping through the reference's own helpers
+#   calc_covariance(d, eigenvalues_ensemble, covariance_ensemble; ...)   src/merit.jl:206-291   (S3)
+#   calc_gls_covariance / calc_wls_covariance / calc_ols_covariance(d, covariance_log)  src/merit.jl:556-629 (S4)
+#   S1  estimate_experiment(::Matrix{UInt8}, ...)             src/estimate.jl:284-301
+#   S2  estimate_gate_eigenvalues(A, F, est; constrain)        src/estimate.jl:492-524 (and the OLS form)
+# sparse_covariance_inv_factor(covariance_log, lengths) (src/merit.jl:378-427) has no Design argument
+# and is NOT overwritten; its callers on the path are (estimate_gate_noise, calc_gls_covariance), and
+# a new method sparse_covariance_inv_factor(d::Design, covariance_log; clipped_indices) is added.
+# Everything else (Stim circuit strings, full_project_gate_eigenvalues, NoiseEstimate / Merit
+# bookkeeping, I/O) stays in QuantumACES.
 module ACESB200
 
-using SparseArrays, LinearAlgebra
+using SparseArrays, LinearAlgebra, Random, Statistics
 import QuantumACES
 import QuantumACES: Design
 
@@ -63,10 +77,52 @@ end
 
 function shutdown!()
     CTX[] == C_NULL && return nothing
+    for t in values(TABLES_CACHE)
+        ccall((:aces_tables_destroy, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), CTX[], t.handle)
+        t.handle = C_NULL
+    end
+    for dd in values(DESIGN_CACHE)
+        ccall((:aces_design_destroy, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), CTX[], dd.handle)
+        dd.handle = C_NULL
+    end
+    empty!(TABLES_CACHE); empty!(DESIGN_CACHE)
+    if PINNED[].ptr != C_NULL
+        ccall((:aces_host_free, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), CTX[], PINNED[].ptr)
+        PINNED[] = PinnedBuffer(C_NULL, 0)
+    end
     ccall((:aces_destroy, LIB[]), Int32, (Ptr{Cvoid},), CTX[])
     CTX[] = C_NULL
     return nothing
 end
+
+# Pinned host staging for the sampled records (aces_host_alloc): Stim's buffer is copied into it with
+# one contiguous memcpy, so the host-to-device copy runs at PCIe line rate instead of through the
+# driver's pageable bounce buffers.
+struct PinnedBuffer
+    ptr::Ptr{Cvoid}
+    bytes::Int
+end
+const PINNED = Ref{PinnedBuffer}(PinnedBuffer(C_NULL, 0))
+
+function pinned_buffer(bytes::Integer)
+    if PINNED[].bytes < bytes
+        if PINNED[].ptr != C_NULL
+            check(ccall((:aces_host_free, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), CTX[], PINNED[].ptr))
+        end
+        ref = Ref{Ptr{Cvoid}}(C_NULL)
+        want = Int(bytes) + Int(bytes) >> 3
+        check(ccall((:aces_host_alloc, LIB[]), Int32, (Ptr{Cvoid}, Int64, Ptr{Ptr{Cvoid}}), CTX[], Int64(want), ref))
+        PINNED[] = PinnedBuffer(ref[], want)
+    end
+    return Ptr{UInt8}(PINNED[].ptr)
+end
+
+# One PauliTables / DeviceDesign per Design, built on first use (keyed by identity of the Design's
+# design matrix, which is not copied when a Design is passed around).
+const TABLES_CACHE = IdDict{Any, Any}()
+const DESIGN_CACHE = IdDict{Any, Any}()
+pauli_tables(d::Design) = get!(() -> PauliTables(d), TABLES_CACHE, d.matrix)
+device_design(d::Design) = get!(() -> DeviceDesign(d), DESIGN_CACHE, d.matrix)
 
 # ---------------------------------------------------------------------------------------------
 # S1: estimate_experiment (src/estimate.jl:284-301)
@@ -163,7 +219,7 @@ function PauliTables(d::Design)
             CTX[], Int32(n), Int32(length(exp_ptr) - 1), exp_ptr, pauli_ptr, bits, ref))
     end
     t = PauliTables(ref[], exp_ptr, n_eig, sign_factor, tuple_of, experiment, covariance_experiment)
-    finalizer(x -> ccall((:aces_tables_destroy, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), CTX[], x.handle), t)
+    finalizer(x -> (CTX[] == C_NULL || ccall((:aces_tables_destroy, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), CTX[], x.handle)), t)
     return t
 end
 
@@ -214,6 +270,111 @@ function estimate_counts!(eig_set, cov_set, t::PauliTables, stim_counts::Vector{
         off += E * K
     end
     return nothing
+end
+
+"""
+    odd_counts_rowmajor!(odd, tables, e, records, rows, prefixes; accumulate)
+
+Odd-parity counts of ONE sampled batch of table experiment `e` (1-based): `records` points at `rows`
+row-major records of `B` bytes (Stim's `sample(bit_packed = true)` buffer, here already in pinned
+memory), `prefixes[k]` = how many of these rows belong to budget `k` (nondecreasing).  The counts of
+all budgets and of both Pauli sets come from one pass; `accumulate = true` adds to `odd`
+(batched sampling, src/simulate.jl:174-186, without the vcat).
+"""
+function odd_counts_rowmajor!(odd::Vector{Int64}, t::PauliTables, e::Int, records::Ptr{UInt8}, rows::Int,
+                              B::Int, prefixes::Vector{Int64}; accumulate::Bool = false)
+    ids = Int32[e - 1]; ptrs = Ptr{UInt8}[records]; nrows = Int64[rows]; pitch = Int64[B]
+    GC.@preserve ids ptrs nrows pitch prefixes odd begin
+        check(ccall((:aces_parity_counts_rowmajor, LIB[]), Int32,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Ptr{UInt8}}, Ptr{Int64}, Ptr{Int64}, Int32,
+             Ptr{Int64}, Ptr{Int64}, Int32),
+            CTX[], t.handle, Int32(1), ids, ptrs, nrows, pitch, Int32(length(prefixes)), prefixes, odd,
+            Int32(accumulate)))
+    end
+    return odd
+end
+
+"""
+Drop-in for `simulate_stim_estimate(d, shots_set; seed, max_samples, detailed_diagnostics)`
+(src/simulate.jl:84-252).  The sampling half is the reference's (same shot division :98-104, same seeds
+:105-121, same circuit strings :146-170, same batches :172-186, Stim on thread 1); the estimation half
+(:188-234) is one `aces_parity_counts_rowmajor` call per sampled batch: the row-major numpy buffer is
+copied once into pinned memory (no pyconvert to a column-major Matrix, no vcat of the batches), every
+budget prefix and both Pauli sets are reduced in the same pass, and the estimates
+`((-1)^sign * pauli_shots) / shots_value` (src/estimate.jl:297-298) are formed here in Float64 from the
+exact integer counts, then pushed in the reference's order (:214-233).
+"""
+function simulate_stim_estimate(d::Design, shots_set::Vector{Int}; seed::Union{UInt64, Nothing} = nothing,
+                                max_samples::Integer = 10^9, detailed_diagnostics::Bool = false)
+    Q = QuantumACES
+    start_time = time()
+    tuple_number = length(d.tuple_set)
+    experiment_numbers = d.experiment_numbers
+    n = d.c.qubit_num
+    B = cld(n, 8)
+    budget_count = length(shots_set)
+    @assert sum(d.shot_weights) ≈ 1.0 "The shot weights are not appropriately normalised."
+    @assert all(d.shot_weights .> 0.0) "The shot weights are not all positive."
+    shots_divided_float = [shots_set[s] * d.shot_weights[t] / experiment_numbers[t] for t in 1:tuple_number, s in 1:budget_count]
+    @assert vec(sum(shots_divided_float .* experiment_numbers; dims = 1)) ≈ shots_set "The shots have not been divided correctly."
+    shots_divided = ceil.(Int, shots_divided_float)
+    shots_maximum = vec(maximum(shots_divided; dims = 2))
+    # seeds exactly as the reference draws them
+    seed !== nothing && Q.Random.seed!(seed)
+    batched_shots = any(shots_maximum * n .> max_samples)
+    stim_seeds = batched_shots ?
+        [[rand(UInt64, length(Q.batch_shots(shots_maximum[i], n, max_samples))) for j in 1:experiment_numbers[i]] for i in 1:tuple_number] :
+        [rand(UInt64, experiment_numbers[i]) for i in 1:tuple_number]
+    seed !== nothing && Q.Random.seed!()
+    t = pauli_tables(d)
+    mapping_lengths = length.(d.mapping_ensemble)
+    covariance_mapping_lengths = [length(ks) for ks in Q.get_covariance_mapping_data(d)[1]]
+    eig_set = [[[Float64[] for j in 1:mapping_lengths[i]] for i in 1:tuple_number] for s in 1:budget_count]
+    cov_set = [[[Float64[] for j in 1:covariance_mapping_lengths[i]] for i in 1:tuple_number] for s in 1:budget_count]
+    order = sortperm(shots_set)                  # the kernel wants nested prefixes; budgets may be unsorted
+    e = 0
+    for i in 1:tuple_number
+        tuple_circuit_string = Q.get_stim_circuit(d.c.circuit[d.tuple_set[i]], d.c.gate_probabilities, d.c.noisy_prep, d.c.noisy_meas)
+        for j in 1:experiment_numbers[i]
+            e += 1
+            prep = Q.get_stim_circuit([d.prep_ensemble[i][j]], d.c.gate_probabilities, d.c.noisy_prep, d.c.noisy_meas;
+                extra_fields = d.c.extra_fields)
+            meas = Q.get_stim_circuit([d.meas_ensemble[i][j]], d.c.gate_probabilities, d.c.noisy_prep, d.c.noisy_meas)
+            circuit_string = prep * tuple_circuit_string * meas
+            shot_batches = batched_shots ? Q.batch_shots(shots_maximum[i], n, max_samples) : [shots_maximum[i]]
+            E = Int(t.exp_ptr[e + 1] - t.exp_ptr[e])
+            odd = zeros(Int64, budget_count * E)
+            done = 0
+            for (b, batch) in pairs(shot_batches)
+                @assert Threads.threadid() == 1 "Stim sampling cannot be multithreaded."
+                sampler = Q.stim.Circuit(circuit_string).compile_sampler(; seed = batched_shots ? stim_seeds[i][j][b] : stim_seeds[i][j])
+                records = Q.PythonCall.PyArray(sampler.sample(; shots = batch, bit_packed = true))   # row-major, no copy
+                @assert size(records) == (batch, B) && strides(records) == (B, 1) "Unexpected layout of the Stim sample buffer."
+                staged = pinned_buffer(batch * B)
+                GC.@preserve records unsafe_copyto!(staged, Ptr{UInt8}(pointer(records)), batch * B)
+                prefixes = Int64[clamp(shots_divided[i, order[k]] - done, 0, batch) for k in 1:budget_count]
+                odd_counts_rowmajor!(odd, t, e, staged, batch, B, prefixes; accumulate = b > 1)
+                done += batch
+            end
+            ne = t.n_eig[e]
+            sf = view(t.sign_factor, (t.exp_ptr[e] + 1):t.exp_ptr[e + 1])
+            for kk in 1:budget_count
+                s = order[kk]; S = shots_divided[i, s]
+                for idx in 1:E
+                    est = (sf[idx] * (S - 2 * odd[(kk - 1) * E + idx])) / S
+                    if idx <= ne
+                        push!(eig_set[s][i][t.experiment[e][idx]], est)
+                    else
+                        push!(cov_set[s][i][t.covariance_experiment[e][idx - ne]], est)
+                    end
+                end
+            end
+            if detailed_diagnostics
+                println("Simulated sampling experiment $(j) of $(experiment_numbers[i]) for tuple $(i) of $(tuple_number). The time elapsed since simulation started is $(round(time() - start_time, digits = 3)) s.")
+            end
+        end
+    end
+    return (eig_set::Vector{Vector{Vector{Vector{Float64}}}}, cov_set::Vector{Vector{Vector{Vector{Float64}}}})
 end
 
 # ---------------------------------------------------------------------------------------------
@@ -300,7 +461,7 @@ function DeviceDesign(d::Design)
     check(ccall((:aces_design_covariance_pattern, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}),
         ref[], colptr, rowval))
     dd = DeviceDesign(ref[], d, size(A, 1), size(A, 2), length(cov_p), mapping_lengths, colptr, rowval)
-    finalizer(x -> ccall((:aces_design_destroy, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), CTX[], x.handle), dd)
+    finalizer(x -> (CTX[] == C_NULL || ccall((:aces_design_destroy, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), CTX[], x.handle)), dd)
     return dd
 end
 
@@ -451,23 +612,225 @@ function calc_ls_covariance(dd::DeviceDesign, covariance_log::SparseMatrixCSC{Fl
 end
 
 # ---------------------------------------------------------------------------------------------
-# install!: method overwrite of the seams inside QuantumACES (SURVEY.md section 8b, option ii)
+# Simplex projection (src/estimate.jl:580-663, src/utils.jl:36-97) -- SURVEY.md section 8f, row f1
+# ---------------------------------------------------------------------------------------------
+
+"Gate index groups of `gate_data` as the CSR arrays of include/aces_b200.h (1-based indices kept)."
+function gate_groups(gate_data)
+    ptr = Int64[0]; idx = Int32[]
+    for gate_idx in gate_data.gate_indices
+        append!(idx, Int32.(gate_idx.indices))
+        push!(ptr, length(idx))
+    end
+    return ptr, idx
+end
+
+"""
+Drop-in for `simple_project_gate_eigenvalues(est_unproj_gate_eigenvalues, gate_data)`
+(src/estimate.jl:635-663): all gates in one launch, same order of floating-point operations.
+Requires the padded indices of the gates to follow each other (`pad_indices` of gate g start at
+`ptr[g] + g`, as get_gate_data builds them for a design that is not `combined`).
+"""
+function simple_project_gate_eigenvalues(est_unproj_gate_eigenvalues::Vector{Float64}, gate_data)
+    ptr, idx = gate_groups(gate_data)
+    N = length(est_unproj_gate_eigenvalues); G = length(ptr) - 1
+    out = Vector{Float64}(undef, N)
+    unproj_probs = Vector{Float64}(undef, length(idx) + G); probs = similar(unproj_probs)
+    GC.@preserve ptr idx est_unproj_gate_eigenvalues out unproj_probs probs begin
+        check(ccall((:aces_project_simplex, LIB[]), Int32,
+            (Ptr{Cvoid}, Int64, Int32, Ptr{Int64}, Ptr{Int32}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            CTX[], Int64(N), Int32(G), ptr, idx, Int32(1), est_unproj_gate_eigenvalues, out, unproj_probs, probs))
+    end
+    return (out, unproj_probs, probs)
+end
+
+"Symplectically ordered Walsh-Hadamard block of a gate with `k` eigenvalues (src/noise.jl:285-312)."
+function wht_block(k::Int)
+    k == 1 && return [1.0 1.0; 1.0 -1.0]
+    n = k == 3 ? 1 : k == 15 ? 2 : throw(error("Unsupported gate size $(k)."))
+    P = k + 1; mask = (1 << n) - 1
+    return [isodd(count_ones((a & mask) & (b >> n)) + count_ones((a >> n) & (b & mask))) ? -1.0 : 1.0 for a in 0:(P - 1), b in 0:(P - 1)]
+end
+
+"""
+`split_project_gate_eigenvalues` (src/estimate.jl:580-628) for the estimator of the LAST `fit(dd, ls_type, ...)`:
+the per-gate slices of the precision matrix come from the device-resident Gram matrix
+(aces_design_precision_blocks), the per-gate quadratic programs are solved in one launch
+(aces_project_nonnegative_batched; exact where the reference iterates SCS to `precision`).
+"""
+function split_project_gate_eigenvalues(dd::DeviceDesign, ls_type::Symbol, est_unproj_gate_eigenvalues::Vector{Float64},
+                                        gate_data; precision::Real = 1e-8)
+    kind = ls_type == :ols ? 0 : ls_type == :wls ? 1 : 2
+    ptr, idx = gate_groups(gate_data)
+    G = length(ptr) - 1
+    sizes = diff(ptr)
+    blocks = Vector{Float64}(undef, sum(sizes .^ 2))
+    GC.@preserve ptr idx est_unproj_gate_eigenvalues blocks begin
+        check(ccall((:aces_design_precision_blocks, LIB[]), Int32,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Ptr{Int64}, Ptr{Int32}, Int32, Ptr{Float64}, Ptr{Float64}),
+            CTX[], dd.handle, Int32(kind), Int32(G), ptr, idx, Int32(1), est_unproj_gate_eigenvalues, blocks))
+    end
+    # per gate: unprojected probabilities, T = W[2:end, 2:end] .- W[2:end, 1], Q = T * P_gg * T'
+    v = Vector{Float64}(undef, length(idx)); Q = Vector{Float64}(undef, length(blocks))
+    qs = Vector{Vector{Float64}}(undef, G); Ws = Vector{Matrix{Float64}}(undef, G)
+    boff = 0
+    for g in 1:G
+        k = Int(sizes[g]); rng = (ptr[g] + 1):ptr[g + 1]
+        W = wht_block(k)
+        q = (W ./ (k + 1)) * vcat(1.0, est_unproj_gate_eigenvalues[idx[rng]])
+        T = W[2:end, 2:end] .- W[2:end, 1]
+        Pgg = reshape(view(blocks, (boff + 1):(boff + k * k)), k, k)
+        Q[(boff + 1):(boff + k * k)] = vec(T * Pgg * T')
+        v[rng] = q[2:end]
+        qs[g] = q; Ws[g] = W
+        boff += k * k
+    end
+    y = Vector{Float64}(undef, length(idx)); failed = Ref{Int32}(0)
+    GC.@preserve ptr Q v y begin
+        check(ccall((:aces_project_nonnegative_batched, LIB[]), Int32,
+            (Ptr{Cvoid}, Int32, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Int32}),
+            CTX[], Int32(G), ptr, Q, v, Float64(precision), y, failed))
+    end
+    est_gate_eigenvalues = copy(est_unproj_gate_eigenvalues)
+    unproj_probs = Float64[]; probs = Float64[]
+    for g in 1:G
+        rng = (ptr[g] + 1):ptr[g + 1]
+        pr = vcat(1.0 - sum(y[rng]), y[rng])
+        est_gate_eigenvalues[idx[rng]] = (Ws[g] * pr)[2:end]
+        append!(unproj_probs, qs[g]); append!(probs, pr)
+    end
+    return (est_gate_eigenvalues, unproj_probs, probs)
+end
+
+# ---------------------------------------------------------------------------------------------
+# estimate_gate_noise (src/estimate.jl:691-941)
+# ---------------------------------------------------------------------------------------------
+
+"The ten per-estimator fields of NoiseEstimate (src/estimate.jl:42-76), in the struct's order."
+function estimator_fields(unproj::Vector{Float64}, proj::Vector{Float64}, unproj_probs_vec::Vector{Float64},
+                          probs_vec::Vector{Float64}, gate_data)
+    Q = QuantumACES
+    unproj_probs = Q.get_gate_probabilities_dict(unproj_probs_vec, gate_data)
+    probs = Q.get_gate_probabilities_dict(probs_vec, gate_data)
+    return (unproj, proj, unproj_probs, probs,
+        Q.get_marginal_gate_eigenvalues(unproj, gate_data), Q.get_marginal_gate_eigenvalues(proj, gate_data),
+        Q.get_marginal_gate_probabilities(unproj_probs), Q.get_marginal_gate_probabilities(probs),
+        Q.get_relative_gate_eigenvalues(unproj, gate_data), Q.get_relative_gate_eigenvalues(proj, gate_data))
+end
+
+"""
+Drop-in for `estimate_gate_noise(d, est_eigenvalues_experiment_ensemble, est_covariance_experiment_ensemble,
+shot_budget; ...)` (src/estimate.jl:691-941).  Same decisions in the same order -- OLS and WLS first, the
+Euclidean projection of OLS decides whether WLS / GLS are projected in the Mahalanobis distance (:744),
+GLS only for a full-covariance design (:820) -- with the numeric work on the GPU: one
+`aces_design_fit` per estimator on the cached device-resident Design (covariance, log-covariance,
+clipping, block factors with the not-PD fallback, whitened least squares), the projections through
+aces_project_simplex / aces_design_precision_blocks / aces_project_nonnegative_batched.  With
+`split = false` the simultaneous projection of all gates stays on the reference's SCS path
+(full_project_gate_eigenvalues), fed with the sparse precision matrix the reference computes.
+"""
+function estimate_gate_noise(d::Design, est_eigenvalues_experiment_ensemble::Vector{Vector{Vector{Float64}}},
+                             est_covariance_experiment_ensemble::Vector{Vector{Vector{Float64}}}, shot_budget::Int;
+                             min_eigenvalue::Float64 = 0.1, clip_warning::Bool = true, N_warn_split::Integer = 5 * 10^3,
+                             split::Bool = (d.c.gate_data.N < N_warn_split ? false : true), split_warning::Bool = true,
+                             precision::Real = 1e-8)
+    Q = QuantumACES
+    gate_data = d.c.gate_data
+    if split_warning && gate_data.N >= N_warn_split && ~split
+        @warn "This circuit has a large number of gate eigenvalues: splitting the gate eigenvalue projection across gates by setting `split` to be `true` is advised."
+    end
+    dd = device_design(d)
+    tuple_number = length(d.tuple_set)
+    est_eigenvalues = vcat([mean.(est_eigenvalues_experiment_ensemble[i]) for i in 1:tuple_number]...)
+    est_cov_eigenvalues = vcat([mean.(est_covariance_experiment_ensemble[i]) for i in 1:tuple_number]...)
+    clipped_indices = Q.get_clipped_indices(est_eigenvalues; min_eigenvalue = min_eigenvalue, warning = clip_warning)
+    kept = length(clipped_indices) == dd.M ? nothing : clipped_indices
+    project(ls_type, unproj, precision_project) = begin
+        if ~precision_project
+            simple_project_gate_eigenvalues(unproj, gate_data)
+        elseif split
+            split_project_gate_eigenvalues(dd, ls_type, unproj, gate_data; precision = precision)
+        else
+            # simultaneous projection of all gates: the reference's SCS path with its own sparse precision matrix
+            design_matrix = convert(SparseMatrixCSC{Float64, Int}, d.matrix[clipped_indices, :])
+            cov_log = calc_covariance(dd, [mean.(e) for e in est_eigenvalues_experiment_ensemble],
+                [mean.(e) for e in est_covariance_experiment_ensemble]; weight_time = false, log_form = true)[clipped_indices, clipped_indices]
+            inv = ls_type == :gls ? Q.sparse_covariance_inv(cov_log, Q.get_clipped_mapping_lengths(dd.mapping_lengths, clipped_indices)) :
+                  sparse(Diagonal(diag(cov_log) .^ (-1)))
+            Q.full_project_gate_eigenvalues(unproj, Q.calc_precision_matrix(design_matrix, unproj, inv), gate_data; precision = precision)
+        end
+    end
+    ols_unproj = fit(dd, :ols, est_eigenvalues, est_cov_eigenvalues; clipped_indices = kept)
+    ols = simple_project_gate_eigenvalues(ols_unproj, gate_data)
+    precision_project = ~(ols[1] ≈ ols_unproj)
+    ols_fields = estimator_fields(ols_unproj, ols[1], ols[2], ols[3], gate_data)
+    wls_unproj = fit(dd, :wls, est_eigenvalues, est_cov_eigenvalues; clipped_indices = kept)
+    wls = project(:wls, wls_unproj, precision_project)      # directly after the WLS fit: the slices are its Gram matrix
+    wls_fields = estimator_fields(wls_unproj, wls[1], wls[2], wls[3], gate_data)
+    if d.full_covariance
+        gls_unproj = fit(dd, :gls, est_eigenvalues, est_cov_eigenvalues; clipped_indices = kept)
+        gls = project(:gls, gls_unproj, precision_project)
+        gls_fields = estimator_fields(gls_unproj, gls[1], gls[2], gls[3], gate_data)
+    else
+        gls_fields = wls_fields
+    end
+    return Q.NoiseEstimate(est_eigenvalues_experiment_ensemble, est_covariance_experiment_ensemble, shot_budget,
+        gls_fields..., wls_fields..., ols_fields...)
+end
+
+# ---------------------------------------------------------------------------------------------
+# S3 / S4 with the reference's signatures
+# ---------------------------------------------------------------------------------------------
+
+"calc_covariance(d, eigenvalues_ensemble, covariance_ensemble; epsilon, weight_time, warning) (src/merit.jl:206-291)."
+function calc_covariance_design(d::Design, eigenvalues_ensemble::Vector{Vector{Float64}},
+                                covariance_ensemble::Vector{Vector{Float64}}; epsilon::Real = 1e-10,
+                                weight_time::Bool = true, warning::Bool = true)
+    if warning && ~d.full_covariance
+        @warn "The design does not include the full covariance matrix; only the diagonal will be calculated."
+    end
+    return calc_covariance(device_design(d), eigenvalues_ensemble, covariance_ensemble; epsilon = epsilon, weight_time = weight_time)
+end
+
+"calc_gls / wls / ols_covariance(d, covariance_log) (src/merit.jl:556-629): Symmetric N x N on the host."
+ls_covariance_design(d::Design, covariance_log::SparseMatrixCSC{Float64, Int}, ls_type::Symbol) =
+    calc_ls_covariance(device_design(d), covariance_log; ls_type = ls_type, want_matrix = true)[1]
+
+# ---------------------------------------------------------------------------------------------
+# install!: method overwrite inside QuantumACES (SURVEY.md section 8b, option ii)
 # ---------------------------------------------------------------------------------------------
 
 """
     install!()
 
-Overwrites, inside QuantumACES, the three pure functions on the hot path with the GPU versions; every
-caller (simulate_aces, estimate_gate_noise, estimate_stim_ensemble, calc_merit, the tests) then runs
-through libaces_b200 unchanged.  The Dict{String,Int} method of estimate_experiment (Qiskit counts,
-src/estimate.jl:255-277) is left alone.
+Overwrites, inside QuantumACES, the functions of the estimation hot path listed at the top of this file;
+every caller (simulate_aces, estimate_stim_ensemble, calc_merit, the optimisers, the tests, user
+scripts) then runs through libaces_b200 unchanged.  The Dict{String,Int} method of
+estimate_experiment (Qiskit counts, src/estimate.jl:255-277) and
+sparse_covariance_inv_factor(covariance_log, mapping_lengths) are left alone.
 """
 function install!()
     CTX[] == C_NULL && init!()
     @eval QuantumACES begin
+        # K1: sampling loop with the estimation half on the GPU (src/simulate.jl:84-252)
+        simulate_stim_estimate(d::Design, shots_set::Vector{Int}; seed::Union{UInt64, Nothing} = nothing,
+            max_samples::Integer = 10^9, detailed_diagnostics::Bool = false) =
+            $(simulate_stim_estimate)(d, shots_set; seed = seed, max_samples = max_samples,
+                detailed_diagnostics = detailed_diagnostics)
+        # S1 (second caller: estimate_stim_ensemble, src/device.jl:201-313)
         estimate_experiment(counts::Matrix{UInt8}, experiment_meas_indices::Vector{Vector{Int}},
             experiment_pauli_signs::Vector{Bool}, shots_value::Integer) =
             $(estimate_experiment)(counts, experiment_meas_indices, experiment_pauli_signs, shots_value)
+        # numeric core of the noise estimate (src/estimate.jl:691-941)
+        estimate_gate_noise(d::Design, est_eigenvalues_experiment_ensemble::Vector{Vector{Vector{Float64}}},
+            est_covariance_experiment_ensemble::Vector{Vector{Vector{Float64}}}, shot_budget::Int;
+            min_eigenvalue::Float64 = 0.1, clip_warning::Bool = true, N_warn_split::Integer = 5 * 10^3,
+            split::Bool = (d.c.gate_data.N < N_warn_split ? false : true), split_warning::Bool = true,
+            precision::Real = 1e-8) =
+            $(estimate_gate_noise)(d, est_eigenvalues_experiment_ensemble, est_covariance_experiment_ensemble, shot_budget;
+                min_eigenvalue = min_eigenvalue, clip_warning = clip_warning, N_warn_split = N_warn_split, split = split,
+                split_warning = split_warning, precision = precision)
+        # S2
         estimate_gate_eigenvalues(design_matrix::SparseMatrixCSC{Float64, Int},
             est_covariance_log_inv_factor::SparseMatrixCSC{Float64, Int}, est_eigenvalues::Vector{Float64};
             constrain::Bool = false) =
@@ -476,11 +839,27 @@ function install!()
         estimate_gate_eigenvalues(design_matrix::SparseMatrixCSC{Float64, Int}, est_eigenvalues::Vector{Float64};
             constrain::Bool = false) =
             $(estimate_gate_eigenvalues)(design_matrix, nothing, est_eigenvalues; constrain = constrain)
+        # S3
+        calc_covariance(d::Design, eigenvalues_ensemble::Vector{Vector{Float64}},
+            covariance_ensemble::Vector{Vector{Float64}}; epsilon::Real = 1e-10, weight_time::Bool = true,
+            warning::Bool = true) =
+            $(calc_covariance_design)(d, eigenvalues_ensemble, covariance_ensemble; epsilon = epsilon,
+                weight_time = weight_time, warning = warning)
+        sparse_covariance_inv_factor(d::Design, covariance_log::SparseMatrixCSC{Float64, Int};
+            clipped_indices::Union{Vector{Int}, Nothing} = nothing, epsilon::Real = 1e-12) =
+            $(sparse_covariance_inv_factor)($(device_design)(d), covariance_log; clipped_indices = clipped_indices,
+                epsilon = epsilon)
+        # S4
+        calc_gls_covariance(d::Design, covariance_log::SparseMatrixCSC{Float64, Int}) = $(ls_covariance_design)(d, covariance_log, :gls)
+        calc_wls_covariance(d::Design, covariance_log::SparseMatrixCSC{Float64, Int}) = $(ls_covariance_design)(d, covariance_log, :wls)
+        calc_ols_covariance(d::Design, covariance_log::SparseMatrixCSC{Float64, Int}) = $(ls_covariance_design)(d, covariance_log, :ols)
     end
     return nothing
 end
 
-export init!, shutdown!, install!, PauliTables, estimate_counts!, DeviceDesign, fit, calc_covariance,
-    sparse_covariance_inv_factor, calc_ls_covariance
+# Only names QuantumACES does not export itself: a user script has `using QuantumACES` in scope, and two
+# modules exporting the same name would make every unqualified use ambiguous.  The GPU versions of
+# QuantumACES functions are reached through install!() or qualified (ACESB200.fit, ...).
+export init!, shutdown!, install!, PauliTables, DeviceDesign, estimate_counts!
 
 end # module
