@@ -190,7 +190,9 @@ int main(int argc, char** argv) {
         char what[64];
         snprintf(what, sizeof what, "design_fit %s, clipped, 1-based kept rows", names[ls]);
         const double e = rel_err(g, F64(names[ls]), N);
-        report(what, e <= 1e-9 && p_aces_last_rank_deficiency(ctx) == 0, e);
+        const int deficiency = p_aces_last_rank_deficiency(ctx);
+        if (deficiency != 0) printf("     rank deficiency reported: %d\n", deficiency);
+        report(what, e <= 1e-9 && deficiency == 0, e);
     }
     {   /* precision slices of the GLS fit that just ran, 1-based gate groups */
         const int32_t G = (int32_t)(CNT("gate_ptr") - 1);

@@ -71,11 +71,17 @@ def test_c_host_runs_the_shim_sequences(ctx, tmp_path):
     s1_signs = np.asarray(fd.pauli_signs[0])[exp0].astype(np.uint8)
     s1_est, _ = ob.estimate_experiment(np.asfortranarray(recs[0]), sup, s1_signs, int(prefix[0, -1]))
     # fit inputs and oracle results
-    eig, cov = noisy_ensembles(fd, seed=3)
-    eig = [[list(v) for v in t] for t in eig]
+    eig0, cov = noisy_ensembles(fd, seed=3)
     multi = np.nonzero(np.diff(sp.csr_matrix(fd.matrix).indptr) >= 2)[0]
     off = np.concatenate([[0], np.cumsum(fd.mapping_lengths)])
-    for r in rng.choice(multi, size=11, replace=False):
+    while True:   # clip 11 rows (circuit eigenvalue 0.05 < 0.1) such that the design keeps full column rank
+        clip = rng.choice(multi, size=11, replace=False)
+        keep_mask = np.ones(fd.M, dtype=bool)
+        keep_mask[clip] = False
+        if np.linalg.matrix_rank(sp.csr_matrix(fd.matrix)[keep_mask].toarray().astype(np.float64)) == fd.matrix.shape[1]:
+            break
+    eig = [[list(v) for v in t] for t in eig0]
+    for r in clip:
         t = int(np.searchsorted(off, r, side="right") - 1)
         eig[t][int(r - off[t])] = [0.05 for _ in eig[t][int(r - off[t])]]
     core = fo.estimate_gate_noise_core(fd, eig, cov)
