@@ -317,6 +317,18 @@ int32_t aces_design_ls_covariance(aces_ctx* ctx, aces_design* design, int32_t ls
                                   const double* gate_eigenvalues, const double* covariance_log_nzval,
                                   double* sigma, double* trace, double* trace_sq);
 
+/* Bookkeeping / test hook: the static task order of the persistent Cholesky kernel for an nb x nb tile
+ * matrix (128 x 128 tiles) scheduled on `workers` CTAs.  out (may be NULL to query the count) receives
+ * 6 ints per task: type (0 factor, 1 panel solve, 2 update, 3 / 4 their 16-row slabs), slab (+ 256 for a
+ * task of the near list), i, j, k0, k1; order: far list, near list, the nb factor tasks of the chain CTA.
+ * No GPU needed. */
+int32_t aces_potrf_schedule(int32_t nb, int32_t workers, int32_t* out, int64_t capacity, int64_t* n_tasks);
+
+/* Development hook: with ACES_POTRF_TRACE=1 in the environment the persistent Cholesky kernel records
+ * per-task timestamps; this returns 9 int64 per task of the last factorisation on ctx (type, slab, i, j,
+ * k0, k1, t_grab, t_ready, t_done in ns).  *n_tasks = 0 when tracing is off. */
+int32_t aces_potrf_trace(aces_ctx* ctx, int64_t* out, int64_t capacity, int64_t* n_tasks);
+
 /* ---- simplex projection of the fitted gate eigenvalues ----------------
  *
  * A gate is a group of 1 (SPAM / mid-circuit reset), 3 (one qubit) or 15 (two qubits) gate

@@ -80,6 +80,8 @@ SIGNATURES = {
     "aces_design_fit_refine_end": (_i32, [_vp, _vp, _p(C.c_double), _p(C.c_double)]),
     "aces_design_fit_end": (_i32, [_vp, _vp, _i32, _vp]),
     "aces_design_precision_blocks": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "aces_potrf_schedule": (_i32, [_i32, _i32, _vp, _i64, _p(_i64)]),
+    "aces_potrf_trace": (_i32, [_vp, _vp, _i64, _p(_i64)]),
     "aces_project_simplex": (_i32, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "aces_project_nonnegative_batched": (_i32, [_vp, _i32, _vp, _vp, _vp, C.c_double, _vp, _p(_i32)]),
 }

@@ -54,6 +54,9 @@ struct aces_ctx {
     // fit workspaces are added by fit.cu through this generic pool
     DevBuf d_work[8];
     DevBuf d_flags;    // inter-CTA flags of the persistent triangular solves
+    DevBuf d_dag_trace;
+    DevBuf d_dag_tasks, d_dag_state;  // task list (cached per matrix size) and counters of the persistent Cholesky
+    int dag_nb = 0, dag_grid = 0, dag_ntasks = 0, dag_nlist = 0;
 };
 
 int aces_fail(aces_ctx* ctx, int code, const char* fmt, ...);

@@ -8,12 +8,24 @@
 #include "dense.cuh"
 
 #include <algorithm>
+#include <functional>
 #include <mutex>
+#include <queue>
+#include <vector>
 
 namespace dense {
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 16, STAGES = 3, GT = 256;
+
+__device__ __forceinline__ int ld_acquire_fwd(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_fwd(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 constexpr int LD_MC = BM + 4;  // row stride of a [BK][BM] tile (operand contiguous along m / n)
 constexpr int LD_KC = BK + 4;  // row stride of a [BM][BK] tile (operand contiguous along k)
 constexpr int OPER_DOUBLES = BM * LD_KC;  // 2560 >= BK * LD_MC = 2112
@@ -56,7 +68,9 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 // warp tile (BMT/2) x 32 = (BMT/16) x 4 DMMA tiles; operands staged by cp.async in a 3-stage ring.
 // The 64-row variant doubles the number of CTAs of a launch: the skinny, short-K updates on the
 // critical path of the Cholesky (a 128-row tile with K = 128 occupies one SM for >= 15 us).
-template <bool A_KC, bool B_KC, int BMT>
+// COH: the C tile is read past L1 (__ldcg) -- for the persistent factorisation kernel, where another SM
+// may have updated the tile since this SM last touched it (operands always come through cp.async.cg).
+template <bool A_KC, bool B_KC, int BMT, bool COH = false>
 __device__ __forceinline__ void gemm_tile(const GemmP& p, const int bm, const int bn, double* sm) {
     constexpr int MI = BMT / 16;  // DMMA tiles per warp along m
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -107,6 +121,23 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const int bm, const in
         if (s < nk) load(s, s);
         cp_async_commit();
     }
+    // COH: the accumulators START from the C tile, acc = (beta / alpha) C, so that the result alpha * acc
+    // = alpha A B' + beta C needs no read-modify-write pass at the end (64 dependent L2 round trips per
+    // thread, a fifth of a K = 512 task); the loads are in flight together with the first operand
+    // stages.  Exact for the |alpha| = |beta| = 1 updates this mode is used for.
+    const bool preload = COH && p.beta != 0.0;
+    if (preload) {
+        const double sc = p.beta / p.alpha;
+        const double* Cg0 = p.C + (int64_t)bm * BMT + (int64_t)bn * BN * p.ldc;
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double* c0 = Cg0 + (wm + i * 8 + g) + (int64_t)(wn + j * 8 + 2 * t) * p.ldc;
+                acc[i][j][0] = sc * __ldcg(c0);
+                acc[i][j][1] = sc * __ldcg(c0 + p.ldc);
+            }
+    }
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
@@ -145,7 +176,7 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const int bm, const in
             double* c0 = Cg + r + (int64_t)c * p.ldc;
             double* c1 = c0 + p.ldc;
             double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
-            if (p.beta != 0.0) {
+            if (p.beta != 0.0 && !preload) {
                 v0 += p.beta * *c0;
                 v1 += p.beta * *c1;
             }
@@ -182,7 +213,8 @@ __global__ void __launch_bounds__(GT, 1) gemm_batched_kernel(const GemmDesc* __r
 constexpr int PLD = DB + 1;
 constexpr int PW = 16;
 constexpr int DIAG_THREADS = 512;
-constexpr size_t DIAG_SMEM = (size_t)(DB * PLD + PW * PLD + 2 * DB) * sizeof(double);
+constexpr int INV_TMP = (DB / 2) * (DB / 2);  // scratch of the inverse: one 64 x 64 product
+constexpr size_t DIAG_SMEM = (size_t)(DB * PLD + INV_TMP + 2 * DB) * sizeof(double);
 
 // 1 / d to full precision without the division subroutine: hardware seed (about 20 bits) and two
 // Newton steps.  d is a pivot that already passed the positivity test.
@@ -245,7 +277,7 @@ __device__ __noinline__ int diag16(double* s, double* rdiag, const double* pfloo
 
 // Trailing update of one row (one lane) for NB columns c0, c0 + 15, ... of the shared-memory block:
 // s(row, j) -= sum_k s(row, k0 + k) * s(j, k0 + k) for the 16 columns k of the current panel.
-template <int NB>
+template <int NB, int CS>
 __device__ __forceinline__ void c2_rows(double* s, const int k0, const int c0, const int row) {
     double acc[NB];
 #pragma unroll
@@ -255,12 +287,107 @@ __device__ __forceinline__ void c2_rows(double* s, const int k0, const int c0, c
         const double* col = s + (k0 + k) * PLD;
         const double ra = col[row];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) acc[b] += ra * col[c0 + 15 * b];
+        for (int b = 0; b < NB; ++b) acc[b] += ra * col[c0 + CS * b];
     }
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-        const int j = c0 + 15 * b;
+        const int j = c0 + CS * b;
         if (row >= j) s[j * PLD + row] -= acc[b];
+    }
+}
+
+// ---- in-place inverse of the lower-triangular factor in shared memory ---------------------------------
+// Recursive doubling: the eight 16 x 16 diagonal pieces are inverted first (one warp each, columns in
+// registers); then pairs of inverted blocks of size h = 16, 32, 64 are merged,
+//     inv([L11 0; L21 L22]) = [X11 0; -X22 L21 X11, X22],
+// all pairs of a level at once, every product as 4 x 4 register tiles (two shared loads per four
+// multiply-adds).  Six block-wide barriers in all; the previous version walked the sixteen-column
+// panels from right to left with one thread per (row, four columns) and a serial inner loop over up
+// to 112 terms, and took 47 k of the 122 k cycles of a diagonal block.
+// One 4 x 4 tile of  T = L21 * X11  (MODE 0: T to tmp)  or  X21 = -X22 * T  (MODE 1: into s).
+template <int MODE>
+__device__ __forceinline__ void inv_tile(double* s, double* tmp, const int o, const int h, const int pair,
+                                         const int r0, const int c0) {
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    double* T = tmp + pair * h * h;  // column-major h x h
+    if (MODE == 0) {
+        // T[r][c] = sum_{m >= c} L21[r][m] * X11[m][c];  L21[r][m] = s(o + h + r, o + m), X11[m][c] = s(o + m, o + c)
+        for (int m = c0; m < h; ++m) {
+            double a[4], x[4];
+            const double* colm = s + (o + m) * PLD;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a[q] = colm[o + h + r0 + q];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) x[q] = (m >= c0 + q) ? s[(o + c0 + q) * PLD + o + m] : 0.0;
+#pragma unroll
+            for (int a_ = 0; a_ < 4; ++a_)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a_][b] += a[a_] * x[b];
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int a_ = 0; a_ < 4; ++a_) T[(c0 + b) * h + r0 + a_] = acc[a_][b];
+    } else {
+        // X21[r][c] = -sum_{m <= r} X22[r][m] * T[m][c];  X22[r][m] = s(o + h + r, o + h + m)
+        for (int m = 0; m < r0 + 4; ++m) {
+            double x[4], t[4];
+            const double* colm = s + (o + h + m) * PLD + o + h + r0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) x[q] = (m <= r0 + q) ? colm[q] : 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) t[q] = T[(c0 + q) * h + m];
+#pragma unroll
+            for (int a_ = 0; a_ < 4; ++a_)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a_][b] += x[a_] * t[b];
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int a_ = 0; a_ < 4; ++a_) s[(o + c0 + b) * PLD + o + h + r0 + a_] = -acc[a_][b];
+    }
+}
+
+template <int NTH>
+__device__ __forceinline__ void invert_lower_inplace(double* s, double* tmp, const double* rdiag, const int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    if (warp < DB / PW) {
+        const int b0 = warp * PW;
+        const int c = lane & (PW - 1);  // lanes 16..31 mirror 0..15 (no divergence), only 0..15 store
+        double x[PW];
+#pragma unroll
+        for (int i = 0; i < PW; ++i) {
+            double v = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < i; ++k) v -= s[(b0 + k) * PLD + b0 + i] * x[k];
+            x[i] = (i < c) ? 0.0 : v * rdiag[b0 + i];
+        }
+        __syncwarp();
+        if (lane < PW)
+#pragma unroll
+            for (int i = 0; i < PW; ++i)
+                if (i >= c) s[(b0 + c) * PLD + b0 + i] = x[i];
+    }
+    __syncthreads();
+    for (int h = PW; h < DB; h *= 2) {
+        const int tiles_per_pair = (h / 4) * (h / 4), pairs = DB / (2 * h), total = tiles_per_pair * pairs;
+        // tiles are dealt so that consecutive threads take consecutive rows of one tile column (shared
+        // loads of a warp then touch consecutive addresses); heavy and light tiles alternate over the passes
+        for (int it = tid; it < total; it += NTH) {
+            const int pair = it / tiles_per_pair, w = it - pair * tiles_per_pair;
+            inv_tile<0>(s, tmp, pair * 2 * h, h, pair, 4 * (w % (h / 4)), 4 * (w / (h / 4)));
+        }
+        __syncthreads();
+        for (int it = tid; it < total; it += NTH) {
+            const int pair = it / tiles_per_pair, w = it - pair * tiles_per_pair;
+            inv_tile<1>(s, tmp, pair * 2 * h, h, pair, 4 * (w % (h / 4)), 4 * (w / (h / 4)));
+        }
+        __syncthreads();
     }
 }
 
@@ -277,27 +404,32 @@ __device__ unsigned long long g_c2_cycles[2] = {0, 0};
 #define DPROF_START
 #define DPROF_WARP(slot, t0)
 #endif
+// NTH threads (512: the stand-alone kernel, 256: inside the persistent factorisation kernel).  Global
+// loads bypass L1 (__ldcg): in the persistent kernel another SM may have written the block since this
+// SM last read it.
+template <int NTH>
 __device__ __forceinline__ void diag_block(const DiagDesc& d, const double rel_tol, double* sh) {
     DPROF_DECL
     DPROF_START
+    constexpr int NWARP = NTH / 32, JB = NTH / DB, C2W = NWARP - 1;
     double* s = sh;                  // s[j*PLD + i] = A(i, j)
-    double* tmp = sh + DB * PLD;     // [PW][PLD] scratch of the inverse
-    double* rdiag = tmp + PW * PLD;  // reciprocals of the diagonal of L
+    double* tmp = sh + DB * PLD;     // scratch of the inverse
+    double* rdiag = tmp + INV_TMP;   // reciprocals of the diagonal of L
     double* pfloor = rdiag + DB;     // smallest acceptable pivot per column
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
-        // 32 elements per thread, loads issued in batches of 8 before their shared-memory stores
-        const int i = tid & (DB - 1), jb = tid >> 7;  // 4 columns in flight per pass
+        // loads issued in batches of 8 before their shared-memory stores
+        const int i = tid & (DB - 1), jb = tid >> 7;  // JB columns in flight per pass
 #pragma unroll
-        for (int j0 = 0; j0 < DB; j0 += 32) {
+        for (int j0 = 0; j0 < DB; j0 += 8 * JB) {
             double v[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = d.A[i + (int64_t)(j0 + 4 * q + jb) * d.lda];
+            for (int q = 0; q < 8; ++q) v[q] = __ldcg(d.A + i + (int64_t)(j0 + JB * q + jb) * d.lda);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) s[(j0 + 4 * q + jb) * PLD + i] = v[q];
+            for (int q = 0; q < 8; ++q) s[(j0 + JB * q + jb) * PLD + i] = v[q];
         }
     }
-    if (tid < DB) pfloor[tid] = d.diag0 ? rel_tol * fabs(d.diag0[tid]) : 0.0;
+    if (tid < DB) pfloor[tid] = d.diag0 ? rel_tol * fabs(__ldcg(d.diag0 + tid)) : 0.0;
     __syncthreads();
     DPROF(0)  // load
     // Right-looking factorisation with look-ahead inside the CTA: after the panel rows of panel p
@@ -328,21 +460,24 @@ __device__ __forceinline__ void diag_block(const DiagDesc& d, const double rel_t
         }
         __syncthreads();
         DPROF(2)  // panel rows
-        // (c1) the columns of the next panel: thread t owns column r0 + (t & 15), rows r0 + (t >> 4) + 32a
+        // (c1) the columns of the next panel: thread t owns column r0 + (t & 15), rows r0 + (t >> 4) + RS a
         {
+            constexpr int RS = NTH / PW, NA = DB / RS;
             const int j = r0 + (tid & (PW - 1)), ib = r0 + (tid >> 4);
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            double acc[NA];
+#pragma unroll
+            for (int a = 0; a < NA; ++a) acc[a] = 0.0;
 #pragma unroll 4
             for (int k = 0; k < PW; ++k) {
                 const double* col = s + (k0 + k) * PLD;
                 const double cj = col[j];
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
-                    if (ib + 32 * a < DB) acc[a] += col[ib + 32 * a] * cj;
+                for (int a = 0; a < NA; ++a)
+                    if (ib + RS * a < DB) acc[a] += col[ib + RS * a] * cj;
             }
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const int i = ib + 32 * a;
+            for (int a = 0; a < NA; ++a) {
+                const int i = ib + RS * a;
                 if (i < DB && i >= j) s[j * PLD + i] -= acc[a];
             }
         }
@@ -355,11 +490,10 @@ __device__ __forceinline__ void diag_block(const DiagDesc& d, const double rel_t
             bad += diag16(s, rdiag, pfloor, r0, lane, repl);
             DPROF_WARP(7, _tw)  // diag16 alone
         } else if (r0 + PW < DB) {
-            // (c2) the columns behind the next panel: warp w owns columns j_b = c0 + 15 b (b = 0, 1, ...
+            // (c2) the columns behind the next panel: warp w owns columns j_b = c0 + C2W b (b = 0, 1, ...
             // while j_b < 128); a group of 32 rows [32 a, 32 a + 31] only needs the columns up to its
             // last row (lower triangle), a prefix of this warp's columns: the k loop runs once per row
-            // group with exactly that many accumulators (a fifth of the multiply-adds of the full
-            // 128 x 120 rectangle over the eight panels).
+            // group with exactly that many accumulators.
             const int c0 = r0 + PW + (warp - 1);
 #ifdef ACES_DIAG_PROFILE
             const long long _tc = clock64();
@@ -367,16 +501,34 @@ __device__ __forceinline__ void diag_block(const DiagDesc& d, const double rel_t
             for (int a = (r0 + PW) >> 5; a < 4; ++a) {
                 const int last = 32 * a + 31;
                 if (last < c0) continue;
-                const int nb = (last - c0) / 15 + 1;  // <= 8
+                const int nb = (last - c0) / C2W + 1;  // <= 8 (15 update warps) or 16 (7)
+                const int row = lane + 32 * a;
                 switch (nb) {
-                    case 1: c2_rows<1>(s, k0, c0, lane + 32 * a); break;
-                    case 2: c2_rows<2>(s, k0, c0, lane + 32 * a); break;
-                    case 3: c2_rows<3>(s, k0, c0, lane + 32 * a); break;
-                    case 4: c2_rows<4>(s, k0, c0, lane + 32 * a); break;
-                    case 5: c2_rows<5>(s, k0, c0, lane + 32 * a); break;
-                    case 6: c2_rows<6>(s, k0, c0, lane + 32 * a); break;
-                    case 7: c2_rows<7>(s, k0, c0, lane + 32 * a); break;
-                    default: c2_rows<8>(s, k0, c0, lane + 32 * a); break;
+                    case 1: c2_rows<1, C2W>(s, k0, c0, row); break;
+                    case 2: c2_rows<2, C2W>(s, k0, c0, row); break;
+                    case 3: c2_rows<3, C2W>(s, k0, c0, row); break;
+                    case 4: c2_rows<4, C2W>(s, k0, c0, row); break;
+                    case 5: c2_rows<5, C2W>(s, k0, c0, row); break;
+                    case 6: c2_rows<6, C2W>(s, k0, c0, row); break;
+                    case 7: c2_rows<7, C2W>(s, k0, c0, row); break;
+                    case 8: c2_rows<8, C2W>(s, k0, c0, row); break;
+                    default:
+                        if constexpr (C2W < 15) {  // fewer update warps: up to 16 columns each, in two halves
+                            c2_rows<8, C2W>(s, k0, c0, row);
+                            switch (nb - 8) {
+                                case 1: c2_rows<1, C2W>(s, k0, c0 + 8 * C2W, row); break;
+                                case 2: c2_rows<2, C2W>(s, k0, c0 + 8 * C2W, row); break;
+                                case 3: c2_rows<3, C2W>(s, k0, c0 + 8 * C2W, row); break;
+                                case 4: c2_rows<4, C2W>(s, k0, c0 + 8 * C2W, row); break;
+                                case 5: c2_rows<5, C2W>(s, k0, c0 + 8 * C2W, row); break;
+                                case 6: c2_rows<6, C2W>(s, k0, c0 + 8 * C2W, row); break;
+                                case 7: c2_rows<7, C2W>(s, k0, c0 + 8 * C2W, row); break;
+                                default: c2_rows<8, C2W>(s, k0, c0 + 8 * C2W, row); break;
+                            }
+                        } else {
+                            c2_rows<8, C2W>(s, k0, c0, row);
+                        }
+                        break;
                 }
             }
 #ifdef ACES_DIAG_PROFILE
@@ -391,68 +543,16 @@ __device__ __forceinline__ void diag_block(const DiagDesc& d, const double rel_t
     __syncthreads();
     DPROF(1)
     // L -> global (strict upper triangle zeroed)
-    for (int e = tid; e < DB * DB; e += DIAG_THREADS) {
+    for (int e = tid; e < DB * DB; e += NTH) {
         const int i = e & (DB - 1), j = e >> 7;
         d.A[i + (int64_t)j * d.lda] = (i >= j) ? s[j * PLD + i] : 0.0;
     }
     __syncthreads();
     DPROF(4)  // store L
     // ---- in-place inverse ------------------------------------------------------------------
-    if (warp < DB / PW) {
-        const int b0 = warp * PW;
-        const int c = lane & (PW - 1);  // lanes 16..31 mirror 0..15 (no divergence), only 0..15 store
-        double x[PW];
-#pragma unroll
-        for (int i = 0; i < PW; ++i) {
-            double v = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-            for (int k = 0; k < i; ++k) v -= s[(b0 + k) * PLD + b0 + i] * x[k];
-            x[i] = (i < c) ? 0.0 : v * rdiag[b0 + i];
-        }
-        __syncwarp();
-        if (lane < PW)
-#pragma unroll
-            for (int i = 0; i < PW; ++i)
-                if (i >= c) s[(b0 + c) * PLD + b0 + i] = x[i];
-    }
-    __syncthreads();
-    for (int j0 = DB - 2 * PW; j0 >= 0; j0 -= PW) {
-        const int r0 = j0 + PW, nr = DB - r0;
-        const int item = tid;
-        const bool active = item < nr * 4;
-        const int il = active ? item % nr : 0, cq = active ? item / nr : 0;
-        const int i = r0 + il;
-        if (active) {
-            // T[i][c] = sum_{k=r0..i} X22[i][k] * L21[k][c]
-            double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-            const double* c0 = s + (j0 + 4 * cq) * PLD;
-            for (int k = r0; k <= i; ++k) {
-                const double xv = s[k * PLD + i];
-                t0 += xv * c0[k];
-                t1 += xv * c0[PLD + k];
-                t2 += xv * c0[2 * PLD + k];
-                t3 += xv * c0[3 * PLD + k];
-            }
-            tmp[(4 * cq + 0) * PLD + il] = t0;
-            tmp[(4 * cq + 1) * PLD + il] = t1;
-            tmp[(4 * cq + 2) * PLD + il] = t2;
-            tmp[(4 * cq + 3) * PLD + il] = t3;
-        }
-        __syncthreads();
-        if (active) {
-            // X21[i][c] = -sum_{c' >= c} T[i][c'] * X11[c'][c]
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int c = 4 * cq + u;
-                double y = 0.0;
-                for (int cp = c; cp < PW; ++cp) y += tmp[cp * PLD + il] * s[(j0 + c) * PLD + j0 + cp];
-                s[(j0 + c) * PLD + i] = -y;
-            }
-        }
-        __syncthreads();
-    }
+    invert_lower_inplace<NTH>(s, tmp, rdiag, tid);
     DPROF(5)  // inverse
-    for (int e = tid; e < DB * DB; e += DIAG_THREADS) {
+    for (int e = tid; e < DB * DB; e += NTH) {
         const int i = e & (DB - 1), j = e >> 7;
         d.dinv[i + j * DB] = (i >= j) ? s[j * PLD + i] : 0.0;
     }
@@ -470,7 +570,177 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) diag_kernel(const DiagDesc* _
     extern __shared__ __align__(16) double sh[];
     const DiagDesc d = descs ? descs[blockIdx.x] : one;
     if (!d.A) return;
-    diag_block(d, rel_tol, sh);
+    diag_block<DIAG_THREADS>(d, rel_tol, sh);
+}
+
+// ---- Cholesky factorisation as ONE persistent kernel over a static task list ---------------------------
+//
+// The blocked right-looking factorisation is a DAG of tile tasks (128 x 128 tiles, nb = n / 128):
+//   F(k)            L_kk = chol(A_kk), inv(L_kk)                         needs every update of tile (k, k)
+//   S(i, k)         A_ik <- A_ik inv(L_kk)'                              needs F(k) and every update of (i, k)
+//   U(i, j, k0, k1) A_ij -= sum_{k0 <= k < k1} L_ik L_jk'  (K = 128 (k1 - k0) <= 512)
+//                                                                      needs S(i, k), S(j, k) and the earlier chunks of (i, j)
+// The host orders the tasks once per matrix size by simulating a list schedule on `grid` workers
+// (critical path first: smallest target column, then row) and uploads that order.  Every CTA of the
+// kernel repeatedly takes the next task of the list (one atomic), waits for the task's dependencies
+// on counters in global memory, runs it and publishes its completion.  Taking tasks strictly in list
+// order makes the scheme deadlock free however many CTAs are resident: a CTA only ever waits for
+// tasks that precede its own in a topological order, and those are held by running CTAs.
+// What this replaces: ~300 kernel launches on three streams per factorisation whose critical chain
+// (diagonal block -> panel tile -> update tile -> next diagonal block) paid a launch gap per link and
+// whose trailing updates could not start a CTA while the chain's small kernels waited for an SM.
+// The two tiles on the critical path of every step, S(k+1, k) and the last update of (k+1, k+1), are
+// split into eight 16-row slabs taken by eight CTAs.
+struct DagTask {
+    uint8_t type;   // 0 F, 1 S, 2 U, 3 S slab, 4 U slab
+    uint8_t slab;   // 16-row slab of the tile (types 3, 4)
+    uint16_t i, j;  // target tile (for F: i = j = k; for S: j = k)
+    uint16_t k0, k1;
+    uint16_t pad;
+};
+static_assert(sizeof(DagTask) == 12, "DagTask layout");
+
+struct DagParams {
+    double* A;
+    int64_t lda;
+    double* dinv;
+    const double* diag0;
+    int* flag;
+    double rel_tol;
+    int dead_mode;
+    int nb;
+    const DagTask* tasks;  // [far | near | F]
+    int n_bulk, n_list;    // far list length; far + near: the F tasks start there
+    int n_near;            // CTAs of the near pool
+    int* next;     // [0] far cursor, [1] arrivals (role), [2] chain cursor, [3] near cursor
+    int* cnt;      // [nb * nb] 8 x (k-blocks applied to tile (i, j))
+    int* sdone;    // [nb * nb] slabs of L_ik that are final (8 = all)
+    int* fdone;    // [nb]
+    unsigned long long* trace;  // [n_tasks][3] globaltimer at grab / dependencies met / done (NULL: off)
+};
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// the counters only grow: wait until *p >= want (sibling slabs of one chunk raise cnt past 8 * k0)
+__device__ __forceinline__ void spin_until(const int* p, int want) {
+    while (ld_acquire_fwd(p) < want) __nanosleep(64);
+}
+
+constexpr size_t DAG_SMEM = DIAG_SMEM > GEMM_SMEM ? DIAG_SMEM : GEMM_SMEM;
+
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Are the dependencies of a list task met?  All counters are read before any is tested (the loads are
+// independent: one L2 round trip); the caller fences after a positive answer.
+__device__ __forceinline__ bool deps_ready(const DagParams& P, const DagTask& tk) {
+    const int nb = P.nb, i = tk.i, j = tk.j;
+    if (tk.type == 1 || tk.type == 3) {
+        const int f = ld_relaxed(P.fdone + j), c = ld_relaxed(P.cnt + i * nb + j);
+        return f >= 1 && c >= 8 * j;
+    }
+    const int k0 = tk.k0, nk = tk.k1 - tk.k0;
+    int v[9];
+    v[0] = ld_relaxed(P.cnt + i * nb + j) - 8 * k0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        v[1 + q] = q < nk ? ld_relaxed(P.sdone + i * nb + k0 + q) - 8 : 0;
+        v[5 + q] = (q < nk && i != j) ? ld_relaxed(P.sdone + j * nb + k0 + q) - 8 : 0;
+    }
+    bool ok = true;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) ok = ok && v[q] >= 0;
+    return ok;
+}
+
+// Task lists (one device array): [far | near | F].  Roles by order of arrival:
+//   chain CTA (first): F(0), F(1), ... in order;
+//   the next P.n_near CTAs: the NEAR list -- everything the chain waits for within a few steps: the 16-row
+//     slabs of S(k+1, k), S(k+2, k) and of the recent updates of tiles (j, j), (j+1, j), the older update
+//     chunks of those tiles, and S(i, k) for the rows just below;
+//   every other CTA: the FAR list (the bulk of the trailing updates).
+// Both lists are taken in order with one atomicAdd per task; a CTA waits for the dependencies of the task
+// it took.  Two pools instead of one list because the far updates are throughput bound and queue up:
+// in a single queue the few tasks the chain is waiting for wait behind them.
+// Every list is a subsequence of one topological order (the simulated start order), every list is served
+// by resident CTAs that take its tasks in order and wait only for earlier tasks: no deadlock.
+__global__ void __launch_bounds__(GT, 1) potrf_dag_kernel(const DagParams P) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ int s_task, s_role;
+    const int tid = threadIdx.x, nb = P.nb;
+    if (tid == 0) s_role = atomicAdd(P.next + 1, 1);
+    __syncthreads();
+    const int role = s_role;  // 0 chain, 1 .. n_near: near pool, above: far pool
+    const bool chain = role == 0, near = role >= 1 && role <= P.n_near;
+    for (;;) {
+        __syncthreads();  // the previous task is done with shared memory and s_task
+        unsigned long long t_grab = 0;
+        if (tid == 0) {
+            if (P.trace) t_grab = global_ns();
+            int got = -1;
+            if (chain) {
+                const int k = atomicAdd(P.next + 2, 1);
+                if (k < nb) got = P.n_list + k;
+            } else if (near) {
+                const int b = atomicAdd(P.next + 3, 1);
+                if (b < P.n_list - P.n_bulk) got = P.n_bulk + b;
+            } else {
+                const int b = atomicAdd(P.next, 1);
+                if (b < P.n_bulk) got = b;
+            }
+            if (got >= 0) {
+                const DagTask tk = P.tasks[got];
+                if (tk.type == 0) spin_until(P.cnt + tk.j * nb + tk.j, 8 * tk.j);
+                else
+                    while (!deps_ready(P, tk)) __nanosleep(32);
+                __threadfence();  // acquire: the counters were read with relaxed loads
+            }
+            s_task = got;
+        }
+        __syncthreads();
+        const int t = s_task;
+        if (t < 0) break;
+        const DagTask tk = P.tasks[t];
+        const int i = tk.i, j = tk.j, k0 = tk.k0, k1 = tk.k1;
+        if (P.trace && tid == 0) {
+            P.trace[3 * (size_t)t] = t_grab;
+            P.trace[3 * (size_t)t + 1] = global_ns();
+        }
+        // ---- run ----
+        double* Aij = P.A + (int64_t)i * DB + (int64_t)j * DB * P.lda;
+        if (tk.type == 0) {
+            DiagDesc d{Aij, P.lda, P.dinv + (int64_t)j * DB * DB, P.diag0 ? P.diag0 + (int64_t)j * DB : nullptr, P.flag,
+                       j + 1, P.dead_mode};
+            diag_block<GT>(d, P.rel_tol, sm);
+        } else if (tk.type == 1 || tk.type == 3) {
+            GemmP g{Aij, P.dinv + (int64_t)j * DB * DB, Aij, P.lda, DB, P.lda, DB, 1.0, 0.0};
+            if (tk.type == 1) gemm_tile<false, false, 128, true>(g, 0, 0, sm);
+            else gemm_tile<false, false, 16, true>(g, tk.slab, 0, sm);
+        } else {
+            const double* Li = P.A + (int64_t)i * DB + (int64_t)k0 * DB * P.lda;
+            const double* Lj = P.A + (int64_t)j * DB + (int64_t)k0 * DB * P.lda;
+            GemmP g{Li, Lj, Aij, P.lda, P.lda, P.lda, (k1 - k0) * DB, -1.0, 1.0};
+            if (tk.type == 2) gemm_tile<false, false, 128, true>(g, 0, 0, sm);
+            else gemm_tile<false, false, 16, true>(g, tk.slab, 0, sm);
+        }
+        // ---- publish ----
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            if (tk.type == 0) st_release_fwd(P.fdone + j, 1);
+            else if (tk.type == 1) atomicAdd(P.sdone + i * nb + j, 8);
+            else if (tk.type == 3) atomicAdd(P.sdone + i * nb + j, 1);
+            else if (tk.type == 2) atomicAdd(P.cnt + i * nb + j, 8 * (k1 - k0));
+            else atomicAdd(P.cnt + i * nb + j, k1 - k0);
+            if (P.trace) P.trace[3 * (size_t)t + 2] = global_ns();
+        }
+    }
 }
 
 // ---- triangular solves with one right-hand side -------------------------------------------------
@@ -737,6 +1007,7 @@ int configure(aces_ctx* ctx) {
     ACES_TRY(set_smem(ctx, gemm_batched_kernel<false, true>, GEMM_SMEM));
     ACES_TRY(set_smem(ctx, gemm_batched_kernel<true, true>, GEMM_SMEM));
     ACES_TRY(set_smem(ctx, diag_kernel, DIAG_SMEM));
+    ACES_TRY(set_smem(ctx, potrf_dag_kernel, DAG_SMEM));
     ACES_TRY(set_smem(ctx, trsv_fwd_persistent, TRSV_SMEM));
     ACES_TRY(set_smem(ctx, trsv_bwd_persistent, TRSV_SMEM));
     done = true;
@@ -822,10 +1093,222 @@ int diag_blocks(aces_ctx* ctx, const DiagDesc* descs, int count, double rel_tol)
     return ACES_OK;
 }
 
+namespace {
+
+// Static schedule of the factorisation DAG for an nb x nb tile matrix on `workers` CTAs: a list schedule
+// simulated with estimated task durations (microseconds), priority = (target column, target row,
+// first k-block) -- the tile that the next diagonal block is waiting for goes first.  The result is
+// the order in which the simulated workers START the tasks, which is a topological order of the DAG.
+// Returned: [far list | near list | F(0) .. F(nb-1)]; *n_far = length of the far list.  Both lists keep the
+// simulated start order.  `pad` = 1 marks a near task.
+std::vector<DagTask> build_dag_schedule(int nb, int workers, int* n_far = nullptr) {
+    struct Node {
+        DagTask t;
+        double cost;
+        int indeg = 0;
+        std::vector<int> succ;
+    };
+    std::vector<Node> nodes;
+    nodes.reserve((size_t)nb * nb * (nb / 24 + 2));
+    auto add = [&](uint8_t type, int slab, int i, int j, int k0, int k1, double cost, int urgent = 0) {
+        Node nd;
+        nd.t = DagTask{type, (uint8_t)slab, (uint16_t)i, (uint16_t)j, (uint16_t)k0, (uint16_t)k1, (uint16_t)urgent};
+        nd.cost = cost;
+        nodes.push_back(nd);
+        return (int)nodes.size() - 1;
+    };
+    auto edge = [&](int from, int to) {
+        nodes[(size_t)from].succ.push_back(to);
+        nodes[(size_t)to].indeg += 1;
+    };
+    // per tile: the task group (1 task, or 8 slabs) of its last update chunk and of its S / F task
+    std::vector<std::vector<int>> last_upd((size_t)nb * nb), solved((size_t)nb * nb);
+    std::vector<int> fac((size_t)nb, -1);
+    static const int NEAR_U = [] { const char* e = getenv("ACES_POTRF_NEAR_U"); return e ? atoi(e) : 3; }();  // recent chunks of tiles with i - j <= NEAR_U are near
+    static const int NEAR_S = [] { const char* e = getenv("ACES_POTRF_NEAR_S"); return e ? atoi(e) : 4; }();  // S(i, j) with i - j <= NEAR_S is near
+    static const int CH = [] { const char* e = getenv("ACES_POTRF_CHUNK"); return e ? std::min(4, std::max(1, atoi(e))) : 4; }();  // k-blocks per update chunk (K = 512)
+    for (int j = 0; j < nb; ++j) {
+        for (int i = j; i < nb; ++i) {
+            // Update chunks of tile (i, j), in order.  How soon is the tile needed after its last inputs
+            // (column j - 1) exist?  Rows j and j + 1 at once (the next diagonal block and the tile under
+            // it): their recent k-blocks are applied as eight 16-row slabs each, the very last one alone.
+            // Rows up to j + NEAR within a few steps: full-tile tasks, but urgent.  Everything that only
+            // involves k-blocks older than a chunk has several steps of slack: bulk.
+            const bool critical = i - j <= 1, close = i - j <= NEAR_U;
+            const int recent = close ? std::max(0, (j - 1 - CH) / CH * CH) : j;  // first k-block handled by the near pool
+            std::vector<int> prev;
+            for (int k0 = 0; k0 < j;) {
+                int k1 = std::min(k0 - k0 % CH + CH, j);
+                if (critical && k1 == j && k0 < j - 1) k1 = j - 1;  // the last k-block of a critical tile alone
+                const bool urgent = k0 >= recent, split = critical && urgent;
+                std::vector<int> grp;
+                if (split)
+                    for (int sl = 0; sl < 8; ++sl)
+                        grp.push_back(add(4, sl, i, j, k0, k1, 4.0 + 3.5 * (k1 - k0), 1));
+                else
+                    grp.push_back(add(2, 0, i, j, k0, k1, 12.0 + 19.0 * (k1 - k0), (critical || urgent) ? 1 : 0));
+                for (int g : grp) {
+                    for (int p : prev) edge(p, g);
+                    for (int k = k0; k < k1; ++k) {
+                        for (int sv : solved[(size_t)i * nb + k]) edge(sv, g);
+                        if (i != j)
+                            for (int sv : solved[(size_t)j * nb + k]) edge(sv, g);
+                    }
+                }
+                prev = grp;
+                k0 = k1;
+            }
+            last_upd[(size_t)i * nb + j] = prev;
+            if (i == j) {
+                fac[(size_t)j] = add(0, 0, j, j, 0, 0, 52.0);
+                for (int p : prev) edge(p, fac[(size_t)j]);
+            } else {
+                std::vector<int> grp;
+                if (i - j <= 2)
+                    for (int sl = 0; sl < 8; ++sl) grp.push_back(add(3, sl, i, j, 0, 0, 6.0, 1));
+                else
+                    grp.push_back(add(1, 0, i, j, 0, 0, 25.0, i - j <= NEAR_S ? 1 : 0));
+                for (int g : grp) {
+                    edge(fac[(size_t)j], g);
+                    for (int p : prev) edge(p, g);
+                }
+                solved[(size_t)i * nb + j] = grp;
+            }
+        }
+    }
+    // list scheduling
+    // Priority = bottom level (the longest path of estimated durations from the task to the end of the
+    // factorisation, critical-path list scheduling): the tasks that feed the chain of diagonal blocks soon
+    // carry the whole remaining chain behind them and go first, however early or late their tile's column
+    // is; the far trailing updates, which nothing waits for, fill the gaps.  Every edge goes from a task
+    // created earlier to one created later, so one backward sweep computes the levels.
+    std::vector<double> level(nodes.size(), 0.0);
+    for (int id = (int)nodes.size() - 1; id >= 0; --id) {
+        double below = 0.0;
+        for (int sc : nodes[(size_t)id].succ) below = std::max(below, level[(size_t)sc]);
+        level[(size_t)id] = nodes[(size_t)id].cost + below;
+    }
+    auto later = [&](int a, int b) {
+        if (level[(size_t)a] != level[(size_t)b]) return level[(size_t)a] < level[(size_t)b];
+        return a > b;
+    };
+    std::priority_queue<int, std::vector<int>, decltype(later)> ready(later);
+    using Ev = std::pair<double, int>;
+    std::priority_queue<Ev, std::vector<Ev>, std::greater<Ev>> events;
+    // (the only task without a dependency is F(0): it goes to the chain worker)
+    std::vector<DagTask> order;
+    order.reserve(nodes.size());
+    double now = 0.0;
+    int free_workers = std::max(workers - 1, 1);  // (one pool in the simulation)
+    bool chain_free = true;
+    std::vector<int> f_ready;  // F tasks whose updates are complete (at most one at a time)
+    for (int id = 0; id < (int)nodes.size(); ++id)
+        if (nodes[(size_t)id].indeg == 0) {
+            if (nodes[(size_t)id].t.type == 0) f_ready.push_back(id);
+            else ready.push(id);
+        }
+    size_t started = 0;
+    while (started < nodes.size()) {
+        if (chain_free && !f_ready.empty()) {
+            const int id = f_ready.back();
+            f_ready.pop_back();
+            events.push({now + nodes[(size_t)id].cost, id});
+            chain_free = false;
+            ++started;
+        }
+        while (free_workers > 0 && !ready.empty()) {
+            const int id = ready.top();
+            ready.pop();
+            order.push_back(nodes[(size_t)id].t);
+            events.push({now + nodes[(size_t)id].cost, id});
+            --free_workers;
+            ++started;
+        }
+        if (events.empty()) break;  // cannot happen for a DAG
+        const Ev ev = events.top();
+        events.pop();
+        now = ev.first;
+        if (nodes[(size_t)ev.second].t.type == 0) chain_free = true;
+        else ++free_workers;
+        for (int sc : nodes[(size_t)ev.second].succ)
+            if (--nodes[(size_t)sc].indeg == 0) {
+                if (nodes[(size_t)sc].t.type == 0) f_ready.push_back(sc);
+                else ready.push(sc);
+            }
+    }
+    // split the start order into the bulk and the urgent list
+    std::vector<DagTask> out;
+    out.reserve(order.size() + (size_t)nb);
+    for (const DagTask& t : order)
+        if (!t.pad) out.push_back(t);
+    if (n_far) *n_far = (int)out.size();
+    for (const DagTask& t : order)
+        if (t.pad) out.push_back(t);
+    for (int k = 0; k < nb; ++k) out.push_back(nodes[(size_t)fac[(size_t)k]].t);
+    order.swap(out);
+    return order;
+}
+
+int potrf_dag(aces_ctx* ctx, int64_t n, double* A, int64_t lda, double* dinv, int* flag, const double* diag0,
+              double rel_tol, int dead_mode) {
+    const int nb = (int)(n / DB);
+    ACES_CHECK(ctx, nb < 65536, "dense::potrf: matrix too large for the task encoding");
+    static const int NEAR_CTAS = [] { const char* e = getenv("ACES_POTRF_NEAR_CTAS"); return e ? std::max(1, atoi(e)) : 26; }();
+    const int grid = std::max(ctx->sm_count, NEAR_CTAS + 2);  // the chain CTA, the near pool and at least one far worker
+    if (ctx->dag_nb != nb || ctx->dag_grid != grid) {
+        int n_bulk = 0;
+        const std::vector<DagTask> order = build_dag_schedule(nb, grid, &n_bulk);
+        ACES_TRY(aces_reserve_dev(ctx, ctx->d_dag_tasks, sizeof(DagTask) * order.size()));
+        ACES_CUDA(ctx, cudaMemcpyAsync(ctx->d_dag_tasks.ptr, order.data(), sizeof(DagTask) * order.size(), cudaMemcpyHostToDevice,
+                                       ctx->stream));
+        ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `order` dies at the end of this block
+        ctx->dag_nb = nb;
+        ctx->dag_grid = grid;
+        ctx->dag_ntasks = n_bulk;
+        ctx->dag_nlist = (int)order.size() - nb;  // far + near lists; the nb F tasks follow
+    }
+    const size_t n_state = 16 + 2 * (size_t)nb * nb + (size_t)nb;
+    ACES_TRY(aces_reserve_dev(ctx, ctx->d_dag_state, sizeof(int) * n_state));
+    int* st = (int*)ctx->d_dag_state.ptr;
+    ACES_CUDA(ctx, cudaMemsetAsync(st, 0, sizeof(int) * n_state, ctx->stream));
+    DagParams P;
+    P.A = A; P.lda = lda; P.dinv = dinv; P.diag0 = diag0; P.flag = flag; P.rel_tol = rel_tol; P.dead_mode = dead_mode;
+    P.nb = nb;
+    P.tasks = (const DagTask*)ctx->d_dag_tasks.ptr;
+    P.n_bulk = ctx->dag_ntasks;
+    P.n_list = ctx->dag_nlist;
+    P.n_near = NEAR_CTAS;
+    P.next = st;
+    P.cnt = st + 16;
+    P.sdone = P.cnt + (size_t)nb * nb;
+    P.fdone = P.sdone + (size_t)nb * nb;
+    P.trace = nullptr;
+    static const bool trace_on = getenv("ACES_POTRF_TRACE") != nullptr;  // development: per-task timestamps
+    if (trace_on) {
+        ACES_TRY(aces_reserve_dev(ctx, ctx->d_dag_trace, sizeof(unsigned long long) * 3 * (size_t)(ctx->dag_nlist + nb)));
+        P.trace = (unsigned long long*)ctx->d_dag_trace.ptr;
+    }
+    potrf_dag_kernel<<<(unsigned)grid, GT, DAG_SMEM, ctx->stream>>>(P);
+    ACES_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return ACES_OK;
+}
+
+}  // namespace
+
 int potrf(aces_ctx* ctx, int64_t n, double* A, int64_t lda, double* dinv, int* flag, const double* diag0,
           double rel_tol, int dead_mode) {
     ACES_CHECK(ctx, n % DB == 0, "dense::potrf: n=%lld is not padded", (long long)n);
     ACES_TRY(configure(ctx));
+    // ACES_POTRF_STREAMS=1 (development knob) selects the previous multi-stream, launch-per-tile version
+    // Which version: the persistent task-DAG kernel wins where the chain of diagonal blocks matters
+    // (rotated d = 9, N = 6784: 5.8 ms against 6.7 ms); for large matrices the factorisation is pure GEMM
+    // throughput and the multi-stream version with its two-CTA-per-SM 64-row tiles is faster (d = 17,
+    // N = 24832: 172 ms against 230 ms, profiles/fit_r02_potrf_variants.txt).  ACES_POTRF_STREAMS = 1 / 0
+    // forces one or the other (development knob).
+    static const int force = [] { const char* e = getenv("ACES_POTRF_STREAMS"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+    const bool use_streams = force >= 0 ? force == 1 : n / DB > 80;
+    if (!use_streams) return potrf_dag(ctx, n, A, lda, dinv, flag, diag0, rel_tol, dead_mode);
     constexpr int64_t NB2 = 4 * DB;  // outer panel: the bulk of the flops runs as K = 512 updates
     // development probe: skip parts of the factorisation to time the others (results are then wrong)
 #ifdef ACES_POTRF_PROBE  // never in a production build: a stray environment variable must not corrupt results
@@ -1049,3 +1532,39 @@ int symmetrize_from_lower(aces_ctx* ctx, int64_t n, double* A, int64_t lda) {
 }
 
 }  // namespace dense
+
+extern "C" int32_t aces_potrf_schedule(int32_t nb, int32_t workers, int32_t* out, int64_t capacity, int64_t* n_tasks) {
+    if (nb < 1 || nb >= 65536 || workers < 1 || !n_tasks) return ACES_E_INVALID;
+    const std::vector<dense::DagTask> order = dense::build_dag_schedule(nb, workers);
+    *n_tasks = (int64_t)order.size();
+    if (out) {
+        if (capacity < (int64_t)order.size()) return ACES_E_INVALID;
+        for (size_t t = 0; t < order.size(); ++t) {
+            const dense::DagTask& k = order[t];
+            int32_t* o = out + 6 * t;
+            o[0] = k.type; o[1] = k.slab | (k.pad << 8); o[2] = k.i; o[3] = k.j; o[4] = k.k0; o[5] = k.k1;
+        }
+    }
+    return ACES_OK;
+}
+
+// Development hook: per-task timestamps (ns) of the last traced factorisation (ACES_POTRF_TRACE=1) together
+// with the task list: 9 int64 per task (type, slab, i, j, k0, k1, t_grab, t_ready, t_done).
+extern "C" int32_t aces_potrf_trace(aces_ctx* ctx, int64_t* out, int64_t capacity, int64_t* n_tasks) {
+    if (!ctx || !n_tasks) return ACES_E_INVALID;
+    *n_tasks = ctx->d_dag_trace.ptr ? ctx->dag_nlist + ctx->dag_nb : 0;
+    if (!out || *n_tasks == 0) return ACES_OK;
+    if (capacity < *n_tasks) return ACES_E_INVALID;
+    ACES_CUDA(ctx, cudaSetDevice(ctx->device));
+    ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<dense::DagTask> tasks((size_t)*n_tasks);
+    std::vector<unsigned long long> tr(3 * (size_t)*n_tasks);
+    ACES_CUDA(ctx, cudaMemcpy(tasks.data(), ctx->d_dag_tasks.ptr, sizeof(dense::DagTask) * tasks.size(), cudaMemcpyDeviceToHost));
+    ACES_CUDA(ctx, cudaMemcpy(tr.data(), ctx->d_dag_trace.ptr, sizeof(unsigned long long) * tr.size(), cudaMemcpyDeviceToHost));
+    for (size_t t = 0; t < tasks.size(); ++t) {
+        int64_t* o = out + 9 * t;
+        o[0] = tasks[t].type; o[1] = tasks[t].slab; o[2] = tasks[t].i; o[3] = tasks[t].j; o[4] = tasks[t].k0; o[5] = tasks[t].k1;
+        o[6] = (int64_t)tr[3 * t]; o[7] = (int64_t)tr[3 * t + 1]; o[8] = (int64_t)tr[3 * t + 2];
+    }
+    return ACES_OK;
+}
