@@ -35,24 +35,53 @@ UNIT = "shot-parities/s"
 SHOTS_SET = [10**6, 10**7, 10**8]
 WORKLOAD = "rotated_d9_wls_1e8shots"
 
+# BASELINE.json configs as workloads (--workload).  The default (the configuration the metric is quoted on)
+# is configs[2]; the others emit the same JSON line for their shape.
+#   sharding "repetitions": one repetition per rank per step (weak); "shots": every rank holds a contiguous
+#   shot range of every experiment and the int64 counts are all-reduced (config 5: 73 GB over 8 GPUs).
+WORKLOADS = {
+    "rotated_d9_wls_1e8shots": dict(kind="rotated", d=9, full=False, shots=[10**6, 10**7, 10**8], fit_full=True, sharding="repetitions",
+                                    baseline="configs[2]: rotated surface code d=9, full_covariance=false WLS, 1e8 shots"),
+    "rotated_d5_gls": dict(kind="rotated", d=5, full=True, shots=[10**6, 10**7, 10**8], fit_full=True, sharding="repetitions",
+                           baseline="configs[1]: rotated surface code d=5, log-normal Pauli noise, full_covariance=true GLS"),
+    "unrotated_d7_gls": dict(kind="unrotated", d=7, full=True, shots=[10**6, 10**7, 10**8], fit_full=True, sharding="repetitions",
+                             baseline="configs[3]: unrotated surface code d=7, log-normal noise, GLS estimate + calc_covariance merit"),
+    "rotated_d17_1e9": dict(kind="rotated", d=17, full=False, shots=[10**7, 10**8, 10**9], fit_full=False, sharding="shots",
+                            baseline="configs[4]: rotated surface code d=17, 1e9-shot synthetic budget, shots sharded over 8 GPUs"),
+}
+WL = WORKLOADS[WORKLOAD]
+
 
 FIT_CONTEXTS = 4         # concurrent fit contexts of the throughput line (--fit-contexts)
 DESIGN_SOURCE = "real"   # "real": circuit_design.rotated_design(9) (the reference's own tables); "synthetic": look-alike
 
 
-def workload_config(n_gpus, fd=None, sizes=None):
+def workload_config(n_gpus, fd=None, sizes=None, bytes_per_gpu=None):
     n_exp = int(fd.experiment_number) if fd is not None else 96
     mean_paulis = float(sum(int(x) for x in sizes)) / n_exp if sizes is not None else None
+    shots_sharded = WL["sharding"] == "shots"
     return {
         "workload": WORKLOAD,
-        "baseline_config": "configs[2]: rotated surface code d=9, full_covariance=false WLS, 1e8 shots",
-        "design": ("generate_design of the rotated planar d=9 circuit restated in numpy (circuit_design.py): real Pauli "
-                   "tables, experiment packing and shot weights" if DESIGN_SOURCE == "real" else "synthetic look-alike tables"),
-        "n_qubits": 161, "bytes_per_shot": 21, "experiments": n_exp, "paulis_per_experiment_mean": mean_paulis,
-        "budgets": SHOTS_SET, "repetitions_per_step": n_gpus,
-        "l2": "inputs (2.1 GB per GPU) exceed the 126 MB L2; no flush needed",
-        "parallelism": f"repetitions x{n_gpus}" if n_gpus > 1 else "single GPU",
+        "baseline_config": WL["baseline"],
+        "design": (f"generate_design of the {WL['kind']} planar d={WL['d']} circuit restated in numpy (inputs/circuit_design.py): "
+                   "real Pauli tables, experiment packing and shot weights" if DESIGN_SOURCE == "real" else "synthetic look-alike tables"),
+        "n_qubits": int(fd.n_qubits) if fd is not None else 161, "bytes_per_shot": int(fd.n_bytes) if fd is not None else 21,
+        "experiments": n_exp, "paulis_per_experiment_mean": mean_paulis,
+        "budgets": [int(x) for x in shots_for(n_gpus)],
+        "repetitions_per_step": 1 if shots_sharded else n_gpus,
+        "l2": (f"inputs ({bytes_per_gpu / 1e9:.2f} GB per GPU) exceed the 126 MB L2; no flush needed" if bytes_per_gpu and bytes_per_gpu > 2.5e8
+               else "inputs fit the 126 MB L2: a 256 MB buffer is overwritten between timed steps"),
+        "parallelism": ((f"shot ranges of every experiment x{n_gpus}, int64 all-reduce of the counts (the full 1e9-shot budget "
+                         "needs 8 GPUs: per-GPU work is fixed, 1/8 of the budget per rank)") if shots_sharded
+                        else (f"repetitions x{n_gpus}" if n_gpus > 1 else "single GPU")),
     }
+
+
+def shots_for(n_gpus):
+    """Budgets of the workload: the shot-sharded config keeps 1/8 of the 1e9-shot budget per rank (weak)."""
+    if WL["sharding"] == "shots":
+        return [s * n_gpus // 8 for s in WL["shots"]]
+    return list(WL["shots"])
 
 
 def measured_peaks():
@@ -132,8 +161,9 @@ def build_design():
     import aces_b200
 
     if DESIGN_SOURCE == "real":
-        return aces_b200.rotated_design(9, full_covariance=False)
-    return aces_b200.synthetic_design("rotated", 9, full_covariance=False)
+        gen = aces_b200.rotated_design if WL["kind"] == "rotated" else aces_b200.unrotated_design
+        return gen(WL["d"], full_covariance=WL["full"])
+    return aces_b200.synthetic_design(WL["kind"], WL["d"], full_covariance=WL["full"])
 
 
 def cpu_sample(fd, est_sizes, seconds_target=12.0):
@@ -147,7 +177,7 @@ def cpu_sample(fd, est_sizes, seconds_target=12.0):
     rng = np.random.default_rng(0)
     ob.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the reference uses every core
     threads = ob.num_threads()
-    shots_divided, shots_max = aces_b200.shots_divide(fd, SHOTS_SET)
+    shots_divided, shots_max = aces_b200.shots_divide(fd, shots_for(1))
     rows = int(shots_max.max())
     m = np.asfortranarray(rng.integers(0, 256, size=(rows, fd.n_bytes), dtype=np.uint8))
     ob.estimate_experiment(m[:1000], [[1]], [0], 1000)  # start the OpenMP team outside the timing
@@ -206,9 +236,10 @@ def fit_inputs():
     import aces_b200
 
     if DESIGN_SOURCE == "real":
-        fd = aces_b200.rotated_design(9, full_covariance=True, noise="lognormal", seed=9)
+        gen = aces_b200.rotated_design if WL["kind"] == "rotated" else aces_b200.unrotated_design
+        fd = gen(WL["d"], full_covariance=True, noise="lognormal", seed=9)
     else:
-        fd = aces_b200.synthetic_design("rotated", 9, full_covariance=True, with_matrix=True)
+        fd = aces_b200.synthetic_design(WL["kind"], WL["d"], full_covariance=True, with_matrix=True)
     eig, cov = aces_b200.synthetic_estimates(fd, shots=10**8, seed=11)
     lam = np.concatenate(aces_b200.mean_ensemble(eig))
     lc = np.concatenate(aces_b200.mean_ensemble(cov))
@@ -223,7 +254,7 @@ def fit_leg(ctx, torch, dist, world, rank, steps, warmup, with_cpu):
 
     fd, eig, cov, lam, lc = fit_inputs()
     dd = aces_b200.DeviceDesign(ctx, fd)
-    out = {"workload": "rotated_d9 GLS (full covariance pattern)", "design": DESIGN_SOURCE, "M": int(fd.M), "N": int(fd.matrix.shape[1]),
+    out = {"workload": f"{WL['kind']}_d{WL['d']} GLS (full covariance pattern)", "design": DESIGN_SOURCE, "M": int(fd.M), "N": int(fd.matrix.shape[1]),
            "tuples": int(fd.tuple_number), "covariance_keys": int(dd.C),
            "api": "aces_design_fit: host estimate vectors in, host gate eigenvalues out (H2D + D2H inside)"}
     res = {}
@@ -291,25 +322,63 @@ def fit_leg(ctx, torch, dist, world, rank, steps, warmup, with_cpu):
     out["phases_ms"] = phases  # CUDA events inside the library, one fit each
     n = fd.matrix.shape[1]
     n_pad = -(-n // 128) * 128
-    out["cholesky"] = {"kernel": "dense::potrf (DMMA trailing updates + 128-block factor/inverse kernel, look-ahead)",
-                       "ms": phases["gls"].get("potrf"), "flops": n_pad ** 3 / 3.0,
-                       "tflops": n_pad ** 3 / 3.0 / (phases["gls"].get("potrf", float("nan")) * 1e-3) / 1e12}
     flops = dd.gram_flops()
     peak = dgemm_peak_tflops(torch)
-    out["roofline"] = {"bound": "tensor", "kernel": "dense::gemm_batched_kernel<TN> (Gram over the column windows of the tuple blocks, DMMA m8n8k4 f64)",
-                       "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                       "frac": flops / (k_ms * 1e-3) / 1e12 / peak, "kernel_ms": k_ms,
-                       "executed_flops_per_launch": flops,
+    potrf_ms = phases["gls"].get("potrf", float("nan"))
+    chol_tf = n_pad ** 3 / 3.0 / (potrf_ms * 1e-3) / 1e12
+    # The dominant kernel of a fit is the Cholesky factorisation of the Gram matrix: it is the roofline entry.
+    out["roofline"] = {"bound": "tensor",
+                       "kernel": ("dense::potrf_dag_kernel (persistent task-DAG Cholesky: DMMA m8n8k4 f64 update / panel tiles, "
+                                  "128-block factor + inverse on the chain CTA)" if n_pad // 128 <= 80 else
+                                  "dense::potrf (multi-stream blocked Cholesky, DMMA m8n8k4 f64 tiles)"),
+                       "achieved": chol_tf, "peak": peak, "unit": "TFLOP/s", "frac": chol_tf / peak, "kernel_ms": potrf_ms,
+                       "flops_per_launch": n_pad ** 3 / 3.0,
                        "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (burst, best of 5)",
-                       "share_of_fit": k_ms / out["gls_ms_per_fit"], "traffic": None}
+                       "share_of_fit": {"gls": potrf_ms / out["gls_ms_per_fit"],
+                                        "wls": phases["wls"].get("potrf", float("nan")) / out["wls_ms_per_fit"]},
+                       "traffic": None,
+                       "note": "latency-bound chain of 128 x 128 diagonal blocks, not a bandwidth- or pipe-bound kernel: "
+                               "see profiles/fit_r02_potrf_variants.txt for the per-task trace"}
+    out["gram"] = {"kernel": "dense::gemm_batched_kernel<TN> (Gram over the column windows of the tuple blocks, DMMA m8n8k4 f64)",
+                   "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                   "frac": flops / (k_ms * 1e-3) / 1e12 / peak, "kernel_ms": k_ms, "executed_flops_per_launch": flops,
+                   "share_of_fit": k_ms / out["gls_ms_per_fit"], "traffic": None}
     gpath = os.path.join(ROOT, "profiles", "fit_gram_traffic.json")
-    if DESIGN_SOURCE == "real" and os.path.exists(gpath):
+    if DESIGN_SOURCE == "real" and WORKLOAD == "rotated_d9_wls_1e8shots" and os.path.exists(gpath):
         try:  # one ncu --set full capture of this kernel (per launch), see profiles/fit_r01_gram_ncu_summary.txt
             gj = json.load(open(gpath))
-            out["roofline"]["traffic"] = gj.get("dram_bytes_per_launch")
-            out["roofline"]["ncu_tensor_pipe_dmma_active_pct"] = gj.get("tensor_pipe_dmma_active_pct")
+            out["gram"]["traffic"] = gj.get("dram_bytes_per_launch")
+            out["gram"]["ncu_tensor_pipe_dmma_active_pct"] = gj.get("tensor_pipe_dmma_active_pct")
         except Exception:
             pass
+    # K6 (calc_gls / wls / ols_covariance + nrmse_moments, src/merit.jl:556-629, 672-682): BASELINE configs[3]'s
+    # "calc_covariance merit", trace moments only (no N x N copy to the host)
+    lam_ens, cov_ens = aces_b200.mean_ensemble(eig), aces_b200.mean_ensemble(cov)
+    cl = dd.calc_covariance(lam_ens, cov_ens, weight_time=False, log_form=True)
+    k6 = {}
+    for name in ("gls", "wls", "ols"):
+        dd.calc_ls_covariance(name, cl, want_matrix=False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(max(steps // 2, 2)):
+            _, tr, trsq = dd.calc_ls_covariance(name, cl, want_matrix=False)
+        torch.cuda.synchronize()
+        k6[name] = {"ms": 1e3 * (time.perf_counter() - t0) / max(steps // 2, 2),
+                    "nrmse_expectation": float(aces_b200.nrmse_moments(tr, trsq, n)[0])}
+    out["ls_covariance"] = dict(k6, api="aces_design_ls_covariance (trace moments; pattern values from the host)")
+    # the whole numeric path of estimate_gate_noise with split projections (src/estimate.jl:703-831)
+    if fd.gate_ptr is not None:
+        eig_p, cov_p = aces_b200.synthetic_estimates(fd, shots=10**6, seed=5)   # few shots: projections are active
+        aces_b200.estimate_gate_noise_projected(dd, eig_p, cov_p, clip_warning=False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = aces_b200.estimate_gate_noise_projected(dd, eig_p, cov_p, clip_warning=False)
+        torch.cuda.synchronize()
+        out["estimate_gate_noise_projected"] = {
+            "ms": 1e3 * (time.perf_counter() - t0), "precision_project": bool(r["precision_project"]),
+            "gates": int(len(fd.gate_ptr) - 1),
+            "what": "means, clipping, OLS + WLS + GLS fits, Euclidean projection of OLS, per-gate Mahalanobis projection of "
+                    "WLS / GLS (precision slices from the device-resident Gram matrix, batched active-set QP), host vectors in / out"}
     if with_cpu and rank == 0:
         # parity at the benchmarked shape: the GPU estimates of the SAME inputs against the CPU
         # restatement (north star: 1e-9 relative in fp64)
@@ -360,7 +429,7 @@ def run_reference(args):
         if i >= args.warmup:
             vals.append(base["value"])
     value = sum(vals) / len(vals)
-    _, shots_max = aces_b200.shots_divide(fd, SHOTS_SET)
+    _, shots_max = aces_b200.shots_divide(fd, shots_for(args.gpus))
     sizes = [len(e) for t in range(fd.tuple_number) for e in fd.experiment_ensemble[t]]
     step_units = sum(len(e) * int(shots_max[t]) for t in range(fd.tuple_number) for e in fd.experiment_ensemble[t])
     base["value"] = value
@@ -379,6 +448,7 @@ def run_reference(args):
 
 
 def main():
+    global DESIGN_SOURCE, FIT_CONTEXTS, WORKLOAD, WL
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -390,10 +460,13 @@ def main():
     ap.add_argument("--fit-steps", type=int, default=5)
     ap.add_argument("--design", default="real", choices=["real", "synthetic"])
     ap.add_argument("--fit-contexts", type=int, default=4)
+    ap.add_argument("--workload", default="rotated_d9_wls_1e8shots", choices=sorted(WORKLOADS))
     args = ap.parse_args()
-    global DESIGN_SOURCE, FIT_CONTEXTS
     DESIGN_SOURCE = args.design
     FIT_CONTEXTS = args.fit_contexts
+    WORKLOAD, WL = args.workload, WORKLOADS[args.workload]
+    if not WL["fit_full"]:
+        args.no_fit = True   # the d = 17 fit is a 25k x 25k factorisation per estimator: tools/fit_sharded.py times it
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
@@ -418,41 +491,87 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    # bind the process to the CPUs next to its GPU before any pinned allocation (first touch places the
+    # pages): the end-to-end leg is a host-to-device copy
+    numa = "unchanged"
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        numa = f"nvmlDeviceSetCpuAffinity: {len(os.sched_getaffinity(0))} CPUs"
+    except Exception as e:  # noqa: BLE001
+        numa = f"not bound ({type(e).__name__})"
+
     fd = build_design()
     ctx = aces_b200.Context(local)
     est = aces_b200.DesignEstimator(ctx, fd)
     # A real (non-default) stream: handle 0 would select the library's own stream and the events
     # below would not bracket its kernels.
     stream = torch.cuda.Stream()
+    comm = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
-    shots_divided, shots_max = aces_b200.shots_divide(fd, SHOTS_SET)
+    shots_set = shots_for(world)
+    K = len(shots_set)
+    shots_divided, shots_max = aces_b200.shots_divide(fd, shots_set)
     n_exp, B = fd.experiment_number, fd.n_bytes
-    rows = [int(shots_max[int(est.tuple_of_experiment[e])]) for e in range(n_exp)]
-    ld = [(r + 127) // 128 * 128 for r in rows]
-    prefix = np.stack([shots_divided[int(est.tuple_of_experiment[e])] for e in range(n_exp)])
+    rows_full = [int(shots_max[int(est.tuple_of_experiment[e])]) for e in range(n_exp)]
+    prefix_full = np.stack([shots_divided[int(est.tuple_of_experiment[e])] for e in range(n_exp)])
+    shot_sharded = WL["sharding"] == "shots"
+    if shot_sharded:
+        # every rank: a contiguous shot range of every experiment, prefixes clamped into it (shard.shard_shots)
+        parts = [aces_b200.shard.shard_shots(rows_full[e], prefix_full[e], world, rank) for e in range(n_exp)]
+        rows = [int(hi - lo) for lo, hi, _ in parts]
+        prefix = np.stack([p for _, _, p in parts])
+    else:
+        rows, prefix = rows_full, prefix_full
+    ld = [max((r + 127) // 128 * 128, 128) for r in rows]
     sizes = est.experiment_sizes()
     g = torch.Generator(device="cuda").manual_seed(0x5EED0000 + rank)
     dev = [torch.randint(0, 256, (B, ld[e]), dtype=torch.uint8, device="cuda", generator=g) for e in range(n_exp)]
     ptrs = [d.data_ptr() for d in dev]
-    n_counts = int(np.sum(sizes) * len(SHOTS_SET))
-    out = torch.zeros(n_counts, dtype=torch.int64, device="cuda")
-    gathered = torch.zeros(world * n_counts, dtype=torch.int64, device="cuda") if world > 1 else None
-    alg_bytes = int(sum(rows[e] * B for e in range(n_exp)))          # read once
+    n_counts = int(np.sum(sizes) * K)
+    outs = [torch.zeros(n_counts, dtype=torch.int64, device="cuda") for _ in range(2)]   # double buffered: the collective
+    gathered = [torch.zeros(world * n_counts, dtype=torch.int64, device="cuda") for _ in range(2)] if world > 1 and not shot_sharded else None
+    alg_bytes = int(sum(rows[e] * B for e in range(n_exp)))          # read once, this rank
     shot_parities = int(sum(rows[e] * int(sizes[e]) for e in range(n_exp)))
     shots = int(sum(rows))
+    small = alg_bytes < 2.5e8   # the inputs would stay in the 126 MB L2 between steps: flush it
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if small else None
 
-    batch = est.prepare(ptrs, rows, ld, prefix, out.data_ptr(), asynchronous=True)
+    batches = [est.prepare(ptrs, rows, ld, prefix, o.data_ptr(), asynchronous=True) for o in outs]
+    done_ev = [torch.cuda.Event(), torch.cuda.Event()]      # kernel of buffer b finished
+    free_ev = [torch.cuda.Event(), torch.cuda.Event()]      # collective of buffer b finished
+    step_no = [0]
 
     def step():
-        batch.launch()  # aces_parity_counts_async: memset + parity kernel + prefix kernel on the stream
+        """One repetition (or one shot shard of it) on this rank: memset + parity kernel + prefix kernel on the
+        compute stream; the NCCL exchange of its small count vector runs on a second stream, overlapped with
+        the next step's kernel (two output buffers)."""
+        b = step_no[0] & 1
+        step_no[0] += 1
+        if flush is not None:
+            flush.fill_(1)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
+            stream.wait_event(free_ev[b])        # the collective that last read this buffer is done
+        batches[b].launch()
+        if world > 1:
+            done_ev[b].record(stream)
+            with torch.cuda.stream(comm):
+                comm.wait_event(done_ev[b])
+                if shot_sharded:
+                    dist.all_reduce(outs[b], op=dist.ReduceOp.SUM)
+                else:
+                    dist.all_gather_into_tensor(gathered[b], outs[b])
+                free_ev[b].record(comm)
 
     def fence():
         if world > 1:
+            comm.synchronize()
             dist.barrier()
         torch.cuda.synchronize()
 
@@ -467,6 +586,8 @@ def main():
         ev0.record(stream)
         for _ in range(args.steps):
             step()
+        if world > 1:
+            stream.wait_stream(comm)   # the timed region ends when the last exchange has finished
         ev1.record(stream)
         fence()
         ms_total = ev0.elapsed_time(ev1)
@@ -478,12 +599,32 @@ def main():
             kernel_ms.append(ctx.last_kernel_ms())
         fence()
     ctx.set_timing(False)
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    flush_ms = 0.0
+    if flush is not None:   # the L2 flush sits inside the timed region: time it alone and take it out
+        fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fe0.record(stream)
+        for _ in range(args.steps):
+            flush.fill_(1)
+        fe1.record(stream)
+        torch.cuda.synchronize()
+        flush_ms = fe0.elapsed_time(fe1)
+    t = torch.tensor([ms_total - flush_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
-    value = world * shot_parities / (ms_per_step * 1e-3)
+    tot = torch.tensor([shot_parities, shots, alg_bytes], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    value = float(tot[0].item()) / (ms_per_step * 1e-3)
+    out = outs[(step_no[0] - 1) & 1]
+    counts_equal = None
+    if shot_sharded and world > 1:   # after the all-reduce every rank holds the same counts: compare a checksum
+        chk = torch.stack([out.sum(), (out * torch.arange(1, n_counts + 1, device="cuda")).sum()]).to(torch.int64)
+        allchk = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allchk, chk)
+        counts_equal = bool(all(torch.equal(c, allchk[0]) for c in allchk))
+        assert counts_equal, "shot-sharded counts differ between ranks after the all-reduce"
 
     # ---- end to end through the public API with host buffers ---------------------------------
     host = [torch.empty((B, ld[e]), dtype=torch.uint8).pin_memory() for e in range(n_exp)]
@@ -492,6 +633,9 @@ def main():
     torch.cuda.synchronize()
     hptrs = [h.data_ptr() for h in host]
     host_out = np.zeros(n_counts, dtype=np.int64)
+    ref_out = torch.zeros(n_counts, dtype=torch.int64, device="cuda")
+    est.prepare(ptrs, rows, ld, prefix, ref_out.data_ptr(), asynchronous=True).launch()   # this rank's own counts
+    torch.cuda.synchronize()
 
     e2e_batch = est.prepare(hptrs, rows, ld, prefix, host_out)
 
@@ -500,19 +644,39 @@ def main():
         e2e_batch.launch()
 
     e2e_step()
-    ref_counts = out.cpu().numpy()
+    ref_counts = ref_out.cpu().numpy()
     assert np.array_equal(host_out, ref_counts), "e2e counts differ from the device-resident run"
-    fence()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_step()
-    fence()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    e2e_value = world * shot_parities * args.e2e_steps / e2e_s
+
+    def timed(fn, n):
+        fence()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        fence()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt.item())
+
+    e2e_s = timed(e2e_step, args.e2e_steps)
+    e2e_value = float(tot[0].item()) * args.e2e_steps / e2e_s
+    # what bounds it: the same bytes as plain pinned host-to-device copies (no kernel), all ranks at once
+    def plain_copies():
+        for e in range(n_exp):
+            dev[e].copy_(host[e], non_blocking=True)
+
+    plain_s = timed(plain_copies, args.e2e_steps)
+    # ingest path: the same records ROW-major, as Stim's sampler returns them
+    rm_host = [torch.empty((max(rows[e], 1), B), dtype=torch.uint8).pin_memory() for e in range(n_exp)]
+    for e in range(n_exp):
+        rm_host[e][:rows[e]].copy_(dev[e][:, :rows[e]].t())
+    torch.cuda.synchronize()
+    rm_out = np.zeros(n_counts, dtype=np.int64)
+    rm_batch = est.prepare([h.data_ptr() for h in rm_host], rows, [B] * n_exp, prefix, rm_out, rowmajor=True)
+    rm_batch.launch()
+    assert np.array_equal(rm_out, ref_counts), "row-major ingest counts differ from the column-major run"
+    rm_s = timed(rm_batch.launch, args.e2e_steps)
+    h2d_bytes = int(sum(rows[e] * B for e in range(n_exp)))
 
     fit = None
     if not args.no_fit:
@@ -521,39 +685,54 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        # Launch duration of the parity kernel: the timed region holds K x (memset + parity kernel +
-        # prefix kernel) back to back on one stream, so its per-step time bounds the kernel's
-        # duration from above (the two helpers take a few microseconds).  Events bracketing a single
-        # launch inside the library add the launch gap and are reported beside it.
+        # Launch duration of the parity kernel for the roofline figure: the median of CUDA events that
+        # bracket a single launch inside the library (aces_set_timing), on the stream the kernel runs on.
+        # The per-step time of the timed region (memset + parity kernel + prefix kernel back to back, and
+        # at N > 1 the exposed part of the exchange) is reported beside it.
         k_iso = sorted(kernel_ms)[len(kernel_ms) // 2]
-        k_ms = min(ms_per_step, k_iso)
+        k_ms = k_iso
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
-        if os.path.exists(tpath):
+        if WORKLOAD == "rotated_d9_wls_1e8shots" and os.path.exists(tpath):
             try:
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        e2e_ms = 1e3 * e2e_s / args.e2e_steps
+        plain_ms = 1e3 * plain_s / args.e2e_steps
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(world, fd, sizes),
-            "shots_per_s": world * shots / (ms_per_step * 1e-3),
+            "config": workload_config(world, fd, sizes, alg_bytes),
+            "shots_per_s": float(tot[1].item()) / (ms_per_step * 1e-3),
             "clocks": clocks.summary(),
+            "exchange": (None if world == 1 else
+                         {"collective": "ncclAllReduce(sum, int64) of the counts" if shot_sharded else "ncclAllGather of the per-repetition counts",
+                          "bytes_per_rank": n_counts * 8, "stream": "second stream, overlapped with the next step's kernel (two count buffers)",
+                          "counts_equal_on_all_ranks": counts_equal}),
             "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": int(sum(rows[e] * B for e in range(n_exp))) * 1,
-                    "d2h_bytes_per_step": n_counts * 8, "steps": args.e2e_steps,
-                    "ms_per_step": 1e3 * e2e_s / args.e2e_steps,
-                    "api": "aces_parity_counts with pinned host matrices and a host count vector"},
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": n_counts * 8, "steps": args.e2e_steps,
+                    "ms_per_step": e2e_ms,
+                    "api": "aces_parity_counts with pinned host matrices and a host count vector",
+                    "h2d_gbs_per_rank": h2d_bytes / (e2e_ms * 1e-3) / 1e9,
+                    "plain_h2d_ms_per_step": plain_ms, "plain_h2d_gbs_per_rank": h2d_bytes / (plain_ms * 1e-3) / 1e9,
+                    "limiter": ("pcie_h2d: the same bytes as plain pinned cudaMemcpyAsync copies, all ranks at once, take "
+                                f"{plain_ms:.1f} ms of the {e2e_ms:.1f} ms" if plain_ms > 0.8 * e2e_ms else "not the copies alone"),
+                    "cpu_binding": numa,
+                    "rowmajor_ingest": {"api": "aces_parity_counts_rowmajor: Stim-native row-major records from pinned memory "
+                                               "(contiguous copy + device transposition + the same kernel)",
+                                        "ms_per_step": 1e3 * rm_s / args.e2e_steps,
+                                        "value": float(tot[0].item()) * args.e2e_steps / rm_s}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k1::parity_kernel_v2<8,128,21,8>", "kernel_ms": k_ms,
-                         "kernel_ms_single_launch_events": k_iso,
-                         "kernel_ms_source": "CUDA events over the timed region / steps (includes the memset and "
-                                             "prefix helper kernels of each step)",
+                         "kernel": "k1::parity_kernel_v2", "kernel_ms": k_ms,
+                         "kernel_ms_source": "median of CUDA events bracketing single launches of the parity kernel inside "
+                                             "the library (its own stream), 10 launches after the timed region",
+                         "step_ms_timed_region": ms_per_step,
+                         "frac_of_step": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
                          "algorithmic_bytes_per_launch": alg_bytes},
         }
         if not args.no_cpu and world == 1:  # the CPU baseline is reported at N=1 only
