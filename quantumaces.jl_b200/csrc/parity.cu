@@ -35,6 +35,7 @@
 #include "parity_v1.cuh"
 #include "parity_v2.cuh"
 #include <cstdlib>
+#include <map>
 
 using namespace k1;
 
@@ -45,7 +46,7 @@ using namespace k1;
 // Paulis on LOCAL record bits 8 * (local column) + bit.  Narrow experiments are one group over
 // all columns; wide records (d = 17: 73 byte columns) and large experiments split into several,
 // so that every stream runs the best-tuned kernel variant (<= 25 columns, 8 rounds of 32 Paulis).
-constexpr int GROUP_COLS = 25;
+constexpr int GROUP_COLS = 22;
 constexpr int GROUP_PAULIS = 256;
 
 struct ColGroup {
@@ -670,33 +671,152 @@ int32_t aces_tables_create(aces_ctx* ctx, int32_t n_qubits, int32_t n_experiment
                 for (int c = 0; c < B; ++c) all[(size_t)c] = c;
                 ACES_CHECK(ctx, emit_group(e, members, all) == ACES_OK, "tables_create: table too large");
             } else {
-                // Paulis in the order of their first column; a group closes when the next Pauli would
-                // push it past GROUP_COLS columns or past its share of the Paulis (equal shares, so
-                // that no group is left with a handful of Paulis)
-                std::stable_sort(members.begin(), members.end(), [&](int x, int y) {
-                    return sups[(size_t)e][(size_t)x].front() < sups[(size_t)e][(size_t)y].front();
+                // Every group re-reads the columns it shares with another group, so the Paulis are
+                // partitioned to share as few as possible.  (1) The byte columns are put in an order
+                // that keeps columns joined by multi-column Paulis close together: starting from the
+                // lowest column, the next one is the unvisited column most strongly connected to the
+                // recently visited ones (a real design pairs a data qubit with an ancilla about n/2
+                // away: the order then alternates data and ancilla columns along the band).  (2) Each
+                // Pauli is keyed by the last position any of its columns takes in that order, and the
+                // sorted list is cut into groups of at most GROUP_COLS columns and an equal share of
+                // the Paulis.  (3) Local search: a column that a group needs only for Paulis which fit
+                // (columns and capacity) into other groups is dropped by moving those Paulis.
+                const size_t nm = members.size();
+                std::vector<std::vector<int32_t>> pc(nm);
+                for (size_t i = 0; i < nm; ++i) {
+                    for (int32_t q : sups[(size_t)e][(size_t)members[i]]) pc[i].push_back(q >> 3);
+                    pc[i].erase(std::unique(pc[i].begin(), pc[i].end()), pc[i].end());  // supports are sorted
+                }
+                std::vector<std::vector<std::pair<int32_t, int32_t>>> nbr((size_t)B);
+                {
+                    std::map<std::pair<int32_t, int32_t>, int32_t> w;
+                    for (size_t i = 0; i < nm; ++i)
+                        for (size_t a = 0; a < pc[i].size(); ++a)
+                            for (size_t b = a + 1; b < pc[i].size(); ++b) w[{pc[i][a], pc[i][b]}] += 1;
+                    for (const auto& kv : w) {
+                        nbr[(size_t)kv.first.first].push_back({kv.first.second, kv.second});
+                        nbr[(size_t)kv.first.second].push_back({kv.first.first, kv.second});
+                    }
+                }
+                std::vector<char> used_col((size_t)B, 0), visited((size_t)B, 0);
+                for (size_t i = 0; i < nm; ++i)
+                    for (int32_t c : pc[i]) used_col[(size_t)c] = 1;
+                std::vector<int32_t> pos((size_t)B, -1);
+                std::vector<double> score((size_t)B, 0.0);
+                int n_used = 0;
+                for (int c = 0; c < B; ++c) n_used += used_col[(size_t)c];
+                for (int k = 0; k < n_used; ++k) {
+                    int best = -1;
+                    for (int c = 0; c < B; ++c)
+                        if (used_col[(size_t)c] && !visited[(size_t)c] && score[(size_t)c] > 0.0 &&
+                            (best < 0 || score[(size_t)c] > score[(size_t)best]))
+                            best = c;
+                    if (best < 0)
+                        for (int c = 0; c < B && best < 0; ++c)
+                            if (used_col[(size_t)c] && !visited[(size_t)c]) best = c;
+                    visited[(size_t)best] = 1;
+                    pos[(size_t)best] = k;
+                    for (int c = 0; c < B; ++c) score[(size_t)c] *= 0.5;  // the band follows the frontier
+                    for (const auto& nb : nbr[(size_t)best])
+                        if (!visited[(size_t)nb.first]) score[(size_t)nb.first] += (double)nb.second;
+                }
+                std::vector<size_t> idx(nm);
+                std::vector<int32_t> last(nm, 0);
+                for (size_t i = 0; i < nm; ++i) {
+                    idx[i] = i;
+                    for (int32_t c : pc[i]) last[i] = std::max(last[i], pos[(size_t)c]);
+                }
+                std::stable_sort(idx.begin(), idx.end(), [&](size_t x, size_t y) {
+                    if (last[x] != last[y]) return last[x] < last[y];
+                    return sups[(size_t)e][(size_t)members[x]].front() < sups[(size_t)e][(size_t)members[y]].front();
                 });
-                const int n_by_count = ((int)members.size() + group_paulis - 1) / group_paulis;
-                const int share = ((int)members.size() + n_by_count - 1) / n_by_count;
-                std::vector<int> cur;
-                std::vector<int32_t> gcols;
-                for (int p : members) {
-                    std::vector<int32_t> merged = gcols;
-                    for (int32_t q : sups[(size_t)e][(size_t)p]) merged.push_back(q >> 3);
-                    std::sort(merged.begin(), merged.end());
-                    merged.erase(std::unique(merged.begin(), merged.end()), merged.end());
-                    if (!cur.empty() && ((int)merged.size() > GROUP_COLS || (int)cur.size() >= share)) {
-                        ACES_CHECK(ctx, emit_group(e, cur, gcols) == ACES_OK, "tables_create: table too large");
-                        cur.clear();
-                        merged.clear();
-                        for (int32_t q : sups[(size_t)e][(size_t)p]) merged.push_back(q >> 3);
+                const int n_by_count = ((int)nm + group_paulis - 1) / group_paulis;
+                const int share = ((int)nm + n_by_count - 1) / n_by_count;
+                std::vector<std::vector<size_t>> gm;   // members (indices into `members`) of every group
+                {
+                    std::vector<size_t> cur;
+                    std::vector<int32_t> gcols;
+                    for (size_t i : idx) {
+                        std::vector<int32_t> merged = gcols;
+                        merged.insert(merged.end(), pc[i].begin(), pc[i].end());
                         std::sort(merged.begin(), merged.end());
                         merged.erase(std::unique(merged.begin(), merged.end()), merged.end());
+                        if (!cur.empty() && ((int)merged.size() > GROUP_COLS || (int)cur.size() >= share)) {
+                            gm.push_back(cur);
+                            cur.clear();
+                            merged = pc[i];
+                        }
+                        cur.push_back(i);
+                        gcols.swap(merged);
                     }
-                    cur.push_back(p);
-                    gcols.swap(merged);
+                    if (!cur.empty()) gm.push_back(cur);
                 }
-                if (!cur.empty()) ACES_CHECK(ctx, emit_group(e, cur, gcols) == ACES_OK, "tables_create: table too large");
+                // local search (3): per group, users of every column
+                {
+                    const size_t G = gm.size();
+                    std::vector<std::vector<int32_t>> cnt(G, std::vector<int32_t>((size_t)B, 0));
+                    for (size_t g = 0; g < G; ++g)
+                        for (size_t i : gm[g])
+                            for (int32_t c : pc[i]) cnt[g][(size_t)c] += 1;
+                    bool improved = G > 1;
+                    int guard = 0;
+                    while (improved && ++guard < 4 * B * (int)G) {
+                        improved = false;
+                        for (size_t g = 0; g < G && !improved; ++g) {
+                            std::vector<int32_t> cols_g;
+                            for (int c = 0; c < B; ++c)
+                                if (cnt[g][(size_t)c] > 0) cols_g.push_back(c);
+                            std::sort(cols_g.begin(), cols_g.end(), [&](int32_t x, int32_t y) {
+                                return cnt[g][(size_t)x] != cnt[g][(size_t)y] ? cnt[g][(size_t)x] < cnt[g][(size_t)y] : x < y;
+                            });
+                            for (int32_t c : cols_g) {
+                                std::vector<int32_t> cap(G);
+                                for (size_t h = 0; h < G; ++h) cap[h] = group_paulis - (int32_t)gm[h].size();
+                                std::vector<std::pair<size_t, size_t>> plan;  // (member, destination group)
+                                bool ok = true;
+                                for (size_t i : gm[g]) {
+                                    if (std::find(pc[i].begin(), pc[i].end(), c) == pc[i].end()) continue;
+                                    bool placed = false;
+                                    for (size_t h = 0; h < G && !placed; ++h) {
+                                        if (h == g || cap[h] <= 0) continue;
+                                        bool fits = true;
+                                        for (int32_t x : pc[i]) fits = fits && cnt[h][(size_t)x] > 0;
+                                        if (fits) {
+                                            plan.push_back({i, h});
+                                            cap[h] -= 1;
+                                            placed = true;
+                                        }
+                                    }
+                                    if (!placed) { ok = false; break; }
+                                }
+                                if (!ok || plan.empty()) continue;
+                                for (const auto& mv : plan) {
+                                    gm[g].erase(std::find(gm[g].begin(), gm[g].end(), mv.first));
+                                    gm[mv.second].push_back(mv.first);
+                                    for (int32_t x : pc[mv.first]) {
+                                        cnt[g][(size_t)x] -= 1;
+                                        cnt[mv.second][(size_t)x] += 1;
+                                    }
+                                }
+                                improved = true;
+                                break;
+                            }
+                        }
+                    }
+                }
+                for (const auto& g : gm) {
+                    if (g.empty()) continue;
+                    std::vector<int> mem;
+                    std::vector<int32_t> gcols;
+                    for (size_t i : g) {
+                        mem.push_back(members[i]);
+                        gcols.insert(gcols.end(), pc[i].begin(), pc[i].end());
+                    }
+                    std::sort(mem.begin(), mem.end());
+                    std::sort(gcols.begin(), gcols.end());
+                    gcols.erase(std::unique(gcols.begin(), gcols.end()), gcols.end());
+                    ACES_CHECK(ctx, emit_group(e, mem, gcols) == ACES_OK, "tables_create: table too large");
+                }
             }
         }
         grp_ptr.push_back((int32_t)groups.size());

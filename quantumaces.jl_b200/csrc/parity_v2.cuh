@@ -21,16 +21,18 @@ namespace k1 {
 
 constexpr int V2_MAX_STAGES = 8;
 constexpr int V2_OFF_EMPTY = 64;
-constexpr int V2_OFF_DESC = 128;
-constexpr int V2_OFF_SACC = V2_OFF_DESC + V2_MAX_STAGES * 64;  // 640
+constexpr int V2_OFF_DESC = 128;                                // 16 bytes per stage: what the consumers read
+constexpr int V2_OFF_TABLES = V2_OFF_DESC + V2_MAX_STAGES * 16;  // 256
 
-// after the shared counters: the table of the third / fourth plane row of weight-3/4 Paulis
-__host__ __device__ constexpr uint32_t v2_s4_off(int rmax) { return (uint32_t)(V2_OFF_SACC + 4 * 32 * rmax); }
-// third table: the first two plane rows of every slot, for the variants whose round count does not
-// leave registers for them (RMAX > 8)
-__host__ __device__ constexpr uint32_t v2_dx_off(int rmax) { return (uint32_t)(V2_OFF_SACC + 2 * 4 * 32 * rmax); }
+// Shared tables behind the header: the third / fourth plane row of weight-3/4 Paulis (s4) and, for
+// the variants whose round count does not leave registers for them (RMAX > 8), the first two plane
+// rows of every slot (dx).  The per-Pauli shared counters of a stream change (sacc) are NOT a table
+// of their own: they alias the start of the plane area, which is dead while the consumers sit in
+// change_stream (see there).
+__host__ __device__ constexpr uint32_t v2_s4_off(int rmax) { (void)rmax; return (uint32_t)V2_OFF_TABLES; }
+__host__ __device__ constexpr uint32_t v2_dx_off(int rmax) { return (uint32_t)(V2_OFF_TABLES + 4 * 32 * rmax); }
 __host__ __device__ constexpr uint32_t v2_planes_off(int rmax) {
-    return (uint32_t)((V2_OFF_SACC + 3 * 4 * 32 * rmax + 127) & ~127);
+    return (uint32_t)((V2_OFF_TABLES + (rmax > 8 ? 2 : 1) * 4 * 32 * rmax + 127) & ~127);
 }
 
 // Byte pitch of a plane row: the SUB / 8 data bytes plus, for rows longer than one 16-byte vector,
@@ -38,6 +40,27 @@ __host__ __device__ constexpr uint32_t v2_planes_off(int rmax) {
 // quarter warp (eight different rows) fall into eight different bank groups.
 __host__ __device__ constexpr int v2_row_pitch(int sub) { return sub / 8 + (sub / 8 > 16 ? 16 : 0); }
 
+// Wait with an explicit back-off: one try_wait (which already suspends the warp for a short,
+// implementation-defined time); while the phase has not flipped, sleep SLEEP_NS before polling again.
+// A bare try_wait loop re-polls every few tens of nanoseconds: the producer warp (which waits for a
+// whole tile's worth of compute) alone burned a tenth of the CTA's issue slots that way.
+template <int SLEEP_NS>
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t addr, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    while (!done) {
+        __nanosleep(SLEEP_NS);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    }
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -94,6 +117,15 @@ __device__ __forceinline__ void v2_phase_a(uint32_t col_s, uint32_t pl_s, int nu
 }
 
 // BMAX = byte columns the plane layout is dimensioned for (B <= BMAX).
+#ifndef ACES_K1_PSLEEP
+#define ACES_K1_PSLEEP 128
+#endif
+#ifndef ACES_K1_CSLEEP
+#define ACES_K1_CSLEEP 32
+#endif
+constexpr int PRODUCER_SLEEP_NS = ACES_K1_PSLEEP;  // back-off of the producer's wait for a free stage
+constexpr int CONSUMER_SLEEP_NS = ACES_K1_CSLEEP;  // back-off of a consumer's wait for a full stage
+
 template <int NW, int SUB, int BMAX, int RMAX>
 __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 16 ? 3 : 2) parity_kernel_v2(const ParityParams P) {
     constexpr int TS = NW * SUB;
@@ -105,12 +137,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 16 ? 3 : 2) parity_kern
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = reinterpret_cast<uint64_t*>(smem + V2_OFF_EMPTY);
-    ItemDesc* sdesc = reinterpret_cast<ItemDesc*>(smem + V2_OFF_DESC);
-    uint32_t* sacc = reinterpret_cast<uint32_t*>(smem + V2_OFF_SACC);
+    int4* sdesc = reinterpret_cast<int4*>(smem + V2_OFF_DESC);
     const int B = P.B;
     const int NS = P.NS;
     constexpr uint32_t planes_bytes = (uint32_t)((8 * BMAX + 1) * RSTR);  // + one all-zero row
     const uint32_t planes_off = v2_planes_off(RMAX);
+    uint32_t* sacc = reinterpret_cast<uint32_t*>(smem + planes_off);  // aliases the planes: see change_stream
     const uint32_t raw_off = (planes_off + NW * planes_bytes + 127u) & ~127u;
     const uint32_t stage_bytes = (uint32_t)(B * CS);
     const uint32_t smem_s = smem_u32(smem);
@@ -133,7 +165,6 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 16 ? 3 : 2) parity_kern
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int p = tid; p < 32 * RMAX; p += (NW + 1) * 32) sacc[p] = 0;
     __syncthreads();
 
     if (warp == NW) {
@@ -146,8 +177,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 16 ? 3 : 2) parity_kern
         int stage = 0;
         uint32_t parity = 1;  // a fresh mbarrier passes a wait on parity 1
         for (int it = 0; it < n_my; ++it) {
-            mbar_wait(&empty[stage], parity);
-            ItemDesc* d = &sdesc[stage];
+            // Everything an item needs is worked out BEFORE the wait for its stage (the producer
+            // blocks there whenever the ring is full): the table reads from global memory are then
+            // off the refill path, and the copies go out as soon as the last consumer lets go.
+            int4 head = make_int4(0, 0, 0, 0);
+            const uint8_t* src = nullptr;
+            int64_t ld = 0;
+            uint32_t bytes = 0;
+            int ncols = 0, cols_off = 0;
             if (lane == 0) {
                 const int64_t item = i0 + it;
                 int s = prod_stream;
@@ -163,35 +200,41 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 16 ? 3 : 2) parity_kern
                 const StreamDesc sd = P.streams[s];
                 const int64_t r0 = (sd.tile_first + (item - P.item_start[s])) * TS;
                 const int64_t avail = sd.copy_rows - r0;
-                const uint32_t bytes = (uint32_t)(avail < TS ? avail : TS);
+                bytes = (uint32_t)(avail < TS ? avail : TS);
                 const int64_t lo = sd.lo - r0, hi = sd.hi - r0;
-                d->stream = s;
-                d->lo_rel = (int32_t)(lo > 0 ? lo : 0);
-                d->hi_rel = (int32_t)(hi < TS ? hi : TS);
                 // bit 0: the tile is not entirely inside the segment; bit 1: the consumers must
                 // flush their counters first (new stream, or 2^19 tiles since the last flush so
                 // that the 32-bit shared counters cannot overflow)
                 const bool flush = (s != last_stream) || (since_flush >= (1u << 19));
                 since_flush = flush ? 1u : since_flush + 1u;
                 last_stream = s;
-                d->boundary = (((lo > 0) || (hi < TS)) ? 1 : 0) | (flush ? 2 : 0);
-                d->src = sd.base + r0;
-                d->ld = sd.ld;
-                d->bytes = bytes;
-                d->ncols = sd.ncols;
-                d->cols_off = sd.cols_off;
-                mbar_arrive_expect_tx(&full[stage], bytes * (uint32_t)sd.ncols);
+                head = make_int4(s, (int32_t)(lo > 0 ? lo : 0), (int32_t)(hi < TS ? hi : TS),
+                                 (((lo > 0) || (hi < TS)) ? 1 : 0) | (flush ? 2 : 0));
+                src = sd.base + r0;
+                ld = sd.ld;
+                ncols = sd.ncols;
+                cols_off = sd.cols_off;
+            }
+            src = (const uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)src, 0);
+            ld = __shfl_sync(0xffffffffu, ld, 0);
+            bytes = __shfl_sync(0xffffffffu, bytes, 0);
+            ncols = __shfl_sync(0xffffffffu, ncols, 0);
+            cols_off = __shfl_sync(0xffffffffu, cols_off, 0);
+            // global column numbers of this lane's copies (local column c holds global column
+            // cols[c] of the sample matrix); a group has at most 41 columns
+            const int32_t* cols = P.cols + cols_off;
+            const int64_t off0 = lane < ncols ? (int64_t)__ldg(cols + lane) * ld : 0;
+            const int64_t off1 = lane + 32 < ncols ? (int64_t)__ldg(cols + lane + 32) * ld : 0;
+            mbar_wait_backoff<PRODUCER_SLEEP_NS>(smem_u32(&empty[stage]), parity);
+            if (lane == 0) {
+                sdesc[stage] = head;
+                mbar_arrive_expect_tx(&full[stage], bytes * (uint32_t)ncols);
             }
             __syncwarp();
-            const uint8_t* src = d->src;
-            const int64_t ld = d->ld;
-            const uint32_t bytes = d->bytes;
-            const int ncols = d->ncols;
-            const int32_t* cols = P.cols + d->cols_off;
             uint8_t* dst = smem + raw_off + (size_t)stage * stage_bytes;
-            // one bulk copy per byte column of the stream's column group (local column c holds
-            // global column cols[c] of the sample matrix)
-            for (int c = lane; c < ncols; c += 32)
+            if (lane < ncols) bulk_g2s(dst + lane * CS, src + off0, bytes, &full[stage], policy);
+            if (lane + 32 < ncols) bulk_g2s(dst + (lane + 32) * CS, src + off1, bytes, &full[stage], policy);
+            for (int c = lane + 64; c < ncols; c += 32)
                 bulk_g2s(dst + c * CS, src + (int64_t)__ldg(cols + c) * ld, bytes, &full[stage], policy);
             if (++stage == NS) { stage = 0; parity ^= 1u; }
         }
@@ -252,7 +295,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 16 ? 3 : 2) parity_kern
 
     // registers -> shared -> global; then (optionally) load the Pauli slice of stream `ns`
     auto change_stream = [&](int ns) {
+        // The shared counters alias the start of the plane area.  Every consumer warp is between two
+        // tiles here, so once all of them have arrived the planes are dead: clear the counters,
+        // add the registers, drain to global memory (which leaves every counter zero again, so a
+        // zero row the counters may overlap is zero when the planes come back into use).
         if (cur_stream >= 0) {
+            asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
+            for (int p = tid; p < 32 * R; p += NCT) sacc[p] = 0;
+            asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
 #pragma unroll
             for (int sl = 0; sl < RMAX; ++sl) {
                 const int r = round_of_slot(sl);
@@ -260,9 +310,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 16 ? 3 : 2) parity_kern
                 if (r >= 0 && p < E && acc[sl] != 0) atomicAdd(&sacc[p], acc[sl]);
                 acc[sl] = 0;
             }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
-        if (cur_stream >= 0) {
+            asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
             for (int p = tid; p < E; p += NCT) {
                 const uint32_t v = sacc[p];
                 if (v != 0) {
@@ -330,8 +378,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, RMAX <= 16 ? 3 : 2) parity_kern
     int stage = 0;
     uint32_t parity = 0;
     for (int it = 0; it < n_my; ++it) {
-        mbar_wait_s(full_s + 8u * (uint32_t)stage, parity);
-        const int4 d = *reinterpret_cast<const int4*>(&sdesc[stage]);  // stream, lo_rel, hi_rel, flags
+        mbar_wait_backoff<CONSUMER_SLEEP_NS>(full_s + 8u * (uint32_t)stage, parity);
+        const int4 d = sdesc[stage];  // stream, lo_rel, hi_rel, flags
         if (d.w & 2) change_stream(d.x);
         const uint32_t stage_s = raw_s + (uint32_t)stage * stage_bytes;
         bool any = true;
@@ -457,7 +505,8 @@ inline bool v2_pick(int B, int max_E, int smem_optin, V2Cfg* cfg) {
     if (B <= 3) { SUB = 512; BMAX = 7; }
     else if (B <= 7) { SUB = 256; BMAX = 7; }
     else if (B <= 13) { SUB = 128; BMAX = 13; }
-    else if (B <= 21) { SUB = 128; BMAX = 21; }  // d = 9 (B = 21): the smaller planes let the 16-round variant keep 3 CTAs/SM
+    else if (B <= 21) { SUB = 128; BMAX = 21; }  // d = 9 (B = 21)
+    else if (B <= 22) { SUB = 128; BMAX = 22; }  // the widest record (or column group) that keeps 3 CTAs/SM with two stages
     else if (B <= 25) { SUB = 128; BMAX = 25; }
     else if (B <= 41) { SUB = 128; BMAX = 41; }
     else return false;
@@ -526,6 +575,7 @@ inline int v2_grid(aces_ctx* ctx, const V2Cfg& cfg) {
                    : cfg.RMAX == 16 ? v2_grid_t<8, SUBV, BMV, 16>(ctx, cfg)     \
                                     : v2_grid_t<8, SUBV, BMV, 32>(ctx, cfg))
     if (cfg.SUB == 128 && cfg.BMAX == 21) return ACES_V2_G(128, 21);
+    if (cfg.SUB == 128 && cfg.BMAX == 22) return ACES_V2_G(128, 22);
     if (cfg.SUB == 128 && cfg.BMAX == 25) return ACES_V2_G(128, 25);
     if (cfg.SUB == 128 && cfg.BMAX == 41) return ACES_V2_G(128, 41);
     if (cfg.SUB == 128) return ACES_V2_G(128, 13);
@@ -540,6 +590,7 @@ inline int v2_launch(aces_ctx* ctx, const ParityParams& P, const V2Cfg& cfg) {
                    : cfg.RMAX == 16 ? v2_launch_t<8, SUBV, BMV, 16>(ctx, P, cfg)         \
                                     : v2_launch_t<8, SUBV, BMV, 32>(ctx, P, cfg))
     if (cfg.SUB == 128 && cfg.BMAX == 21) return ACES_V2_R(128, 21);
+    if (cfg.SUB == 128 && cfg.BMAX == 22) return ACES_V2_R(128, 22);
     if (cfg.SUB == 128 && cfg.BMAX == 25) return ACES_V2_R(128, 25);
     if (cfg.SUB == 128 && cfg.BMAX == 41) return ACES_V2_R(128, 41);
     if (cfg.SUB == 128) return ACES_V2_R(128, 13);
