@@ -317,6 +317,29 @@ int32_t aces_design_ls_covariance(aces_ctx* ctx, aces_design* design, int32_t ls
                                   const double* gate_eigenvalues, const double* covariance_log_nzval,
                                   double* sigma, double* trace, double* trace_sq);
 
+/* the figure of merit of a design at the shot weights `shot_weights` and its gradient
+ * with respect to the LOGARITHMS of the shot weights -- calc_gls_merit_grad_log /
+ * calc_wls_merit_grad_log / calc_ols_merit_grad_log (src/optimise_weights.jl:103-152, 327-391,
+ * 563-606) for ls_type 2 / 1 / 0, the inner step of gls_ / wls_ / ols_optimise_weights
+ * (src/optimise_weights.jl:160-321, 398-555, 613-790).
+ *   covariance_log_unweighted_nzval  covariance_log * get_shot_weights_factor_inv(d.shot_weights, ...)
+ *                                    (src/optimise_weights.jl:183-184) in the design's pattern (symmetric;
+ *                                    the GLS method of the reference takes its block inverse, which is
+ *                                    formed here)
+ *   shot_weights, tuple_times [T]    the (Nesterov) shot weights of this step and d.tuple_times
+ *   tt_colptr / tt_rowval / tt_nzval T'T for gate_transform_matrix T = get_transform(d, est_type) *
+ *                                    Diagonal(get_gate_eigenvalues(d)) (n_transformed x N): N x N CSC,
+ *                                    symmetric, both triangles stored
+ *   n_transformed                    size(gate_transform_matrix, 1), the N of the merit's normalisation
+ * Outputs (any may be NULL): merit, merit_grad_log [T], sigma_tr = tr(Sigma), sigma_sq_tr = tr(Sigma^2).
+ * Nothing larger than N x N is formed: the reference's M x N / M x M intermediates only enter through
+ * per-tuple sums that are inner products with N x N matrices (csrc/merit_grad.cuh). */
+int32_t aces_design_merit_grad(aces_ctx* ctx, aces_design* design, int32_t ls_type,
+                               const double* covariance_log_unweighted_nzval, const double* shot_weights,
+                               const double* tuple_times, int64_t n_transformed, const int64_t* tt_colptr,
+                               const int64_t* tt_rowval, const double* tt_nzval, int32_t index_base,
+                               double* merit, double* merit_grad_log, double* sigma_tr, double* sigma_sq_tr);
+
 /* Bookkeeping / test hook: the static task order of the persistent Cholesky kernel for an nb x nb tile
  * matrix (128 x 128 tiles) scheduled on `workers` CTAs.  out (may be NULL to query the count) receives
  * 6 ints per task: type (0 factor, 1 panel solve, 2 update, 3 / 4 their 16-row slabs), slab (+ 256 for a

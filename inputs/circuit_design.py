@@ -734,6 +734,7 @@ def generate_design(c: Circuit, tuple_set: Optional[List[List[int]]] = None, ful
     # gate index ranges in the order of get_gate_index_dict (src/noise.jl:271-277)
     fd.gate_ptr = np.asarray([c.gate_offset[g] for g in c.total_gates] + [c.N], dtype=np.int64)
     assert np.all(np.diff(fd.gate_ptr) == [c.gate_size[g] for g in c.total_gates])
+    fd.gate_types = [g[0] for g in c.total_gates]
     if full_covariance:
         fd.cov_keys, fd.cov_meas_indices, fd.cov_signs = cov_keys, cov_meas, cov_signs
         fd.cov_counts, fd.cov_rows = cov_counts, cov_rows

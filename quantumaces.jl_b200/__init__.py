@@ -12,6 +12,10 @@ from .estimate import DesignEstimator, estimate_experiment  # noqa: F401
 from . import merit  # noqa: F401
 from . import shard  # noqa: F401
 from . import project  # noqa: F401
+from . import optimise  # noqa: F401
+from .optimise import (  # noqa: F401
+    OptimOptions, calc_gls_merit_grad_log, calc_ols_merit_grad_log, calc_wls_merit_grad_log, get_transform, optimise_weights,
+)
 from .merit import (  # noqa: F401
     calc_gls_covariance_from_factor, calc_precision_matrix_from_factor, estimate_gate_eigenvalues,
     get_clipped_indices, get_clipped_mapping_lengths, DeviceDesign, estimate_gate_noise_core, mean_ensemble,

@@ -76,6 +76,10 @@ struct aces_design {
     int64_t *d_cols_off = nullptr, *d_atc_off = nullptr;
     double *Atc = nullptr, *Gt = nullptr;
     GemmDesc* g_gram = nullptr;    // [T]
+    // --- workspaces of aces_design_merit_grad (merit_grad.cuh), allocated on first use ---
+    double *W3 = nullptr, *W4 = nullptr;   // two more Np x Np matrices
+    double *mg_rows = nullptr, *mg_cu = nullptr;
+    int64_t* mg_win = nullptr;     // ct | cpt | cols_off | gt_off
     // --- tuple shard ("one large Gram"): this design works on the tuples that are on;
     //     the host sums the partial Gram matrix and right-hand sides over the shards ---
     std::vector<uint8_t> tuple_on;  // [T], all 1 by default
@@ -1093,7 +1097,7 @@ int32_t aces_design_create(aces_ctx* ctx, int32_t T, const int64_t* mapping_leng
         }
         d->n_wcols = (int64_t)w_cols.size();
         d->windowed = flops_w < 0.5 * (double)d->Mp * (double)d->Np * (double)d->Np;
-        if (d->windowed) {
+        {   // uploaded even when the fit uses the dense Gram: aces_design_merit_grad needs the per-tuple blocks
             int rcw;
 #define UPW(field, vecname) if ((rcw = dev_upload(ctx, d, &d->field, vecname)) != ACES_OK) return fail(rcw)
             UPW(w_blk, w_blk); UPW(w_ptr, w_ptr); UPW(w_row, w_row); UPW(w_val, w_val); UPW(w_cols, w_cols);
@@ -1577,3 +1581,5 @@ int32_t aces_design_ls_covariance(aces_ctx* ctx, aces_design* d, int32_t ls_type
 }
 
 }  // extern "C"
+
+#include "merit_grad.cuh"

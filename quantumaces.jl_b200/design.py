@@ -48,6 +48,7 @@ class FlatDesign:
     # gates as groups of consecutive gate eigenvalues (GateIndex.indices, src/noise.jl:16-24): gate g owns
     # columns gate_ptr[g] .. gate_ptr[g+1]-1 of the design matrix (1, 3 or 15 of them)
     gate_ptr: Optional[np.ndarray] = None
+    gate_types: Optional[List[str]] = None   # Gate.type of every gate, in the order of gate_ptr (src/tableau.jl:88-92)
     name: str = ""
 
     @property

@@ -27,6 +27,8 @@
 #        slices, split projection); NoiseEstimate bookkeeping through the reference's own helpers
 #   calc_covariance(d, eigenvalues_ensemble, covariance_ensemble; ...)   src/merit.jl:206-291   (S3)
 #   calc_gls_covariance / calc_wls_covariance / calc_ols_covariance(d, covariance_log)  src/merit.jl:556-629 (S4)
+#   gls_ / wls_ / ols_optimise_weights(d, covariance_log; options)   src/optimise_weights.jl:160-790   the
+#        descent loop restated once, its gradient (calc_*_merit_grad_log) on the GPU        (f3)
 #   S1  estimate_experiment(::Matrix{UInt8}, ...)             src/estimate.jl:284-301
 #   S2  estimate_gate_eigenvalues(A, F, est; constrain)        src/estimate.jl:492-524 (and the OLS form)
 # sparse_covariance_inv_factor(covariance_log, lengths) (src/merit.jl:378-427) has no Design argument
@@ -797,6 +799,124 @@ ls_covariance_design(d::Design, covariance_log::SparseMatrixCSC{Float64, Int}, l
     calc_ls_covariance(device_design(d), covariance_log; ls_type = ls_type, want_matrix = true)[1]
 
 # ---------------------------------------------------------------------------------------------
+# Shot-weight optimisation (src/optimise_weights.jl) -- SURVEY.md section 8f, row f3
+# ---------------------------------------------------------------------------------------------
+
+"""
+    merit_grad_log(dd, ls_type, shot_weights, covariance_log_unweighted, gate_transform_matrix)
+
+calc_gls_merit_grad_log / calc_wls_merit_grad_log / calc_ols_merit_grad_log
+(src/optimise_weights.jl:103-152, 327-391, 563-606) -> (merit_grad_log, merit) through
+aces_design_merit_grad.  Every estimator takes covariance_log_unweighted itself (the GLS method of the
+reference takes its block inverse, the OLS method three dense matrices built from it).
+"""
+function merit_grad_log(dd::DeviceDesign, ls_type::Symbol, shot_weights::Vector{Float64},
+                        covariance_log_unweighted::SparseMatrixCSC{Float64, Int},
+                        gate_transform_matrix::SparseMatrixCSC{Float64, Int})
+    kind = ls_type == :ols ? 0 : ls_type == :wls ? 1 : 2
+    nz = [covariance_log_unweighted[dd.cov_rowval[e] + 1, c] for c in 1:dd.M for e in (dd.cov_colptr[c] + 1):dd.cov_colptr[c + 1]]
+    tt = SparseMatrixCSC{Float64, Int}(gate_transform_matrix' * gate_transform_matrix)
+    tt_colptr = Int64.(tt.colptr); tt_rowval = Int64.(tt.rowval); tt_nzval = Float64.(tt.nzval)
+    tau = Float64.(dd.d.tuple_times)
+    grad = Vector{Float64}(undef, length(shot_weights))
+    merit = Ref{Float64}(0.0); tr = Ref{Float64}(0.0); trsq = Ref{Float64}(0.0)
+    GC.@preserve nz shot_weights tau tt_colptr tt_rowval tt_nzval grad begin
+        check(ccall((:aces_design_merit_grad, LIB[]), Int32,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int64}, Ptr{Int64},
+             Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            CTX[], dd.handle, Int32(kind), nz, shot_weights, tau, Int64(size(gate_transform_matrix, 1)), tt_colptr,
+            tt_rowval, tt_nzval, Int32(1), merit, grad, tr, trsq))
+    end
+    return (grad, merit[])
+end
+
+"""
+    ls_optimise_weights(d, covariance_log; options)
+
+gls_ / wls_ / ols_optimise_weights (src/optimise_weights.jl:160-321, 398-555, 613-790): the reference's
+Nesterov descent on the logarithms of the shot weights, restated once for the three estimators, with the
+gradient of every step on the GPU.
+"""
+function ls_optimise_weights(d::Design, covariance_log::SparseMatrixCSC{Float64, Int}, ls_type::Symbol;
+                             options = QuantumACES.OptimOptions())
+    @assert options.ls_type == ls_type "Inappropriate least squares optimisation type $(options.ls_type) supplied."
+    est_type = options.est_type
+    est_weight = options.est_weight
+    momentum = options.momentum
+    convergence_steps = options.convergence_steps
+    convergence_threshold = options.convergence_threshold
+    dd = device_design(d)
+    tuple_number = length(d.tuple_set)
+    shot_weights = QuantumACES.project_simplex(d.shot_weights)
+    mapping_lengths = length.(d.mapping_ensemble)
+    covariance_log_unweighted = SparseMatrixCSC{Float64, Int}(covariance_log *
+        QuantumACES.get_shot_weights_factor_inv(d.shot_weights, d.tuple_times, mapping_lengths))
+    gate_eigenvalues_diag = sparse(Diagonal(QuantumACES.get_gate_eigenvalues(d)))
+    transforms = (est_type == :sum || est_type == :prod) ?
+        [QuantumACES.get_transform(d, :ordinary) * gate_eigenvalues_diag, QuantumACES.get_transform(d, :relative) * gate_eigenvalues_diag] :
+        [QuantumACES.get_transform(d, est_type) * gate_eigenvalues_diag]
+    function grad_and_merit(w::Vector{Float64})
+        res = [merit_grad_log(dd, ls_type, w, covariance_log_unweighted, SparseMatrixCSC{Float64, Int}(tm)) for tm in transforms]
+        if est_type == :sum
+            return (est_weight * res[1][1] + (1 - est_weight) * res[2][1], est_weight * res[1][2] + (1 - est_weight) * res[2][2])
+        elseif est_type == :prod
+            merit = res[1][2]^(est_weight) * res[2][2]^(1 - est_weight)
+            return (merit * (est_weight * res[1][1] / res[1][2] + (1 - est_weight) * res[2][1] / res[2][2]), merit)
+        else
+            return res[1]
+        end
+    end
+    stepping = true
+    step = 1
+    recently_pruned = 0
+    recently_zeroed = 0
+    scaled_learning_rate = options.learning_rate
+    old_shot_weights = deepcopy(shot_weights)
+    velocity = zeros(tuple_number)
+    merit_descent = Vector{Float64}()
+    while stepping
+        nesterov_log_shot_weights = -log.(shot_weights) + momentum * velocity
+        nesterov_shot_weights = exp.(-nesterov_log_shot_weights) / sum(exp.(-nesterov_log_shot_weights))
+        (merit_grad, merit) = grad_and_merit(nesterov_shot_weights)
+        push!(merit_descent, merit)
+        velocity = momentum * velocity - scaled_learning_rate * merit_grad
+        log_shot_weights_update = -log.(shot_weights) + velocity
+        shot_weights_update = exp.(-log_shot_weights_update) / sum(exp.(-log_shot_weights_update))
+        if (length(merit_descent) >= 2) && (merit_descent[end] > merit_descent[end - 1])
+            shot_weights = old_shot_weights
+            velocity = zeros(tuple_number)
+            if recently_zeroed > 0
+                scaled_learning_rate /= options.learning_rate_scale_factor
+            end
+            recently_pruned += 1
+            recently_zeroed = convergence_steps
+        else
+            old_shot_weights = deepcopy(nesterov_shot_weights)
+            shot_weights = shot_weights_update
+        end
+        if step >= convergence_steps
+            merit_converged = all([abs(1 - merit_descent[idx_2] / merit_descent[idx_1]) < convergence_steps * convergence_threshold
+                                   for idx_1 in (step - convergence_steps + 1):step for idx_2 in (step - convergence_steps + 1):step]) &&
+                              (abs(1 - merit_descent[end - 1] / merit_descent[end]) < convergence_threshold)
+        else
+            merit_converged = false
+        end
+        if (merit_converged || step >= options.max_steps) && recently_pruned == 0
+            stepping = false
+        else
+            step += 1
+            recently_pruned > 0 && (recently_pruned -= 1)
+            recently_zeroed > 0 && (recently_zeroed -= 1)
+        end
+    end
+    shot_weights_factor = QuantumACES.get_shot_weights_factor(shot_weights, d.tuple_times, mapping_lengths)
+    covariance_log_new = SparseMatrixCSC{Float64, Int}(covariance_log_unweighted * shot_weights_factor)
+    d_new = QuantumACES.Accessors.@set d.shot_weights = QuantumACES.project_simplex(shot_weights)
+    d_new = QuantumACES.Accessors.@set d_new.ls_type = ls_type
+    return (d_new::Design, covariance_log_new::SparseMatrixCSC{Float64, Int}, merit_descent::Vector{Float64})
+end
+
+# ---------------------------------------------------------------------------------------------
 # install!: method overwrite inside QuantumACES (SURVEY.md section 8b, option ii)
 # ---------------------------------------------------------------------------------------------
 
@@ -853,6 +973,13 @@ function install!()
         calc_gls_covariance(d::Design, covariance_log::SparseMatrixCSC{Float64, Int}) = $(ls_covariance_design)(d, covariance_log, :gls)
         calc_wls_covariance(d::Design, covariance_log::SparseMatrixCSC{Float64, Int}) = $(ls_covariance_design)(d, covariance_log, :wls)
         calc_ols_covariance(d::Design, covariance_log::SparseMatrixCSC{Float64, Int}) = $(ls_covariance_design)(d, covariance_log, :ols)
+        # f3: the descent loops of the shot-weight optimiser (src/optimise_weights.jl:160-321, 398-555, 613-790)
+        gls_optimise_weights(d::Design, covariance_log::SparseMatrixCSC{Float64, Int}; options::OptimOptions = OptimOptions()) =
+            $(ls_optimise_weights)(d, covariance_log, :gls; options = options)
+        wls_optimise_weights(d::Design, covariance_log::SparseMatrixCSC{Float64, Int}; options::OptimOptions = OptimOptions()) =
+            $(ls_optimise_weights)(d, covariance_log, :wls; options = options)
+        ols_optimise_weights(d::Design, covariance_log::SparseMatrixCSC{Float64, Int}; options::OptimOptions = OptimOptions()) =
+            $(ls_optimise_weights)(d, covariance_log, :ols; options = options)
     end
     return nothing
 end
