@@ -340,6 +340,36 @@ int32_t aces_design_merit_grad(aces_ctx* ctx, aces_design* design, int32_t ls_ty
                                const int64_t* tt_rowval, const double* tt_nzval, int32_t index_base,
                                double* merit, double* merit_grad_log, double* sigma_tr, double* sigma_sq_tr);
 
+/* ---- calc_merit tail ------------------------------------------------------
+ *
+ * All eigenvalues (ascending) of the symmetric n x n matrix a -- drop-in for
+ * LinearAlgebra.eigvals(::Symmetric{Float64, Matrix{Float64}}) (LAPACK dsyevr, JOBZ = 'N') as calc_merit
+ * calls it nine times per design (src/merit.jl:954-986).  a: column-major, leading dimension lda, host or
+ * device; like Julia's Symmetric (uplo = :U) only the UPPER triangle is read.  Householder
+ * tridiagonalisation (panels of 64 reflectors in one persistent kernel each, trailing update on the FP64
+ * tensor pipe) and bisection on Sturm counts; absolute accuracy eps * ||a|| like LAPACK's.  Orders up to
+ * 192 rows per SM (28 416 on a B200) are supported. */
+int32_t aces_symmetric_eigenvalues(aces_ctx* ctx, int64_t n, const double* a, int64_t lda, double* eigenvalues);
+
+/* The numeric core of calc_merit(d::Design) (src/merit.jl:925-1006) for a design with full covariance data:
+ * for ls_type GLS, WLS, OLS (in this order) the estimator covariance Sigma of src/merit.jl:556-629 (as
+ * aces_design_ls_covariance), its marginal and relative transforms T Sigma T' (get_marginal_gate_covariance /
+ * get_relative_gate_covariance, src/merit.jl:477-509) and the eigenvalues of all three, ascending.
+ *   gate_eigenvalues [N], covariance_log_nzval   as for aces_design_ls_covariance
+ *   marg_* / rel_*   get_transform(d, :marginal) / (d, :relative) (src/noise.jl:689-741) as Julia stores them:
+ *                    SparseMatrixCSC n_marginal x N / n_relative x N (colptr [N+1], rowval, nzval)
+ *   cov_eigenvalues  [3][N + n_marginal + n_relative]: per estimator the ordinary, marginal and relative spectra
+ *                    (the Merit fields *_cov_eigenvalues; nrmse_moments(::Vector) of src/merit.jl:684-692 is
+ *                    two sums over them and stays with the host)
+ *   gram_extremes    [2] (may be NULL): largest and smallest eigenvalue of d.matrix' * d.matrix, whose square
+ *                    roots give design_matrix_cond_num and design_matrix_pinv_norm (src/merit.jl:993-1006; the
+ *                    reference asks ARPACK for the two extremes, here the whole spectrum is computed). */
+int32_t aces_design_merit(aces_ctx* ctx, aces_design* design, const double* gate_eigenvalues,
+                          const double* covariance_log_nzval, int64_t n_marginal, const int64_t* marg_colptr,
+                          const int64_t* marg_rowval, const double* marg_nzval, int64_t n_relative,
+                          const int64_t* rel_colptr, const int64_t* rel_rowval, const double* rel_nzval,
+                          int32_t index_base, double* cov_eigenvalues, double* gram_extremes);
+
 /* Bookkeeping / test hook: the static task order of the persistent Cholesky kernel for an nb x nb tile
  * matrix (128 x 128 tiles) scheduled on `workers` CTAs.  out (may be NULL to query the count) receives
  * 6 ints per task: type (0 factor, 1 panel solve, 2 update, 3 / 4 their 16-row slabs), slab (+ 256 for a

@@ -19,5 +19,5 @@ from .optimise import (  # noqa: F401
 from .merit import (  # noqa: F401
     calc_gls_covariance_from_factor, calc_precision_matrix_from_factor, estimate_gate_eigenvalues,
     get_clipped_indices, get_clipped_mapping_lengths, DeviceDesign, estimate_gate_noise_core, mean_ensemble,
-    nrmse_moments, estimate_gate_noise_projected,
+    nrmse_moments, estimate_gate_noise_projected, calc_merit, eigvals, nrmse_moments_eigenvalues,
 )

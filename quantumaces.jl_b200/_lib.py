@@ -73,6 +73,8 @@ SIGNATURES = {
     "aces_design_fit": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, C.c_double, _i32, _vp]),
     "aces_design_ls_covariance": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "aces_design_merit_grad": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "aces_symmetric_eigenvalues": (_i32, [_vp, _i64, _vp, _i64, _vp]),
+    "aces_design_merit": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp]),
     "aces_design_set_tuple_shard": (_i32, [_vp, _vp, _vp]),
     "aces_design_fit_begin": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, C.c_double]),
     "aces_design_fit_buffers": (_i32, [_vp, _p(_vp), _p(_i64), _p(_vp), _p(_i64)]),

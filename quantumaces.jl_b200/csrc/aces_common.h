@@ -55,6 +55,7 @@ struct aces_ctx {
     DevBuf d_work[8];
     DevBuf d_flags;    // inter-CTA flags of the persistent triangular solves
     DevBuf d_dag_trace;
+    DevBuf d_eig, d_eigA;  // workspace / matrix copy of the symmetric eigenvalue solver (eigen.cu)
     DevBuf d_dag_tasks, d_dag_state;  // task list (cached per matrix size) and counters of the persistent Cholesky
     int dag_nb = 0, dag_grid = 0, dag_ntasks = 0, dag_nlist = 0;
 };

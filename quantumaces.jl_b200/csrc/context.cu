@@ -136,7 +136,7 @@ int32_t aces_destroy(aces_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
     if (ctx->aux2_stream) cudaStreamSynchronize(ctx->aux2_stream);
-    DevBuf* dev[] = {&ctx->d_arena, &ctx->d_raw, &ctx->d_tdesc, &ctx->d_dag_tasks, &ctx->d_dag_state, &ctx->d_dag_trace, &ctx->d_streams, &ctx->d_seg, &ctx->d_odd, &ctx->d_flags};
+    DevBuf* dev[] = {&ctx->d_arena, &ctx->d_raw, &ctx->d_tdesc, &ctx->d_dag_tasks, &ctx->d_dag_state, &ctx->d_dag_trace, &ctx->d_streams, &ctx->d_seg, &ctx->d_odd, &ctx->d_flags, &ctx->d_eig, &ctx->d_eigA};
     for (DevBuf* b : dev)
         if (b->ptr) cudaFree(b->ptr);
     for (DevBuf& b : ctx->d_work)

@@ -1522,13 +1522,12 @@ int32_t aces_design_precision_blocks(aces_ctx* ctx, aces_design* d, int32_t ls_t
     return ACES_OK;
 }
 
-int32_t aces_design_ls_covariance(aces_ctx* ctx, aces_design* d, int32_t ls_type, const double* gate_eigenvalues,
-                                  const double* covariance_log_nzval, double* sigma, double* trace,
-                                  double* trace_sq) {
-    ACES_TRY(check_design(ctx, d, "design_ls_covariance"));
-    ACES_CHECK(ctx, !d->sharded, "design_ls_covariance: the design is a tuple shard");
-    ACES_CHECK(ctx, ls_type >= 0 && ls_type <= 2, "design_ls_covariance: ls_type must be 0 (OLS), 1 (WLS) or 2 (GLS)");
-    ACES_CHECK(ctx, gate_eigenvalues && covariance_log_nzval, "design_ls_covariance: NULL argument");
+}  // extern "C"
+
+// calc_gls / wls / ols_covariance on the device: *S_out is the N x N estimator covariance inside an
+// Np x Np buffer of the design (d->G for GLS, d->Cn otherwise), exactly symmetric.
+int ls_covariance_device(aces_ctx* ctx, aces_design* d, int32_t ls_type, const double* gate_eigenvalues,
+                         const double* covariance_log_nzval, double** S_out) {
     d->est_ls_type = -1;
     const bool gls = ls_type == 2;
     ACES_TRY(ensure_workspaces(ctx, d, gls, gls, true, !gls));
@@ -1536,8 +1535,9 @@ int32_t aces_design_ls_covariance(aces_ctx* ctx, aces_design* d, int32_t ls_type
     FitVectors fv = fit_vectors(d);
     const int64_t Np = d->Np, N = d->N;
     std::vector<int64_t> kept(d->m.begin(), d->m.end());
-    ACES_CUDA(ctx, cudaMemcpyAsync(d->covval, covariance_log_nzval, sizeof(double) * (size_t)d->nnz_cov, cudaMemcpyDefault,
-                                   ctx->stream));
+    if (covariance_log_nzval != d->covval)
+        ACES_CUDA(ctx, cudaMemcpyAsync(d->covval, covariance_log_nzval, sizeof(double) * (size_t)d->nnz_cov,
+                                       cudaMemcpyDefault, ctx->stream));
     ACES_TRY(prepare_estimator(ctx, d, ls_type, d->covval, nullptr, kept, fv));
     // inv(G) = X' X with X = inv(L): lower tiles on the tensor pipe, then mirrored
     ACES_TRY(dense::trtri(ctx, Np, d->G, Np, d->dinvG, d->Xn, Np));
@@ -1564,11 +1564,29 @@ int32_t aces_design_ls_covariance(aces_ctx* ctx, aces_design* d, int32_t ls_type
     double* gdev = fv.t2;
     ACES_CUDA(ctx, cudaMemcpyAsync(gdev, gate_eigenvalues, sizeof(double) * (size_t)N, cudaMemcpyDefault, ctx->stream));
     scale_sym_kernel<<<148 * 8, 256, 0, ctx->stream>>>(N, S, Np, gdev);
+    ACES_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    *S_out = S;
+    return ACES_OK;
+}
+
+extern "C" {
+
+int32_t aces_design_ls_covariance(aces_ctx* ctx, aces_design* d, int32_t ls_type, const double* gate_eigenvalues,
+                                  const double* covariance_log_nzval, double* sigma, double* trace,
+                                  double* trace_sq) {
+    ACES_TRY(check_design(ctx, d, "design_ls_covariance"));
+    ACES_CHECK(ctx, !d->sharded, "design_ls_covariance: the design is a tuple shard");
+    ACES_CHECK(ctx, ls_type >= 0 && ls_type <= 2, "design_ls_covariance: ls_type must be 0 (OLS), 1 (WLS) or 2 (GLS)");
+    ACES_CHECK(ctx, gate_eigenvalues && covariance_log_nzval, "design_ls_covariance: NULL argument");
+    const int64_t Np = d->Np, N = d->N;
+    double* S = nullptr;
+    ACES_TRY(ls_covariance_device(ctx, d, ls_type, gate_eigenvalues, covariance_log_nzval, &S));
     double* mom = d->mom;
     moments_kernel<<<148 * 4, 256, 0, ctx->stream>>>(N, S, Np, mom);
     moments_final_kernel<<<1, 32, 0, ctx->stream>>>(148 * 4, mom);
     ACES_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 3;
+    ctx->launches += 2;
     double hm[2] = {0.0, 0.0};
     ACES_CUDA(ctx, cudaMemcpyAsync(hm, mom, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (sigma)
@@ -1583,3 +1601,4 @@ int32_t aces_design_ls_covariance(aces_ctx* ctx, aces_design* d, int32_t ls_type
 }  // extern "C"
 
 #include "merit_grad.cuh"
+#include "merit_tail.cuh"

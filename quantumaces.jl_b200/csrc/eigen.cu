@@ -1,0 +1,602 @@
+// eigen.cu -- all eigenvalues of a dense symmetric FP64 matrix on the GPU.
+//
+// Replaces LinearAlgebra.eigvals(::Symmetric{Float64, Matrix{Float64}}) (LAPACK dsyevr, JOBZ = 'N') as
+// calc_merit calls it nine times per design (src/merit.jl:954-986).  Two stages:
+//
+//  1. Householder tridiagonalisation Q' A Q = T, blocked like LAPACK's dsytrd / dlatrd: the reflectors of a
+//     panel of NB columns are accumulated as A - V W' - W V' and applied to the trailing matrix by one
+//     DMMA GEMM per panel (dense::gemm, K = 2 NB); inside the panel every column costs one product of the
+//     (not yet updated) trailing matrix with the new reflector -- the memory-bound half of the flops:
+//     sum_j 8 (n - j)^2 bytes = 8 n^3 / 3 read once each.  A panel is ONE persistent cooperative kernel
+//     (a CTA per SM, two grid barriers per column): the rows of V and W a CTA owns stay in its shared
+//     memory for the whole panel, the trailing product is cut into 128-row x CW-column items dealt round
+//     robin, and every reduction runs in a fixed order (results are deterministic).
+//  2. Eigenvalues of T by bisection on Sturm counts (LAPACK dstebz's recurrence with its pivmin guard),
+//     one thread per eigenvalue; absolute accuracy eps * ||T||, as dsyevr's.
+//
+// The matrix is held in full (both triangles) so that the trailing product is a plain streaming read;
+// it is scaled by a power of two to unit max-norm first (exact), as dsyev scales badly scaled input.
+#include <algorithm>
+#include <cmath>
+
+#include "aces_common.h"
+#include "dense.cuh"
+#include "eigen.cuh"
+
+namespace eigen {
+
+namespace {
+
+constexpr int NB = 64;            // reflectors per panel
+constexpr int THREADS = 512;
+constexpr int NWARP = THREADS / 32;
+constexpr int RB = 128;           // rows of one item of the trailing product
+constexpr int KS = 8;             // the panel passes cut the NB reflectors into KS slices of KW
+constexpr int KW = NB / KS;
+constexpr int P1 = 2 * NB + 2;    // per-CTA partials of phase A: [0] |x|^2, [1 + k] V'x, [1 + NB + k] W'x
+constexpr int MAX_CC = 32;        // column chunks of the trailing product (partial result vectors)
+constexpr int MAX_SL = 6;         // 32-row slots a CTA can own (shared-memory bound)
+
+struct PanelArgs {
+    const double* A;
+    int64_t lda;
+    int n, Np;
+    int j0, ncols;
+    double *P, *Q;      // Np x 2NB each: P = [V | W], Q = [W | V]
+    double *d, *e;
+    double* ypart;      // [MAX_CC][Np]
+    double* part1;      // [grid][P1]
+    double* part2;      // [grid]
+    double* pq;         // [2 NB]: V'v then W'v
+    unsigned* bar;
+    int SL, CW;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// all CTAs are co-resident (cooperative launch): a monotonic arrival counter, zeroed before the launch
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& round) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        round += gridDim.x;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (ld_acquire_u32(bar) < round) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double warp_sum(double t) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return t;
+}
+
+// sum over the CTAs of one entry of a per-CTA partial table, by one warp, in a fixed order
+__device__ __forceinline__ double sum_over_ctas(const double* tab, int stride, int G, int lane) {
+    double s = 0.0;
+    for (int c = lane; c < G; c += 32) s += __ldcg(tab + (int64_t)c * stride);
+    return warp_sum(s);
+}
+
+size_t panel_smem(int SL) {
+    const size_t R = (size_t)SL * 32;
+    const size_t un = std::max((size_t)NWARP * RB, (size_t)KS * R + (size_t)SL * 2 * NB);
+    return sizeof(double) * (2 * NB * R + R + 4 * NB + 16 + un);
+}
+
+__global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    const int R = a.SL * 32;
+    double* Vs = sm;                 // [NB][R] rows of V this CTA owns
+    double* Ws = Vs + NB * R;        // [NB][R]
+    double* xs = Ws + NB * R;        // [R] the current column (before normalisation)
+    double* Vrow = xs + R;           // V[j, 0..jj) of the column being reduced
+    double* Wrow = Vrow + NB;
+    double* ps = Wrow + NB;          // W'v
+    double* qs = ps + NB;            // V'v
+    double* scal = qs + NB;          // tau, scale, alpha, beta, alpha2, scratch
+    double* un = scal + 16;
+    double* red = un;                // [KS][R]
+    double* dots = red + KS * R;     // [SL][2 NB]
+    double* redg = un;               // [NWARP][RB] (phase B only)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int n = a.n, Np = a.Np;
+    unsigned round = 0;
+    // global row of local row li
+    auto grow = [&](int li) -> int64_t { return ((int64_t)((li >> 5) * G + cta)) * 32 + (li & 31); };
+
+    for (int jj = 0; jj < a.ncols; ++jj) {
+        const int j = a.j0 + jj;
+        const bool reflect = j + 2 < n;
+        // ---------------- phase A: column j with the panel's reflectors applied -----------------------
+        for (int u = warp; u < a.SL * KS; u += NWARP) {
+            const int li = (u / KS) * 32 + lane, ks = u % KS;
+            const int k1 = min(jj, (ks + 1) * KW);
+            double c = 0.0;
+            for (int k = ks * KW; k < k1; ++k) c += Vs[k * R + li] * Wrow[k] + Ws[k * R + li] * Vrow[k];
+            red[ks * R + li] = c;
+        }
+        __syncthreads();
+        double nrm = 0.0;
+        if (tid < R) {
+            const int64_t i = grow(tid);
+            double x = 0.0;
+            if (i >= j && i < n) {
+                double c = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) c += red[ks * R + tid];
+                x = a.A[i + (int64_t)j * a.lda] - c;
+                if (i == j) {
+                    a.d[j] = x;
+                    x = 0.0;
+                } else if (reflect) {
+                    __stcg(a.P + i + (int64_t)jj * Np, x);
+                    if (i >= j + 2) nrm = x * x;
+                } else if (i == j + 1) {
+                    a.e[j] = x;
+                }
+            }
+            xs[tid] = x;
+        }
+        if (!reflect) {
+            // the last two columns only give d (and e): no reflector (a zero column of V and W).  Uniform
+            // over the grid.  The next column needs row j + 1 of V and W, whose newest entry was stored by
+            // its owner after the last barrier: one more barrier, then read the row from global memory.
+            if (tid < R) Vs[jj * R + tid] = Ws[jj * R + tid] = 0.0;
+            grid_barrier(a.bar, round);
+            if (tid <= jj) {
+                const bool have = tid < jj && j + 1 < n;
+                Vrow[tid] = have ? __ldcg(a.P + (j + 1) + (int64_t)tid * Np) : 0.0;
+                Wrow[tid] = have ? __ldcg(a.P + (j + 1) + (int64_t)(NB + tid) * Np) : 0.0;
+            }
+            __syncthreads();
+            continue;
+        }
+        nrm = warp_sum(nrm);
+        if (lane == 0 && warp < a.SL) scal[8 + warp] = nrm;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int w = 0; w < a.SL; ++w) s += scal[8 + w];
+            __stcg(a.part1 + (int64_t)cta * P1, s);
+        }
+        for (int u = warp; u < a.SL * KS; u += NWARP) {
+            const int slot = u / KS, ks = u % KS, li = slot * 32 + lane;
+            const int k1 = min(jj, (ks + 1) * KW);
+            const double x = xs[li];
+            for (int k = ks * KW; k < k1; ++k) {
+                const double tv = warp_sum(Vs[k * R + li] * x);
+                const double tw = warp_sum(Ws[k * R + li] * x);
+                if (lane == 0) {
+                    dots[slot * 2 * NB + k] = tv;
+                    dots[slot * 2 * NB + NB + k] = tw;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < 2 * NB && (tid & (NB - 1)) < jj) {
+            double s = 0.0;
+            for (int slot = 0; slot < a.SL; ++slot) s += dots[slot * 2 * NB + tid];
+            __stcg(a.part1 + (int64_t)cta * P1 + 1 + tid, s);
+        }
+        grid_barrier(a.bar, round);
+
+        // ---------------- phase B: the reflector, then (trailing matrix) * v ---------------------------
+        if (warp == 0) {
+            const double nrm2 = sum_over_ctas(a.part1, P1, G, lane);
+            if (lane == 0) {
+                const double alpha = __ldcg(a.P + (j + 1) + (int64_t)jj * Np);
+                double tau = 0.0, scale = 0.0, beta = alpha;
+                if (nrm2 > 0.0) {
+                    beta = -copysign(sqrt(alpha * alpha + nrm2), alpha);
+                    tau = (beta - alpha) / beta;
+                    scale = 1.0 / (alpha - beta);
+                }
+                scal[0] = tau;
+                scal[1] = scale;
+                scal[2] = alpha;
+                scal[3] = beta;
+                if (cta == 0) a.e[j] = beta;
+            }
+        }
+        __syncthreads();
+        const double tau = scal[0], scale = scal[1];
+        // entries of V'v and W'v: one warp each, spread over the grid
+        for (int e = cta, w = 0; e < 2 * NB; e += G, ++w) {
+            if ((e & (NB - 1)) < jj && (w % NWARP) == warp) {
+                const double s = sum_over_ctas(a.part1 + 1 + e, P1, G, lane);
+                if (lane == 0) {
+                    const double coef = __ldcg(a.P + (j + 1) + (int64_t)e * Np);
+                    __stcg(a.pq + e, scale * s + coef * (1.0 - scale * scal[2]));
+                }
+            }
+        }
+        auto vcol = [&](int c) -> double {
+            if (c <= j || c >= n) return 0.0;
+            if (c == j + 1) return 1.0;
+            return __ldcg(a.P + c + (int64_t)jj * Np) * scale;
+        };
+        {
+            const int CW = a.CW;
+            const int rb0 = (j + 1) / RB, nrb = (n + RB - 1) / RB - rb0;
+            const int cc0 = (j + 1) / CW, ncc = (n + CW - 1) / CW - cc0;
+            const int items = nrb * ncc;
+            double yv = 0.0;
+            for (int t = cta; t < items; t += G) {
+                const int rb = rb0 + t / ncc, cc = cc0 + t % ncc;
+                const double* Ab = a.A + (int64_t)rb * RB + 2 * lane;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                for (int sub = cc * CW; sub < (cc + 1) * CW && sub < Np; sub += 128) {
+                    // this warp's eight columns of the 128: sub + warp + 16 m
+                    const double vv = vcol(sub + warp + 16 * (lane & 7));
+                    double2 lo[8], hi[8];
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        const double* p = Ab + (int64_t)(sub + warp + 16 * m) * a.lda;
+                        lo[m] = __ldg(reinterpret_cast<const double2*>(p));
+                        hi[m] = __ldg(reinterpret_cast<const double2*>(p + 64));
+                    }
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        const double v = __shfl_sync(0xffffffffu, vv, m);
+                        a0 += lo[m].x * v;
+                        a1 += lo[m].y * v;
+                        a2 += hi[m].x * v;
+                        a3 += hi[m].y * v;
+                    }
+                }
+                redg[warp * RB + 2 * lane] = a0;
+                redg[warp * RB + 2 * lane + 1] = a1;
+                redg[warp * RB + 64 + 2 * lane] = a2;
+                redg[warp * RB + 64 + 2 * lane + 1] = a3;
+                __syncthreads();
+                if (tid < RB) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int w = 0; w < NWARP; ++w) s += redg[w * RB + tid];
+                    const int r = rb * RB + tid;
+                    __stcg(a.ypart + (int64_t)cc * Np + r, s);
+                    yv += vcol(r) * s;
+                }
+                __syncthreads();
+            }
+            // v'(A v) partial of this CTA
+            yv = warp_sum(yv);
+            if (lane == 0 && warp < RB / 32) scal[8 + warp] = yv;
+            __syncthreads();
+            if (tid == 0) __stcg(a.part2 + cta, (scal[8] + scal[9]) + (scal[10] + scal[11]));
+        }
+        grid_barrier(a.bar, round);
+
+        // ---------------- phase C: w = tau (A v - V (W'v) - W (V'v)) - (tau/2)(w'v) v --------------------
+        if (tid < jj) {
+            qs[tid] = __ldcg(a.pq + tid);
+            ps[tid] = __ldcg(a.pq + NB + tid);
+        }
+        if (warp == 0) {
+            const double yv = sum_over_ctas(a.part2, 1, G, lane);
+            if (lane == 0) scal[5] = yv;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double t = 0.0;
+            for (int k = lane; k < jj; k += 32) t += ps[k] * qs[k];
+            t = warp_sum(t);
+            if (lane == 0) scal[4] = -0.5 * tau * (tau * (scal[5] - 2.0 * t));
+        }
+        const int cc0 = (j + 1) / a.CW, ncc = (n + a.CW - 1) / a.CW - cc0;
+        __syncthreads();
+        const double alpha2 = scal[4];
+        if (warp == 1) {
+            // row j + 1 of V and W including the column being formed: every CTA needs it for the next column
+            double c2 = 0.0, y = 0.0;
+            double vn[2], wn[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = lane + 32 * h;
+                vn[h] = wn[h] = 0.0;
+                if (k < jj) {
+                    vn[h] = __ldcg(a.P + (j + 1) + (int64_t)k * Np);
+                    wn[h] = __ldcg(a.P + (j + 1) + (int64_t)(NB + k) * Np);
+                    c2 += vn[h] * ps[k] + wn[h] * qs[k];
+                }
+            }
+            for (int cc = lane; cc < ncc; cc += 32) y += __ldcg(a.ypart + (int64_t)(cc0 + cc) * Np + (j + 1));
+            c2 = warp_sum(c2);
+            y = warp_sum(y);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = lane + 32 * h;
+                if (k < jj) {
+                    Vrow[k] = vn[h];
+                    Wrow[k] = wn[h];
+                }
+            }
+            if (lane == 0) {
+                Vrow[jj] = 1.0;
+                Wrow[jj] = tau * (y - c2) + alpha2;
+            }
+        }
+        for (int u = warp; u < a.SL * KS; u += NWARP) {
+            const int li = (u / KS) * 32 + lane, ks = u % KS;
+            const int k1 = min(jj, (ks + 1) * KW);
+            double c = 0.0;
+            for (int k = ks * KW; k < k1; ++k) c += Vs[k * R + li] * ps[k] + Ws[k * R + li] * qs[k];
+            red[ks * R + li] = c;
+        }
+        __syncthreads();
+        if (tid < R) {
+            const int64_t i = grow(tid);
+            double v = 0.0, w = 0.0;
+            if (i >= j + 1 && i < n) {
+                double y = 0.0, c = 0.0;
+                for (int cc = 0; cc < ncc; ++cc) y += __ldcg(a.ypart + (int64_t)(cc0 + cc) * Np + i);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) c += red[ks * R + tid];
+                v = (i == j + 1) ? 1.0 : xs[tid] * scale;
+                w = tau * (y - c) + alpha2 * v;
+                __stcg(a.P + i + (int64_t)jj * Np, v);
+                __stcg(a.P + i + (int64_t)(NB + jj) * Np, w);
+                __stcg(a.Q + i + (int64_t)jj * Np, w);
+                __stcg(a.Q + i + (int64_t)(NB + jj) * Np, v);
+            }
+            Vs[jj * R + tid] = v;
+            Ws[jj * R + tid] = w;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- preparation ---------------------------------------------------------------------------------------
+__global__ void maxabs_kernel(int64_t n, const double* A, int64_t lda, double* part) {
+    double m = 0.0;
+    for (int64_t j = blockIdx.x; j < n; j += gridDim.x)
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const double v = fabs(A[i + j * lda]);
+            m = (v > m || v != v) ? v : m;  // a NaN sticks
+        }
+    __shared__ double s[256];
+    s[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            const double b = s[threadIdx.x + o], c = s[threadIdx.x];
+            s[threadIdx.x] = (b > c || b != b) ? b : c;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = s[0];
+}
+
+// sc[0] = power of two that brings max|a_ij| into [1, 2), sc[1] = its inverse (1, 1 for a zero matrix)
+__global__ void scale_factor_kernel(int nparts, const double* part, double* sc) {
+    double m = 0.0;
+    for (int i = 0; i < nparts; ++i) m = (part[i] > m || part[i] != part[i]) ? part[i] : m;
+    double f = 1.0, fi = 1.0;
+    if (m > 0.0 && m < 1.0e308) {
+        const int ex = ilogb(m);
+        f = scalbn(1.0, -ex);
+        fi = scalbn(1.0, ex);
+    }
+    sc[0] = f;
+    sc[1] = fi;
+    sc[2] = m;
+}
+
+// scales the n x n block and zeroes the padding rows / columns of the Np x Np buffer
+__global__ void scale_clear_kernel(int64_t n, int64_t Np, double* A, int64_t lda, const double* sc) {
+    const double f = sc[0];
+    for (int64_t j = blockIdx.x; j < Np; j += gridDim.x)
+        for (int64_t i = threadIdx.x; i < Np; i += blockDim.x) {
+            double* p = A + i + j * lda;
+            *p = (i < n && j < n) ? *p * f : 0.0;
+        }
+}
+
+// ---- eigenvalues of the tridiagonal matrix: bisection on Sturm counts ------------------------------------
+constexpr int BIS_THREADS = 128;
+constexpr int BIS_CHUNK = 2048;
+
+__global__ void tridiag_bounds_kernel(int n, const double* d, const double* e, double* bnd) {
+    // Gershgorin interval, |T|_1 and max e^2 (one block)
+    double lo = INFINITY, hi = -INFINITY, tn = 0.0, e2 = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double el = i > 0 ? fabs(e[i - 1]) : 0.0, er = i + 1 < n ? fabs(e[i]) : 0.0;
+        lo = fmin(lo, d[i] - el - er);
+        hi = fmax(hi, d[i] + el + er);
+        tn = fmax(tn, fabs(d[i]) + el + er);
+        e2 = fmax(e2, er * er);
+    }
+    __shared__ double s[4][256];
+    s[0][threadIdx.x] = lo;
+    s[1][threadIdx.x] = hi;
+    s[2][threadIdx.x] = tn;
+    s[3][threadIdx.x] = e2;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            s[0][threadIdx.x] = fmin(s[0][threadIdx.x], s[0][threadIdx.x + o]);
+            s[1][threadIdx.x] = fmax(s[1][threadIdx.x], s[1][threadIdx.x + o]);
+            s[2][threadIdx.x] = fmax(s[2][threadIdx.x], s[2][threadIdx.x + o]);
+            s[3][threadIdx.x] = fmax(s[3][threadIdx.x], s[3][threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double eps = 2.220446049250313e-16, safemin = 2.2250738585072014e-308;
+        const double tnorm = s[2][0];
+        const double pivmin = safemin * fmax(1.0, s[3][0]);
+        bnd[0] = s[0][0] - 2.0 * tnorm * eps * n - 2.0 * pivmin;
+        bnd[1] = s[1][0] + 2.0 * tnorm * eps * n + 2.0 * pivmin;
+        bnd[2] = tnorm;
+        bnd[3] = pivmin;
+    }
+}
+
+// eigenvalue number blockIdx.x * blockDim.x + threadIdx.x (ascending), scaled back by sc[1]
+__global__ void __launch_bounds__(BIS_THREADS) tridiag_bisect_kernel(int n, const double* __restrict__ d,
+                                                                     const double* __restrict__ e,
+                                                                     const double* __restrict__ bnd,
+                                                                     const double* __restrict__ sc, double* w) {
+    __shared__ double sd[BIS_CHUNK], se2[BIS_CHUNK];
+    const int k = blockIdx.x * BIS_THREADS + threadIdx.x;
+    const double eps = 2.220446049250313e-16;
+    double lo = bnd[0], hi = bnd[1];
+    const double tnorm = bnd[2], pivmin = bnd[3];
+    const double atol = 0.25 * eps * tnorm + 2.0 * pivmin;
+    bool active = k < n;
+    for (int it = 0; it < 200; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        const bool go = active && (hi - lo > atol + 2.0 * eps * fmax(fabs(lo), fabs(hi))) && mid > lo && mid < hi;
+        if (!__syncthreads_or(go)) break;
+        int cnt = 0;
+        double q = 1.0;
+        for (int c0 = 0; c0 < n; c0 += BIS_CHUNK) {
+            const int len = min(BIS_CHUNK, n - c0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < len; i += BIS_THREADS) {
+                sd[i] = d[c0 + i];
+                const double ev = (c0 + i > 0) ? e[c0 + i - 1] : 0.0;
+                se2[i] = ev * ev;
+            }
+            __syncthreads();
+            if (go) {
+#pragma unroll 4
+                for (int i = 0; i < len; ++i) {
+                    q = sd[i] - mid - se2[i] / q;  // se2 of the first row is 0
+                    if (fabs(q) < pivmin) q = -pivmin;
+                    cnt += q < 0.0;
+                }
+            }
+        }
+        if (go) {
+            if (cnt <= k) lo = mid; else hi = mid;
+        }
+    }
+    if (active) w[k] = 0.5 * (lo + hi) * sc[1];
+}
+
+struct Work {
+    double *P, *Q, *ypart, *d, *e, *part1, *part2, *pq, *sc, *bnd, *mx;
+    unsigned* bar;
+};
+
+int carve(aces_ctx* ctx, int64_t Np, int grid, Work* w) {
+    size_t doubles = (size_t)Np * 2 * NB * 2 + (size_t)MAX_CC * Np + 2 * (size_t)Np + (size_t)grid * P1 + grid + 2 * NB + 8 + 8 + 1024;
+    ACES_TRY(aces_reserve_dev(ctx, ctx->d_eig, sizeof(double) * doubles + 256));
+    double* p = (double*)ctx->d_eig.ptr;
+    w->P = p; p += (size_t)Np * 2 * NB;
+    w->Q = p; p += (size_t)Np * 2 * NB;
+    w->ypart = p; p += (size_t)MAX_CC * Np;
+    w->d = p; p += Np;
+    w->e = p; p += Np;
+    w->part1 = p; p += (size_t)grid * P1;
+    w->part2 = p; p += grid;
+    w->pq = p; p += 2 * NB;
+    w->sc = p; p += 8;
+    w->bnd = p; p += 8;
+    w->mx = p; p += 1024;
+    w->bar = (unsigned*)p;
+    return ACES_OK;
+}
+
+}  // namespace
+
+int64_t max_order(const aces_ctx* ctx) { return (int64_t)MAX_SL * 32 * ctx->sm_count; }
+
+int syev_values(aces_ctx* ctx, int64_t n, int64_t Np, double* A, int64_t lda, double* w_dev) {
+    ACES_CHECK(ctx, n >= 1 && Np % dense::DB == 0 && Np >= n && lda >= Np && lda % 2 == 0,
+               "eigen::syev_values: the matrix is not padded to a multiple of 128");
+    ACES_CHECK(ctx, n <= max_order(ctx), "eigen::syev_values: order %lld exceeds the supported %lld", (long long)n,
+               (long long)max_order(ctx));
+    const int grid = ctx->sm_count;
+    int SL = (int)(((n + 31) / 32 + grid - 1) / grid);
+    SL = std::max(SL, 1);
+    const size_t smem = panel_smem(SL);
+    ACES_CHECK(ctx, (int)smem <= ctx->smem_optin, "eigen::syev_values: panel needs %zu bytes of shared memory", smem);
+    ACES_CUDA(ctx, cudaFuncSetAttribute(sytrd_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    Work w;
+    ACES_TRY(carve(ctx, Np, grid, &w));
+    cudaStream_t st = ctx->stream;
+    // scale to unit max-norm by a power of two, clear the padding
+    maxabs_kernel<<<1024, 256, 0, st>>>(n, A, lda, w.mx);
+    scale_factor_kernel<<<1, 1, 0, st>>>(1024, w.mx, w.sc);
+    scale_clear_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(n, Np, A, lda, w.sc);
+    ACES_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 3;
+    int CW = 128;
+    while ((n + CW - 1) / CW > MAX_CC) CW *= 2;
+    if (n > 2048 && CW < 256) CW = 256;
+    for (int64_t j0 = 0; j0 < n; j0 += NB) {
+        const int ncols = (int)std::min<int64_t>(NB, n - j0);
+        ACES_CUDA(ctx, cudaMemsetAsync(w.P, 0, sizeof(double) * (size_t)Np * 2 * NB * 2, st));  // P and Q are adjacent
+        ACES_CUDA(ctx, cudaMemsetAsync(w.bar, 0, sizeof(unsigned), st));
+        PanelArgs pa;
+        pa.A = A; pa.lda = lda; pa.n = (int)n; pa.Np = (int)Np; pa.j0 = (int)j0; pa.ncols = ncols;
+        pa.P = w.P; pa.Q = w.Q; pa.d = w.d; pa.e = w.e; pa.ypart = w.ypart; pa.part1 = w.part1; pa.part2 = w.part2;
+        pa.pq = w.pq; pa.bar = w.bar; pa.SL = SL; pa.CW = CW;
+        void* args[] = {(void*)&pa};
+        ACES_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)sytrd_panel_kernel, dim3((unsigned)grid), dim3(THREADS),
+                                                   args, smem, st));
+        ctx->launches += 1;
+        const int64_t t0 = j0 + ncols;
+        if (t0 < n) {
+            // trailing matrix -= V W' + W V' (from the 128-aligned row at or above t0: the rows in between
+            // belong to columns that are already reduced and are never read again)
+            const int64_t r0 = t0 / dense::DB * dense::DB;
+            ACES_TRY(dense::gemm(ctx, dense::GEMM_NT, Np - r0, Np - r0, 2 * NB, -1.0, w.P + r0, Np, w.Q + r0, Np, 1.0,
+                                 A + r0 * (lda + 1), lda, 0));
+        }
+    }
+    tridiag_bounds_kernel<<<1, 256, 0, st>>>((int)n, w.d, w.e, w.bnd);
+    tridiag_bisect_kernel<<<(unsigned)((n + BIS_THREADS - 1) / BIS_THREADS), BIS_THREADS, 0, st>>>((int)n, w.d, w.e, w.bnd,
+                                                                                                 w.sc, w_dev);
+    ACES_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    return ACES_OK;
+}
+
+namespace {
+// lower triangle <- upper triangle (Julia's Symmetric(A) reads uplo = :U, as does dsyevr called with it)
+__global__ void mirror_upper_kernel(int64_t n, double* A, int64_t lda) {
+    for (int64_t j = blockIdx.x; j < n; j += gridDim.x)
+        for (int64_t i = j + 1 + threadIdx.x; i < n; i += blockDim.x) A[i + j * lda] = A[j + i * lda];
+}
+}  // namespace
+
+int mirror_upper(aces_ctx* ctx, int64_t n, double* A, int64_t lda) {
+    mirror_upper_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(n, A, lda);
+    ACES_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return ACES_OK;
+}
+
+}  // namespace eigen
+
+extern "C" int32_t aces_symmetric_eigenvalues(aces_ctx* ctx, int64_t n, const double* a, int64_t lda,
+                                              double* eigenvalues) {
+    if (!ctx) return ACES_E_INVALID;
+    ACES_CHECK(ctx, n >= 1 && a && eigenvalues && lda >= n, "symmetric_eigenvalues: bad argument");
+    ACES_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t Np = dense::pad_up(n);
+    ACES_TRY(aces_reserve_dev(ctx, ctx->d_eigA, sizeof(double) * (size_t)Np * Np + sizeof(double) * (size_t)Np));
+    double* A = (double*)ctx->d_eigA.ptr;
+    double* w = A + (size_t)Np * Np;
+    ACES_CUDA(ctx, cudaMemsetAsync(A, 0, sizeof(double) * (size_t)Np * Np, ctx->stream));
+    ACES_CUDA(ctx, cudaMemcpy2DAsync(A, sizeof(double) * (size_t)Np, a, sizeof(double) * (size_t)lda,
+                                     sizeof(double) * (size_t)n, (size_t)n, cudaMemcpyDefault, ctx->stream));
+    ACES_TRY(eigen::mirror_upper(ctx, n, A, Np));
+    ACES_TRY(eigen::syev_values(ctx, n, Np, A, Np, w));
+    ACES_CUDA(ctx, cudaMemcpyAsync(eigenvalues, w, sizeof(double) * (size_t)n, cudaMemcpyDefault, ctx->stream));
+    ACES_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ACES_OK;
+}

@@ -206,6 +206,22 @@ class DeviceDesign:
             1 if log_form else 0, _ptr(out)))
         return self._sparse(out)
 
+    def calc_covariance_log_of_gates(self, gate_eigenvalues, epsilon: float = 1e-10, weight_time: bool = True):
+        """calc_covariance_log(d) (src/merit.jl:366-377) for the design's circuit at `gate_eigenvalues`:
+        the circuit eigenvalues exp(A log g) (src/design.jl:255-258) and the covariance circuit
+        eigenvalues of the keys' design rows (calc_covariance_eigenvalues, src/merit.jl:171-190) are
+        plain host products, the covariance values and the log form run on the device."""
+        fd = self.fd
+        lg = np.log(np.asarray(gate_eigenvalues, dtype=np.float64))
+        lam = np.exp(sp.csr_matrix(fd.matrix).astype(np.float64) @ lg)
+        off = np.concatenate([[0], np.cumsum(self._keep["ml"])])
+        eig = [lam[off[t]:off[t + 1]] for t in range(self.T)]
+        cov = None
+        if self.C:
+            cov = [np.exp(fd.cov_rows[t].astype(np.float64) @ lg) if len(fd.cov_keys[t]) else np.zeros(0)
+                   for t in range(self.T)]
+        return self.calc_covariance(eig, cov, epsilon=epsilon, weight_time=weight_time, log_form=True)
+
     # -- K3 -------------------------------------------------------------------------------------
     def fallback_count(self) -> int:
         """Blocks that took the not-positive-definite fallback (src/merit.jl:403-424) in the last call."""
@@ -343,6 +359,75 @@ class DeviceDesign:
             self.ctx.handle, self.handle, LS_TYPES[ls_type], _ptr(g), _ptr(val), _ptr(sigma), C.byref(tr),
             C.byref(trsq)))
         return sigma, float(tr.value), float(trsq.value)
+
+
+def eigvals(ctx: _lib.Context, matrix) -> np.ndarray:
+    """LinearAlgebra.eigvals(::Symmetric{Float64, Matrix{Float64}}) as calc_merit calls it
+    (src/merit.jl:954-986): all eigenvalues, ascending, of the symmetric matrix whose UPPER triangle is
+    `matrix`'s (Julia's Symmetric default) -- aces_symmetric_eigenvalues."""
+    a = np.asarray(matrix, dtype=np.float64)
+    assert a.ndim == 2 and a.shape[0] == a.shape[1], "The matrix is not square."
+    a = np.asfortranarray(a)
+    n = a.shape[0]
+    w = np.zeros(n, dtype=np.float64)
+    ctx.check(ctx.lib.aces_symmetric_eigenvalues(ctx.handle, n, _ptr(a), n, _ptr(w)))
+    return w
+
+
+def nrmse_moments_eigenvalues(cov_eigenvalues):
+    """nrmse_moments(gate_eigenvalues_cov_eigenvalues::Vector{Float64}) (src/merit.jl:684-692)."""
+    ev = np.asarray(cov_eigenvalues, dtype=np.float64)
+    return nrmse_moments(float(np.sum(ev)), float(np.sum(ev ** 2)), len(ev))
+
+
+MERIT_LS = ("gls", "wls", "ols")
+MERIT_EST = ("", "_marginal", "_relative")
+
+
+def calc_merit(dd: "DeviceDesign", gate_eigenvalues=None, covariance_log=None, transforms=None) -> dict:
+    """The numeric fields of calc_merit(d::Design) (src/merit.jl:925-1006; `Merit`, src/merit.jl:30-73) for a
+    design with full covariance data, keyed by the reference's field names: for gls / wls / ols and the
+    ordinary / marginal / relative estimators `<ls><est>_cov_eigenvalues`, `<ls><est>_expectation`,
+    `<ls><est>_variance`, plus `cond_num` and `pinv_norm` of the design matrix.  One call of
+    aces_design_merit: covariances, transforms and the nine spectra stay on the device.
+      gate_eigenvalues   get_gate_eigenvalues(d) (default: the design's)
+      covariance_log     calc_covariance_log(d) (default: formed on the device from gate_eigenvalues)
+      transforms         (get_transform(d, :marginal), get_transform(d, :relative)); default from the
+                         design's gate types (optimise.get_transform)"""
+    from .optimise import get_transform
+
+    fd, ctx = dd.fd, dd.ctx
+    g = np.ascontiguousarray(fd.gate_eigenvalues if gate_eigenvalues is None else gate_eigenvalues, dtype=np.float64)
+    assert g.shape == (dd.N,)
+    if covariance_log is None:
+        covariance_log = dd.calc_covariance_log_of_gates(g)
+    val = dd.pattern_values(covariance_log) if sp.issparse(covariance_log) else \
+        np.ascontiguousarray(covariance_log, dtype=np.float64)
+    if transforms is None:
+        transforms = (get_transform(fd, "marginal"), get_transform(fd, "relative"))
+    tm, tr = (sp.csc_matrix(t) for t in transforms)
+    assert tm.shape[1] == dd.N and tr.shape[1] == dd.N
+    mc, mr, mv = _csc64(tm)
+    rc, rr, rv = _csc64(tr)
+    nm, nr = tm.shape[0], tr.shape[0]
+    per = dd.N + nm + nr
+    ev = np.zeros(3 * per, dtype=np.float64)
+    ext = np.zeros(2, dtype=np.float64)
+    ctx.check(ctx.lib.aces_design_merit(ctx.handle, dd.handle, _ptr(g), _ptr(val), nm, _ptr(mc), _ptr(mr), _ptr(mv),
+                                        nr, _ptr(rc), _ptr(rr), _ptr(rv), 0, _ptr(ev), _ptr(ext)))
+    out = {"N": dd.N, "N_marginal": nm, "N_relative": nr}
+    for k, ls in enumerate(MERIT_LS):
+        blk = ev[k * per:(k + 1) * per]
+        for est, sl in zip(MERIT_EST, (slice(0, dd.N), slice(dd.N, dd.N + nm), slice(dd.N + nm, per))):
+            spec = blk[sl].copy()
+            out[f"{ls}{est}_cov_eigenvalues"] = spec
+            if len(spec):
+                out[f"{ls}{est}_expectation"], out[f"{ls}{est}_variance"] = nrmse_moments_eigenvalues(spec)
+    # src/merit.jl:993-1006: singular values of d.matrix from the extreme eigenvalues of its Gram matrix
+    largest, smallest = np.sqrt(ext[0]), np.sqrt(max(ext[1], 0.0))
+    out["cond_num"] = float(largest / smallest) if smallest > 0 else float("inf")
+    out["pinv_norm"] = float(1.0 / smallest) if smallest > 0 else float("inf")
+    return out
 
 
 def nrmse_moments(sigma_tr: float, sigma_sq_tr: float, N: int):
