@@ -6,16 +6,18 @@
 //  1. Householder tridiagonalisation Q' A Q = T, blocked like LAPACK's dsytrd / dlatrd: the reflectors of a
 //     panel of NB columns are accumulated as A - V W' - W V' and applied to the trailing matrix by one
 //     DMMA GEMM per panel (dense::gemm, K = 2 NB); inside the panel every column costs one product of the
-//     (not yet updated) trailing matrix with the new reflector -- the memory-bound half of the flops:
-//     sum_j 8 (n - j)^2 bytes = 8 n^3 / 3 read once each.  A panel is ONE persistent cooperative kernel
-//     (a CTA per SM, two grid barriers per column): the rows of V and W a CTA owns stay in its shared
-//     memory for the whole panel, the trailing product is cut into 128-row x CW-column items dealt round
-//     robin, and every reduction runs in a fixed order (results are deterministic).
-//  2. Eigenvalues of T by bisection on Sturm counts (LAPACK dstebz's recurrence with its pivmin guard),
-//     one thread per eigenvalue; absolute accuracy eps * ||T||, as dsyevr's.
+//     (not yet updated) trailing matrix with the new reflector -- the memory-bound half of the flops.
+//     The trailing matrix is symmetric, so only its 128 x 128 tiles on and below the block diagonal are
+//     read: an off-diagonal tile serves both A v and (transposed) its mirror image, sum_j 4 (n - j)^2
+//     bytes = 4 n^3 / 3 in total.  A panel is ONE persistent cooperative kernel (a CTA per SM, two grid
+//     barriers per column): the rows of V and W a CTA owns stay in its shared memory for the whole
+//     panel, the tiles are dealt round robin, and every reduction runs in a fixed order (results are
+//     deterministic).
+//  2. Eigenvalues of T by multisection on Sturm counts (LAPACK dstebz's recurrence with its pivmin
+//     guard): eight lanes x two points per eigenvalue, 17 sections per step; absolute accuracy
+//     eps * ||T||, as dsyevr's.
 //
-// The matrix is held in full (both triangles) so that the trailing product is a plain streaming read;
-// it is scaled by a power of two to unit max-norm first (exact), as dsyev scales badly scaled input.
+// The caller passes the matrix in full (both triangles); the diagonal tiles are used in full.  It is scaled by a power of two to unit max-norm first (exact), as dsyev scales badly scaled input.
 #include <algorithm>
 #include <cmath>
 
@@ -34,7 +36,6 @@ constexpr int RB = 128;           // rows of one item of the trailing product
 constexpr int KS = 8;             // the panel passes cut the NB reflectors into KS slices of KW
 constexpr int KW = NB / KS;
 constexpr int P1 = 2 * NB + 2;    // per-CTA partials of phase A: [0] |x|^2, [1 + k] V'x, [1 + NB + k] W'x
-constexpr int MAX_CC = 32;        // column chunks of the trailing product (partial result vectors)
 constexpr int MAX_SL = 6;         // 32-row slots a CTA can own (shared-memory bound)
 
 struct PanelArgs {
@@ -44,12 +45,12 @@ struct PanelArgs {
     int j0, ncols;
     double *P, *Q;      // Np x 2NB each: P = [V | W], Q = [W | V]
     double *d, *e;
-    double* ypart;      // [MAX_CC][Np]
+    double* ypart;      // [Np / 128][Np]: partial products, [source block][target row]
     double* part1;      // [grid][P1]
     double* part2;      // [grid]
     double* pq;         // [2 NB]: V'v then W'v
     unsigned* bar;
-    int SL, CW;
+    int SL;
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -87,7 +88,7 @@ __device__ __forceinline__ double sum_over_ctas(const double* tab, int stride, i
 
 size_t panel_smem(int SL) {
     const size_t R = (size_t)SL * 32;
-    const size_t un = std::max((size_t)NWARP * RB, (size_t)KS * R + (size_t)SL * 2 * NB);
+    const size_t un = std::max((size_t)NWARP * RB, (size_t)KS * R + std::max((size_t)SL * 2 * NB, (size_t)KS * R));
     return sizeof(double) * (2 * NB * R + R + 4 * NB + 16 + un);
 }
 
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
     double* scal = qs + NB;          // tau, scale, alpha, beta, alpha2, scratch
     double* un = scal + 16;
     double* red = un;                // [KS][R]
-    double* dots = red + KS * R;     // [SL][2 NB]
+    double* dots = red + KS * R;     // [SL][2 NB] (phase A), [YG <= KS][R] (phase C)
     double* redg = un;               // [NWARP][RB] (phase B only)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -191,6 +192,9 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
         grid_barrier(a.bar, round);
 
         // ---------------- phase B: the reflector, then (trailing matrix) * v ---------------------------
+        // warp 0: |x|^2 over the grid -> tau, scale; meanwhile warps 1.. sum this CTA's entries of V'x / W'x
+        double pq_sum = 0.0, pq_coef = 0.0;
+        int pq_e = -1;
         if (warp == 0) {
             const double nrm2 = sum_over_ctas(a.part1, P1, G, lane);
             if (lane == 0) {
@@ -207,52 +211,72 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
                 scal[3] = beta;
                 if (cta == 0) a.e[j] = beta;
             }
+        } else {
+            const int e = cta + (warp - 1) * G;  // entry of [V'x | W'x] this warp reduces over the grid
+            if (e < 2 * NB && (e & (NB - 1)) < jj) {
+                pq_e = e;
+                pq_sum = sum_over_ctas(a.part1 + 1 + e, P1, G, lane);
+                pq_coef = __ldcg(a.P + (j + 1) + (int64_t)e * Np);
+            }
         }
         __syncthreads();
         const double tau = scal[0], scale = scal[1];
-        // entries of V'v and W'v: one warp each, spread over the grid
-        for (int e = cta, w = 0; e < 2 * NB; e += G, ++w) {
-            if ((e & (NB - 1)) < jj && (w % NWARP) == warp) {
-                const double s = sum_over_ctas(a.part1 + 1 + e, P1, G, lane);
-                if (lane == 0) {
-                    const double coef = __ldcg(a.P + (j + 1) + (int64_t)e * Np);
-                    __stcg(a.pq + e, scale * s + coef * (1.0 - scale * scal[2]));
-                }
-            }
-        }
+        // v = scale * x except v[j+1] = 1:  V'v = scale V'x + V[j+1, :] (1 - scale alpha)
+        if (pq_e >= 0 && lane == 0) __stcg(a.pq + pq_e, scale * pq_sum + pq_coef * (1.0 - scale * scal[2]));
         auto vcol = [&](int c) -> double {
             if (c <= j || c >= n) return 0.0;
             if (c == j + 1) return 1.0;
             return __ldcg(a.P + c + (int64_t)jj * Np) * scale;
         };
         {
-            const int CW = a.CW;
-            const int rb0 = (j + 1) / RB, nrb = (n + RB - 1) / RB - rb0;
-            const int cc0 = (j + 1) / CW, ncc = (n + CW - 1) / CW - cc0;
-            const int items = nrb * ncc;
+            // The trailing matrix is symmetric: only its 128 x 128 tiles on and below the block diagonal
+            // are read.  Tile (rb, cb), rb > cb, gives rows rb of A v from columns cb AND (transposed) rows
+            // cb from columns rb; a diagonal tile (stored in full) only the former.  Partial results go to
+            // ypart[source block][target row]: the two uses of a tile never share a slot.
+            const int b0 = (j + 1) / RB, m = (n + RB - 1) / RB - b0;
+            const int tiles = m * (m + 1) / 2;
             double yv = 0.0;
-            for (int t = cta; t < items; t += G) {
-                const int rb = rb0 + t / ncc, cc = cc0 + t % ncc;
-                const double* Ab = a.A + (int64_t)rb * RB + 2 * lane;
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                for (int sub = cc * CW; sub < (cc + 1) * CW && sub < Np; sub += 128) {
-                    // this warp's eight columns of the 128: sub + warp + 16 m
-                    const double vv = vcol(sub + warp + 16 * (lane & 7));
-                    double2 lo[8], hi[8];
+            for (int t = cta; t < tiles; t += G) {
+                int r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+                while (r * (r + 1) / 2 > t) --r;
+                while ((r + 1) * (r + 2) / 2 <= t) ++r;
+                const int rb = b0 + r, cb = b0 + (t - r * (r + 1) / 2);
+                const bool offdiag = rb != cb;
+                const double* Ab = a.A + (int64_t)rb * RB + 2 * lane + (int64_t)cb * RB * a.lda;
+                // this warp's eight columns of the tile: warp + 16 m (lane m < 8 holds v of column m)
+                const double vv = vcol(cb * RB + warp + 16 * (lane & 7));
+                double2 lo[8], hi[8];
 #pragma unroll
-                    for (int m = 0; m < 8; ++m) {
-                        const double* p = Ab + (int64_t)(sub + warp + 16 * m) * a.lda;
-                        lo[m] = __ldg(reinterpret_cast<const double2*>(p));
-                        hi[m] = __ldg(reinterpret_cast<const double2*>(p + 64));
-                    }
+                for (int q = 0; q < 8; ++q) {
+                    const double* p = Ab + (int64_t)(warp + 16 * q) * a.lda;
+                    lo[q] = __ldg(reinterpret_cast<const double2*>(p));
+                    hi[q] = __ldg(reinterpret_cast<const double2*>(p + 64));
+                }
+                double vr0 = 0.0, vr1 = 0.0, vr2 = 0.0, vr3 = 0.0;
+                if (offdiag) {
+                    const int r0 = rb * RB + 2 * lane;
+                    vr0 = vcol(r0);
+                    vr1 = vcol(r0 + 1);
+                    vr2 = vcol(r0 + 64);
+                    vr3 = vcol(r0 + 65);
+                }
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, tmine = 0.0;
 #pragma unroll
-                    for (int m = 0; m < 8; ++m) {
-                        const double v = __shfl_sync(0xffffffffu, vv, m);
-                        a0 += lo[m].x * v;
-                        a1 += lo[m].y * v;
-                        a2 += hi[m].x * v;
-                        a3 += hi[m].y * v;
+                for (int q = 0; q < 8; ++q) {
+                    const double v = __shfl_sync(0xffffffffu, vv, q);
+                    a0 += lo[q].x * v;
+                    a1 += lo[q].y * v;
+                    a2 += hi[q].x * v;
+                    a3 += hi[q].y * v;
+                    if (offdiag) {  // uniform over the CTA
+                        const double tq = warp_sum((lo[q].x * vr0 + lo[q].y * vr1) + (hi[q].x * vr2 + hi[q].y * vr3));
+                        if (lane == q) tmine = tq;
                     }
+                }
+                if (offdiag && lane < 8) {
+                    const int c = cb * RB + warp + 16 * lane;
+                    __stcg(a.ypart + (int64_t)rb * Np + c, tmine);
+                    yv += vv * tmine;
                 }
                 redg[warp * RB + 2 * lane] = a0;
                 redg[warp * RB + 2 * lane + 1] = a1;
@@ -260,20 +284,24 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
                 redg[warp * RB + 64 + 2 * lane + 1] = a3;
                 __syncthreads();
                 if (tid < RB) {
-                    double s = 0.0;
+                    double sd = 0.0;
 #pragma unroll
-                    for (int w = 0; w < NWARP; ++w) s += redg[w * RB + tid];
-                    const int r = rb * RB + tid;
-                    __stcg(a.ypart + (int64_t)cc * Np + r, s);
-                    yv += vcol(r) * s;
+                    for (int w = 0; w < NWARP; ++w) sd += redg[w * RB + tid];
+                    const int rr = rb * RB + tid;
+                    __stcg(a.ypart + (int64_t)cb * Np + rr, sd);
+                    yv += vcol(rr) * sd;
                 }
                 __syncthreads();
             }
             // v'(A v) partial of this CTA
             yv = warp_sum(yv);
-            if (lane == 0 && warp < RB / 32) scal[8 + warp] = yv;
+            if (lane == 0) redg[warp] = yv;
             __syncthreads();
-            if (tid == 0) __stcg(a.part2 + cta, (scal[8] + scal[9]) + (scal[10] + scal[11]));
+            if (tid == 0) {
+                double sy = 0.0;
+                for (int w = 0; w < NWARP; ++w) sy += redg[w];
+                __stcg(a.part2 + cta, sy);
+            }
         }
         grid_barrier(a.bar, round);
 
@@ -293,7 +321,7 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
             t = warp_sum(t);
             if (lane == 0) scal[4] = -0.5 * tau * (tau * (scal[5] - 2.0 * t));
         }
-        const int cc0 = (j + 1) / a.CW, ncc = (n + a.CW - 1) / a.CW - cc0;
+        const int cc0 = (j + 1) / RB, ncc = (n + RB - 1) / RB - cc0;  // source blocks of the partial products
         __syncthreads();
         const double alpha2 = scal[4];
         if (warp == 1) {
@@ -326,6 +354,23 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
                 Wrow[jj] = tau * (y - c2) + alpha2;
             }
         }
+        // (A v)[own rows]: the partial products of all source blocks, split over YG thread groups
+        const int YG = min(THREADS / R, KS);
+        double* ysum = dots;  // [YG][R]: dots is dead in this phase
+        if (tid < YG * R) {
+            const int g = tid / R, li = tid - g * R;
+            const int64_t i = grow(li);
+            double y0 = 0.0, y1 = 0.0;
+            if (i >= j + 1 && i < n) {
+                int cc = g;
+                for (; cc + YG < ncc; cc += 2 * YG) {
+                    y0 += __ldcg(a.ypart + (int64_t)(cc0 + cc) * Np + i);
+                    y1 += __ldcg(a.ypart + (int64_t)(cc0 + cc + YG) * Np + i);
+                }
+                if (cc < ncc) y0 += __ldcg(a.ypart + (int64_t)(cc0 + cc) * Np + i);
+            }
+            ysum[g * R + li] = y0 + y1;
+        }
         for (int u = warp; u < a.SL * KS; u += NWARP) {
             const int li = (u / KS) * 32 + lane, ks = u % KS;
             const int k1 = min(jj, (ks + 1) * KW);
@@ -339,7 +384,7 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
             double v = 0.0, w = 0.0;
             if (i >= j + 1 && i < n) {
                 double y = 0.0, c = 0.0;
-                for (int cc = 0; cc < ncc; ++cc) y += __ldcg(a.ypart + (int64_t)(cc0 + cc) * Np + i);
+                for (int g = 0; g < YG; ++g) y += ysum[g * R + tid];
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) c += red[ks * R + tid];
                 v = (i == j + 1) ? 1.0 : xs[tid] * scale;
@@ -404,9 +449,8 @@ __global__ void scale_clear_kernel(int64_t n, int64_t Np, double* A, int64_t lda
 
 // ---- eigenvalues of the tridiagonal matrix: bisection on Sturm counts ------------------------------------
 constexpr int BIS_THREADS = 128;
-constexpr int BIS_CHUNK = 2048;
 
-__global__ void tridiag_bounds_kernel(int n, const double* d, const double* e, double* bnd) {
+__global__ void tridiag_bounds_kernel(int n, const double* d, const double* e, double* e2out, double* bnd) {
     // Gershgorin interval, |T|_1 and max e^2 (one block)
     double lo = INFINITY, hi = -INFINITY, tn = 0.0, e2 = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -415,6 +459,7 @@ __global__ void tridiag_bounds_kernel(int n, const double* d, const double* e, d
         hi = fmax(hi, d[i] + el + er);
         tn = fmax(tn, fabs(d[i]) + el + er);
         e2 = fmax(e2, er * er);
+        e2out[i] = el * el;  // e2out[i] = e[i-1]^2, 0 for the first row
     }
     __shared__ double s[4][256];
     s[0][threadIdx.x] = lo;
@@ -442,63 +487,69 @@ __global__ void tridiag_bounds_kernel(int n, const double* d, const double* e, d
     }
 }
 
-// eigenvalue number blockIdx.x * blockDim.x + threadIdx.x (ascending), scaled back by sc[1]
+// Eigenvalue k (ascending), scaled back by sc[1].  Eight lanes per eigenvalue, two Sturm counts per lane:
+// every step cuts the bracket into 17 parts (14 steps for 54 bits instead of 54).  The new bracket is the
+// largest point whose count is <= k and the smallest whose count is > k, whatever the counts in between.
+constexpr int LPE = 8;
 __global__ void __launch_bounds__(BIS_THREADS) tridiag_bisect_kernel(int n, const double* __restrict__ d,
-                                                                     const double* __restrict__ e,
+                                                                     const double* __restrict__ e2,
                                                                      const double* __restrict__ bnd,
                                                                      const double* __restrict__ sc, double* w) {
-    __shared__ double sd[BIS_CHUNK], se2[BIS_CHUNK];
-    const int k = blockIdx.x * BIS_THREADS + threadIdx.x;
+    const int sub = threadIdx.x & (LPE - 1);
+    const int k = (int)((blockIdx.x * (unsigned)BIS_THREADS + threadIdx.x) / LPE);
     const double eps = 2.220446049250313e-16;
     double lo = bnd[0], hi = bnd[1];
     const double tnorm = bnd[2], pivmin = bnd[3];
     const double atol = 0.25 * eps * tnorm + 2.0 * pivmin;
     bool active = k < n;
-    for (int it = 0; it < 200; ++it) {
-        const double mid = 0.5 * (lo + hi);
-        const bool go = active && (hi - lo > atol + 2.0 * eps * fmax(fabs(lo), fabs(hi))) && mid > lo && mid < hi;
-        if (!__syncthreads_or(go)) break;
-        int cnt = 0;
-        double q = 1.0;
-        for (int c0 = 0; c0 < n; c0 += BIS_CHUNK) {
-            const int len = min(BIS_CHUNK, n - c0);
-            __syncthreads();
-            for (int i = threadIdx.x; i < len; i += BIS_THREADS) {
-                sd[i] = d[c0 + i];
-                const double ev = (c0 + i > 0) ? e[c0 + i - 1] : 0.0;
-                se2[i] = ev * ev;
-            }
-            __syncthreads();
-            if (go) {
+    for (int it = 0; it < 64; ++it) {
+        active = active && (hi - lo > atol + 2.0 * eps * fmax(fabs(lo), fabs(hi)));
+        if (!__any_sync(0xffffffffu, active)) break;
+        const double h = (hi - lo) * (1.0 / 17.0);
+        const double x0 = lo + h * (double)(2 * sub + 1), x1 = lo + h * (double)(2 * sub + 2);
+        int c0 = 0, c1 = 0;
+        double q0 = 1.0, q1 = 1.0;
 #pragma unroll 4
-                for (int i = 0; i < len; ++i) {
-                    q = sd[i] - mid - se2[i] / q;  // se2 of the first row is 0
-                    if (fabs(q) < pivmin) q = -pivmin;
-                    cnt += q < 0.0;
-                }
-            }
+        for (int i = 0; i < n; ++i) {
+            const double di = __ldg(d + i), ei = __ldg(e2 + i);
+            q0 = di - x0 - ei / q0;
+            q1 = di - x1 - ei / q1;
+            if (fabs(q0) < pivmin) q0 = -pivmin;
+            if (fabs(q1) < pivmin) q1 = -pivmin;
+            c0 += q0 < 0.0;
+            c1 += q1 < 0.0;
         }
-        if (go) {
-            if (cnt <= k) lo = mid; else hi = mid;
+        double nlo = lo, nhi = hi;
+        if (c0 <= k) nlo = fmax(nlo, x0); else nhi = fmin(nhi, x0);
+        if (c1 <= k) nlo = fmax(nlo, x1); else nhi = fmin(nhi, x1);
+#pragma unroll
+        for (int o = LPE / 2; o > 0; o >>= 1) {
+            nlo = fmax(nlo, __shfl_xor_sync(0xffffffffu, nlo, o));
+            nhi = fmin(nhi, __shfl_xor_sync(0xffffffffu, nhi, o));
+        }
+        if (active) {
+            if (!(nlo > lo || nhi < hi) || !(nlo < nhi)) active = false;  // no representable point left inside
+            else { lo = nlo; hi = nhi; }
         }
     }
-    if (active) w[k] = 0.5 * (lo + hi) * sc[1];
+    if (k < n && sub == 0) w[k] = 0.5 * (lo + hi) * sc[1];
 }
 
 struct Work {
-    double *P, *Q, *ypart, *d, *e, *part1, *part2, *pq, *sc, *bnd, *mx;
+    double *P, *Q, *ypart, *d, *e, *e2, *part1, *part2, *pq, *sc, *bnd, *mx;
     unsigned* bar;
 };
 
 int carve(aces_ctx* ctx, int64_t Np, int grid, Work* w) {
-    size_t doubles = (size_t)Np * 2 * NB * 2 + (size_t)MAX_CC * Np + 2 * (size_t)Np + (size_t)grid * P1 + grid + 2 * NB + 8 + 8 + 1024;
+    size_t doubles = (size_t)Np * 2 * NB * 2 + (size_t)(Np / RB) * Np + 3 * (size_t)Np + (size_t)grid * P1 + grid + 2 * NB + 8 + 8 + 1024;
     ACES_TRY(aces_reserve_dev(ctx, ctx->d_eig, sizeof(double) * doubles + 256));
     double* p = (double*)ctx->d_eig.ptr;
     w->P = p; p += (size_t)Np * 2 * NB;
     w->Q = p; p += (size_t)Np * 2 * NB;
-    w->ypart = p; p += (size_t)MAX_CC * Np;
+    w->ypart = p; p += (size_t)(Np / RB) * Np;
     w->d = p; p += Np;
     w->e = p; p += Np;
+    w->e2 = p; p += Np;
     w->part1 = p; p += (size_t)grid * P1;
     w->part2 = p; p += grid;
     w->pq = p; p += 2 * NB;
@@ -519,6 +570,7 @@ int syev_values(aces_ctx* ctx, int64_t n, int64_t Np, double* A, int64_t lda, do
     ACES_CHECK(ctx, n <= max_order(ctx), "eigen::syev_values: order %lld exceeds the supported %lld", (long long)n,
                (long long)max_order(ctx));
     const int grid = ctx->sm_count;
+    ACES_CHECK(ctx, grid * (NWARP - 1) >= 2 * NB, "eigen::syev_values: too few SMs");
     int SL = (int)(((n + 31) / 32 + grid - 1) / grid);
     SL = std::max(SL, 1);
     const size_t smem = panel_smem(SL);
@@ -533,9 +585,6 @@ int syev_values(aces_ctx* ctx, int64_t n, int64_t Np, double* A, int64_t lda, do
     scale_clear_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(n, Np, A, lda, w.sc);
     ACES_CUDA(ctx, cudaGetLastError());
     ctx->launches += 3;
-    int CW = 128;
-    while ((n + CW - 1) / CW > MAX_CC) CW *= 2;
-    if (n > 2048 && CW < 256) CW = 256;
     for (int64_t j0 = 0; j0 < n; j0 += NB) {
         const int ncols = (int)std::min<int64_t>(NB, n - j0);
         ACES_CUDA(ctx, cudaMemsetAsync(w.P, 0, sizeof(double) * (size_t)Np * 2 * NB * 2, st));  // P and Q are adjacent
@@ -543,7 +592,7 @@ int syev_values(aces_ctx* ctx, int64_t n, int64_t Np, double* A, int64_t lda, do
         PanelArgs pa;
         pa.A = A; pa.lda = lda; pa.n = (int)n; pa.Np = (int)Np; pa.j0 = (int)j0; pa.ncols = ncols;
         pa.P = w.P; pa.Q = w.Q; pa.d = w.d; pa.e = w.e; pa.ypart = w.ypart; pa.part1 = w.part1; pa.part2 = w.part2;
-        pa.pq = w.pq; pa.bar = w.bar; pa.SL = SL; pa.CW = CW;
+        pa.pq = w.pq; pa.bar = w.bar; pa.SL = SL;
         void* args[] = {(void*)&pa};
         ACES_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)sytrd_panel_kernel, dim3((unsigned)grid), dim3(THREADS),
                                                    args, smem, st));
@@ -554,11 +603,11 @@ int syev_values(aces_ctx* ctx, int64_t n, int64_t Np, double* A, int64_t lda, do
             // belong to columns that are already reduced and are never read again)
             const int64_t r0 = t0 / dense::DB * dense::DB;
             ACES_TRY(dense::gemm(ctx, dense::GEMM_NT, Np - r0, Np - r0, 2 * NB, -1.0, w.P + r0, Np, w.Q + r0, Np, 1.0,
-                                 A + r0 * (lda + 1), lda, 0));
+                                 A + r0 * (lda + 1), lda, 1));
         }
     }
-    tridiag_bounds_kernel<<<1, 256, 0, st>>>((int)n, w.d, w.e, w.bnd);
-    tridiag_bisect_kernel<<<(unsigned)((n + BIS_THREADS - 1) / BIS_THREADS), BIS_THREADS, 0, st>>>((int)n, w.d, w.e, w.bnd,
+    tridiag_bounds_kernel<<<1, 256, 0, st>>>((int)n, w.d, w.e, w.e2, w.bnd);
+    tridiag_bisect_kernel<<<(unsigned)((n * LPE + BIS_THREADS - 1) / BIS_THREADS), BIS_THREADS, 0, st>>>((int)n, w.d, w.e2, w.bnd,
                                                                                                  w.sc, w_dev);
     ACES_CUDA(ctx, cudaGetLastError());
     ctx->launches += 2;
