@@ -29,6 +29,8 @@
 #   calc_gls_covariance / calc_wls_covariance / calc_ols_covariance(d, covariance_log)  src/merit.jl:556-629 (S4)
 #   gls_ / wls_ / ols_optimise_weights(d, covariance_log; options)   src/optimise_weights.jl:160-790   the
 #        descent loop restated once, its gradient (calc_*_merit_grad_log) on the GPU        (f3)
+#   calc_merit(d; warning)                                      src/merit.jl:925-1043    estimator covariances,
+#        marginal / relative transforms and the nine eigvals on the GPU in one call (aces_design_merit)  (f2)
 #   S1  estimate_experiment(::Matrix{UInt8}, ...)             src/estimate.jl:284-301
 #   S2  estimate_gate_eigenvalues(A, F, est; constrain)        src/estimate.jl:492-524 (and the OLS form)
 # sparse_covariance_inv_factor(covariance_log, lengths) (src/merit.jl:378-427) has no Design argument
@@ -920,6 +922,104 @@ end
 # install!: method overwrite inside QuantumACES (SURVEY.md section 8b, option ii)
 # ---------------------------------------------------------------------------------------------
 
+# ---------------------------------------------------------------------------------------------
+# calc_merit tail (src/merit.jl:925-1006) -- SURVEY.md section 8f, row f2
+# ---------------------------------------------------------------------------------------------
+
+"""
+    symmetric_eigenvalues(A::Symmetric{Float64, Matrix{Float64}})
+
+LinearAlgebra.eigvals(A) as calc_merit calls it (src/merit.jl:954-986) through
+aces_symmetric_eigenvalues: all eigenvalues, ascending.  The library reads the upper triangle of the
+buffer it is given (Julia's default uplo); a Symmetric stored in its lower triangle is copied out first.
+"""
+function symmetric_eigenvalues(A::Symmetric{Float64, Matrix{Float64}})
+    n = size(A, 1)
+    data = A.uplo == 'U' ? parent(A) : Matrix{Float64}(A)
+    w = Vector{Float64}(undef, n)
+    GC.@preserve data w begin
+        check(ccall((:aces_symmetric_eigenvalues, LIB[]), Int32,
+            (Ptr{Cvoid}, Int64, Ptr{Float64}, Int64, Ptr{Float64}),
+            CTX[], Int64(n), data, Int64(stride(data, 2)), w))
+    end
+    return w
+end
+
+"""
+    merit_spectra(dd, covariance_log) -> (spectra, gram_extremes)
+
+The nine spectra of calc_merit in ONE call of aces_design_merit: `spectra[(ls, est)]` for
+ls in (:gls, :wls, :ols), est in (:ordinary, :marginal, :relative); the estimator covariances, their
+transforms and the tridiagonalisations never leave the device.  gram_extremes = (largest, smallest)
+eigenvalue of d.matrix' * d.matrix.
+"""
+function merit_spectra(dd::DeviceDesign, covariance_log::SparseMatrixCSC{Float64, Int})
+    d = dd.d
+    nz = [covariance_log[dd.cov_rowval[e] + 1, c] for c in 1:dd.M for e in (dd.cov_colptr[c] + 1):dd.cov_colptr[c + 1]]
+    g = QuantumACES.get_gate_eigenvalues(d)
+    tm = QuantumACES.get_transform(d, :marginal)
+    tr = QuantumACES.get_transform(d, :relative)
+    nm = size(tm, 1); nr = size(tr, 1)
+    mc = Int64.(tm.colptr); mr = Int64.(tm.rowval); mv = Float64.(tm.nzval)
+    rc = Int64.(tr.colptr); rr = Int64.(tr.rowval); rv = Float64.(tr.nzval)
+    per = dd.N + nm + nr
+    ev = Vector{Float64}(undef, 3 * per)
+    ext = Vector{Float64}(undef, 2)
+    GC.@preserve nz g mc mr mv rc rr rv ev ext begin
+        check(ccall((:aces_design_merit, LIB[]), Int32,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64,
+             Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}),
+            CTX[], dd.handle, g, nz, Int64(nm), mc, mr, mv, Int64(nr), rc, rr, rv, Int32(1), ev, ext))
+    end
+    spectra = Dict{Tuple{Symbol, Symbol}, Vector{Float64}}()
+    for (k, ls) in enumerate((:gls, :wls, :ols))
+        base = (k - 1) * per
+        spectra[(ls, :ordinary)] = ev[(base + 1):(base + dd.N)]
+        spectra[(ls, :marginal)] = ev[(base + dd.N + 1):(base + dd.N + nm)]
+        spectra[(ls, :relative)] = ev[(base + dd.N + nm + 1):(base + per)]
+    end
+    return (spectra, (ext[1], ext[2]))
+end
+
+"""
+    calc_merit(d::Design; warning = true)
+
+calc_merit(d) (src/merit.jl:925-1043) with its numeric core on the GPU; the `Merit` object is assembled
+exactly as the reference does (same field order, nrmse_moments of the spectra on the host).  A design
+without full covariance data goes through get_full_design like the reference, and its GLS fields are
+the WLS ones (src/merit.jl:934-938).
+"""
+function calc_merit(d::Design; warning::Bool = true)
+    d_cov = d
+    if ~d.full_covariance
+        if warning
+            println("The design does not have full covariance matrix data. Generating this data.\nBE CAREFUL: this may consume extreme amounts of memory and be extremely slow.")
+        end
+        d_cov = QuantumACES.get_full_design(d)
+    end
+    covariance_log = QuantumACES.calc_covariance_log(d_cov)
+    (spectra, (largest, smallest)) = merit_spectra(device_design(d_cov), covariance_log)
+    if ~d.full_covariance
+        for est in (:ordinary, :marginal, :relative)
+            spectra[(:gls, est)] = deepcopy(spectra[(:wls, est)])
+        end
+    end
+    fields = Any[]
+    for ls in (:gls, :wls, :ols), est in (:ordinary, :marginal, :relative)
+        ev = spectra[(ls, est)]
+        (expectation, variance) = QuantumACES.nrmse_moments(ev)
+        push!(fields, expectation, variance, ev)
+    end
+    largest_singular_value = sqrt(largest)
+    smallest_singular_value = sqrt(smallest)
+    design_matrix_cond_num = largest_singular_value / smallest_singular_value
+    design_matrix_pinv_norm = 1 / smallest_singular_value
+    return QuantumACES.Merit(
+        d.c.circuit_param, d.c.noise_param, d.tuple_set_data, d.tuple_times, d.shot_weights, d.experiment_numbers,
+        d.experiment_number, d.c.gate_data.N, d.c.gate_data.N_marginal, d.c.gate_data.N_relative,
+        length(d.c.total_gates), fields..., design_matrix_cond_num, design_matrix_pinv_norm)
+end
+
 """
     install!()
 
@@ -973,6 +1073,8 @@ function install!()
         calc_gls_covariance(d::Design, covariance_log::SparseMatrixCSC{Float64, Int}) = $(ls_covariance_design)(d, covariance_log, :gls)
         calc_wls_covariance(d::Design, covariance_log::SparseMatrixCSC{Float64, Int}) = $(ls_covariance_design)(d, covariance_log, :wls)
         calc_ols_covariance(d::Design, covariance_log::SparseMatrixCSC{Float64, Int}) = $(ls_covariance_design)(d, covariance_log, :ols)
+        # f2: calc_merit with the covariances, transforms and nine spectra on the GPU (src/merit.jl:925-1043)
+        calc_merit(d::Design; warning::Bool = true) = $(calc_merit)(d; warning = warning)
         # f3: the descent loops of the shot-weight optimiser (src/optimise_weights.jl:160-321, 398-555, 613-790)
         gls_optimise_weights(d::Design, covariance_log::SparseMatrixCSC{Float64, Int}; options::OptimOptions = OptimOptions()) =
             $(ls_optimise_weights)(d, covariance_log, :gls; options = options)

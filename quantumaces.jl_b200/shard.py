@@ -90,6 +90,43 @@ def shard_tuples(mapping_lengths: Sequence[int], world: int) -> List[List[int]]:
     return [sorted(x) for x in out]
 
 
+MERIT_FARM_FIELDS = tuple(f"{ls}{est}_{what}" for ls in ("gls", "wls", "ols") for est in ("", "_marginal", "_relative")
+                          for what in ("expectation", "variance"))
+
+
+def merit_farm(merit_fn, gate_eigenvalue_sets, group=None) -> np.ndarray:
+    """The repetition loop of calc_ensemble_scaling (src/scaling.jl:510-536: one calc_merit per random noise
+    instance of the same design, up to 10^4 per distance) as a replica farm: instance r runs on rank
+    r % world (`merit_fn(gate_eigenvalues) -> dict`, e.g. lambda g: merit.calc_merit(dd, gate_eigenvalues=g)
+    on that rank's DeviceDesign), the 18 moments of every instance (MERIT_FARM_FIELDS) are gathered on every
+    rank.  No data-path collective: one all_gather of [instances / world, 18] doubles at the end.  The
+    convergence test of the reference (relative standard error of the GLS / WLS expectations) is host
+    logic on the returned table."""
+    import torch
+    import torch.distributed as dist
+
+    sets = [np.asarray(g, dtype=np.float64) for g in gate_eigenvalue_sets]
+    R = len(sets)
+    on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    world, rank = (dist.get_world_size(group), dist.get_rank(group)) if on else (1, 0)
+    per = -(-R // world)
+    local = np.full((per, len(MERIT_FARM_FIELDS)), np.nan, dtype=np.float64)
+    for slot, r in enumerate(shard_repetitions(R, world, rank)):
+        m = merit_fn(sets[r])
+        local[slot] = [m[k] for k in MERIT_FARM_FIELDS]
+    if not on:
+        return local[:R]
+    backend = dist.get_backend(group)
+    t = torch.from_numpy(local.reshape(-1))
+    if backend == "nccl":
+        t = t.cuda()
+    allv = all_gather_vectors(t, group).cpu().numpy().reshape(world, per, len(MERIT_FARM_FIELDS))
+    out = np.empty((R, len(MERIT_FARM_FIELDS)), dtype=np.float64)
+    for r in range(R):
+        out[r] = allv[r % world, r // world]
+    return out
+
+
 class _DeviceBuffer:
     """A raw device pointer as a __cuda_array_interface__ object (float64, 1-D)."""
 

@@ -4,6 +4,7 @@ are combined with the same collectives bench.py / a multi-GPU run use, and the r
 the unsharded counts bit for bit."""
 import os
 import socket
+import sys
 
 import numpy as np
 import pytest
@@ -35,6 +36,10 @@ def _problem():
         sups.append([(pauli_bits[pauli_ptr[p]:pauli_ptr[p + 1]] + 1).tolist()
                      for p in range(int(exp_ptr[e]), int(exp_ptr[e + 1]))])
     return fd, mats, np.asarray(prefix, dtype=np.int64), sups
+
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+import merit_oracle as mo  # noqa: E402
 
 
 def _odd(mat, sup, prefix):
@@ -134,3 +139,41 @@ def test_shard_tuples_partition_is_balanced():
         assert sorted(t for p in parts for t in p) == list(range(len(m)))
         cost = [sum(float(m[t]) ** 3 for t in p) for p in parts]
         assert max(cost) <= sum(cost) / world + max(float(x) ** 3 for x in m)
+
+
+def _merit_worker(rank, world, port, ret):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        fd, sets = _merit_problem()
+        table = shard.merit_farm(lambda g: mo.calc_merit(fd, gate_eigenvalues=g), sets)
+        if rank == 0:
+            ret["table"] = table
+    finally:
+        dist.destroy_process_group()
+
+
+def _merit_problem():
+    import aces_b200
+
+    fd = aces_b200.example_design(full_covariance=True)
+    rng = np.random.default_rng(8)
+    g0 = np.asarray(fd.gate_eigenvalues, dtype=np.float64)
+    return fd, [1.0 - (1.0 - g0) * rng.uniform(0.5, 1.5, size=len(g0)) for _ in range(5)]
+
+
+def test_merit_farm_world_size_2_gloo():
+    """calc_ensemble_scaling's repetition loop as replicas: 5 noise instances over 2 ranks
+    (uneven: 3 + 2), every rank ends up with the whole table, equal to the serial one."""
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_merit_worker, args=(2, port, ret), nprocs=2, join=True)
+    fd, sets = _merit_problem()
+    serial = shard.merit_farm(lambda g: mo.calc_merit(fd, gate_eigenvalues=g), sets)
+    assert serial.shape == (5, 18) and np.all(np.isfinite(serial))
+    assert np.array_equal(ret["table"], serial)
