@@ -46,6 +46,7 @@ struct aces_ctx {
     DevBuf d_odd;      // cumulative odd counts when the caller's output is on the host
     DevBuf h_stage;    // pinned staging for the small per-call tables (two slots, used alternately so
     DevBuf h_stage2;   // that the host can prepare call i+1 while call i's copy is still queued)
+    DevBuf h_pack;     // pinned staging of small host sample matrices (one upload for all of them)
     cudaEvent_t ev2 = nullptr;
     int stage_slot = 0;
     std::vector<uint8_t> tbl_scratch, tbl_uploaded;  // K1 tables: last upload (skipped when unchanged)

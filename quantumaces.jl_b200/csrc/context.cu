@@ -143,6 +143,7 @@ int32_t aces_destroy(aces_ctx* ctx) {
         if (b.ptr) cudaFree(b.ptr);
     if (ctx->h_stage.ptr) cudaFreeHost(ctx->h_stage.ptr);
     if (ctx->h_stage2.ptr) cudaFreeHost(ctx->h_stage2.ptr);
+    if (ctx->h_pack.ptr) cudaFreeHost(ctx->h_pack.ptr);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->ev) cudaEventDestroy(ctx->ev);
     if (ctx->t0) cudaEventDestroy(ctx->t0);

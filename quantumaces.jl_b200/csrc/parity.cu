@@ -155,8 +155,9 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
     std::vector<int32_t> item_E(n_items);
     std::vector<char> in_place(n_items);
     std::vector<size_t> arena_off(n_items, 0), raw_off(n_items, 0);
-    std::vector<char> src_dev(n_items, 0);
-    size_t arena_bytes = 0, raw_bytes = 0;
+    std::vector<char> src_dev(n_items, 0), packed(n_items, 0);
+    size_t arena_bytes = 0, raw_bytes = 0, pack_bytes = 0;
+    constexpr size_t PACK_LIMIT = 256 * 1024;
     int max_E = 0;
     for (int i = 0; i < n_items; ++i) {
         const int e = experiment_ids[i];
@@ -187,6 +188,14 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
         in_place[i] = layout == 0 && dev && (((uintptr_t)counts[i]) % 16 == 0) && (ld[i] % 16 == 0);
         if (!in_place[i] && rows[i] > 0) {
             const size_t pitch = ((size_t)rows[i] + 127) & ~(size_t)127;
+            if (layout == 0 && !dev && pitch * B <= PACK_LIMIT) {
+                // a small host matrix (estimate_stim_ensemble: thousands of 64 ... 10^4-shot circuits per job,
+                // src/device.jl:178-229): packed into pinned staging, all of them uploaded by ONE copy
+                packed[i] = 1;
+                arena_off[i] = pack_bytes;
+                pack_bytes += pitch * B;
+                continue;
+            }
             arena_off[i] = arena_bytes;
             arena_bytes += pitch * B;
             if (layout == 1) {
@@ -215,7 +224,24 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
     std::vector<StreamDesc> streams;
     std::vector<double> stream_cost;  // estimated warp instructions per tile (cost-balanced partition below)
     std::vector<int64_t> item_start(1, 0);
-    if (arena_bytes > 0) ACES_TRY(aces_reserve_dev(ctx, ctx->d_arena, arena_bytes));
+    if (pack_bytes > 0) {
+        // the packed matrices sit behind the others in the arena
+        for (int i = 0; i < n_items; ++i)
+            if (packed[i]) arena_off[i] += arena_bytes;
+        ACES_TRY(aces_reserve_host(ctx, ctx->h_pack, pack_bytes));
+        ACES_TRY(aces_reserve_dev(ctx, ctx->d_arena, arena_bytes + pack_bytes));
+        uint8_t* hp = (uint8_t*)ctx->h_pack.ptr;
+        for (int i = 0; i < n_items; ++i) {
+            if (!packed[i]) continue;
+            const size_t pitch = ((size_t)rows[i] + 127) & ~(size_t)127;
+            uint8_t* dst = hp + (arena_off[i] - arena_bytes);
+            for (int c = 0; c < B; ++c) memcpy(dst + (size_t)c * pitch, counts[i] + (size_t)c * (size_t)ld[i], (size_t)rows[i]);
+        }
+        // blocking entry point: the copy has completed before the next call can touch h_pack
+        ACES_CUDA(ctx, cudaMemcpyAsync((uint8_t*)ctx->d_arena.ptr + arena_bytes, hp, pack_bytes, cudaMemcpyHostToDevice,
+                                       ctx->stream));
+    }
+    if (arena_bytes > 0) ACES_TRY(aces_reserve_dev(ctx, ctx->d_arena, arena_bytes + pack_bytes));
     if (layout == 1 && arena_bytes > 0) {
         // row-major records: contiguous copies into the raw staging area, then ONE batched transposition
         if (raw_bytes > 0) ACES_TRY(aces_reserve_dev(ctx, ctx->d_raw, raw_bytes));
@@ -262,7 +288,7 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
         } else {
             const size_t pitch = ((size_t)rows[i] + 127) & ~(size_t)127;
             uint8_t* dst = (uint8_t*)ctx->d_arena.ptr + arena_off[i];
-            if (layout == 0)
+            if (layout == 0 && !packed[i])
                 ACES_CUDA(ctx, cudaMemcpy2DAsync(dst, pitch, counts[i], (size_t)ld[i], (size_t)rows[i],
                                                  (size_t)B, cudaMemcpyDefault, ctx->stream));
             base = dst;

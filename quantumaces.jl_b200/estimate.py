@@ -114,6 +114,53 @@ class DesignEstimator:
         odd = self.odd_counts(mats, rows, ld, prefix[:, order], rowmajor=rowmajor)
         return self.scatter(odd, prefix[:, order], order)
 
+    def estimate_ensemble(self, jobs, job_indices, pauli_sign_ensemble, covariance_pauli_sign_ensemble,
+                          experiment_shots: int):
+        """The estimation loop of estimate_stim_ensemble (src/device.jl:178-229; the Matrix{UInt8} half of
+        estimate_qiskit_ensemble, :272-323, is the same): a randomised design runs thousands of small
+        circuits (64 ... 10^4 shots each) in jobs; circuit c of job b ran experiment j of tuple i under
+        randomisation r -- job_indices[b][c] = (i, j, r), 0-based -- with the Pauli signs
+        pauli_sign_ensemble[i][j][r] (and covariance_pauli_sign_ensemble[i][j][r]).  Where the reference
+        calls estimate_experiment twice per circuit, here ALL circuits of a job go through one
+        aces_parity_counts launch (n_items = circuits of the job, K = 1, both Pauli sets of the experiment in
+        the same pass; small host matrices are packed into one pinned upload).  Returns
+        (est_eigenvalues_experiment_ensemble, est_covariance_experiment_ensemble): [i][pauli_idx] -> list."""
+        fd = self.fd
+        has_cov = bool(fd.cov_keys)
+        eig_ens = [[[] for _ in range(int(m))] for m in fd.mapping_lengths]
+        cov_ens = [[[] for _ in range(len(fd.cov_keys[t]) if has_cov else 0)] for t in range(fd.tuple_number)]
+        exp0 = np.concatenate([[0], np.cumsum(fd.experiment_numbers)]).astype(np.int64)
+        S = int(experiment_shots)
+        for counts_list, indices in zip(jobs, job_indices):
+            # src/device.jl:192
+            assert len(counts_list) == len(indices), "The number of circuits in the job does not match the number of counts."
+            if not len(indices):
+                continue
+            eids = np.asarray([exp0[i] + j for (i, j, _) in indices], dtype=np.int32)
+            mats = [m if m.flags.f_contiguous else np.asfortranarray(m) for m in counts_list]
+            rows = [m.shape[0] for m in mats]
+            ld = [max(m.shape[0], 1) for m in mats]
+            prefix = np.full((len(mats), 1), S, dtype=np.int64)
+            odd = self.odd_counts(mats, rows, ld, prefix, experiment_ids=eids)
+            off = 0
+            for (i, j, r), e in zip(indices, eids):
+                E = int(self.exp_ptr[e + 1] - self.exp_ptr[e])
+                ne = int(self.n_eig[e])
+                pauli_shots = S - 2 * odd[off:off + E]
+                off += E
+                sg = np.asarray(pauli_sign_ensemble[i][j][r], dtype=np.int64)
+                assert len(sg) == ne, "The number of signs does not match the number of circuit eigenvalues."
+                est = ((1 - 2 * sg) * pauli_shots[:ne]) / np.float64(S)      # src/estimate.jl:297-298
+                for idx, pidx in enumerate(fd.experiment_ensemble[i][j]):
+                    eig_ens[i][int(pidx)].append(float(est[idx]))
+                if has_cov and len(fd.cov_keys[i]) > 0:
+                    csg = np.asarray(covariance_pauli_sign_ensemble[i][j][r], dtype=np.int64)
+                    assert len(csg) == E - ne
+                    cest = ((1 - 2 * csg) * pauli_shots[ne:]) / np.float64(S)
+                    for idx, cidx in enumerate(fd.cov_experiment_ensemble[i][j]):
+                        cov_ens[i][int(cidx)].append(float(cest[idx]))
+        return eig_ens, cov_ens
+
     def scatter(self, odd: np.ndarray, prefix_sorted: np.ndarray, order: np.ndarray):
         """Forms ((-1)^sign * pauli_shots) / shots_value (src/estimate.jl:297-298) from the odd
         counts and pushes each estimate into [s][t][pauli_idx] (src/simulate.jl:214-233)."""

@@ -31,6 +31,8 @@
 #        descent loop restated once, its gradient (calc_*_merit_grad_log) on the GPU        (f3)
 #   calc_merit(d; warning)                                      src/merit.jl:925-1043    estimator covariances,
 #        marginal / relative transforms and the nine eigvals on the GPU in one call (aces_design_merit)  (f2)
+#   estimate_stim_ensemble(d_rand, experiment_shots; ...)       src/device.jl:156-244    the job loop with ONE
+#        aces_parity_counts launch per job (thousands of 64 ... 10^4-shot circuits as items of one batch)
 #   S1  estimate_experiment(::Matrix{UInt8}, ...)             src/estimate.jl:284-301
 #   S2  estimate_gate_eigenvalues(A, F, est; constrain)        src/estimate.jl:492-524 (and the OLS form)
 # sparse_covariance_inv_factor(covariance_log, lengths) (src/merit.jl:378-427) has no Design argument
@@ -274,6 +276,90 @@ function estimate_counts!(eig_set, cov_set, t::PauliTables, stim_counts::Vector{
         off += E * K
     end
     return nothing
+end
+
+"""
+    estimate_job!(eig_ens, cov_ens, tables, job_counts, circuit_indices, pauli_sign_ensemble,
+                  covariance_pauli_sign_ensemble, experiment_shots, exp_offset)
+
+One job of a randomised design (src/device.jl:190-229): circuit `c` ran experiment `j` of tuple `i` under
+randomisation `r` (`circuit_indices[c] = (i, j, r)`).  Where the reference calls estimate_experiment
+twice per circuit, ALL circuits of the job go through ONE aces_parity_counts launch (n_items = circuits,
+K = 1; both Pauli sets of an experiment in the same pass; the library packs the small host matrices
+into one pinned upload).  Estimates are pushed in the reference's order.
+"""
+function estimate_job!(eig_ens, cov_ens, t::PauliTables, job_counts::Vector{Matrix{UInt8}},
+                       circuit_indices, pauli_sign_ensemble, covariance_pauli_sign_ensemble,
+                       experiment_shots::Integer, exp_offset::Vector{Int})
+    n_items = length(job_counts)
+    n_items == 0 && return nothing
+    eids = [exp_offset[i] + j for (i, j, r) in circuit_indices]          # 1-based table experiments
+    ids = Int32.(eids .- 1)
+    ptrs = [pointer(m) for m in job_counts]
+    rows = Int64[size(m, 1) for m in job_counts]
+    ld = max.(rows, 1)
+    prefix = fill(Int64(experiment_shots), n_items)
+    total = sum(Int(t.exp_ptr[e + 1] - t.exp_ptr[e]) for e in eids)
+    odd = zeros(Int64, total)
+    GC.@preserve job_counts ids ptrs rows ld prefix odd begin
+        check(ccall((:aces_parity_counts, LIB[]), Int32,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Ptr{UInt8}}, Ptr{Int64}, Ptr{Int64}, Int32,
+             Ptr{Int64}, Ptr{Int64}, Int32),
+            CTX[], t.handle, Int32(n_items), ids, ptrs, rows, ld, Int32(1), prefix, odd, Int32(0)))
+    end
+    S = Int(experiment_shots)
+    off = 0
+    for (c, (i, j, r)) in pairs(circuit_indices)
+        e = eids[c]
+        E = Int(t.exp_ptr[e + 1] - t.exp_ptr[e]); ne = t.n_eig[e]
+        signs = pauli_sign_ensemble[i][j][r]
+        @assert length(signs) == ne "The number of signs does not match the number of circuit eigenvalues."
+        for idx in 1:ne
+            pauli_shots = S - 2 * odd[off + idx]
+            push!(eig_ens[i][t.experiment[e][idx]], ((-1)^signs[idx] * pauli_shots) / S)
+        end
+        if E > ne
+            csigns = covariance_pauli_sign_ensemble[i][j][r]
+            for idx in 1:(E - ne)
+                pauli_shots = S - 2 * odd[off + ne + idx]
+                push!(cov_ens[i][t.covariance_experiment[e][idx]], ((-1)^csigns[idx] * pauli_shots) / S)
+            end
+        end
+        off += E
+    end
+    return nothing
+end
+
+"""
+Drop-in for `estimate_stim_ensemble(d_rand, experiment_shots; fail_jobs, simulation_seed, min_eigenvalue,
+split, precision)` (src/device.jl:156-244): the reference's job loop with one launch per job
+(`estimate_job!`), then the reference's estimate_gate_noise(d_rand, ...) (whose numeric core install!()
+routes to the GPU as well).
+"""
+function estimate_stim_ensemble(d_rand, experiment_shots::Integer; fail_jobs::Vector{Int} = Int[],
+                                simulation_seed::Union{UInt64, Nothing} = nothing, min_eigenvalue::Real = 0.1,
+                                split::Bool = false, precision::Real = 1e-8)
+    d = d_rand.d
+    tuple_number = length(d.tuple_set)
+    backend = simulation_seed !== nothing ? "stim_$(simulation_seed)" : "stim"
+    t = get!(() -> PauliTables(d), TABLES_CACHE, d.matrix)
+    mapping_lengths = length.(d.mapping_ensemble)
+    covariance_mapping_lengths = length.(QuantumACES.get_covariance_experiment_data(d)[2])   # src/device.jl:181-184
+    exp_offset = [0; cumsum(d.experiment_numbers)[1:(end - 1)]]
+    job_indices = d_rand.job_indices
+    job_number = length(job_indices)
+    @assert all(fail_jobs .> 1) && all(fail_jobs .<= job_number) "The failed job indices are not consistent with the number of jobs."
+    success_jobs = setdiff(1:job_number, fail_jobs)
+    eig_ens = [[Float64[] for j in 1:mapping_lengths[i]] for i in 1:tuple_number]
+    cov_ens = [[Float64[] for j in 1:covariance_mapping_lengths[i]] for i in 1:tuple_number]
+    for job_idx in success_jobs
+        job_counts = QuantumACES.load_rand_design_job(d_rand, backend, job_idx)
+        @assert length(job_counts) == length(job_indices[job_idx]) "The number of circuits in the job does not match the number of counts."
+        estimate_job!(eig_ens, cov_ens, t, Vector{Matrix{UInt8}}(job_counts), job_indices[job_idx],
+                      d_rand.pauli_sign_ensemble, d_rand.covariance_pauli_sign_ensemble, experiment_shots, exp_offset)
+    end
+    return QuantumACES.estimate_gate_noise(d_rand, eig_ens, cov_ens; min_eigenvalue = min_eigenvalue, split = split,
+                                           precision = precision)
 end
 
 """
@@ -1037,7 +1123,13 @@ function install!()
             max_samples::Integer = 10^9, detailed_diagnostics::Bool = false) =
             $(simulate_stim_estimate)(d, shots_set; seed = seed, max_samples = max_samples,
                 detailed_diagnostics = detailed_diagnostics)
-        # S1 (second caller: estimate_stim_ensemble, src/device.jl:201-313)
+        # second caller of S1: one launch per job instead of two estimate_experiment calls per circuit
+        estimate_stim_ensemble(d_rand::RandDesign, experiment_shots::Integer; fail_jobs::Vector{Int} = Int[],
+            simulation_seed::Union{UInt64, Nothing} = nothing, min_eigenvalue::Real = 0.1, split::Bool = false,
+            precision::Real = 1e-8) =
+            $(estimate_stim_ensemble)(d_rand, experiment_shots; fail_jobs = fail_jobs, simulation_seed = simulation_seed,
+                min_eigenvalue = min_eigenvalue, split = split, precision = precision)
+        # S1 (remaining caller: estimate_qiskit_ensemble on parsed counts, src/device.jl:295-313)
         estimate_experiment(counts::Matrix{UInt8}, experiment_meas_indices::Vector{Vector{Int}},
             experiment_pauli_signs::Vector{Bool}, shots_value::Integer) =
             $(estimate_experiment)(counts, experiment_meas_indices, experiment_pauli_signs, shots_value)

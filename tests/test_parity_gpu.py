@@ -502,3 +502,65 @@ def test_rowmajor_design_batch_equals_colmajor(ctx):
     eig_r, cov_r = est.simulate_estimate(recs, shots_set)                           # C order -> row-major ingest
     eig_c, cov_c = est.simulate_estimate([np.asfortranarray(r) for r in recs], shots_set)
     assert eig_r == eig_c and cov_r == cov_c
+
+
+@pytest.mark.parametrize("source", ["synthetic3", "real5"])
+def test_estimate_ensemble_thousands_of_small_circuits(ctx, source):
+    """estimate_stim_ensemble (src/device.jl:156-244): a randomised design runs thousands of small circuits
+    (64 ... 10^4 shots, here 64 ... 1200 with odd counts) with per-randomisation Pauli signs; every job goes
+    through ONE launch (n_items = its circuits).  Each circuit is checked against two estimate_experiment
+    calls of the oracle, as the reference makes them, and the ensemble nesting against the reference's."""
+    import aces_b200
+
+    if source == "synthetic3":
+        fd = aces_b200.synthetic_design("rotated", 3, full_covariance=True, stress_weights=True)
+    else:
+        fd = aces_b200.rotated_design(5, full_covariance=True)
+    est = aces_b200.DesignEstimator(ctx, fd)
+    rng = np.random.default_rng(23)
+    S = 257
+    randomisations = 12 if source == "synthetic3" else 3
+    has_cov = bool(fd.cov_keys)
+    # signs per (tuple, experiment, randomisation)
+    sign_ens, cov_sign_ens, circuits = [], [], []
+    for i in range(fd.tuple_number):
+        sign_ens.append([])
+        cov_sign_ens.append([])
+        for j in range(int(fd.experiment_numbers[i])):
+            ne = len(fd.experiment_ensemble[i][j])
+            nc = len(fd.cov_experiment_ensemble[i][j]) if has_cov and len(fd.cov_keys[i]) else 0
+            sign_ens[i].append([rng.integers(0, 2, size=ne).astype(bool) for _ in range(randomisations)])
+            cov_sign_ens[i].append([rng.integers(0, 2, size=nc).astype(bool) for _ in range(randomisations)])
+            circuits += [(i, j, r) for r in range(randomisations)]
+    order = rng.permutation(len(circuits))
+    circuits = [circuits[k] for k in order]
+    n_jobs = 3
+    job_indices = [circuits[b::n_jobs] for b in range(n_jobs)]
+    assert sum(len(x) for x in job_indices) >= (1000 if source == "synthetic3" else 250)
+    jobs = []
+    for b, idx in enumerate(job_indices):
+        mats = []
+        for c in range(len(idx)):
+            rows = S + int(rng.integers(0, 3)) * 64 if c % 7 else S        # some circuits carry spare rows
+            mats.append(np.asfortranarray(rng.integers(0, 256, size=(rows, fd.n_bytes), dtype=np.uint8)))
+        jobs.append(mats)
+    launches0 = ctx.kernel_launches()
+    eig_ens, cov_ens = est.estimate_ensemble(jobs, job_indices, sign_ens, cov_sign_ens, S)
+    assert ctx.kernel_launches() - launches0 <= 3 * n_jobs     # parity kernel + prefix kernel (+ table upload) per job
+    # the reference loop with the oracle's estimate_experiment
+    exp0 = np.concatenate([[0], np.cumsum(fd.experiment_numbers)]).astype(int)
+    want_eig = [[[] for _ in range(int(m))] for m in fd.mapping_lengths]
+    want_cov = [[[] for _ in range(len(fd.cov_keys[t]) if has_cov else 0)] for t in range(fd.tuple_number)]
+    for mats, idx in zip(jobs, job_indices):
+        for m, (i, j, r) in zip(mats, idx):
+            sup = ob.table_supports(est, exp0[i] + j)
+            ne = len(fd.experiment_ensemble[i][j])
+            e1, _ = ob.estimate_experiment(m, sup[:ne], sign_ens[i][j][r], S)
+            for k, p in enumerate(fd.experiment_ensemble[i][j]):
+                want_eig[i][int(p)].append(float(e1[k]))
+            if has_cov and len(fd.cov_keys[i]):
+                e2, _ = ob.estimate_experiment(m, sup[ne:], cov_sign_ens[i][j][r], S)
+                for k, p in enumerate(fd.cov_experiment_ensemble[i][j]):
+                    want_cov[i][int(p)].append(float(e2[k]))
+    assert eig_ens == want_eig          # bit-exact, same nesting and order
+    assert cov_ens == want_cov
