@@ -47,28 +47,66 @@ struct PanelArgs {
     double *d, *e;
     double* ypart;      // [Np / 128][Np]: partial products, [source block][target row]
     double* part1;      // [grid][P1]
-    double* part2;      // [grid]
     double* pq;         // [2 NB]: V'v then W'v
-    unsigned* bar;
+    LLSlot* ll;         // [2][grid]
     int SL;
 };
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+// Grid barrier fused with a reduction, in the style of NCCL's LL protocol: every CTA publishes two doubles as
+// four 64-bit words, each carrying 32 bits of payload and the 32-bit epoch of this barrier, so a reader
+// that sees the epoch in a word has the payload of that word too (64-bit stores are single-copy atomic).
+// One warp of every CTA polls all slots: the barrier and the cross-CTA sums behind it cost ONE round of
+// loads instead of an atomic, a poll and a read.  The sums run over the CTAs in a fixed order.  All CTAs
+// are co-resident (cooperative launch).  Two slot arrays alternate (a CTA that has passed barrier b + 1
+// knows every CTA has read the slots of barrier b), epochs are unique within one factorisation and the
+// arrays are zeroed before it.
+struct LLSlot {
+    unsigned long long w[4];
+};
+__device__ __forceinline__ void ll_publish(LLSlot* slot, double v0, double v1, unsigned epoch) {
+    const unsigned long long b0 = (unsigned long long)__double_as_longlong(v0), b1 = (unsigned long long)__double_as_longlong(v1);
+    const unsigned long long ep = (unsigned long long)epoch << 32;
+    const unsigned long long w0 = (b0 & 0xffffffffull) | ep, w1 = (b0 >> 32) | ep;
+    const unsigned long long w2 = (b1 & 0xffffffffull) | ep, w3 = (b1 >> 32) | ep;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot->w), "l"(w0), "l"(w1) : "memory");
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot->w + 2), "l"(w2), "l"(w3) : "memory");
 }
-
-// all CTAs are co-resident (cooperative launch): a monotonic arrival counter, zeroed before the launch
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& round) {
+__device__ __forceinline__ void ll_wait(const LLSlot* slot, unsigned epoch, double* v0, double* v1) {
+    unsigned long long w0, w1, w2, w3;
+    do {
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot->w) : "memory");
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "l"(slot->w + 2) : "memory");
+    } while ((unsigned)(w0 >> 32) != epoch || (unsigned)(w1 >> 32) != epoch || (unsigned)(w2 >> 32) != epoch ||
+             (unsigned)(w3 >> 32) != epoch);
+    *v0 = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    *v1 = __longlong_as_double((long long)((w2 & 0xffffffffull) | (w3 << 32)));
+}
+// v0, v1: this CTA's contributions (thread 0's are used); out[0], out[1] (shared memory): the sums over the grid
+__device__ __forceinline__ void ll_barrier(LLSlot* slots, unsigned epoch, double v0, double v1, double* out) {
     __syncthreads();
-    if (threadIdx.x == 0) {
-        round += gridDim.x;
-        __threadfence();
-        atomicAdd(bar, 1u);
-        while (ld_acquire_u32(bar) < round) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x, G = gridDim.x;
+        if (lane == 0) {
+            __threadfence();  // release: everything this CTA wrote before the barrier
+            ll_publish(slots + blockIdx.x, v0, v1, epoch);
         }
-        __threadfence();
+        double s0 = 0.0, s1 = 0.0;
+        for (int c = lane; c < G; c += 32) {
+            double t0, t1;
+            ll_wait(slots + c, epoch, &t0, &t1);
+            s0 += t0;
+            s1 += t1;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        __threadfence();  // acquire: what the other CTAs wrote before they published
+        if (lane == 0) {
+            out[0] = s0;
+            out[1] = s1;
+        }
     }
     __syncthreads();
 }
@@ -111,7 +149,9 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, cta = blockIdx.x;
     const int n = a.n, Np = a.Np;
-    unsigned round = 0;
+    LLSlot* const ll1 = a.ll;
+    LLSlot* const ll2 = a.ll + G;
+    double anext = 0.0;   // A[own row, j + 1], fetched one column ahead
     // global row of local row li
     auto grow = [&](int li) -> int64_t { return ((int64_t)((li >> 5) * G + cta)) * 32 + (li & 31); };
 
@@ -135,7 +175,7 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
                 double c = 0.0;
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) c += red[ks * R + tid];
-                x = a.A[i + (int64_t)j * a.lda] - c;
+                x = (jj > 0 ? anext : a.A[i + (int64_t)j * a.lda]) - c;
                 if (i == j) {
                     a.d[j] = x;
                     x = 0.0;
@@ -153,7 +193,11 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
             // over the grid.  The next column needs row j + 1 of V and W, whose newest entry was stored by
             // its owner after the last barrier: one more barrier, then read the row from global memory.
             if (tid < R) Vs[jj * R + tid] = Ws[jj * R + tid] = 0.0;
-            grid_barrier(a.bar, round);
+            ll_barrier(ll1, (unsigned)(j + 1), 0.0, 0.0, scal + 6);
+            if (tid < R && j + 1 < n) {
+                const int64_t i = grow(tid);
+                anext = (i >= j + 1 && i < n) ? a.A[i + (int64_t)(j + 1) * a.lda] : 0.0;
+            }
             if (tid <= jj) {
                 const bool have = tid < jj && j + 1 < n;
                 Vrow[tid] = have ? __ldcg(a.P + (j + 1) + (int64_t)tid * Np) : 0.0;
@@ -164,12 +208,7 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
         }
         nrm = warp_sum(nrm);
         if (lane == 0 && warp < a.SL) scal[8 + warp] = nrm;
-        __syncthreads();
-        if (tid == 0) {
-            double s = 0.0;
-            for (int w = 0; w < a.SL; ++w) s += scal[8 + w];
-            __stcg(a.part1 + (int64_t)cta * P1, s);
-        }
+        if (tid < R && grow(tid) == j + 1) scal[14] = xs[tid];  // alpha, on the CTA that owns row j + 1
         for (int u = warp; u < a.SL * KS; u += NWARP) {
             const int slot = u / KS, ks = u % KS, li = slot * 32 + lane;
             const int k1 = min(jj, (ks + 1) * KW);
@@ -189,16 +228,25 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
             for (int slot = 0; slot < a.SL; ++slot) s += dots[slot * 2 * NB + tid];
             __stcg(a.part1 + (int64_t)cta * P1 + 1 + tid, s);
         }
-        grid_barrier(a.bar, round);
+        {
+            // |x|^2 (rows >= j + 2) and alpha = x[j + 1] (non-zero on its owner only) ride on the barrier
+            double mine = 0.0, alpha_mine = 0.0;
+            if (tid == 0) {
+                for (int w = 0; w < a.SL; ++w) mine += scal[8 + w];
+                const int64_t owner_blk = (j + 1) / 32;
+                if ((int)(owner_blk % G) == cta) alpha_mine = scal[14];
+            }
+            ll_barrier(ll1, (unsigned)(j + 1), mine, alpha_mine, scal + 6);
+        }
 
         // ---------------- phase B: the reflector, then (trailing matrix) * v ---------------------------
-        // warp 0: |x|^2 over the grid -> tau, scale; meanwhile warps 1.. sum this CTA's entries of V'x / W'x
+        // warp 0: tau, scale; meanwhile warps 1.. sum this CTA's entries of V'x / W'x over the grid
         double pq_sum = 0.0, pq_coef = 0.0;
         int pq_e = -1;
         if (warp == 0) {
-            const double nrm2 = sum_over_ctas(a.part1, P1, G, lane);
+            const double nrm2 = scal[6];
             if (lane == 0) {
-                const double alpha = __ldcg(a.P + (j + 1) + (int64_t)jj * Np);
+                const double alpha = scal[7];
                 double tau = 0.0, scale = 0.0, beta = alpha;
                 if (nrm2 > 0.0) {
                     beta = -copysign(sqrt(alpha * alpha + nrm2), alpha);
