@@ -20,6 +20,7 @@
 // The caller passes the matrix in full (both triangles); the diagonal tiles are used in full.  It is scaled by a power of two to unit max-norm first (exact), as dsyev scales badly scaled input.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 
 #include "aces_common.h"
 #include "dense.cuh"
@@ -38,6 +39,7 @@ constexpr int KW = NB / KS;
 constexpr int P1 = 2 * NB + 2;    // per-CTA partials of phase A: [0] |x|^2, [1 + k] V'x, [1 + NB + k] W'x
 constexpr int MAX_SL = 6;         // 32-row slots a CTA can own (shared-memory bound)
 
+struct LLSlot;
 struct PanelArgs {
     const double* A;
     int64_t lda;
@@ -48,61 +50,56 @@ struct PanelArgs {
     double* ypart;      // [Np / 128][Np]: partial products, [source block][target row]
     double* part1;      // [grid][P1]
     double* pq;         // [2 NB]: V'v then W'v
-    LLSlot* ll;         // [2][grid]
+    LLSlot* ll;         // [2][grid] partial sums + one slot holding the arrival counter
+    unsigned epoch0;    // barriers executed by the panels before this one
     int SL;
 };
 
-// Grid barrier fused with a reduction, in the style of NCCL's LL protocol: every CTA publishes two doubles as
-// four 64-bit words, each carrying 32 bits of payload and the 32-bit epoch of this barrier, so a reader
-// that sees the epoch in a word has the payload of that word too (64-bit stores are single-copy atomic).
-// One warp of every CTA polls all slots: the barrier and the cross-CTA sums behind it cost ONE round of
-// loads instead of an atomic, a poll and a read.  The sums run over the CTAs in a fixed order.  All CTAs
-// are co-resident (cooperative launch).  Two slot arrays alternate (a CTA that has passed barrier b + 1
-// knows every CTA has read the slots of barrier b), epochs are unique within one factorisation and the
-// arrays are zeroed before it.
+// Grid barrier fused with a reduction: every CTA stores two doubles, arrives on a monotonic counter, waits for
+// the whole grid and sums everybody's doubles in a fixed order.  All CTAs are co-resident (cooperative launch).
+// bidx is the running index of the barrier within the factorisation (uniform over the grid): the slot array
+// alternates with its parity (a CTA that has passed barrier b + 1 knows every CTA has read the slots of
+// barrier b), the counter never resets (target (bidx + 1) * grid; zeroed before the first panel).
+// Measured alternatives at N = 6779 / 1024 (device-resident, profiles/eig_r02_barrier_variants.txt): all-to-all
+// polling of (value, epoch) words packed NCCL-LL style, one round of loads instead of three round trips:
+// 358 / 25 ms -- 148 x 148 polled slots congest the L2; the same with back-off 372 / 27 ms; the last arriver
+// summing and handing every CTA the result in its own slot 251 / 19 ms; this one 242 / 18 ms.
 struct LLSlot {
     unsigned long long w[4];
 };
-__device__ __forceinline__ void ll_publish(LLSlot* slot, double v0, double v1, unsigned epoch) {
-    const unsigned long long b0 = (unsigned long long)__double_as_longlong(v0), b1 = (unsigned long long)__double_as_longlong(v1);
-    const unsigned long long ep = (unsigned long long)epoch << 32;
-    const unsigned long long w0 = (b0 & 0xffffffffull) | ep, w1 = (b0 >> 32) | ep;
-    const unsigned long long w2 = (b1 & 0xffffffffull) | ep, w3 = (b1 >> 32) | ep;
-    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot->w), "l"(w0), "l"(w1) : "memory");
-    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot->w + 2), "l"(w2), "l"(w3) : "memory");
-}
-__device__ __forceinline__ void ll_wait(const LLSlot* slot, unsigned epoch, double* v0, double* v1) {
-    unsigned long long w0, w1, w2, w3;
-    do {
-        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot->w) : "memory");
-        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "l"(slot->w + 2) : "memory");
-    } while ((unsigned)(w0 >> 32) != epoch || (unsigned)(w1 >> 32) != epoch || (unsigned)(w2 >> 32) != epoch ||
-             (unsigned)(w3 >> 32) != epoch);
-    *v0 = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
-    *v1 = __longlong_as_double((long long)((w2 & 0xffffffffull) | (w3 << 32)));
-}
 // v0, v1: this CTA's contributions (thread 0's are used); out[0], out[1] (shared memory): the sums over the grid
-__device__ __forceinline__ void ll_barrier(LLSlot* slots, unsigned epoch, double v0, double v1, double* out) {
+__device__ __noinline__ void ll_barrier(LLSlot* ll, unsigned bidx, double v0, double v1, double* out) {
+    const int G = gridDim.x;
+    LLSlot* slots = ll + (bidx & 1u) * G;
     __syncthreads();
     if (threadIdx.x < 32) {
-        const int lane = threadIdx.x, G = gridDim.x;
+        const int lane = threadIdx.x;
+        unsigned* counter = reinterpret_cast<unsigned*>(ll + 2 * G);
         if (lane == 0) {
+            double* mine = reinterpret_cast<double*>(slots[blockIdx.x].w);
+            __stcg(mine, v0);
+            __stcg(mine + 1, v1);
             __threadfence();  // release: everything this CTA wrote before the barrier
-            ll_publish(slots + blockIdx.x, v0, v1, epoch);
+            atomicAdd(counter, 1u);
+            const unsigned target = (bidx + 1u) * (unsigned)G;
+            unsigned seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+            } while (seen < target);
         }
+        __syncwarp();
+        __threadfence();  // acquire: what the other CTAs wrote before they arrived
         double s0 = 0.0, s1 = 0.0;
         for (int c = lane; c < G; c += 32) {
-            double t0, t1;
-            ll_wait(slots + c, epoch, &t0, &t1);
-            s0 += t0;
-            s1 += t1;
+            const double* p = reinterpret_cast<const double*>(slots[c].w);
+            s0 += __ldcg(p);
+            s1 += __ldcg(p + 1);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             s0 += __shfl_xor_sync(0xffffffffu, s0, o);
             s1 += __shfl_xor_sync(0xffffffffu, s1, o);
         }
-        __threadfence();  // acquire: what the other CTAs wrote before they published
         if (lane == 0) {
             out[0] = s0;
             out[1] = s1;
@@ -126,8 +123,8 @@ __device__ __forceinline__ double sum_over_ctas(const double* tab, int stride, i
 
 size_t panel_smem(int SL) {
     const size_t R = (size_t)SL * 32;
-    const size_t un = std::max((size_t)NWARP * RB, (size_t)KS * R + std::max((size_t)SL * 2 * NB, (size_t)KS * R));
-    return sizeof(double) * (2 * NB * R + R + 4 * NB + 16 + un);
+    const size_t un = std::max((size_t)(SL < MAX_SL ? 2 : 1) * (NWARP * RB + RB), (size_t)KS * R + std::max((size_t)SL * 2 * NB, (size_t)KS * R));
+    return sizeof(double) * (2 * NB * R + R + 4 * NB + 32 + un);
 }
 
 __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
@@ -140,17 +137,23 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
     double* Wrow = Vrow + NB;
     double* ps = Wrow + NB;          // W'v
     double* qs = ps + NB;            // V'v
-    double* scal = qs + NB;          // tau, scale, alpha, beta, alpha2, scratch
-    double* un = scal + 16;
+    double* scal = qs + NB;          // [32] tau, scale, alpha, beta, alpha2, scratch, barrier sums
+    double* un = scal + 32;
     double* red = un;                // [KS][R]
     double* dots = red + KS * R;     // [SL][2 NB] (phase A), [YG <= KS][R] (phase C)
-    double* redg = un;               // [NWARP][RB] (phase B only)
+    double* redg = un;               // [1 or 2][NWARP + 1][RB] (phase B only)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, cta = blockIdx.x;
     const int n = a.n, Np = a.Np;
-    LLSlot* const ll1 = a.ll;
-    LLSlot* const ll2 = a.ll + G;
+    unsigned bidx = a.epoch0;  // barriers of the factorisation so far
+#ifdef EIG_PROFILE
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long pc = clock64();
+#define EIG_MARK(k) do { const long long now_ = clock64(); pt[k] += now_ - pc; pc = now_; } while (0)
+#else
+#define EIG_MARK(k) do { } while (0)
+#endif
     double anext = 0.0;   // A[own row, j + 1], fetched one column ahead
     // global row of local row li
     auto grow = [&](int li) -> int64_t { return ((int64_t)((li >> 5) * G + cta)) * 32 + (li & 31); };
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
             // over the grid.  The next column needs row j + 1 of V and W, whose newest entry was stored by
             // its owner after the last barrier: one more barrier, then read the row from global memory.
             if (tid < R) Vs[jj * R + tid] = Ws[jj * R + tid] = 0.0;
-            ll_barrier(ll1, (unsigned)(j + 1), 0.0, 0.0, scal + 6);
+            ll_barrier(a.ll, bidx++, 0.0, 0.0, scal + 6);
             if (tid < R && j + 1 < n) {
                 const int64_t i = grow(tid);
                 anext = (i >= j + 1 && i < n) ? a.A[i + (int64_t)(j + 1) * a.lda] : 0.0;
@@ -209,6 +212,7 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
         nrm = warp_sum(nrm);
         if (lane == 0 && warp < a.SL) scal[8 + warp] = nrm;
         if (tid < R && grow(tid) == j + 1) scal[14] = xs[tid];  // alpha, on the CTA that owns row j + 1
+        __syncthreads();  // xs complete
         for (int u = warp; u < a.SL * KS; u += NWARP) {
             const int slot = u / KS, ks = u % KS, li = slot * 32 + lane;
             const int k1 = min(jj, (ks + 1) * KW);
@@ -236,7 +240,9 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
                 const int64_t owner_blk = (j + 1) / 32;
                 if ((int)(owner_blk % G) == cta) alpha_mine = scal[14];
             }
-            ll_barrier(ll1, (unsigned)(j + 1), mine, alpha_mine, scal + 6);
+            EIG_MARK(0);
+            ll_barrier(a.ll, bidx++, mine, alpha_mine, scal + 6);
+            EIG_MARK(1);
         }
 
         // ---------------- phase B: the reflector, then (trailing matrix) * v ---------------------------
@@ -284,41 +290,79 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
             const int b0 = (j + 1) / RB, m = (n + RB - 1) / RB - b0;
             const int tiles = m * (m + 1) / 2;
             double yv = 0.0;
-            for (int t = cta; t < tiles; t += G) {
+            // tile t of the lower triangle, row-major: (r, c) with t = r (r + 1) / 2 + c
+            auto coords = [&](int t, int& rb, int& cb) {
                 int r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
                 while (r * (r + 1) / 2 > t) --r;
                 while ((r + 1) * (r + 2) / 2 <= t) ++r;
-                const int rb = b0 + r, cb = b0 + (t - r * (r + 1) / 2);
-                const bool offdiag = rb != cb;
+                rb = b0 + r;
+                cb = b0 + (t - r * (r + 1) / 2);
+            };
+            // A warp owns eight columns of a tile (warp + 16 q); they are loaded in two halves of four
+            // and the loads run one half ahead of the arithmetic, ACROSS tiles: the first half of the next
+            // tile (and its slice of v) is in flight while this tile is reduced through shared memory.
+            double2 lo0[4], hi0[4], lo1[4], hi1[4];
+            double vvN = 0.0, vrN0 = 0.0, vrN1 = 0.0, vrN2 = 0.0, vrN3 = 0.0;
+            int rbN = 0, cbN = 0;
+            auto load_half = [&](double2* lo, double2* hi, int rb, int cb, int half) {
                 const double* Ab = a.A + (int64_t)rb * RB + 2 * lane + (int64_t)cb * RB * a.lda;
-                // this warp's eight columns of the tile: warp + 16 m (lane m < 8 holds v of column m)
-                const double vv = vcol(cb * RB + warp + 16 * (lane & 7));
-                double2 lo[8], hi[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const double* p = Ab + (int64_t)(warp + 16 * q) * a.lda;
+                for (int q = 0; q < 4; ++q) {
+                    const double* p = Ab + (int64_t)(warp + 16 * (4 * half + q)) * a.lda;
                     lo[q] = __ldg(reinterpret_cast<const double2*>(p));
                     hi[q] = __ldg(reinterpret_cast<const double2*>(p + 64));
                 }
-                double vr0 = 0.0, vr1 = 0.0, vr2 = 0.0, vr3 = 0.0;
-                if (offdiag) {
-                    const int r0 = rb * RB + 2 * lane;
-                    vr0 = vcol(r0);
-                    vr1 = vcol(r0 + 1);
-                    vr2 = vcol(r0 + 64);
-                    vr3 = vcol(r0 + 65);
-                }
+            };
+            auto load_vectors = [&](int rb, int cb) {
+                vvN = vcol(cb * RB + warp + 16 * (lane & 7));  // lane q < 8 holds v of column warp + 16 q
+                const int r0 = rb * RB + 2 * lane;  // v of the rows this lane holds (transposed product, v'(A v))
+                vrN0 = vcol(r0);
+                vrN1 = vcol(r0 + 1);
+                vrN2 = vcol(r0 + 64);
+                vrN3 = vcol(r0 + 65);
+            };
+            EIG_MARK(2);
+            int t = cta, it = 0;
+            const int nbuf = a.SL < MAX_SL ? 2 : 1;
+            if (t < tiles) {
+                coords(t, rbN, cbN);
+                load_vectors(rbN, cbN);
+                load_half(lo0, hi0, rbN, cbN, 0);
+            }
+            while (t < tiles) {
+                const int rb = rbN, cb = cbN;
+                const bool offdiag = rb != cb;
+                const double vv = vvN, vr0 = vrN0, vr1 = vrN1, vr2 = vrN2, vr3 = vrN3;
+                load_half(lo1, hi1, rb, cb, 1);
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, tmine = 0.0;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < 4; ++q) {
                     const double v = __shfl_sync(0xffffffffu, vv, q);
-                    a0 += lo[q].x * v;
-                    a1 += lo[q].y * v;
-                    a2 += hi[q].x * v;
-                    a3 += hi[q].y * v;
+                    a0 += lo0[q].x * v;
+                    a1 += lo0[q].y * v;
+                    a2 += hi0[q].x * v;
+                    a3 += hi0[q].y * v;
                     if (offdiag) {  // uniform over the CTA
-                        const double tq = warp_sum((lo[q].x * vr0 + lo[q].y * vr1) + (hi[q].x * vr2 + hi[q].y * vr3));
+                        const double tq = warp_sum((lo0[q].x * vr0 + lo0[q].y * vr1) + (hi0[q].x * vr2 + hi0[q].y * vr3));
                         if (lane == q) tmine = tq;
+                    }
+                }
+                const int tn = t + G;
+                if (tn < tiles) {
+                    coords(tn, rbN, cbN);
+                    load_vectors(rbN, cbN);
+                    load_half(lo0, hi0, rbN, cbN, 0);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double v = __shfl_sync(0xffffffffu, vv, 4 + q);
+                    a0 += lo1[q].x * v;
+                    a1 += lo1[q].y * v;
+                    a2 += hi1[q].x * v;
+                    a3 += hi1[q].y * v;
+                    if (offdiag) {
+                        const double tq = warp_sum((lo1[q].x * vr0 + lo1[q].y * vr1) + (hi1[q].x * vr2 + hi1[q].y * vr3));
+                        if (lane == 4 + q) tmine = tq;
                     }
                 }
                 if (offdiag && lane < 8) {
@@ -326,85 +370,69 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
                     __stcg(a.ypart + (int64_t)rb * Np + c, tmine);
                     yv += vv * tmine;
                 }
-                redg[warp * RB + 2 * lane] = a0;
-                redg[warp * RB + 2 * lane + 1] = a1;
-                redg[warp * RB + 64 + 2 * lane] = a2;
-                redg[warp * RB + 64 + 2 * lane + 1] = a3;
+                // cross-warp sum of the direct product through shared memory; with two buffers (all but the
+                // largest row-slot count) one barrier per tile is enough: the buffer is written again two
+                // tiles later, after the barrier of the tile in between
+                double* rbuf = redg + (size_t)(it & (nbuf - 1)) * (NWARP * RB + RB);
+                rbuf[warp * RB + 2 * lane] = a0;
+                rbuf[warp * RB + 2 * lane + 1] = a1;
+                rbuf[warp * RB + 64 + 2 * lane] = a2;
+                rbuf[warp * RB + 64 + 2 * lane + 1] = a3;
+                if (warp == 0) {
+                    double* vsm = rbuf + NWARP * RB;
+                    vsm[2 * lane] = vr0;
+                    vsm[2 * lane + 1] = vr1;
+                    vsm[64 + 2 * lane] = vr2;
+                    vsm[64 + 2 * lane + 1] = vr3;
+                }
                 __syncthreads();
                 if (tid < RB) {
                     double sd = 0.0;
 #pragma unroll
-                    for (int w = 0; w < NWARP; ++w) sd += redg[w * RB + tid];
-                    const int rr = rb * RB + tid;
-                    __stcg(a.ypart + (int64_t)cb * Np + rr, sd);
-                    yv += vcol(rr) * sd;
+                    for (int w = 0; w < NWARP; ++w) sd += rbuf[w * RB + tid];
+                    __stcg(a.ypart + (int64_t)cb * Np + rb * RB + tid, sd);
+                    yv += rbuf[NWARP * RB + tid] * sd;
                 }
-                __syncthreads();
+                if (nbuf == 1) __syncthreads();
+                t = tn;
+                ++it;
             }
-            // v'(A v) partial of this CTA
+            __syncthreads();
+            // v'(A v): this CTA's part rides on the barrier
             yv = warp_sum(yv);
             if (lane == 0) redg[warp] = yv;
             __syncthreads();
-            if (tid == 0) {
-                double sy = 0.0;
+            double sy = 0.0;
+            if (tid == 0)
                 for (int w = 0; w < NWARP; ++w) sy += redg[w];
-                __stcg(a.part2 + cta, sy);
-            }
+            EIG_MARK(3);
+            ll_barrier(a.ll, bidx++, sy, 0.0, scal + 16);
+            EIG_MARK(4);
         }
-        grid_barrier(a.bar, round);
 
         // ---------------- phase C: w = tau (A v - V (W'v) - W (V'v)) - (tau/2)(w'v) v --------------------
+        // every global load of this phase is issued before the first barrier, so they overlap: V'v / W'v,
+        // the partial products of the own rows and of row j + 1, row j + 1 of V and W, and column j + 1 of
+        // A for the next phase A
+        const int cc0 = (j + 1) / RB, ncc = (n + RB - 1) / RB - cc0;  // source blocks of the partial products
+        const int YG = min(THREADS / R, KS);
+        double* ysum = dots;  // [YG][R]: dots is dead in this phase
         if (tid < jj) {
             qs[tid] = __ldcg(a.pq + tid);
             ps[tid] = __ldcg(a.pq + NB + tid);
         }
-        if (warp == 0) {
-            const double yv = sum_over_ctas(a.part2, 1, G, lane);
-            if (lane == 0) scal[5] = yv;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            double t = 0.0;
-            for (int k = lane; k < jj; k += 32) t += ps[k] * qs[k];
-            t = warp_sum(t);
-            if (lane == 0) scal[4] = -0.5 * tau * (tau * (scal[5] - 2.0 * t));
-        }
-        const int cc0 = (j + 1) / RB, ncc = (n + RB - 1) / RB - cc0;  // source blocks of the partial products
-        __syncthreads();
-        const double alpha2 = scal[4];
+        double vn[2] = {0.0, 0.0}, wn[2] = {0.0, 0.0}, ynext = 0.0;
         if (warp == 1) {
-            // row j + 1 of V and W including the column being formed: every CTA needs it for the next column
-            double c2 = 0.0, y = 0.0;
-            double vn[2], wn[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int k = lane + 32 * h;
-                vn[h] = wn[h] = 0.0;
                 if (k < jj) {
                     vn[h] = __ldcg(a.P + (j + 1) + (int64_t)k * Np);
                     wn[h] = __ldcg(a.P + (j + 1) + (int64_t)(NB + k) * Np);
-                    c2 += vn[h] * ps[k] + wn[h] * qs[k];
                 }
             }
-            for (int cc = lane; cc < ncc; cc += 32) y += __ldcg(a.ypart + (int64_t)(cc0 + cc) * Np + (j + 1));
-            c2 = warp_sum(c2);
-            y = warp_sum(y);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int k = lane + 32 * h;
-                if (k < jj) {
-                    Vrow[k] = vn[h];
-                    Wrow[k] = wn[h];
-                }
-            }
-            if (lane == 0) {
-                Vrow[jj] = 1.0;
-                Wrow[jj] = tau * (y - c2) + alpha2;
-            }
+            for (int cc = lane; cc < ncc; cc += 32) ynext += __ldcg(a.ypart + (int64_t)(cc0 + cc) * Np + (j + 1));
         }
-        // (A v)[own rows]: the partial products of all source blocks, split over YG thread groups
-        const int YG = min(THREADS / R, KS);
-        double* ysum = dots;  // [YG][R]: dots is dead in this phase
         if (tid < YG * R) {
             const int g = tid / R, li = tid - g * R;
             const int64_t i = grow(li);
@@ -419,6 +447,40 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
             }
             ysum[g * R + li] = y0 + y1;
         }
+        if (tid < R) {
+            const int64_t i = grow(tid);
+            anext = (i >= j + 1 && i < n) ? a.A[i + (int64_t)(j + 1) * a.lda] : 0.0;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double t = 0.0;
+            for (int k = lane; k < jj; k += 32) t += ps[k] * qs[k];
+            t = warp_sum(t);
+            if (lane == 0) scal[4] = -0.5 * tau * (tau * (scal[16] - 2.0 * t));
+        }
+        if (warp == 1) {
+            // row j + 1 of V and W including the column being formed: every CTA needs it for the next column
+            double c2 = 0.0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = lane + 32 * h;
+                if (k < jj) c2 += vn[h] * ps[k] + wn[h] * qs[k];
+            }
+            c2 = warp_sum(c2);
+            ynext = warp_sum(ynext);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = lane + 32 * h;
+                if (k < jj) {
+                    Vrow[k] = vn[h];
+                    Wrow[k] = wn[h];
+                }
+            }
+            if (lane == 0) {
+                Vrow[jj] = 1.0;
+                scal[5] = tau * (ynext - c2);  // + alpha2 below, once warp 0 has it
+            }
+        }
         for (int u = warp; u < a.SL * KS; u += NWARP) {
             const int li = (u / KS) * 32 + lane, ks = u % KS;
             const int k1 = min(jj, (ks + 1) * KW);
@@ -427,6 +489,8 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
             red[ks * R + li] = c;
         }
         __syncthreads();
+        const double alpha2 = scal[4];
+        if (tid == 0) Wrow[jj] = scal[5] + alpha2;
         if (tid < R) {
             const int64_t i = grow(tid);
             double v = 0.0, w = 0.0;
@@ -446,7 +510,12 @@ __global__ void __launch_bounds__(THREADS, 1) sytrd_panel_kernel(PanelArgs a) {
             Ws[jj * R + tid] = w;
         }
         __syncthreads();
+        EIG_MARK(5);
     }
+#ifdef EIG_PROFILE
+    if (tid == 0 && (cta == 0 || cta == G - 1 || cta == G / 2))
+        printf("panel j0=%d cta=%d cycles: A %lld | bar1 %lld | B-pre %lld | tiles %lld | bar2 %lld | C %lld\n", a.j0, cta, pt[0], pt[1], pt[2], pt[3], pt[4], pt[5]);
+#endif
 }
 
 // ---- preparation ---------------------------------------------------------------------------------------
@@ -584,12 +653,12 @@ __global__ void __launch_bounds__(BIS_THREADS) tridiag_bisect_kernel(int n, cons
 }
 
 struct Work {
-    double *P, *Q, *ypart, *d, *e, *e2, *part1, *part2, *pq, *sc, *bnd, *mx;
-    unsigned* bar;
+    double *P, *Q, *ypart, *d, *e, *e2, *part1, *pq, *sc, *bnd, *mx;
+    LLSlot* ll;
 };
 
 int carve(aces_ctx* ctx, int64_t Np, int grid, Work* w) {
-    size_t doubles = (size_t)Np * 2 * NB * 2 + (size_t)(Np / RB) * Np + 3 * (size_t)Np + (size_t)grid * P1 + grid + 2 * NB + 8 + 8 + 1024;
+    size_t doubles = (size_t)Np * 2 * NB * 2 + (size_t)(Np / RB) * Np + 3 * (size_t)Np + (size_t)grid * P1 + 2 * NB + 8 + 8 + 1024 + (size_t)grid * 8 + 16;
     ACES_TRY(aces_reserve_dev(ctx, ctx->d_eig, sizeof(double) * doubles + 256));
     double* p = (double*)ctx->d_eig.ptr;
     w->P = p; p += (size_t)Np * 2 * NB;
@@ -599,12 +668,11 @@ int carve(aces_ctx* ctx, int64_t Np, int grid, Work* w) {
     w->e = p; p += Np;
     w->e2 = p; p += Np;
     w->part1 = p; p += (size_t)grid * P1;
-    w->part2 = p; p += grid;
     w->pq = p; p += 2 * NB;
     w->sc = p; p += 8;
     w->bnd = p; p += 8;
     w->mx = p; p += 1024;
-    w->bar = (unsigned*)p;
+    w->ll = (LLSlot*)p;  // [2][grid], 32 bytes each (p is 8-byte aligned: 64-bit words)
     return ACES_OK;
 }
 
@@ -633,14 +701,16 @@ int syev_values(aces_ctx* ctx, int64_t n, int64_t Np, double* A, int64_t lda, do
     scale_clear_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(n, Np, A, lda, w.sc);
     ACES_CUDA(ctx, cudaGetLastError());
     ctx->launches += 3;
+    ACES_CUDA(ctx, cudaMemsetAsync(w.ll, 0, sizeof(LLSlot) * (2 * (size_t)grid + 1), st));
+    unsigned epoch0 = 0;  // epoch 0 = never published
     for (int64_t j0 = 0; j0 < n; j0 += NB) {
         const int ncols = (int)std::min<int64_t>(NB, n - j0);
         ACES_CUDA(ctx, cudaMemsetAsync(w.P, 0, sizeof(double) * (size_t)Np * 2 * NB * 2, st));  // P and Q are adjacent
-        ACES_CUDA(ctx, cudaMemsetAsync(w.bar, 0, sizeof(unsigned), st));
         PanelArgs pa;
         pa.A = A; pa.lda = lda; pa.n = (int)n; pa.Np = (int)Np; pa.j0 = (int)j0; pa.ncols = ncols;
-        pa.P = w.P; pa.Q = w.Q; pa.d = w.d; pa.e = w.e; pa.ypart = w.ypart; pa.part1 = w.part1; pa.part2 = w.part2;
-        pa.pq = w.pq; pa.bar = w.bar; pa.SL = SL;
+        pa.P = w.P; pa.Q = w.Q; pa.d = w.d; pa.e = w.e; pa.ypart = w.ypart; pa.part1 = w.part1;
+        pa.pq = w.pq; pa.ll = w.ll; pa.SL = SL; pa.epoch0 = epoch0;
+        for (int64_t j = j0; j < j0 + ncols; ++j) epoch0 += (j + 2 < n) ? 2u : 1u;  // barriers of this panel
         void* args[] = {(void*)&pa};
         ACES_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)sytrd_panel_kernel, dim3((unsigned)grid), dim3(THREADS),
                                                    args, smem, st));
