@@ -46,6 +46,9 @@ WORKLOADS = {
                            baseline="configs[1]: rotated surface code d=5, log-normal Pauli noise, full_covariance=true GLS"),
     "unrotated_d7_gls": dict(kind="unrotated", d=7, full=True, shots=[10**6, 10**7, 10**8], fit_full=True, sharding="repetitions",
                              baseline="configs[3]: unrotated surface code d=7, log-normal noise, GLS estimate + calc_covariance merit"),
+    "rotated_d9_wls_experiments": dict(kind="rotated", d=9, full=False, shots=[10**6, 10**7, 10**8], fit_full=False, sharding="experiments",
+                                       baseline="configs[2] with ONE repetition split over the GPUs by experiment (SURVEY 8e, second axis): "
+                                                "strong scaling, int64 all-reduce of the counts"),
     "rotated_d17_1e9": dict(kind="rotated", d=17, full=False, shots=[10**7, 10**8, 10**9], fit_full=False, sharding="shots",
                             baseline="configs[4]: rotated surface code d=17, 1e9-shot synthetic budget, shots sharded over 8 GPUs"),
 }
@@ -68,12 +71,14 @@ def workload_config(n_gpus, fd=None, sizes=None, bytes_per_gpu=None):
         "n_qubits": int(fd.n_qubits) if fd is not None else 161, "bytes_per_shot": int(fd.n_bytes) if fd is not None else 21,
         "experiments": n_exp, "paulis_per_experiment_mean": mean_paulis,
         "budgets": [int(x) for x in shots_for(n_gpus)],
-        "repetitions_per_step": 1 if shots_sharded else n_gpus,
+        "repetitions_per_step": 1 if (shots_sharded or WL["sharding"] == "experiments") else n_gpus,
         "l2": (f"inputs ({bytes_per_gpu / 1e9:.2f} GB per GPU) exceed the 126 MB L2; no flush needed" if bytes_per_gpu and bytes_per_gpu > 2.5e8
                else "inputs fit the 126 MB L2: a 256 MB buffer is overwritten between timed steps"),
         "parallelism": ((f"shot ranges of every experiment x{n_gpus}, int64 all-reduce of the counts (the full 1e9-shot budget "
                          "needs 8 GPUs: per-GPU work is fixed, 1/8 of the budget per rank)") if shots_sharded
-                        else (f"repetitions x{n_gpus}" if n_gpus > 1 else "single GPU")),
+                        else (f"the experiments of one repetition dealt to {n_gpus} GPUs by bytes (greedy), int64 all-reduce of the counts"
+                              if WL["sharding"] == "experiments" and n_gpus > 1
+                              else (f"repetitions x{n_gpus}" if n_gpus > 1 else "single GPU"))),
     }
 
 
@@ -568,8 +573,17 @@ def main():
         parts = [aces_b200.shard.shard_shots(rows_full[e], prefix_full[e], world, rank) for e in range(n_exp)]
         rows = [int(hi - lo) for lo, hi, _ in parts]
         prefix = np.stack([p for _, _, p in parts])
+    elif WL["sharding"] == "experiments" and world > 1:
+        # one repetition over all ranks: every rank reduces the experiments dealt to it (shard.shard_experiments,
+        # greedy by bytes); the others are empty items, so the count vector keeps the full layout and the
+        # all-reduce (sum, int64) hands every rank the complete, exact counts
+        mine = set(aces_b200.shard.shard_experiments([rows_full[e] * B for e in range(n_exp)], world)[rank])
+        rows = [rows_full[e] if e in mine else 0 for e in range(n_exp)]
+        prefix = np.stack([prefix_full[e] if e in mine else np.zeros_like(prefix_full[e]) for e in range(n_exp)])
     else:
         rows, prefix = rows_full, prefix_full
+    exp_sharded = WL["sharding"] == "experiments" and world > 1
+    reduce_counts = shot_sharded or exp_sharded
     ld = [max((r + 127) // 128 * 128, 128) for r in rows]
     sizes = est.experiment_sizes()
     g = torch.Generator(device="cuda").manual_seed(0x5EED0000 + rank)
@@ -577,7 +591,7 @@ def main():
     ptrs = [d.data_ptr() for d in dev]
     n_counts = int(np.sum(sizes) * K)
     outs = [torch.zeros(n_counts, dtype=torch.int64, device="cuda") for _ in range(2)]   # double buffered: the collective
-    gathered = [torch.zeros(world * n_counts, dtype=torch.int64, device="cuda") for _ in range(2)] if world > 1 and not shot_sharded else None
+    gathered = [torch.zeros(world * n_counts, dtype=torch.int64, device="cuda") for _ in range(2)] if world > 1 and not reduce_counts else None
     alg_bytes = int(sum(rows[e] * B for e in range(n_exp)))          # read once, this rank
     shot_parities = int(sum(rows[e] * int(sizes[e]) for e in range(n_exp)))
     shots = int(sum(rows))
@@ -604,7 +618,7 @@ def main():
             done_ev[b].record(stream)
             with torch.cuda.stream(comm):
                 comm.wait_event(done_ev[b])
-                if shot_sharded:
+                if reduce_counts:
                     dist.all_reduce(outs[b], op=dist.ReduceOp.SUM)
                 else:
                     dist.all_gather_into_tensor(gathered[b], outs[b])
@@ -660,7 +674,7 @@ def main():
     value = float(tot[0].item()) / (ms_per_step * 1e-3)
     out = outs[(step_no[0] - 1) & 1]
     counts_equal = None
-    if shot_sharded and world > 1:   # after the all-reduce every rank holds the same counts: compare a checksum
+    if reduce_counts and world > 1:   # after the all-reduce every rank holds the same counts: compare a checksum
         chk = torch.stack([out.sum(), (out * torch.arange(1, n_counts + 1, device="cuda")).sum()]).to(torch.int64)
         allchk = [torch.zeros_like(chk) for _ in range(world)]
         dist.all_gather(allchk, chk)
@@ -745,12 +759,12 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "scaling": "strong" if WL["sharding"] == "experiments" else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(world, fd, sizes, alg_bytes),
             "shots_per_s": float(tot[1].item()) / (ms_per_step * 1e-3),
             "clocks": clocks.summary(),
             "exchange": (None if world == 1 else
-                         {"collective": "ncclAllReduce(sum, int64) of the counts" if shot_sharded else "ncclAllGather of the per-repetition counts",
+                         {"collective": "ncclAllReduce(sum, int64) of the counts" if reduce_counts else "ncclAllGather of the per-repetition counts",
                           "bytes_per_rank": n_counts * 8, "stream": "second stream, overlapped with the next step's kernel (two count buffers)",
                           "counts_equal_on_all_ranks": counts_equal}),
             "e2e": {"value": e2e_value, "unit": UNIT,
