@@ -297,6 +297,29 @@ int32_t aces_design_fit_refine_begin(aces_ctx* ctx, aces_design* design);
 int32_t aces_design_fit_refine_end(aces_ctx* ctx, aces_design* design, double* x_max, double* delta_max);
 int32_t aces_design_fit_end(aces_ctx* ctx, aces_design* design, int32_t constrain, double* gate_eigenvalues);
 
+/* The Cholesky factorisation inside aces_design_fit_solve, distributed over the shards (SURVEY.md section 8e,
+ * "one large Gram": at rotated d = 17 the replicated N^3 / 3 factorisation is what limits the sharded fit).
+ * After aces_design_fit_begin and the sum of the buffers every shard holds the whole Gram matrix.  Block
+ * columns (a multiple of 128 columns each, 512 in the hosts here) are owned cyclically.  For block column p:
+ *   the owner calls _dist_factor(col0, ncols): the block column becomes the block column of L, in place,
+ *     and the inverses of its 128 x 128 diagonal blocks are stored;
+ *   the host broadcasts from the owner the ncols FULL columns -- gram + col0 * Np, ncols * Np doubles, one
+ *     contiguous range (Np = N padded to 128, gram from aces_design_fit_buffers) -- and the block inverses,
+ *     block_inverses + col0 * 128, ncols * 128 doubles (ncclBroadcast over NVLink);
+ *   every shard calls _dist_update(col0, ncols, targets): the panel is applied to the later block columns
+ *     this shard owns; columns it does not own are left alone (they arrive final with their owner's broadcast).
+ * _dist_begin comes before the first block column (it records the diagonal for the relative pivot test);
+ * _dist_solve replaces aces_design_fit_solve (x = inv(G) rhs with the now complete factor).  The count of
+ * eliminated (numerically dependent) columns accumulates in *dead_columns on the owner of each block column:
+ * sum it over the shards (an int32 on the device) before _dist_solve if aces_last_rank_deficiency matters. */
+int32_t aces_design_fit_dist_begin(aces_ctx* ctx, aces_design* design);
+int32_t aces_design_fit_dist_factor(aces_ctx* ctx, aces_design* design, int64_t col0, int64_t ncols);
+int32_t aces_design_fit_dist_update(aces_ctx* ctx, aces_design* design, int64_t panel_col0, int64_t panel_ncols,
+                                    int32_t n_targets, const int64_t* target_col0, const int64_t* target_ncols);
+int32_t aces_design_fit_dist_buffers(aces_design* design, double** block_inverses, int64_t* block_inverse_elems,
+                                     int32_t** dead_columns);
+int32_t aces_design_fit_dist_solve(aces_ctx* ctx, aces_design* design);
+
 /* Per-gate diagonal blocks of calc_precision_matrix(design_matrix, gate_eigenvalues, covariance_log_inv)
  * (src/merit.jl:754-770) = D^-1 A' Omega'^-1 A D^-1 -- all that split_project_gate_eigenvalues reads of
  * it (src/estimate.jl:606-612: est_precision_matrix[indices, indices] per gate).  Must directly follow

@@ -82,6 +82,11 @@ SIGNATURES = {
     "aces_design_fit_refine_begin": (_i32, [_vp, _vp]),
     "aces_design_fit_refine_end": (_i32, [_vp, _vp, _p(C.c_double), _p(C.c_double)]),
     "aces_design_fit_end": (_i32, [_vp, _vp, _i32, _vp]),
+    "aces_design_fit_dist_begin": (_i32, [_vp, _vp]),
+    "aces_design_fit_dist_factor": (_i32, [_vp, _vp, _i64, _i64]),
+    "aces_design_fit_dist_update": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp]),
+    "aces_design_fit_dist_buffers": (_i32, [_vp, _p(_vp), _p(_i64), _p(_vp)]),
+    "aces_design_fit_dist_solve": (_i32, [_vp, _vp]),
     "aces_design_precision_blocks": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "aces_potrf_schedule": (_i32, [_i32, _i32, _vp, _i64, _p(_i64)]),
     "aces_potrf_trace": (_i32, [_vp, _vp, _i64, _p(_i64)]),

@@ -1455,6 +1455,81 @@ int32_t aces_design_fit_solve(aces_ctx* ctx, aces_design* d) {
     return fit_solve(ctx, d, true, nullptr);
 }
 
+// ---- Cholesky of the summed Gram matrix distributed over the shards (last row) ---------------
+// Every shard holds the whole summed Gram matrix after the all-reduce.  Block columns of DIST_PW columns are
+// owned cyclically; step p: the owner factorises block column p in place (diagonal block by dense::potrf,
+// the rows below it with the explicit inverse of that block on the tensor pipe), the host broadcasts the
+// DIST_PW full columns (one contiguous range of the column-major matrix) and the inverses of their
+// 128-blocks to every shard, and every shard applies the panel to the block columns IT owns.  Columns a
+// shard does not own are never updated there: they arrive, final, with their owner's broadcast.  After the
+// last step every shard holds the complete factor, and the triangular solves run replicated as before.
+int32_t aces_design_fit_dist_begin(aces_ctx* ctx, aces_design* d) {
+    ACES_TRY(check_design(ctx, d, "design_fit_dist_begin"));
+    ACES_CHECK(ctx, d->fs_stage == 1, "design_fit_dist_begin: call aces_design_fit_begin (and sum the buffers) first");
+    FitVectors fv = fit_vectors(d);
+    // the diagonal before the factorisation: reference of the relative pivot test, as in factor_gram_matrix
+    ACES_TRY(dense::get_diag(ctx, d->Np, d->G, d->Np, fv.t2));
+    ACES_CUDA(ctx, cudaMemcpyAsync(fv.t1, fv.t2, sizeof(double) * (size_t)d->Np, cudaMemcpyDeviceToDevice, ctx->stream));
+    return ACES_OK;
+}
+
+int32_t aces_design_fit_dist_factor(aces_ctx* ctx, aces_design* d, int64_t col0, int64_t ncols) {
+    ACES_TRY(check_design(ctx, d, "design_fit_dist_factor"));
+    const int64_t Np = d->Np;
+    ACES_CHECK(ctx, d->fs_stage == 1 && col0 >= 0 && ncols > 0 && col0 % DB == 0 && ncols % DB == 0 && col0 + ncols <= Np,
+               "design_fit_dist_factor: bad block column [%lld, %lld)", (long long)col0, (long long)(col0 + ncols));
+    FitVectors fv = fit_vectors(d);
+    double* Akk = d->G + col0 * (Np + 1);
+    double* dinv = d->dinvG + (col0 / DB) * DB * DB;
+    ACES_TRY(dense::potrf(ctx, ncols, Akk, Np, dinv, d->flags + d->T, fv.t1 + col0, 1e-13, 1));
+    const int64_t rows = Np - col0 - ncols;
+    if (rows > 0) {
+        // rows below: L_below = A_below * inv(L_kk)': X = inv(L_kk), a copy of A_below, one NT GEMM back in place
+        ACES_TRY(aces_reserve_dev(ctx, ctx->d_work[7], sizeof(double) * (size_t)(ncols * ncols + rows * ncols)));
+        double* X = (double*)ctx->d_work[7].ptr;
+        double* Tm = X + ncols * ncols;
+        ACES_TRY(dense::trtri(ctx, ncols, Akk, Np, dinv, X, ncols));
+        double* below = Akk + ncols;
+        ACES_CUDA(ctx, cudaMemcpy2DAsync(Tm, sizeof(double) * (size_t)rows, below, sizeof(double) * (size_t)Np,
+                                         sizeof(double) * (size_t)rows, (size_t)ncols, cudaMemcpyDeviceToDevice, ctx->stream));
+        ACES_TRY(dense::gemm(ctx, dense::GEMM_NT, rows, ncols, ncols, 1.0, Tm, rows, X, ncols, 0.0, below, Np, 0));
+    }
+    return ACES_OK;
+}
+
+int32_t aces_design_fit_dist_update(aces_ctx* ctx, aces_design* d, int64_t pcol0, int64_t pncols, int32_t n_targets,
+                                    const int64_t* target_col0, const int64_t* target_ncols) {
+    ACES_TRY(check_design(ctx, d, "design_fit_dist_update"));
+    const int64_t Np = d->Np;
+    ACES_CHECK(ctx, d->fs_stage == 1 && pcol0 >= 0 && pncols > 0 && pcol0 % DB == 0 && pncols % 16 == 0 && pcol0 + pncols <= Np,
+               "design_fit_dist_update: bad panel");
+    ACES_CHECK(ctx, n_targets >= 0 && (n_targets == 0 || (target_col0 && target_ncols)), "design_fit_dist_update: NULL targets");
+    for (int q = 0; q < n_targets; ++q) {
+        const int64_t t0 = target_col0[q], tn = target_ncols[q];
+        ACES_CHECK(ctx, t0 >= pcol0 + pncols && tn > 0 && t0 % DB == 0 && tn % DB == 0 && t0 + tn <= Np,
+                   "design_fit_dist_update: target block column [%lld, %lld) is not behind the panel", (long long)t0,
+                   (long long)(t0 + tn));
+        // G[t0:, t0:t0+tn] -= L[t0:, panel] * L[t0:t0+tn, panel]'
+        const double* P = d->G + t0 + pcol0 * Np;
+        ACES_TRY(dense::gemm(ctx, dense::GEMM_NT, Np - t0, tn, pncols, -1.0, P, Np, P, Np, 1.0, d->G + t0 * (Np + 1), Np, 0));
+    }
+    return ACES_OK;
+}
+
+int32_t aces_design_fit_dist_buffers(aces_design* d, double** block_inverses, int64_t* block_inverse_elems,
+                                     int32_t** dead_columns) {
+    if (!d || !d->G) return ACES_E_INVALID;
+    if (block_inverses) *block_inverses = d->dinvG;
+    if (block_inverse_elems) *block_inverse_elems = d->Np * DB;
+    if (dead_columns) *dead_columns = d->flags + d->T;
+    return ACES_OK;
+}
+
+int32_t aces_design_fit_dist_solve(aces_ctx* ctx, aces_design* d) {
+    ACES_TRY(check_design(ctx, d, "design_fit_dist_solve"));
+    return fit_solve(ctx, d, false, nullptr);
+}
+
 int32_t aces_design_fit_refine_begin(aces_ctx* ctx, aces_design* d) {
     ACES_TRY(check_design(ctx, d, "design_fit_refine_begin"));
     ACES_CHECK(ctx, d->fs_stage == 2, "design_fit_refine_begin: call aces_design_fit_solve first");

@@ -316,11 +316,45 @@ class DeviceDesign:
         self.ctx.check(self.ctx.lib.aces_design_fit_buffers(self.handle, C.byref(g), C.byref(ng), C.byref(r), C.byref(nr)))
         return (int(g.value), int(ng.value)), (int(r.value), int(nr.value))
 
+    DIST_PANEL = 512   # columns per block column of the distributed Cholesky
+
+    def factor_distributed(self, rank: int, world: int, broadcast, reduce_int=None) -> None:
+        """The Cholesky factorisation of the summed Gram matrix over `world` shards (aces_design_fit_dist_*):
+        block columns of DIST_PANEL columns owned cyclically; the owner factorises its block column, the
+        DIST_PANEL full columns and the inverses of their 128-blocks are broadcast
+        (`broadcast(device_pointer, n_doubles, src_rank)`, e.g. shard.broadcast_device: ncclBroadcast over
+        NVLink), every shard applies the panel to the later block columns it owns.  Afterwards every shard
+        holds the complete factor.  `reduce_int(device_pointer)` (optional) sums the int32 count of
+        eliminated columns over the shards."""
+        lib, h = self.ctx.lib, self.ctx.handle
+        (gram, _), _ = self.fit_buffers()
+        dinv, n_dinv, dead = C.c_void_p(), C.c_int64(), C.c_void_p()
+        self.ctx.check(lib.aces_design_fit_dist_buffers(self.handle, C.byref(dinv), C.byref(n_dinv), C.byref(dead)))
+        Np = n_dinv.value // 128
+        pw = self.DIST_PANEL
+        panels = [(c, min(pw, Np - c)) for c in range(0, Np, pw)]
+        self.ctx.check(lib.aces_design_fit_dist_begin(h, self.handle))
+        for p, (col0, ncols) in enumerate(panels):
+            owner = p % world
+            if rank == owner:
+                self.ctx.check(lib.aces_design_fit_dist_factor(h, self.handle, col0, ncols))
+            if world > 1:
+                broadcast(gram + 8 * col0 * Np, ncols * Np, owner)
+                broadcast(dinv.value + 8 * col0 * 128, ncols * 128, owner)
+            mine = [(c, n) for q, (c, n) in enumerate(panels) if q > p and q % world == rank]
+            if mine:
+                t0 = np.asarray([c for c, _ in mine], dtype=np.int64)
+                tn = np.asarray([n for _, n in mine], dtype=np.int64)
+                self.ctx.check(lib.aces_design_fit_dist_update(h, self.handle, col0, ncols, len(mine), _ptr(t0), _ptr(tn)))
+        if world > 1 and reduce_int is not None:
+            reduce_int(dead.value)
+
     def fit_sharded(self, ls_type: str, est_eigenvalues, est_covariance_eigenvalues, reduce, clipped_indices=None,
-                    epsilon: float = 1e-10, constrain: bool = False) -> np.ndarray:
+                    epsilon: float = 1e-10, constrain: bool = False, distributed=None) -> np.ndarray:
         """The stages of `fit` with `reduce(device_pointer, n_doubles)` (an in-place sum over the
         shards, e.g. shard.all_reduce_device) at the reduction points.  Every shard returns the
-        same gate eigenvalues."""
+        same gate eigenvalues.  `distributed` = (rank, world, broadcast[, reduce_int]) also distributes the
+        Cholesky factorisation of the summed Gram matrix (factor_distributed) instead of replicating it."""
         lam = np.ascontiguousarray(est_eigenvalues, dtype=np.float64)
         lc = None
         if self.C:
@@ -333,7 +367,11 @@ class DeviceDesign:
         self.ctx.synchronize()
         reduce(gram, n_gram)
         reduce(rhs, n_rhs)
-        self.ctx.check(lib.aces_design_fit_solve(h, self.handle))
+        if distributed is not None:
+            self.factor_distributed(*distributed)
+            self.ctx.check(lib.aces_design_fit_dist_solve(h, self.handle))
+        else:
+            self.ctx.check(lib.aces_design_fit_solve(h, self.handle))
         for it in range(2):
             self.ctx.check(lib.aces_design_fit_refine_begin(h, self.handle))
             self.ctx.synchronize()

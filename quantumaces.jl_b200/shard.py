@@ -144,10 +144,42 @@ def all_reduce_device(ptr: int, n: int, group=None) -> None:
     torch.cuda.current_stream().synchronize()
 
 
-def fit_tuple_sharded(dd, ls_type: str, est_eigenvalues, est_covariance_eigenvalues=None, group=None, **kw):
+class _DeviceBufferI32:
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+
+
+def broadcast_device(ptr: int, n: int, src: int, group=None, sync: bool = True) -> None:
+    """Broadcast of `n` doubles at device pointer `ptr` from rank `src` of `group` (ncclBroadcast over NVLink)."""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.as_tensor(_DeviceBuffer(ptr, n), device="cuda")
+    dist.broadcast(t, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+    if sync:
+        torch.cuda.current_stream().synchronize()
+
+
+def all_reduce_device_i32(ptr: int, group=None) -> None:
+    import torch
+    import torch.distributed as dist
+
+    t = torch.as_tensor(_DeviceBufferI32(ptr, 1), device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    torch.cuda.current_stream().synchronize()
+
+
+def fit_tuple_sharded(dd, ls_type: str, est_eigenvalues, est_covariance_eigenvalues=None, group=None,
+                      distributed_cholesky: bool = False, **kw):
     """One fit with the tuple blocks sharded over the ranks of `group`: block factors and partial
-    Gram matrices per rank, ncclAllReduce of the Gram matrix and the right-hand sides, replicated
-    Cholesky and solves.  `dd` is the rank's DeviceDesign; the shard is set here."""
+    Gram matrices per rank, ncclAllReduce of the Gram matrix and the right-hand sides, then the Cholesky
+    factorisation either replicated or -- `distributed_cholesky` -- distributed by block columns with
+    ncclBroadcast of every factorised panel (DeviceDesign.factor_distributed); the triangular solves are
+    replicated.  `dd` is the rank's DeviceDesign; the shard is set here.
+
+    With `distributed_cholesky` the library and NCCL share ONE stream (the library's kernels and the
+    collectives are ordered on the device: no host synchronisation per panel)."""
+    import torch
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -155,7 +187,28 @@ def fit_tuple_sharded(dd, ls_type: str, est_eigenvalues, est_covariance_eigenval
     on = [1 if t in mine else 0 for t in range(dd.fd.tuple_number)]
     dd.set_tuple_shard(on)
     try:
-        return dd.fit_sharded(ls_type, est_eigenvalues, est_covariance_eigenvalues,
-                              lambda p, n: all_reduce_device(p, n, group), **kw)
+        if not distributed_cholesky:
+            return dd.fit_sharded(ls_type, est_eigenvalues, est_covariance_eigenvalues,
+                                  lambda p, n: all_reduce_device(p, n, group), **kw)
+        stream = getattr(dd, "_dist_stream", None)
+        if stream is None:
+            stream = dd._dist_stream = torch.cuda.Stream()
+        dd.ctx.set_stream(stream.cuda_stream)
+        try:
+            with torch.cuda.stream(stream):
+                def reduce(p, n):
+                    t = torch.as_tensor(_DeviceBuffer(p, n), device="cuda")
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+                def reduce_int(p):
+                    t = torch.as_tensor(_DeviceBufferI32(p, 1), device="cuda")
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+                return dd.fit_sharded(ls_type, est_eigenvalues, est_covariance_eigenvalues, reduce,
+                                      distributed=(rank, world, lambda p, n, src: broadcast_device(p, n, src, group, sync=False),
+                                                   reduce_int), **kw)
+        finally:
+            stream.synchronize()
+            dd.ctx.set_stream(None)
     finally:
         dd.set_tuple_shard(None)

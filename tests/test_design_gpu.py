@@ -493,6 +493,88 @@ def test_tuple_sharded_fit_equals_unsharded(ctx, shards, ls_type):
         c.close()
 
 
+@pytest.mark.parametrize("shards,panel,ls_type", [(2, 128, "gls"), (3, 256, "gls"), (4, 128, "wls"), (2, 512, "gls")])
+def test_tuple_sharded_fit_with_distributed_cholesky(ctx, shards, panel, ls_type):
+    """SURVEY 8e, last row: the Cholesky factorisation of the summed Gram matrix distributed over the shards
+    by block columns (aces_design_fit_dist_*): the owner factorises a block column, its full columns and
+    block inverses are broadcast, every shard updates the block columns it owns.  Shards are contexts on one
+    GPU here and the broadcast is a device copy; across GPUs it is shard.broadcast_device = ncclBroadcast.
+    Every shard must end with the same factor (bit for bit) and the fit must equal the unsharded one."""
+    import threading
+
+    import torch
+
+    import aces_b200
+    from aces_b200 import shard
+
+    fd = aces_b200.rotated_design(3, full_covariance=True, noise="lognormal", seed=4)
+    eig, cov = noisy_ensembles(fd, seed=21)
+    lam = np.concatenate(aces_b200.mean_ensemble(eig))
+    lc = np.concatenate(aces_b200.mean_ensemble(cov))
+    dd0 = aces_b200.DeviceDesign(ctx, fd)
+    want = dd0.fit(ls_type, lam, lc)
+    dd0.close()
+    parts = shard.shard_tuples(fd.mapping_lengths, shards)
+    ctxs = [aces_b200.Context(0) for _ in range(shards)]
+    dds = [aces_b200.DeviceDesign(c, fd) for c in ctxs]
+    for dd, mine in zip(dds, parts):
+        dd.set_tuple_shard([1 if t in mine else 0 for t in range(fd.tuple_number)])
+        dd.DIST_PANEL = panel
+    barrier = threading.Barrier(shards)
+    slots = [None] * shards
+
+    def reducer(i):
+        def reduce(ptr, n):
+            slots[i] = torch.as_tensor(shard._DeviceBuffer(ptr, n), device="cuda")
+            barrier.wait()
+            if i == 0:
+                torch.cuda.synchronize()
+                total = torch.stack(slots).sum(dim=0)
+                for s in slots:
+                    s.copy_(total)
+                torch.cuda.synchronize()
+            barrier.wait()
+        return reduce
+
+    def broadcaster(i):
+        def broadcast(ptr, n, src):
+            dds[i].ctx.synchronize()                     # the owner's factorisation / this shard's updates are done
+            slots[i] = torch.as_tensor(shard._DeviceBuffer(ptr, n), device="cuda")
+            barrier.wait()
+            if i != src:
+                slots[i].copy_(slots[src])
+                torch.cuda.synchronize()
+            barrier.wait()
+        return broadcast
+
+    outs, grams, errs = [None] * shards, [None] * shards, []
+
+    def work(i):
+        try:
+            outs[i] = dds[i].fit_sharded(ls_type, lam, lc, reducer(i), distributed=(i, shards, broadcaster(i)))
+            (g, n), _ = dds[i].fit_buffers()
+            dds[i].ctx.synchronize()
+            grams[i] = torch.as_tensor(shard._DeviceBuffer(g, n), device="cuda").clone()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+            barrier.abort()
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(shards)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not errs, errs
+    Np = int(round(np.sqrt(grams[0].numel())))
+    low = torch.tril(torch.ones(Np, Np, dtype=torch.bool, device="cuda")).T.reshape(-1)   # column-major lower triangle
+    for i in range(1, shards):
+        assert torch.equal(grams[i][low], grams[0][low])     # the same factor on every shard
+        assert np.array_equal(outs[i], outs[0])
+    assert rel(outs[0], want) < 1e-12
+    for dd in dds:
+        dd.close()
+    for c in ctxs:
+        c.close()
+
+
 def test_fit_matches_golden_fixture(ctx):
     """The committed known answers (tests/golden/fit_golden.npz: a literal dense transcription of the
     reference's formulas on the real example and rotated d=3 designs) through the CUDA path."""
