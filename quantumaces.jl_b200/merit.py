@@ -318,14 +318,20 @@ class DeviceDesign:
 
     DIST_PANEL = 512   # columns per block column of the distributed Cholesky
 
-    def factor_distributed(self, rank: int, world: int, broadcast, reduce_int=None) -> None:
+    def factor_distributed(self, rank: int, world: int, broadcast, reduce_int=None, streams=None) -> None:
         """The Cholesky factorisation of the summed Gram matrix over `world` shards (aces_design_fit_dist_*):
         block columns of DIST_PANEL columns owned cyclically; the owner factorises its block column, the
         DIST_PANEL full columns and the inverses of their 128-blocks are broadcast
         (`broadcast(device_pointer, n_doubles, src_rank)`, e.g. shard.broadcast_device: ncclBroadcast over
         NVLink), every shard applies the panel to the later block columns it owns.  Afterwards every shard
         holds the complete factor.  `reduce_int(device_pointer)` (optional) sums the int32 count of
-        eliminated columns over the shards."""
+        eliminated columns over the shards.
+
+        `streams` = (main, comm) torch streams -- the library runs on `main` -- turns on look-ahead: the
+        broadcasts run on `comm`; the owner of block column p + 1 applies panel p to that block column first,
+        factorises it and hands it to `comm` BEFORE applying panel p to the rest of its columns, and the
+        receivers post the broadcast before their own updates, so panel p + 1 travels while panel p is still
+        being applied.  The arithmetic is the same in both orders (bit-identical factors)."""
         lib, h = self.ctx.lib, self.ctx.handle
         (gram, _), _ = self.fit_buffers()
         dinv, n_dinv, dead = C.c_void_p(), C.c_int64(), C.c_void_p()
@@ -333,19 +339,63 @@ class DeviceDesign:
         Np = n_dinv.value // 128
         pw = self.DIST_PANEL
         panels = [(c, min(pw, Np - c)) for c in range(0, Np, pw)]
+
+        def factor(p):
+            self.ctx.check(lib.aces_design_fit_dist_factor(h, self.handle, panels[p][0], panels[p][1]))
+
+        def update(p, blocks):
+            if blocks:
+                t0 = np.asarray([panels[q][0] for q in blocks], dtype=np.int64)
+                tn = np.asarray([panels[q][1] for q in blocks], dtype=np.int64)
+                self.ctx.check(lib.aces_design_fit_dist_update(h, self.handle, panels[p][0], panels[p][1], len(blocks),
+                                                               _ptr(t0), _ptr(tn)))
+
+        def send(p):
+            col0, ncols = panels[p]
+            broadcast(gram + 8 * col0 * Np, ncols * Np, p % world)
+            broadcast(dinv.value + 8 * col0 * 128, ncols * 128, p % world)
+
         self.ctx.check(lib.aces_design_fit_dist_begin(h, self.handle))
-        for p, (col0, ncols) in enumerate(panels):
-            owner = p % world
-            if rank == owner:
-                self.ctx.check(lib.aces_design_fit_dist_factor(h, self.handle, col0, ncols))
-            if world > 1:
-                broadcast(gram + 8 * col0 * Np, ncols * Np, owner)
-                broadcast(dinv.value + 8 * col0 * 128, ncols * 128, owner)
-            mine = [(c, n) for q, (c, n) in enumerate(panels) if q > p and q % world == rank]
-            if mine:
-                t0 = np.asarray([c for c, _ in mine], dtype=np.int64)
-                tn = np.asarray([n for _, n in mine], dtype=np.int64)
-                self.ctx.check(lib.aces_design_fit_dist_update(h, self.handle, col0, ncols, len(mine), _ptr(t0), _ptr(tn)))
+        owned = lambda p: [q for q in range(p + 1, len(panels)) if q % world == rank]  # noqa: E731
+        if streams is None or world == 1:
+            for p in range(len(panels)):
+                if rank == p % world:
+                    factor(p)
+                if world > 1:
+                    send(p)
+                update(p, owned(p))
+        else:
+            import torch
+
+            main, comm = streams
+            arrived = [torch.cuda.Event() for _ in panels]
+            ready = torch.cuda.Event()
+
+            def post(p):  # the broadcast of panel p on the communication stream
+                if rank == p % world:
+                    ready.record(main)
+                    comm.wait_event(ready)
+                with torch.cuda.stream(comm):
+                    send(p)
+                    arrived[p].record(comm)
+
+            if rank == 0:
+                factor(0)
+            post(0)
+            for p in range(len(panels)):
+                main.wait_event(arrived[p])
+                mine = owned(p)
+                nxt = p + 1
+                if nxt < len(panels) and rank == nxt % world:
+                    update(p, [nxt])
+                    factor(nxt)
+                    post(nxt)
+                    update(p, [q for q in mine if q != nxt])
+                else:
+                    if nxt < len(panels):
+                        post(nxt)
+                    update(p, mine)
+            main.wait_stream(comm)
         if world > 1 and reduce_int is not None:
             reduce_int(dead.value)
 

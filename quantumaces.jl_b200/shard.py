@@ -170,15 +170,16 @@ def all_reduce_device_i32(ptr: int, group=None) -> None:
 
 
 def fit_tuple_sharded(dd, ls_type: str, est_eigenvalues, est_covariance_eigenvalues=None, group=None,
-                      distributed_cholesky: bool = False, **kw):
+                      distributed_cholesky: bool = False, lookahead: bool = True, **kw):
     """One fit with the tuple blocks sharded over the ranks of `group`: block factors and partial
     Gram matrices per rank, ncclAllReduce of the Gram matrix and the right-hand sides, then the Cholesky
     factorisation either replicated or -- `distributed_cholesky` -- distributed by block columns with
     ncclBroadcast of every factorised panel (DeviceDesign.factor_distributed); the triangular solves are
     replicated.  `dd` is the rank's DeviceDesign; the shard is set here.
 
-    With `distributed_cholesky` the library and NCCL share ONE stream (the library's kernels and the
-    collectives are ordered on the device: no host synchronisation per panel)."""
+    With `distributed_cholesky` the library's kernels and the collectives are ordered on the device (torch
+    streams and events: no host synchronisation per panel); with `lookahead` the broadcasts run on a second
+    stream and the next block column is factorised and sent while the current panel is still being applied."""
     import torch
     import torch.distributed as dist
 
@@ -193,6 +194,8 @@ def fit_tuple_sharded(dd, ls_type: str, est_eigenvalues, est_covariance_eigenval
         stream = getattr(dd, "_dist_stream", None)
         if stream is None:
             stream = dd._dist_stream = torch.cuda.Stream()
+            dd._comm_stream = torch.cuda.Stream()
+        comm = dd._comm_stream
         dd.ctx.set_stream(stream.cuda_stream)
         try:
             with torch.cuda.stream(stream):
@@ -206,7 +209,7 @@ def fit_tuple_sharded(dd, ls_type: str, est_eigenvalues, est_covariance_eigenval
 
                 return dd.fit_sharded(ls_type, est_eigenvalues, est_covariance_eigenvalues, reduce,
                                       distributed=(rank, world, lambda p, n, src: broadcast_device(p, n, src, group, sync=False),
-                                                   reduce_int), **kw)
+                                                   reduce_int, (stream, comm) if lookahead else None), **kw)
         finally:
             stream.synchronize()
             dd.ctx.set_stream(None)

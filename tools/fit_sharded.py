@@ -31,14 +31,15 @@ gen = aces_b200.rotated_design if kind == "rotated" else aces_b200.unrotated_des
 # rank 0 generates the design (minutes at d = 17) and shares it through a file; the others wait
 import pickle  # noqa: E402
 
-path = f"/tmp/aces_design_{kind}_{d}.pkl"
-if rank == 0:
+shipped = os.path.join(ROOT, "build", f"aces_design_{kind}_{d}.pkl")   # optional: tools/make_design_pickle.py, made beforehand
+path = shipped if os.path.exists(shipped) else f"/tmp/aces_design_{kind}_{d}.pkl"
+if rank == 0 and path != shipped:
     fd = gen(d, full_covariance=True, noise="lognormal", seed=9)
     with open(path + ".tmp", "wb") as f:
         pickle.dump(fd, f, protocol=4)
     os.replace(path + ".tmp", path)
 dist.barrier()
-if rank != 0:
+if rank != 0 or path == shipped:
     with open(path, "rb") as f:
         fd = pickle.load(f)
 eig, cov = aces_b200.synthetic_estimates(fd, shots=10**8, seed=11)
@@ -64,8 +65,11 @@ def timed(fn):
 
 single, ms_single = timed(lambda: dd.fit(ls, lam, lc))
 sharded, ms_sharded = timed(lambda: shard.fit_tuple_sharded(dd, ls, lam, lc))
+plain, ms_plain = timed(lambda: shard.fit_tuple_sharded(dd, ls, lam, lc, distributed_cholesky=True, lookahead=False))
+distributed, ms_dist = timed(lambda: shard.fit_tuple_sharded(dd, ls, lam, lc, distributed_cholesky=True))
+assert np.array_equal(plain, distributed)
 gathered = [None] * world
-dist.all_gather_object(gathered, sharded.tobytes())
+dist.all_gather_object(gathered, sharded.tobytes() + distributed.tobytes())
 if rank == 0:
     same = all(g == gathered[0] for g in gathered)
     print(json.dumps({
@@ -73,6 +77,13 @@ if rank == 0:
         "M": int(fd.M), "N": int(fd.matrix.shape[1]), "tuples": int(fd.tuple_number), "n_gpus": world,
         "tuple_shards": shard.shard_tuples(fd.mapping_lengths, world),
         "ms_per_fit_single_gpu": ms_single, "ms_per_fit_tuple_sharded": ms_sharded,
+        "ms_per_fit_tuple_sharded_distributed_cholesky": ms_dist,
+        "ms_per_fit_tuple_sharded_distributed_cholesky_no_lookahead": ms_plain,
+        "distributed_cholesky": {"block_columns": int(-(-dd.N // 128) * 128 // dd.DIST_PANEL + (1 if (-(-dd.N // 128) * 128) % dd.DIST_PANEL else 0)),
+                                 "panel_columns": dd.DIST_PANEL,
+                                 "broadcast_bytes_per_fit": int(8 * (-(-dd.N // 128) * 128) ** 2 + 8 * (-(-dd.N // 128) * 128) * 128),
+                                 "collective": "ncclBroadcast of the factorised block column (full columns) + its block inverses, per block column"},
+        "rel_diff_distributed_vs_single": float(np.linalg.norm(distributed - single) / np.linalg.norm(single)),
         "gram_allreduce_bytes": int(8 * dd.fit_buffers()[0][1]),
         "rel_diff_sharded_vs_single": float(np.linalg.norm(sharded - single) / np.linalg.norm(single)),
         "all_ranks_identical": bool(same),
