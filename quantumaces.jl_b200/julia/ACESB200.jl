@@ -616,7 +616,7 @@ same gate eigenvalues.
 function fit_tuple_sharded(dd::DeviceDesign, ls_type::Symbol, est_eigenvalues::Vector{Float64},
                            est_covariance_eigenvalues::Vector{Float64}, tuple_on::Vector{Bool}, allreduce!::Function;
                            clipped_indices::Union{Vector{Int}, Nothing} = nothing, epsilon::Real = 1e-10,
-                           constrain::Bool = false)
+                           constrain::Bool = false, distributed::Union{Nothing, Tuple{Int, Int, Function}} = nothing)
     kind = ls_type == :ols ? 0 : ls_type == :wls ? 1 : ls_type == :gls ? 2 :
            throw(error("The least squares type $(ls_type) must be either :gls, :wls, or :ols."))
     on = UInt8.(tuple_on)
@@ -637,7 +637,13 @@ function fit_tuple_sharded(dd::DeviceDesign, ls_type::Symbol, est_eigenvalues::V
             check(ccall((:aces_synchronize, LIB[]), Int32, (Ptr{Cvoid},), CTX[]))
             allreduce!(gram[], Int(n_gram[]))
             allreduce!(rhs[], Int(n_rhs[]))
-            check(ccall((:aces_design_fit_solve, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), CTX[], dd.handle))
+            if distributed === nothing
+                check(ccall((:aces_design_fit_solve, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), CTX[], dd.handle))
+            else
+                (rank, world, broadcast!) = distributed
+                factor_distributed!(dd, gram[], rank, world, broadcast!)
+                check(ccall((:aces_design_fit_dist_solve, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), CTX[], dd.handle))
+            end
             for it in 1:2
                 check(ccall((:aces_design_fit_refine_begin, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), CTX[], dd.handle))
                 check(ccall((:aces_synchronize, LIB[]), Int32, (Ptr{Cvoid},), CTX[]))
@@ -654,6 +660,48 @@ function fit_tuple_sharded(dd::DeviceDesign, ls_type::Symbol, est_eigenvalues::V
         end
     end
     return g
+end
+
+"""
+    factor_distributed!(dd, gram, rank, world, broadcast!; panel = 512)
+
+The Cholesky factorisation of the summed Gram matrix distributed over `world` processes (0-based `rank`):
+block columns of `panel` columns owned cyclically; the owner factorises its block column in place, then
+`broadcast!(ptr, n, src)` -- `n` doubles at a DEVICE pointer from process `src` (NCCL.jl Broadcast! /
+CUDA-aware MPI.Bcast!) -- distributes its full columns and the inverses of their 128-blocks, and every
+process applies the panel to the later block columns it owns.  In-order version of
+DeviceDesign.factor_distributed of the Python host (which adds look-ahead on a second stream).
+"""
+function factor_distributed!(dd::DeviceDesign, gram::Ptr{Float64}, rank::Int, world::Int, broadcast!::Function;
+                             panel::Int = 512)
+    dinv = Ref{Ptr{Float64}}(C_NULL); n_dinv = Ref{Int64}(0); dead = Ref{Ptr{Int32}}(C_NULL)
+    check(ccall((:aces_design_fit_dist_buffers, LIB[]), Int32,
+        (Ptr{Cvoid}, Ptr{Ptr{Float64}}, Ptr{Int64}, Ptr{Ptr{Int32}}), dd.handle, dinv, n_dinv, dead))
+    Np = Int(n_dinv[]) ÷ 128
+    panels = [(c, min(panel, Np - c)) for c in 0:panel:(Np - 1)]
+    check(ccall((:aces_design_fit_dist_begin, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), CTX[], dd.handle))
+    for (p, (col0, ncols)) in enumerate(panels)
+        owner = (p - 1) % world
+        if rank == owner
+            check(ccall((:aces_design_fit_dist_factor, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64),
+                CTX[], dd.handle, Int64(col0), Int64(ncols)))
+        end
+        if world > 1
+            check(ccall((:aces_synchronize, LIB[]), Int32, (Ptr{Cvoid},), CTX[]))
+            broadcast!(gram + 8 * col0 * Np, ncols * Np, owner)
+            broadcast!(dinv[] + 8 * col0 * 128, ncols * 128, owner)
+        end
+        mine = [(c, n) for (q, (c, n)) in enumerate(panels) if q > p && (q - 1) % world == rank]
+        if !isempty(mine)
+            t0 = Int64[c for (c, n) in mine]; tn = Int64[n for (c, n) in mine]
+            GC.@preserve t0 tn begin
+                check(ccall((:aces_design_fit_dist_update, LIB[]), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Int64}, Ptr{Int64}),
+                    CTX[], dd.handle, Int64(col0), Int64(ncols), Int32(length(mine)), t0, tn))
+            end
+        end
+    end
+    return nothing
 end
 
 """

@@ -352,7 +352,11 @@ class DeviceDesign:
 
         def send(p):
             col0, ncols = panels[p]
-            broadcast(gram + 8 * col0 * Np, ncols * Np, p % world)
+            if callable(getattr(broadcast, "panel", None)):
+                # the host packs the lower trapezoid of the block column (rows col0 .. Np) and sends half the bytes
+                broadcast.panel(gram, Np, col0, ncols, p % world)
+            else:
+                broadcast(gram + 8 * col0 * Np, ncols * Np, p % world)
             broadcast(dinv.value + 8 * col0 * 128, ncols * 128, p % world)
 
         self.ctx.check(lib.aces_design_fit_dist_begin(h, self.handle))
@@ -415,7 +419,10 @@ class DeviceDesign:
                                                  0 if kept is None else len(kept), 0, float(epsilon)))
         (gram, n_gram), (rhs, n_rhs) = self.fit_buffers()
         self.ctx.synchronize()
-        reduce(gram, n_gram)
+        if callable(getattr(reduce, "lower", None)):
+            reduce.lower(gram, int(round(n_gram ** 0.5)))      # only the lower triangle holds data: half the bytes
+        else:
+            reduce(gram, n_gram)
         reduce(rhs, n_rhs)
         if distributed is not None:
             self.factor_distributed(*distributed)

@@ -169,6 +169,17 @@ def all_reduce_device_i32(ptr: int, group=None) -> None:
     torch.cuda.current_stream().synchronize()
 
 
+def _staging(dd, name: str, n: int):
+    """A float64 device buffer of at least n elements cached on the DeviceDesign (packing area of the collectives)."""
+    import torch
+
+    t = getattr(dd, name, None)
+    if t is None or t.numel() < n:
+        t = torch.empty(n, dtype=torch.float64, device="cuda")
+        setattr(dd, name, t)
+    return t
+
+
 def fit_tuple_sharded(dd, ls_type: str, est_eigenvalues, est_covariance_eigenvalues=None, group=None,
                       distributed_cholesky: bool = False, lookahead: bool = True, **kw):
     """One fit with the tuple blocks sharded over the ranks of `group`: block factors and partial
@@ -199,17 +210,55 @@ def fit_tuple_sharded(dd, ls_type: str, est_eigenvalues, est_covariance_eigenval
         dd.ctx.set_stream(stream.cuda_stream)
         try:
             with torch.cuda.stream(stream):
+                pw = dd.DIST_PANEL
+
+                def columns(p, Np):   # the column-major matrix as [column][row]
+                    return torch.as_tensor(_DeviceBuffer(p, Np * Np), device="cuda").view(Np, Np)
+
                 def reduce(p, n):
                     t = torch.as_tensor(_DeviceBuffer(p, n), device="cuda")
                     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+                def reduce_lower(p, Np):
+                    # The partial Gram matrices only hold their lower triangle: pack the lower trapezoid of every
+                    # block column (rows col0 .. Np) into one contiguous buffer, ONE all-reduce of half the bytes,
+                    # unpack.  (The strict upper parts inside the diagonal blocks travel too: 1 % at d = 17.)
+                    G = columns(p, Np)
+                    pieces = [(c, min(pw, Np - c)) for c in range(0, Np, pw)]
+                    total = sum(n * (Np - c) for c, n in pieces)
+                    stage = _staging(dd, "_gram_stage", total)
+                    off = 0
+                    for c, n in pieces:
+                        stage[off:off + n * (Np - c)].view(n, Np - c).copy_(G[c:c + n, c:])
+                        off += n * (Np - c)
+                    dist.all_reduce(stage[:total], op=dist.ReduceOp.SUM, group=group)
+                    off = 0
+                    for c, n in pieces:
+                        G[c:c + n, c:].copy_(stage[off:off + n * (Np - c)].view(n, Np - c))
+                        off += n * (Np - c)
+
+                reduce.lower = reduce_lower
+
+                def bcast(p, n, src):
+                    broadcast_device(p, n, src, group, sync=False)
+
+                def bcast_panel(p, Np, col0, ncols, src):
+                    view = columns(p, Np)[col0:col0 + ncols, col0:]
+                    stage = _staging(dd, "_panel_stage", pw * Np)[:ncols * (Np - col0)].view(ncols, Np - col0)
+                    if rank == src:
+                        stage.copy_(view)
+                    dist.broadcast(stage, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+                    if rank != src:
+                        view.copy_(stage)
+
+                bcast.panel = bcast_panel
 
                 def reduce_int(p):
                     t = torch.as_tensor(_DeviceBufferI32(p, 1), device="cuda")
                     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
                 return dd.fit_sharded(ls_type, est_eigenvalues, est_covariance_eigenvalues, reduce,
-                                      distributed=(rank, world, lambda p, n, src: broadcast_device(p, n, src, group, sync=False),
-                                                   reduce_int, (stream, comm) if lookahead else None), **kw)
+                                      distributed=(rank, world, bcast, reduce_int, (stream, comm) if lookahead else None), **kw)
         finally:
             stream.synchronize()
             dd.ctx.set_stream(None)

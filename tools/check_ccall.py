@@ -27,6 +27,7 @@ JL2C = {
     "Ptr{UInt8}": {"uint8_t*", "const uint8_t*", "char*"},
     "Ptr{Ptr{UInt8}}": {"const uint8_t* const*", "uint8_t**"},
     "Ptr{Ptr{Float64}}": {"double**"},
+    "Ptr{Ptr{Int32}}": {"int32_t**"},
 }
 HANDLES = {"aces_ctx*", "const aces_ctx*", "aces_tables*", "const aces_tables*", "aces_design*", "const aces_design*", "void*"}
 HANDLE_OUT = {"aces_ctx**", "aces_tables**", "aces_design**", "void**"}

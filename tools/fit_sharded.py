@@ -68,6 +68,7 @@ sharded, ms_sharded = timed(lambda: shard.fit_tuple_sharded(dd, ls, lam, lc))
 plain, ms_plain = timed(lambda: shard.fit_tuple_sharded(dd, ls, lam, lc, distributed_cholesky=True, lookahead=False))
 distributed, ms_dist = timed(lambda: shard.fit_tuple_sharded(dd, ls, lam, lc, distributed_cholesky=True))
 assert np.array_equal(plain, distributed)
+NP = -(-dd.N // 128) * 128
 gathered = [None] * world
 dist.all_gather_object(gathered, sharded.tobytes() + distributed.tobytes())
 if rank == 0:
@@ -81,8 +82,11 @@ if rank == 0:
         "ms_per_fit_tuple_sharded_distributed_cholesky_no_lookahead": ms_plain,
         "distributed_cholesky": {"block_columns": int(-(-dd.N // 128) * 128 // dd.DIST_PANEL + (1 if (-(-dd.N // 128) * 128) % dd.DIST_PANEL else 0)),
                                  "panel_columns": dd.DIST_PANEL,
-                                 "broadcast_bytes_per_fit": int(8 * (-(-dd.N // 128) * 128) ** 2 + 8 * (-(-dd.N // 128) * 128) * 128),
-                                 "collective": "ncclBroadcast of the factorised block column (full columns) + its block inverses, per block column"},
+                                 "broadcast_bytes_per_fit": int(8 * sum(min(dd.DIST_PANEL, NP - c) * (NP - c) for c in range(0, NP, dd.DIST_PANEL)) + 8 * NP * 128),
+                                 "allreduce_bytes_per_fit": int(8 * sum(min(dd.DIST_PANEL, NP - c) * (NP - c) for c in range(0, NP, dd.DIST_PANEL))),
+                                 "collectives": "ONE ncclAllReduce of the packed lower trapezoids of the partial Gram matrices; per block column "
+                                                "ncclBroadcast of its packed lower trapezoid + its block inverses, on a second stream "
+                                                "(look-ahead: the next block column is factorised and sent while the current panel is applied)"},
         "rel_diff_distributed_vs_single": float(np.linalg.norm(distributed - single) / np.linalg.norm(single)),
         "gram_allreduce_bytes": int(8 * dd.fit_buffers()[0][1]),
         "rel_diff_sharded_vs_single": float(np.linalg.norm(sharded - single) / np.linalg.norm(single)),
