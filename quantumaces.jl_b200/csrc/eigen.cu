@@ -38,6 +38,9 @@ constexpr int KS = 8;             // the panel passes cut the NB reflectors into
 constexpr int KW = NB / KS;
 constexpr int P1 = 2 * NB + 2;    // per-CTA partials of phase A: [0] |x|^2, [1 + k] V'x, [1 + NB + k] W'x
 constexpr int MAX_SL = 6;         // 32-row slots a CTA can own (shared-memory bound)
+#ifndef EIG_MIN_GRID
+#define EIG_MIN_GRID 16
+#endif
 
 struct LLSlot;
 struct PanelArgs {
@@ -685,8 +688,12 @@ int syev_values(aces_ctx* ctx, int64_t n, int64_t Np, double* A, int64_t lda, do
                "eigen::syev_values: the matrix is not padded to a multiple of 128");
     ACES_CHECK(ctx, n <= max_order(ctx), "eigen::syev_values: order %lld exceeds the supported %lld", (long long)n,
                (long long)max_order(ctx));
-    const int grid = ctx->sm_count;
-    ACES_CHECK(ctx, grid * (NWARP - 1) >= 2 * NB, "eigen::syev_values: too few SMs");
+    // One CTA per SM for large matrices; a small matrix has fewer 128 x 128 tiles than SMs, and a grid barrier
+    // among fewer CTAs is cheaper (less skew, fewer arrivals on the counter's L2 slice), and leaves SMs to other
+    // contexts (replicas of calc_merit on one GPU).
+    const int64_t mt = (n + RB - 1) / RB;
+    const int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(mt * (mt + 1) / 2, EIG_MIN_GRID));
+    ACES_CHECK(ctx, grid * (NWARP - 1) >= 2 * NB && ctx->sm_count >= grid, "eigen::syev_values: too few SMs");
     int SL = (int)(((n + 31) / 32 + grid - 1) / grid);
     SL = std::max(SL, 1);
     const size_t smem = panel_smem(SL);
