@@ -506,6 +506,8 @@ def main():
     ap.add_argument("--fit-steps", type=int, default=5)
     ap.add_argument("--design", default="real", choices=["real", "synthetic"])
     ap.add_argument("--fit-contexts", type=int, default=4)
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="count exchange of the multi-GPU run: push / pull kernels over peer memory (NVLink), or NCCL")
     ap.add_argument("--workload", default="rotated_d9_wls_1e8shots", choices=sorted(WORKLOADS))
     args = ap.parse_args()
     DESIGN_SOURCE = args.design
@@ -598,6 +600,21 @@ def main():
     small = alg_bytes < 2.5e8   # the inputs would stay in the 126 MB L2 between steps: flush it
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if small else None
 
+    # multi-GPU count exchange: kernels over peer memory (csrc/exchange.cu) unless NCCL is asked for or IPC fails
+    xch, xch_note = None, None
+    if world > 1 and args.exchange == "peer":
+        try:
+            xch = aces_b200.shard.PeerExchange(ctx, n_counts)
+        except Exception as e:  # noqa: BLE001
+            xch_note = f"peer exchange unavailable ({type(e).__name__}: {e}); NCCL used"
+        ok = torch.tensor([1 if xch is not None else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0 and xch is not None:
+            xch.close()
+            xch = None
+    reduced = [torch.zeros(n_counts, dtype=torch.int64, device="cuda") for _ in range(2)] if xch is not None and reduce_counts else None
+    if xch is not None and gathered is None and not reduce_counts:
+        gathered = [torch.zeros(world * n_counts, dtype=torch.int64, device="cuda") for _ in range(2)]
     batches = [est.prepare(ptrs, rows, ld, prefix, o.data_ptr(), asynchronous=True) for o in outs]
     done_ev = [torch.cuda.Event(), torch.cuda.Event()]      # kernel of buffer b finished
     free_ev = [torch.cuda.Event(), torch.cuda.Event()]      # collective of buffer b finished
@@ -614,7 +631,17 @@ def main():
         if world > 1:
             stream.wait_event(free_ev[b])        # the collective that last read this buffer is done
         batches[b].launch()
-        if world > 1:
+        if world > 1 and xch is not None:
+            # push on the compute stream behind the prefix kernel (stores into every rank's buffer over NVLink),
+            # pull on the second stream (waits for every rank's flag); a slot parity is reused two steps later,
+            # after this rank's pull of the step in between
+            stream.wait_event(free_ev[1 - b])
+            xch.push(outs[b].data_ptr(), stream.cuda_stream)
+            done_ev[b].record(stream)
+            comm.wait_event(done_ev[b])
+            xch.pull((reduced[b] if reduce_counts else gathered[b]).data_ptr(), reduce_counts, comm.cuda_stream)
+            free_ev[b].record(comm)
+        elif world > 1:
             done_ev[b].record(stream)
             with torch.cuda.stream(comm):
                 comm.wait_event(done_ev[b])
@@ -673,6 +700,10 @@ def main():
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     value = float(tot[0].item()) / (ms_per_step * 1e-3)
     out = outs[(step_no[0] - 1) & 1]
+    if xch is not None:
+        xch.status()      # raises if a pull timed out
+        if reduce_counts:
+            out = reduced[(step_no[0] - 1) & 1]
     counts_equal = None
     if reduce_counts and world > 1:   # after the all-reduce every rank holds the same counts: compare a checksum
         chk = torch.stack([out.sum(), (out * torch.arange(1, n_counts + 1, device="cuda")).sum()]).to(torch.int64)
@@ -764,7 +795,11 @@ def main():
             "shots_per_s": float(tot[1].item()) / (ms_per_step * 1e-3),
             "clocks": clocks.summary(),
             "exchange": (None if world == 1 else
-                         {"collective": "ncclAllReduce(sum, int64) of the counts" if reduce_counts else "ncclAllGather of the per-repetition counts",
+                         {"collective": (("push / pull kernels over peer memory (CUDA IPC, NVLink stores + release / acquire flags): "
+                                          + ("sum of the counts" if reduce_counts else "counts of all repetitions side by side"))
+                                         if xch is not None else
+                                         ("ncclAllReduce(sum, int64) of the counts" if reduce_counts else "ncclAllGather of the per-repetition counts")),
+                          "note": xch_note,
                           "bytes_per_rank": n_counts * 8, "stream": "second stream, overlapped with the next step's kernel (two count buffers)",
                           "counts_equal_on_all_ranks": counts_equal}),
             "e2e": {"value": e2e_value, "unit": UNIT,

@@ -320,6 +320,36 @@ int32_t aces_design_fit_dist_buffers(aces_design* design, double** block_inverse
                                      int32_t** dead_columns);
 int32_t aces_design_fit_dist_solve(aces_ctx* ctx, aces_design* design);
 
+/* ---- count exchange of the sharded K1 path over peer memory -----------------------
+ *
+ * Repetitions, experiments and shot ranges shard over the GPUs of a node with one small exchange per step: every
+ * rank needs the odd-parity counts of all ranks (side by side for repetitions, summed for experiments / shots;
+ * int64, 0.4 - 1.4 MB).  Instead of a collective library call between launches, a rank PUSHES its counts with a
+ * kernel that stores them into a slot of every rank's exchange buffer over NVLink and releases a flag there, and
+ * PULLS with a kernel that waits for the flags of all ranks and sums (or copies) the slots.  The push goes on
+ * the stream of the parity kernel, the pull on a second stream: the next repetition's kernel is not held up.
+ *   aces_exchange_bytes   size of one rank's buffer for `world` ranks of n_counts counts each
+ *   aces_peer_alloc       device buffer (zeroed) + its 64-byte CUDA IPC handle, to be handed to the other ranks
+ *   aces_peer_open/_close map / unmap another rank's buffer from its handle (another process of this node)
+ *   aces_exchange_create  peer_base[r] = rank r's buffer as mapped HERE (own buffer: the pointer of aces_peer_alloc)
+ *   aces_exchange_push    local_counts: device, 16-byte aligned; cuda_stream NULL = the context's stream
+ *   aces_exchange_pull    reduce != 0: out[n_counts] = sum over ranks; else out[world][n_counts]; device pointer
+ *   aces_exchange_status  ACES_E_CUDA if a pull gave up after ~2 s without a peer's flag (blocking: reads a flag)
+ * Every rank must call push and pull once per step, in the same order.  Sums of integers: exact, identical on
+ * every rank. */
+typedef struct aces_exchange aces_exchange;
+int64_t aces_exchange_bytes(int32_t world, int64_t n_counts);
+int32_t aces_peer_alloc(aces_ctx* ctx, int64_t bytes, void** dev_ptr, uint8_t* handle_out /* [64] */);
+int32_t aces_peer_open(aces_ctx* ctx, const uint8_t* handle /* [64] */, void** dev_ptr);
+int32_t aces_peer_close(aces_ctx* ctx, void* dev_ptr);
+int32_t aces_peer_free(aces_ctx* ctx, void* dev_ptr);
+int32_t aces_exchange_create(aces_ctx* ctx, int32_t world, int32_t rank, int64_t n_counts, void* const* peer_base,
+                             aces_exchange** out);
+int32_t aces_exchange_destroy(aces_ctx* ctx, aces_exchange* exchange);
+int32_t aces_exchange_push(aces_ctx* ctx, aces_exchange* exchange, const int64_t* local_counts, void* cuda_stream);
+int32_t aces_exchange_pull(aces_ctx* ctx, aces_exchange* exchange, int32_t reduce, int64_t* out, void* cuda_stream);
+int32_t aces_exchange_status(aces_ctx* ctx, aces_exchange* exchange);
+
 /* Per-gate diagonal blocks of calc_precision_matrix(design_matrix, gate_eigenvalues, covariance_log_inv)
  * (src/merit.jl:754-770) = D^-1 A' Omega'^-1 A D^-1 -- all that split_project_gate_eigenvalues reads of
  * it (src/estimate.jl:606-612: est_precision_matrix[indices, indices] per gate).  Must directly follow

@@ -87,6 +87,16 @@ SIGNATURES = {
     "aces_design_fit_dist_update": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp]),
     "aces_design_fit_dist_buffers": (_i32, [_vp, _p(_vp), _p(_i64), _p(_vp)]),
     "aces_design_fit_dist_solve": (_i32, [_vp, _vp]),
+    "aces_exchange_bytes": (_i64, [_i32, _i64]),
+    "aces_peer_alloc": (_i32, [_vp, _i64, _p(_vp), _vp]),
+    "aces_peer_open": (_i32, [_vp, _vp, _p(_vp)]),
+    "aces_peer_close": (_i32, [_vp, _vp]),
+    "aces_peer_free": (_i32, [_vp, _vp]),
+    "aces_exchange_create": (_i32, [_vp, _i32, _i32, _i64, _vp, _p(_vp)]),
+    "aces_exchange_destroy": (_i32, [_vp, _vp]),
+    "aces_exchange_push": (_i32, [_vp, _vp, _vp, _vp]),
+    "aces_exchange_pull": (_i32, [_vp, _vp, _i32, _vp, _vp]),
+    "aces_exchange_status": (_i32, [_vp, _vp]),
     "aces_design_precision_blocks": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "aces_potrf_schedule": (_i32, [_i32, _i32, _vp, _i64, _p(_i64)]),
     "aces_potrf_trace": (_i32, [_vp, _vp, _i64, _p(_i64)]),
