@@ -36,7 +36,7 @@ constexpr int NWARP = THREADS / 32;
 constexpr int RB = 128;           // rows of one item of the trailing product
 constexpr int KS = 8;             // the panel passes cut the NB reflectors into KS slices of KW
 constexpr int KW = NB / KS;
-constexpr int P1 = 2 * NB + 2;    // per-CTA partials of phase A: [0] |x|^2, [1 + k] V'x, [1 + NB + k] W'x
+constexpr int P1 = 2 * NB + 2;    // per-CTA partials of phase A: [1 + k] V'x, [1 + NB + k] W'x ([0] unused: |x|^2 rides on the barrier)
 constexpr int MAX_SL = 6;         // 32-row slots a CTA can own (shared-memory bound)
 #ifndef EIG_MIN_GRID
 #define EIG_MIN_GRID 16
