@@ -612,6 +612,8 @@ def main():
         if int(ok.item()) == 0 and xch is not None:
             xch.close()
             xch = None
+    if xch is not None:
+        xch.attach()
     reduced = [torch.zeros(n_counts, dtype=torch.int64, device="cuda") for _ in range(2)] if xch is not None and reduce_counts else None
     if xch is not None and gathered is None and not reduce_counts:
         gathered = [torch.zeros(world * n_counts, dtype=torch.int64, device="cuda") for _ in range(2)]
@@ -630,13 +632,14 @@ def main():
             flush.fill_(1)
         if world > 1:
             stream.wait_event(free_ev[b])        # the collective that last read this buffer is done
+        if world > 1 and xch is not None:
+            stream.wait_event(free_ev[1 - b])   # this rank's pull of the previous step: its slot parity is free again
         batches[b].launch()
         if world > 1 and xch is not None:
-            # push on the compute stream behind the prefix kernel (stores into every rank's buffer over NVLink),
-            # pull on the second stream (waits for every rank's flag); a slot parity is reused two steps later,
+            # the push is fused into K1's prefix kernel (exchange attached to the context: the kernel that forms
+            # the counts stores them into every rank's buffer over NVLink and releases the flags); the pull runs
+            # on the second stream (waits for every rank's flag); a slot parity is reused two steps later,
             # after this rank's pull of the step in between
-            stream.wait_event(free_ev[1 - b])
-            xch.push(outs[b].data_ptr(), stream.cuda_stream)
             done_ev[b].record(stream)
             comm.wait_event(done_ev[b])
             xch.pull((reduced[b] if reduce_counts else gathered[b]).data_ptr(), reduce_counts, comm.cuda_stream)
@@ -702,6 +705,7 @@ def main():
     out = outs[(step_no[0] - 1) & 1]
     if xch is not None:
         xch.status()      # raises if a pull timed out
+        xch.attach(False)
         if reduce_counts:
             out = reduced[(step_no[0] - 1) & 1]
     counts_equal = None
@@ -795,7 +799,8 @@ def main():
             "shots_per_s": float(tot[1].item()) / (ms_per_step * 1e-3),
             "clocks": clocks.summary(),
             "exchange": (None if world == 1 else
-                         {"collective": (("push / pull kernels over peer memory (CUDA IPC, NVLink stores + release / acquire flags): "
+                         {"collective": (("K1's prefix kernel stores the counts into every rank's buffer over peer memory (CUDA IPC, NVLink stores + "
+                                          "release / acquire flags), a pull kernel on a second stream collects them: "
                                           + ("sum of the counts" if reduce_counts else "counts of all repetitions side by side"))
                                          if xch is not None else
                                          ("ncclAllReduce(sum, int64) of the counts" if reduce_counts else "ncclAllGather of the per-repetition counts")),

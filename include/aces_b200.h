@@ -334,6 +334,10 @@ int32_t aces_design_fit_dist_solve(aces_ctx* ctx, aces_design* design);
  *   aces_exchange_create  peer_base[r] = rank r's buffer as mapped HERE (own buffer: the pointer of aces_peer_alloc)
  *   aces_exchange_push    local_counts: device, 16-byte aligned; cuda_stream NULL = the context's stream
  *   aces_exchange_pull    reduce != 0: out[n_counts] = sum over ranks; else out[world][n_counts]; device pointer
+ *   aces_exchange_attach  fuses the push into K1: while an exchange is attached to the context (NULL detaches),
+ *                         the prefix kernel of every aces_parity_counts_async call stores each count into this
+ *                         rank's slot of every rank's buffer as it forms it and releases the flags itself -- no
+ *                         separate push (the call must produce exactly n_counts counts, accumulate = 0)
  *   aces_exchange_status  ACES_E_CUDA if a pull gave up after ~2 s without a peer's flag (blocking: reads a flag)
  * Every rank must call push and pull once per step, in the same order.  Sums of integers: exact, identical on
  * every rank. */
@@ -348,6 +352,7 @@ int32_t aces_exchange_create(aces_ctx* ctx, int32_t world, int32_t rank, int64_t
 int32_t aces_exchange_destroy(aces_ctx* ctx, aces_exchange* exchange);
 int32_t aces_exchange_push(aces_ctx* ctx, aces_exchange* exchange, const int64_t* local_counts, void* cuda_stream);
 int32_t aces_exchange_pull(aces_ctx* ctx, aces_exchange* exchange, int32_t reduce, int64_t* out, void* cuda_stream);
+int32_t aces_exchange_attach(aces_ctx* ctx, aces_exchange* exchange);
 int32_t aces_exchange_status(aces_ctx* ctx, aces_exchange* exchange);
 
 /* Per-gate diagonal blocks of calc_precision_matrix(design_matrix, gate_eigenvalues, covariance_log_inv)

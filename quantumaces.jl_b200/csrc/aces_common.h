@@ -19,6 +19,8 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+struct aces_exchange;
+
 struct aces_ctx {
     int device = 0;
     int sm_count = 0;
@@ -34,6 +36,7 @@ struct aces_ctx {
     int timing = 0;
     int timed = 0;
     int64_t launches = 0;
+    aces_exchange* xch = nullptr;  // attached count exchange: aces_parity_counts_async pushes from its prefix kernel
     int rank_deficiency = 0;  // columns eliminated by the last fit (aces_last_rank_deficiency)
     std::string err;
 

@@ -24,26 +24,13 @@
 #include <vector>
 
 #include "aces_common.h"
-
-struct aces_exchange {
-    int world = 0, rank = 0;
-    int64_t n = 0;                // slot stride: the count rounded up to even (16-byte stores)
-    int64_t nc = 0;               // counts per rank
-    unsigned epoch = 0;
-    std::vector<uint8_t*> base;   // [world] mapped base address of every rank's buffer (own included)
-    uint8_t** d_base = nullptr;   // the same on the device
-    unsigned* d_ticket = nullptr; // CTA ticket of the push kernel
-    int* d_err = nullptr;         // set by a pull that timed out
-};
+#include "exchange.cuh"
 
 namespace {
 
-__host__ __device__ inline size_t slots_bytes(int world, int64_t n) { return sizeof(int64_t) * 2 * (size_t)world * (size_t)n; }
-__host__ __device__ inline size_t flags_off(int world, int64_t n) { return (slots_bytes(world, n) + 255) & ~(size_t)255; }
+using xchg::flags_off;
+using xchg::st_release_sys;
 
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -67,19 +54,9 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(uint8_t* const* base
         const int64_t v = local[nc - 1];
         for (int p = 0; p < world; ++p) reinterpret_cast<int64_t*>(base[p])[slot + nc - 1] = v;
     }
-    __threadfence_system();
-    __syncthreads();
-    __shared__ unsigned last;
-    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
-    __syncthreads();
-    if (last) {
-        if (threadIdx.x == 0) *ticket = 0;  // ready for the next push (stream order)
-        __threadfence_system();
-        if ((int)threadIdx.x < world) {
-            unsigned* f = reinterpret_cast<unsigned*>(base[threadIdx.x] + flags_off(world, n)) + (size_t)(epoch & 1u) * world + rank;
-            st_release_sys(f, epoch);
-        }
-    }
+    xchg::PushArgs pa;
+    pa.base = base; pa.world = world; pa.rank = rank; pa.n = n; pa.epoch = epoch; pa.ticket = ticket;
+    xchg::publish_flags(pa, gridDim.x);
 }
 
 // waits for the flags of all ranks, then out = sum of the slots (reduce) or the slots side by side (gather)
@@ -205,6 +182,7 @@ int32_t aces_exchange_create(aces_ctx* ctx, int32_t world, int32_t rank, int64_t
 int32_t aces_exchange_destroy(aces_ctx* ctx, aces_exchange* x) {
     if (!ctx) return ACES_E_INVALID;
     if (!x) return ACES_OK;
+    if (ctx->xch == x) ctx->xch = nullptr;
     cudaSetDevice(ctx->device);
     if (x->d_base) cudaFree(x->d_base);
     delete x;
@@ -234,6 +212,12 @@ int32_t aces_exchange_pull(aces_ctx* ctx, aces_exchange* x, int32_t reduce, int6
                                                             out, x->d_err);
     ACES_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
+    return ACES_OK;
+}
+
+int32_t aces_exchange_attach(aces_ctx* ctx, aces_exchange* x) {
+    if (!ctx) return ACES_E_INVALID;
+    ctx->xch = x;  // NULL detaches
     return ACES_OK;
 }
 

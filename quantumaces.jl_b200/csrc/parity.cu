@@ -447,9 +447,20 @@ static int parity_run(aces_ctx* ctx, const aces_tables* t, int32_t n_items,
     }
     {
         dim3 grid((unsigned)std::min<int64_t>(((int64_t)max_E + 255) / 256, 64), (unsigned)std::min(n_items, 16384));
+        xchg::PushArgs push;
+        if (ctx->xch && async_only) {
+            // the exchange attached to this context: the prefix kernel publishes the counts to every rank
+            aces_exchange* x = ctx->xch;
+            ACES_CHECK(ctx, !accumulate && x->nc == total_out,
+                       "parity_counts: the attached exchange holds %lld counts per rank, this call produces %lld%s",
+                       (long long)x->nc, (long long)total_out, accumulate ? " (and accumulate is not supported)" : "");
+            x->epoch += 1;
+            push.base = x->d_base; push.world = x->world; push.rank = x->rank; push.n = x->n; push.epoch = x->epoch;
+            push.ticket = x->d_ticket;
+        }
         prefix_kernel<<<grid, 256, 0, ctx->stream>>>((unsigned long long*)ctx->d_seg.ptr, d_out,
                                                     (const int64_t*)(ds + o_ioff),
-                                                    (const int32_t*)(ds + o_iE), n_items, K, acc_dev);
+                                                    (const int32_t*)(ds + o_iE), n_items, K, acc_dev, push);
         ACES_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
         ctx->seg_clean = true;

@@ -1,5 +1,6 @@
 // parity_common.cuh -- structures and PTX helpers shared by the K1 parity kernels.
 #pragma once
+#include "exchange.cuh"
 #include "aces_common.h"
 
 namespace k1 {
@@ -150,11 +151,14 @@ __device__ __forceinline__ uint4 xor4(uint4 x, const uint4 y) {
     return x;
 }
 // Per-segment counts -> per-prefix (cumulative) counts; optionally added to the output.  Clears the
-// segment counters it has consumed.
+// segment counters it has consumed.  With an exchange attached (push.base != NULL) the same kernel IS the
+// push of the multi-GPU count exchange: every count is also stored into this rank's slot of every rank's
+// exchange buffer (peer memory, NVLink), and the last CTA releases the flags (exchange.cuh).
 __global__ void prefix_kernel(unsigned long long* __restrict__ seg,
                               long long* __restrict__ out, const int64_t* __restrict__ item_off,
                               const int32_t* __restrict__ item_E, int n_items, int K,
-                              int accumulate) {
+                              int accumulate, const xchg::PushArgs push) {
+    const size_t slot = push.base ? ((size_t)(push.epoch & 1u) * push.world + push.rank) * (size_t)push.n : 0;
     for (int item = blockIdx.y; item < n_items; item += gridDim.y) {
         const int E = item_E[item];
         const int64_t off = item_off[item];
@@ -165,9 +169,12 @@ __global__ void prefix_kernel(unsigned long long* __restrict__ seg,
                 run += (long long)seg[idx];
                 seg[idx] = 0ull;  // leave the counters clean for the next call
                 out[idx] = accumulate ? out[idx] + run : run;
+                if (push.base)
+                    for (int r = 0; r < push.world; ++r) reinterpret_cast<long long*>(push.base[r])[slot + idx] = run;
             }
         }
     }
+    if (push.base) xchg::publish_flags(push, gridDim.x * gridDim.y);
 }
 
 

@@ -147,6 +147,11 @@ class PeerExchange:
     def pull(self, out_ptr: int, reduce: bool, stream: int = None) -> None:
         self.ctx.check(self.ctx.lib.aces_exchange_pull(self.ctx.handle, self.handle, 1 if reduce else 0, out_ptr, stream))
 
+    def attach(self, on: bool = True) -> None:
+        """Fuses the push into K1: while attached, the prefix kernel of every asynchronous parity launch on this
+        context publishes the counts to all ranks itself (aces_exchange_attach); only `pull` remains per step."""
+        self.ctx.check(self.ctx.lib.aces_exchange_attach(self.ctx.handle, self.handle if on else None))
+
     def status(self) -> None:
         self.ctx.check(self.ctx.lib.aces_exchange_status(self.ctx.handle, self.handle))
 

@@ -62,3 +62,59 @@ def test_pull_without_a_peer_times_out_instead_of_hanging(ctx):
     with pytest.raises(aces_b200.AcesError):
         x0.status()
     x0.close()
+
+
+def test_push_fused_into_the_prefix_kernel(ctx):
+    """aces_exchange_attach: K1's prefix kernel publishes the counts to every rank as it forms them (no separate
+    push launch).  Two emulated ranks reduce different sample matrices of the same design; after the pull each
+    holds the sum of both count vectors, bit for bit, over several steps (both slot parities)."""
+    import torch
+
+    import aces_b200
+    from aces_b200 import shard
+
+    fd = aces_b200.synthetic_design("rotated", 3, full_covariance=True)
+    world = 2
+    ctxs = [aces_b200.Context(0) for _ in range(world)]
+    ests = [aces_b200.DesignEstimator(c, fd) for c in ctxs]
+    shots_divided, shots_max = aces_b200.shots_divide(fd, [3000, 20000])
+    n_exp = fd.experiment_number
+    rows = [int(shots_max[int(ests[0].tuple_of_experiment[e])]) for e in range(n_exp)]
+    prefix = np.stack([shots_divided[int(ests[0].tuple_of_experiment[e])] for e in range(n_exp)])
+    ld = [(r + 127) // 128 * 128 for r in rows]
+    n_counts = int(np.sum(ests[0].experiment_sizes()) * prefix.shape[1])
+    nbytes = shard.PeerExchange.buffer_bytes(ctx, world, n_counts)
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    xs = [shard.PeerExchange(ctxs[r], n_counts, peers=(r, [b.data_ptr() for b in bufs])) for r in range(world)]
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for step in range(4):
+        mats = [[torch.randint(0, 256, (fd.n_bytes, ld[e]), dtype=torch.uint8, device="cuda", generator=gen) for e in range(n_exp)]
+                for _ in range(world)]
+        plain = []
+        for r in range(world):        # reference: the same launches without the exchange
+            o = torch.zeros(n_counts, dtype=torch.int64, device="cuda")
+            ests[r].prepare([m.data_ptr() for m in mats[r]], rows, ld, prefix, o.data_ptr(), asynchronous=True).launch()
+            ctxs[r].synchronize()
+            plain.append(o)
+        launches = [c.kernel_launches() for c in ctxs]
+        outs, sums = [], []
+        for r in range(world):
+            xs[r].attach()
+            o = torch.zeros(n_counts, dtype=torch.int64, device="cuda")
+            ests[r].prepare([m.data_ptr() for m in mats[r]], rows, ld, prefix, o.data_ptr(), asynchronous=True).launch()
+            outs.append(o)
+        for r in range(world):
+            s = torch.full((n_counts,), -1, dtype=torch.int64, device="cuda")
+            xs[r].pull(s.data_ptr(), True)
+            sums.append(s)
+        for r in range(world):
+            ctxs[r].synchronize()
+            xs[r].status()
+            xs[r].attach(False)
+            assert ctxs[r].kernel_launches() - launches[r] == 3          # parity + prefix(+push) + pull: no push launch
+            assert torch.equal(outs[r], plain[r])                        # the local counts are unchanged
+            assert torch.equal(sums[r], plain[0] + plain[1])
+    for x in xs:
+        x.close()
+    for c in ctxs:
+        c.close()
