@@ -338,7 +338,8 @@ int32_t aces_design_fit_dist_solve(aces_ctx* ctx, aces_design* design);
  *                         the prefix kernel of every aces_parity_counts_async call stores each count into this
  *                         rank's slot of every rank's buffer as it forms it and releases the flags itself -- no
  *                         separate push (the call must produce exactly n_counts counts, accumulate = 0)
- *   aces_exchange_status  ACES_E_CUDA if a pull gave up after ~2 s without a peer's flag (blocking: reads a flag)
+ *   aces_exchange_status  ACES_E_CUDA if a pull gave up without a peer's flag (blocking: reads a flag); the wait is
+ *                         bounded (about 10 s by default, aces_exchange_set_timeout) so that a dead peer cannot hang the GPU
  * Every rank must call push and pull once per step, in the same order.  Sums of integers: exact, identical on
  * every rank. */
 typedef struct aces_exchange aces_exchange;
@@ -353,6 +354,7 @@ int32_t aces_exchange_destroy(aces_ctx* ctx, aces_exchange* exchange);
 int32_t aces_exchange_push(aces_ctx* ctx, aces_exchange* exchange, const int64_t* local_counts, void* cuda_stream);
 int32_t aces_exchange_pull(aces_ctx* ctx, aces_exchange* exchange, int32_t reduce, int64_t* out, void* cuda_stream);
 int32_t aces_exchange_attach(aces_ctx* ctx, aces_exchange* exchange);
+int32_t aces_exchange_set_timeout(aces_ctx* ctx, aces_exchange* exchange, int64_t milliseconds);
 int32_t aces_exchange_status(aces_ctx* ctx, aces_exchange* exchange);
 
 /* Per-gate diagonal blocks of calc_precision_matrix(design_matrix, gate_eigenvalues, covariance_log_inv)

@@ -18,7 +18,7 @@
 // The two parities alternate: rank A can only push exchange e + 2 after its pull of e + 1, which needed
 // B's flag of e + 1, which B released after (stream order) its own pull of e -- so nobody overwrites a slot
 // that is still being read.  Integer sums: the result is exact and identical on every rank.  A pull that
-// does not see its flags within about two seconds gives up and reports it (a dead peer must not hang the GPU).
+// does not see its flags within its time-out (ten seconds by default) gives up and reports it (a dead peer must not hang the GPU).
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(uint8_t* const* base
 
 // waits for the flags of all ranks, then out = sum of the slots (reduce) or the slots side by side (gather)
 __global__ void __launch_bounds__(256) exchange_pull_kernel(uint8_t* mine, int world, int64_t n, int64_t nc, unsigned epoch,
-                                                            int reduce, int64_t* __restrict__ out, int* err) {
+                                                            int reduce, int64_t* __restrict__ out, int* err, long long timeout_cycles) {
     __shared__ int ok;
     if (threadIdx.x == 0) ok = 1;
     __syncthreads();
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) exchange_pull_kernel(uint8_t* mine, int w
         const long long t0 = clock64();
         while (ld_acquire_sys(f) != epoch) {
             __nanosleep(200);
-            if (clock64() - t0 > 4000000000ll) {  // ~2 s at 2 GHz: a peer is gone
+            if (clock64() - t0 > timeout_cycles) {  // a peer is gone
                 ok = 0;
                 break;
             }
@@ -209,9 +209,16 @@ int32_t aces_exchange_pull(aces_ctx* ctx, aces_exchange* x, int32_t reduce, int6
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     const int grid = (int)std::min<int64_t>((x->nc + 255) / 256, (int64_t)ctx->sm_count);
     exchange_pull_kernel<<<std::max(grid, 1), 256, 0, st>>>(x->base[(size_t)x->rank], x->world, x->n, x->nc, x->epoch, reduce ? 1 : 0,
-                                                            out, x->d_err);
+                                                            out, x->d_err, x->timeout_cycles);
     ACES_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
+    return ACES_OK;
+}
+
+int32_t aces_exchange_set_timeout(aces_ctx* ctx, aces_exchange* x, int64_t milliseconds) {
+    if (!ctx) return ACES_E_INVALID;
+    ACES_CHECK(ctx, x && milliseconds > 0, "exchange_set_timeout: bad argument");
+    x->timeout_cycles = (long long)milliseconds * 2000000ll;  // SM clock of about 2 GHz
     return ACES_OK;
 }
 

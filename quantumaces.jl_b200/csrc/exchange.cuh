@@ -14,6 +14,7 @@ struct aces_exchange {
     uint8_t** d_base = nullptr;   // the same on the device
     unsigned* d_ticket = nullptr; // CTA ticket of the push kernel
     int* d_err = nullptr;         // set by a pull that timed out
+    long long timeout_cycles = 20000000000ll;  // ~10 s: how long a pull waits for a peer before giving up
 };
 
 namespace xchg {

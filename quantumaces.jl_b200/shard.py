@@ -152,6 +152,9 @@ class PeerExchange:
         context publishes the counts to all ranks itself (aces_exchange_attach); only `pull` remains per step."""
         self.ctx.check(self.ctx.lib.aces_exchange_attach(self.ctx.handle, self.handle if on else None))
 
+    def set_timeout(self, milliseconds: int) -> None:
+        self.ctx.check(self.ctx.lib.aces_exchange_set_timeout(self.ctx.handle, self.handle, int(milliseconds)))
+
     def status(self) -> None:
         self.ctx.check(self.ctx.lib.aces_exchange_status(self.ctx.handle, self.handle))
 

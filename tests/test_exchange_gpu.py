@@ -54,6 +54,7 @@ def test_pull_without_a_peer_times_out_instead_of_hanging(ctx):
     n = 100
     bufs = [torch.zeros(shard.PeerExchange.buffer_bytes(ctx, 2, n), dtype=torch.uint8, device="cuda") for _ in range(2)]
     x0 = shard.PeerExchange(ctx, n, peers=(0, [b.data_ptr() for b in bufs]))
+    x0.set_timeout(300)
     local = torch.ones(n, dtype=torch.int64, device="cuda")
     out = torch.zeros(n, dtype=torch.int64, device="cuda")
     x0.push(local.data_ptr())
