@@ -44,6 +44,8 @@ WORKLOADS = {
                                     baseline="configs[2]: rotated surface code d=9, full_covariance=false WLS, 1e8 shots"),
     "rotated_d5_gls": dict(kind="rotated", d=5, full=True, shots=[10**6, 10**7, 10**8], fit_full=True, sharding="repetitions",
                            baseline="configs[1]: rotated surface code d=5, log-normal Pauli noise, full_covariance=true GLS"),
+    "rotated_d9_gls": dict(kind="rotated", d=9, full=True, shots=[10**6, 10**7, 10**8], fit_full=True, sharding="repetitions",
+                           baseline="configs[2]'s circuit with full_covariance=true: the covariance Paulis are reduced in the same pass (449 Paulis per experiment)"),
     "unrotated_d7_gls": dict(kind="unrotated", d=7, full=True, shots=[10**6, 10**7, 10**8], fit_full=True, sharding="repetitions",
                              baseline="configs[3]: unrotated surface code d=7, log-normal noise, GLS estimate + calc_covariance merit"),
     "rotated_d9_wls_experiments": dict(kind="rotated", d=9, full=False, shots=[10**6, 10**7, 10**8], fit_full=False, sharding="experiments",
