@@ -468,6 +468,26 @@ int32_t aces_project_simplex(aces_ctx* ctx, int64_t N, int32_t G, const int64_t*
 int32_t aces_project_nonnegative_batched(aces_ctx* ctx, int32_t n_problems, const int64_t* ptr, const double* Q,
                                          const double* v, double threshold, double* y, int32_t* n_failed);
 
+/* Drop-in for the numeric core of full_project_gate_eigenvalues(est_unproj_gate_eigenvalues, est_precision_matrix,
+ * gate_data; precision) (src/estimate.jl:532-573), the simultaneous Mahalanobis projection of all gates -- the
+ * reference's default below 5000 gate eigenvalues (split = false).  Must directly follow aces_design_fit of the
+ * same ls_type on this design: the precision matrix D^-1 A' Omega'^-1 A D^-1 (src/merit.jl:754-770) is that of
+ * the fit's Gram matrix, rebuilt on the device; it never leaves it.
+ *   group_ptr / group_idx  the gates (as for aces_design_precision_blocks); they must cover the N gate eigenvalues
+ *   gate_eigenvalues [N]   the unprojected estimate (the D of the precision matrix)
+ *   transform_blocks       per gate the n_g x n_g block of probs_transform = pad' * W * pad_probs
+ *                          (src/estimate.jl:553), row-major, gate after gate: T[a][b] = W[a+1][b+1] - W[a+1][0]
+ *   v [N]                  the unprojected unpadded gate probabilities (src/estimate.jl:548-551)
+ *   y [N]                  argmin (y - v)' (T P T') (y - v) over y >= 0, entries below `threshold` set to 0
+ *                          (scs_project_nonnegative, src/utils.jl:57-97, which iterates SCS to eps = threshold = 1e-8)
+ * The quadratic program is solved exactly by block principal pivoting: a few Cholesky factorisations of the free
+ * block on the FP64 tensor pipe; *iterations receives their number.  The caller maps y back to padded
+ * probabilities and gate eigenvalues (pad_probs * y + mask, W *, pad' *) as the reference does. */
+int32_t aces_design_project_full(aces_ctx* ctx, aces_design* design, int32_t ls_type, int32_t G, const int64_t* group_ptr,
+                                 const int32_t* group_idx, int32_t index_base, const double* gate_eigenvalues,
+                                 const double* transform_blocks, const double* v, double threshold, double* y,
+                                 int32_t* iterations);
+
 #ifdef __cplusplus
 }
 #endif

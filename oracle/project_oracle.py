@@ -121,3 +121,30 @@ def split_project_gate_eigenvalues(unproj, precision_matrix, gate_ptr, precision
         up.append(q)
         pp.append(pr)
     return out, np.concatenate(up), np.concatenate(pp)
+
+
+def full_project_gate_eigenvalues(unproj, precision_matrix, gate_ptr, precision: float = 1e-8):
+    """src/estimate.jl:532-573 with a dense or scipy-sparse N x N precision matrix: ONE non-negative quadratic
+    program over the unpadded probabilities of all gates, Q = probs_transform * P * probs_transform' (block
+    diagonal transform, src/estimate.jl:553-556)."""
+    unproj = np.asarray(unproj, dtype=np.float64)
+    N, G = len(unproj), len(gate_ptr) - 1
+    P = precision_matrix.toarray() if hasattr(precision_matrix, "toarray") else np.asarray(precision_matrix, dtype=np.float64)
+    T = np.zeros((N, N))
+    v = np.zeros(N)
+    qs = []
+    for g in range(G):
+        a, b = int(gate_ptr[g]), int(gate_ptr[g + 1])
+        q = get_wht_matrix(b - a, inverse=True) @ np.concatenate([[1.0], unproj[a:b]])
+        T[a:b, a:b] = probs_transform_block(b - a)
+        v[a:b] = q[1:]
+        qs.append(q)
+    y = scs_project_nonnegative(v, T @ P @ T.T, precision=precision)
+    out = unproj.copy()
+    pp = []
+    for g in range(G):
+        a, b = int(gate_ptr[g]), int(gate_ptr[g + 1])
+        pr = np.concatenate([[1.0 - y[a:b].sum()], y[a:b]])
+        out[a:b] = (get_wht_matrix(b - a) @ pr)[1:]
+        pp.append(pr)
+    return out, np.concatenate(qs), np.concatenate(pp)

@@ -99,6 +99,7 @@ SIGNATURES = {
     "aces_exchange_attach": (_i32, [_vp, _vp]),
     "aces_exchange_set_timeout": (_i32, [_vp, _vp, _i64]),
     "aces_exchange_status": (_i32, [_vp, _vp]),
+    "aces_design_project_full": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, C.c_double, _vp, _p(_i32)]),
     "aces_design_precision_blocks": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "aces_potrf_schedule": (_i32, [_i32, _i32, _vp, _i64, _p(_i64)]),
     "aces_potrf_trace": (_i32, [_vp, _vp, _i64, _p(_i64)]),

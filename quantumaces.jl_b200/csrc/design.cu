@@ -1677,3 +1677,4 @@ int32_t aces_design_ls_covariance(aces_ctx* ctx, aces_design* d, int32_t ls_type
 
 #include "merit_grad.cuh"
 #include "merit_tail.cuh"
+#include "project_full.cuh"

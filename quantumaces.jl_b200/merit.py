@@ -557,18 +557,21 @@ def isapprox(x, y) -> bool:
 
 def estimate_gate_noise_projected(dd: DeviceDesign, est_eigenvalues_experiment_ensemble,
                                   est_covariance_experiment_ensemble, min_eigenvalue: float = 0.1,
-                                  clip_warning: bool = True, precision: float = 1e-8):
+                                  clip_warning: bool = True, precision: float = 1e-8, split: Optional[bool] = None,
+                                  N_warn_split: int = 5 * 10 ** 3):
     """estimate_gate_noise (src/estimate.jl:703-831) up to the NoiseEstimate bookkeeping, with
     split = true: unprojected OLS / WLS / GLS gate eigenvalues, the Euclidean projection of the OLS
     estimate (simple_project_gate_eigenvalues), and -- when that projection moved it
     (`precision_project`, :744) -- the per-gate Mahalanobis projection of WLS / GLS with the slices
-    of their precision matrices (split_project_gate_eigenvalues), else the Euclidean one.  The
-    simultaneous projection of all gates (full_project_gate_eigenvalues, the reference's default below
-    5000 gate eigenvalues) stays on the reference's SCS path."""
+    of their precision matrices (split_project_gate_eigenvalues) when `split`, or the simultaneous
+    projection of all gates (full_project_gate_eigenvalues) otherwise; else the Euclidean one.  `split`
+    defaults as in the reference (src/estimate.jl:698): false below N_warn_split = 5000 gate eigenvalues."""
     from . import project
 
     fd, ctx = dd.fd, dd.ctx
     assert fd.gate_ptr is not None, "the design carries no gate index ranges"
+    if split is None:
+        split = dd.N >= N_warn_split
     est = np.concatenate(mean_ensemble(est_eigenvalues_experiment_ensemble))
     cov = np.concatenate(mean_ensemble(est_covariance_experiment_ensemble)) if dd.C else None
     clipped = get_clipped_indices(est, min_eigenvalue=min_eigenvalue, warning=clip_warning)
@@ -581,9 +584,11 @@ def estimate_gate_noise_projected(dd: DeviceDesign, est_eigenvalues_experiment_e
     for k in (("wls", "gls") if fd.full_covariance else ("wls",)):
         un = dd.fit(k, est, cov, kept)
         out[k + "_unproj"] = un
-        if out["precision_project"]:
+        if out["precision_project"] and split:
             blocks = dd.precision_blocks(k, fd.gate_ptr, un)
             res = project.split_project_gate_eigenvalues(ctx, un, blocks, fd.gate_ptr, precision=precision)
+        elif out["precision_project"]:
+            res = project.full_project_gate_eigenvalues(dd, k, un, fd.gate_ptr, precision=precision)
         else:
             res = project.simple_project_gate_eigenvalues(ctx, un, fd.gate_ptr)
         out[k], out[k + "_unproj_probabilities"], out[k + "_probabilities"] = res

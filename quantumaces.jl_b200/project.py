@@ -88,3 +88,43 @@ def split_project_gate_eigenvalues(ctx: _lib.Context, est_unproj_gate_eigenvalue
         out[a:b] = (Ws[g] @ pr)[1:]
         pp.append(pr)
     return out, np.concatenate(qs), np.concatenate(pp)
+
+
+def full_project_gate_eigenvalues(dd, ls_type: str, est_unproj_gate_eigenvalues, gate_ptr, precision: float = 1e-8):
+    """full_project_gate_eigenvalues(est_unproj_gate_eigenvalues, est_precision_matrix, gate_data; precision)
+    (src/estimate.jl:532-573), the simultaneous projection of all gates (the reference's default below 5000
+    gate eigenvalues), for the estimator of the LAST `dd.fit(ls_type, ...)`: the precision matrix
+    (calc_precision_matrix, src/merit.jl:754-770) is rebuilt on the device from that fit's Gram matrix and never
+    leaves it; the N-variable non-negative quadratic program is solved exactly by block principal pivoting
+    (aces_design_project_full).  The per-gate transforms in and out are the host's, as in the split version.
+    Returns (gate eigenvalues, unprojected padded probabilities, projected padded probabilities)."""
+    from .merit import LS_TYPES
+
+    un = np.ascontiguousarray(est_unproj_gate_eigenvalues, dtype=np.float64)
+    N = len(un)
+    gp, gi = _groups(N, gate_ptr, None)
+    G = len(gp) - 1
+    v, blocks, qs, Ws = np.zeros(N), [], [], []
+    for g in range(G):
+        a, b = int(gp[g]), int(gp[g + 1])
+        W = _wht(b - a)
+        q = (W / (b - a + 1)) @ np.concatenate([[1.0], un[a:b]])
+        v[a:b] = q[1:]
+        blocks.append((W[1:, 1:] - W[1:, :1]).ravel())     # block of probs_transform = pad' * W * pad_probs
+        qs.append(q)
+        Ws.append(W)
+    T = np.ascontiguousarray(np.concatenate(blocks))
+    y = np.zeros(N)
+    its = C.c_int32()
+    ctx = dd.ctx
+    ctx.check(ctx.lib.aces_design_project_full(ctx.handle, dd.handle, LS_TYPES[ls_type], G, _ptr(gp), _ptr(gi), 0, _ptr(un),
+                                               _ptr(T), _ptr(v), float(precision), _ptr(y), C.byref(its)))
+    out = un.copy()
+    pp = []
+    for g in range(G):
+        a, b = int(gp[g]), int(gp[g + 1])
+        pr = np.concatenate([[1.0 - y[a:b].sum()], y[a:b]])
+        out[a:b] = (Ws[g] @ pr)[1:]
+        pp.append(pr)
+    full_project_gate_eigenvalues.last_iterations = int(its.value)
+    return out, np.concatenate(qs), np.concatenate(pp)

@@ -103,10 +103,63 @@ def test_split_projection_of_a_fit_vs_oracle(ctx, ls_type):
     assert np.all(got[2] >= 0)
 
 
-@pytest.mark.parametrize("name,shots", [("real3", 10**6), ("real5", 10**7), ("real3", 10**10)])
-def test_estimate_gate_noise_projected_vs_oracle(ctx, name, shots):
-    """The whole numeric path of estimate_gate_noise with split = true (src/estimate.jl:703-831): fits,
-    precision-matrix slices from the design-resident Gram matrix, projections -- against the oracles."""
+@pytest.mark.parametrize("name,ls_type,shots", [("real3", "gls", 10**6), ("real3", "wls", 10**6), ("real3", "ols", 10**5),
+                                                 ("example", "gls", 10**5), ("real5", "gls", 10**6)])
+def test_full_projection_of_a_fit_vs_oracle(ctx, name, ls_type, shots):
+    """full_project_gate_eigenvalues (src/estimate.jl:532-573), the reference's default below 5000 gate
+    eigenvalues: the simultaneous Mahalanobis projection of all gates.  GPU: precision matrix from the fit's own
+    Gram matrix, exact block principal pivoting; oracle: the reference's sparse precision matrix
+    (calc_precision_matrix) and an exact NNLS solve of the same N-variable program."""
+    import scipy.sparse as sp
+
+    import aces_b200
+
+    fd = (aces_b200.example_design(full_covariance=True) if name == "example"
+          else aces_b200.rotated_design(int(name[-1]), full_covariance=True, noise="lognormal", seed=4))
+    eig, cov = noisy_ensembles(fd, shots=shots, seed=8)       # few shots: negative probabilities appear
+    core = fo.estimate_gate_noise_core(fd, eig, cov)
+    unproj = core[ls_type]
+    cl = core["covariance_log"]
+    kept = core["clipped_indices"]
+    A = sp.csr_matrix(fd.matrix)[kept, :].astype(np.float64)
+    if ls_type == "gls":
+        inv = fo.sparse_covariance_inv(cl, fo.get_clipped_mapping_lengths(fd.mapping_lengths, kept))
+    elif ls_type == "wls":
+        inv = sp.diags(1.0 / cl.diagonal())
+    else:
+        inv = sp.identity(A.shape[0])
+    P = fo.calc_precision_matrix(A, unproj, inv).toarray()
+    want = po.full_project_gate_eigenvalues(unproj, P, fd.gate_ptr)
+    assert np.any(want[1] < 0)
+    dd = aces_b200.DeviceDesign(ctx, fd)
+    try:
+        est = np.concatenate(aces_b200.mean_ensemble(eig))
+        covm = np.concatenate(aces_b200.mean_ensemble(cov))
+        clipped = None if len(kept) == dd.M else kept
+        un_gpu = dd.fit(ls_type, est, covm, clipped)
+        assert np.linalg.norm(un_gpu - unproj) < 1e-9 * np.linalg.norm(unproj)
+        got = aces_b200.project.full_project_gate_eigenvalues(dd, ls_type, un_gpu, fd.gate_ptr)
+        its = aces_b200.project.full_project_gate_eigenvalues.last_iterations
+        assert 1 <= its <= 60
+        assert np.all(got[2] >= 0)
+        assert np.max(np.abs(got[2] - want[2])) < 1e-8 and np.max(np.abs(got[0] - want[0])) < 1e-7
+        # the joint solution is at least as close (Mahalanobis) as the per-gate one, and differs from it
+        dist = lambda x: float((x - unproj) @ P @ (x - unproj))  # noqa: E731
+        split = po.split_project_gate_eigenvalues(unproj, P, fd.gate_ptr)
+        assert dist(got[0]) <= dist(split[0]) * (1 + 1e-9)
+        # must follow a fit of the same estimator
+        with pytest.raises(aces_b200.AcesError):
+            aces_b200.project.full_project_gate_eigenvalues(dd, ls_type, un_gpu, fd.gate_ptr)
+    finally:
+        dd.close()
+
+
+@pytest.mark.parametrize("name,shots,split", [("real3", 10**6, True), ("real5", 10**7, True), ("real3", 10**10, True),
+                                               ("real3", 10**6, False), ("real5", 10**7, None)])
+def test_estimate_gate_noise_projected_vs_oracle(ctx, name, shots, split):
+    """The whole numeric path of estimate_gate_noise (src/estimate.jl:703-831): fits, precision matrix from the
+    design-resident Gram matrix, projections -- against the oracles; split = true (per gate), false (all gates
+    at once) and the reference's default (None: false below 5000 gate eigenvalues)."""
     import scipy.sparse as sp
 
     import aces_b200
@@ -115,7 +168,7 @@ def test_estimate_gate_noise_projected_vs_oracle(ctx, name, shots):
     eig, cov = noisy_ensembles(fd, shots=shots, seed=5)
     dd = aces_b200.DeviceDesign(ctx, fd)
     try:
-        got = aces_b200.estimate_gate_noise_projected(dd, eig, cov, clip_warning=False)
+        got = aces_b200.estimate_gate_noise_projected(dd, eig, cov, clip_warning=False, split=split)
         core = fo.estimate_gate_noise_core(fd, eig, cov)
         ols = po.simple_project_gate_eigenvalues(core["ols"], fd.gate_ptr)
         assert np.max(np.abs(got["ols"] - ols[0])) < 1e-9
@@ -131,17 +184,19 @@ def test_estimate_gate_noise_projected_vs_oracle(ctx, name, shots):
                        if k == "gls" else sp.diags(1.0 / cl.diagonal()))
                 P = fo.calc_precision_matrix(A, core[k], inv)
                 # the precision-matrix slices themselves: 1e-9 (src/merit.jl:754-770)
-                blocks = dd.precision_blocks(k, fd.gate_ptr, got[k + "_unproj"]) if k == "gls" else None
+                blocks = dd.precision_blocks(k, fd.gate_ptr, got[k + "_unproj"]) if (k == "gls" and split) else None
                 if blocks is not None:
                     for (a, b), blk in zip(zip(fd.gate_ptr[:-1], fd.gate_ptr[1:]), blocks):
                         w = P[a:b, a:b].toarray()
                         assert np.linalg.norm(blk - w) <= 1e-9 * np.linalg.norm(w)
-                want = po.split_project_gate_eigenvalues(core[k], P, fd.gate_ptr)
+                want = (po.split_project_gate_eigenvalues if split else po.full_project_gate_eigenvalues)(core[k], P, fd.gate_ptr)
             else:
                 want = po.simple_project_gate_eigenvalues(core[k], fd.gate_ptr)
             assert np.max(np.abs(got[k + "_probabilities"] - want[2])) < 2e-8, k
             assert np.max(np.abs(got[k] - want[0])) < 2e-7, k
         with pytest.raises(aces_b200.AcesError):   # the slices belong to the LAST fit's estimator
             dd.precision_blocks("ols", fd.gate_ptr)
+        if not split:
+            assert fd.matrix.shape[1] < 5000     # the default took the simultaneous projection
     finally:
         dd.close()

@@ -76,3 +76,43 @@ def test_mahalanobis_projection_kkt():
     lam = np.concatenate([(po.get_wht_matrix(3) @ p1)[1:], (po.get_wht_matrix(15) @ p2)[1:]])
     out, up, pp = po.split_project_gate_eigenvalues(lam, np.eye(18), gate_ptr)
     assert np.allclose(out, lam, atol=1e-12)
+
+
+def test_full_projection_oracle_properties():
+    """full_project_gate_eigenvalues (src/estimate.jl:532-573): with a precision matrix that is block diagonal
+    by gate the simultaneous projection IS the per-gate one (split_project, :580-628); with correlations between
+    the gates it satisfies the Karush-Kuhn-Tucker conditions of the joint problem and never does worse in the
+    Mahalanobis distance than the split solution."""
+    rng = np.random.default_rng(11)
+    gate_ptr = np.array([0, 1, 4, 19, 22, 37])
+    N = int(gate_ptr[-1])
+    lam = np.concatenate([(po.get_wht_matrix(b - a) @ np.abs(rng.dirichlet(np.full(b - a + 1, 0.3))))[1:]
+                          for a, b in zip(gate_ptr[:-1], gate_ptr[1:])])
+    lam = lam + rng.normal(0, 0.02, size=N)          # noisy: some probabilities go negative
+    blocks = []
+    for a, b in zip(gate_ptr[:-1], gate_ptr[1:]):
+        B = rng.normal(size=(b - a + 2, b - a))
+        blocks.append(B.T @ B + 0.1 * np.eye(b - a))
+    import scipy.linalg as sla
+    Pd = sla.block_diag(*blocks)
+    full = po.full_project_gate_eigenvalues(lam, Pd, gate_ptr, precision=0.0)
+    split = po.split_project_gate_eigenvalues(lam, Pd, gate_ptr, precision=0.0)
+    assert np.any(full[1] < 0)
+    for x, y in zip(full, split):
+        assert np.allclose(x, y, atol=1e-10)
+    C = rng.normal(size=(N + 5, N))
+    P = Pd + 0.3 * C.T @ C                            # gates correlated
+    out, up, pp = po.full_project_gate_eigenvalues(lam, P, gate_ptr, precision=0.0)
+    for a, b in zip(gate_ptr[:-1], gate_ptr[1:]):     # every gate's distribution sums to one (only the
+                                                      # non-identity probabilities are constrained, as in the reference)
+        g = np.searchsorted(gate_ptr, a)
+        assert abs(pp[a + g:b + g + 1].sum() - 1.0) < 1e-12
+    dist = lambda x: float((x - lam) @ P @ (x - lam))  # noqa: E731
+    assert dist(out) <= dist(po.split_project_gate_eigenvalues(lam, P, gate_ptr, precision=0.0)[0]) * (1 + 1e-12)
+    # KKT in the space of unpadded probabilities: Q (y - v) >= 0, complementary to y
+    T = sla.block_diag(*[po.probs_transform_block(b - a) for a, b in zip(gate_ptr[:-1], gate_ptr[1:])])
+    strip = np.concatenate([np.arange(a + g + 1, b + g + 1) for g, (a, b) in enumerate(zip(gate_ptr[:-1], gate_ptr[1:]))])
+    y, v = pp[strip], up[strip]
+    grad = (T @ P @ T.T) @ (y - v)
+    s = np.abs((T @ P @ T.T) @ v).max()
+    assert np.all(y >= 0) and np.all(grad >= -1e-9 * s) and abs(y @ grad) <= 1e-9 * s
