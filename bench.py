@@ -386,6 +386,15 @@ def fit_leg(ctx, torch, dist, world, rank, steps, warmup, with_cpu):
             "gates": int(len(fd.gate_ptr) - 1),
             "what": "means, clipping, OLS + WLS + GLS fits, Euclidean projection of OLS, per-gate Mahalanobis projection of "
                     "WLS / GLS (precision slices from the device-resident Gram matrix, batched active-set QP), host vectors in / out"}
+        # the simultaneous projection of all gates (split = false, the reference's default below 5000 gate eigenvalues)
+        aces_b200.estimate_gate_noise_projected(dd, eig_p, cov_p, clip_warning=False, split=False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rf = aces_b200.estimate_gate_noise_projected(dd, eig_p, cov_p, clip_warning=False, split=False)
+        torch.cuda.synchronize()
+        out["estimate_gate_noise_projected"]["split_false_ms"] = 1e3 * (time.perf_counter() - t0)
+        out["estimate_gate_noise_projected"]["split_false_pivoting_steps_last"] = int(aces_b200.project.full_project_gate_eigenvalues.last_iterations)
+        out["estimate_gate_noise_projected"]["split_false_max_diff_vs_split"] = float(np.max(np.abs(rf["gls"] - r["gls"])))
     # calc_merit (src/merit.jl:925-1006): three estimator covariances, marginal / relative
     # transforms and nine spectra in one call; and the eigenvalue solver alone on the GLS covariance
     if fd.gate_types is not None and fd.gate_ptr is not None:

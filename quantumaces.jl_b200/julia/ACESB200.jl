@@ -38,8 +38,8 @@
 # sparse_covariance_inv_factor(covariance_log, lengths) (src/merit.jl:378-427) has no Design argument
 # and is NOT overwritten; its callers on the path are (estimate_gate_noise, calc_gls_covariance), and
 # a new method sparse_covariance_inv_factor(d::Design, covariance_log; clipped_indices) is added.
-# Everything else (Stim circuit strings, full_project_gate_eigenvalues, NoiseEstimate / Merit
-# bookkeeping, I/O) stays in QuantumACES.
+# Everything else (Stim circuit strings, NoiseEstimate / Merit bookkeeping, the NRMSE pdf, I/O) stays in
+# QuantumACES.
 module ACESB200
 
 using SparseArrays, LinearAlgebra, Random, Statistics
@@ -840,6 +840,52 @@ function split_project_gate_eigenvalues(dd::DeviceDesign, ls_type::Symbol, est_u
     return (est_gate_eigenvalues, unproj_probs, probs)
 end
 
+"""
+`full_project_gate_eigenvalues` (src/estimate.jl:532-573), the simultaneous projection of all gates (the
+reference's default below 5000 gate eigenvalues), for the estimator of the LAST `fit(dd, ls_type, ...)`: the
+precision matrix is rebuilt on the device from that fit's Gram matrix, transformed to the space of unpadded gate
+probabilities and the N-variable non-negative quadratic program solved exactly by block principal pivoting
+(aces_design_project_full) where the reference iterates SCS to `precision`.
+"""
+function full_project_gate_eigenvalues(dd::DeviceDesign, ls_type::Symbol, est_unproj_gate_eigenvalues::Vector{Float64},
+                                       gate_data; precision::Real = 1e-8)
+    kind = ls_type == :ols ? 0 : ls_type == :wls ? 1 : 2
+    ptr, idx = gate_groups(gate_data)
+    G = length(ptr) - 1
+    sizes = diff(ptr)
+    v = Vector{Float64}(undef, length(idx)); T = Vector{Float64}(undef, sum(sizes .^ 2))
+    qs = Vector{Vector{Float64}}(undef, G); Ws = Vector{Matrix{Float64}}(undef, G)
+    boff = 0
+    for g in 1:G
+        k = Int(sizes[g]); rng = (ptr[g] + 1):ptr[g + 1]
+        W = wht_block(k)
+        q = (W ./ (k + 1)) * vcat(1.0, est_unproj_gate_eigenvalues[idx[rng]])
+        Tg = W[2:end, 2:end] .- W[2:end, 1]
+        T[(boff + 1):(boff + k * k)] = vec(permutedims(Tg))        # row-major block
+        v[idx[rng]] = q[2:end]
+        qs[g] = q; Ws[g] = W
+        boff += k * k
+    end
+    y = Vector{Float64}(undef, length(idx)); its = Ref{Int32}(0)
+    GC.@preserve ptr idx est_unproj_gate_eigenvalues T v y begin
+        check(ccall((:aces_design_project_full, LIB[]), Int32,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Ptr{Int64}, Ptr{Int32}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Float64, Ptr{Float64}, Ptr{Int32}),
+            CTX[], dd.handle, Int32(kind), Int32(G), ptr, idx, Int32(1), est_unproj_gate_eigenvalues, T, v,
+            Float64(precision), y, its))
+    end
+    est_gate_eigenvalues = copy(est_unproj_gate_eigenvalues)
+    unproj_probs = Float64[]; probs = Float64[]
+    for g in 1:G
+        rng = (ptr[g] + 1):ptr[g + 1]
+        yg = y[idx[rng]]
+        pr = vcat(1.0 - sum(yg), yg)
+        est_gate_eigenvalues[idx[rng]] = (Ws[g] * pr)[2:end]
+        append!(unproj_probs, qs[g]); append!(probs, pr)
+    end
+    return (est_gate_eigenvalues, unproj_probs, probs)
+end
+
 # ---------------------------------------------------------------------------------------------
 # estimate_gate_noise (src/estimate.jl:691-941)
 # ---------------------------------------------------------------------------------------------
@@ -864,8 +910,8 @@ GLS only for a full-covariance design (:820) -- with the numeric work on the GPU
 `aces_design_fit` per estimator on the cached device-resident Design (covariance, log-covariance,
 clipping, block factors with the not-PD fallback, whitened least squares), the projections through
 aces_project_simplex / aces_design_precision_blocks / aces_project_nonnegative_batched.  With
-`split = false` the simultaneous projection of all gates stays on the reference's SCS path
-(full_project_gate_eigenvalues), fed with the sparse precision matrix the reference computes.
+`split = false` the simultaneous projection of all gates runs on the GPU as well (full_project_gate_eigenvalues:
+aces_design_project_full on the precision matrix of the fit's own Gram matrix).
 """
 function estimate_gate_noise(d::Design, est_eigenvalues_experiment_ensemble::Vector{Vector{Vector{Float64}}},
                              est_covariance_experiment_ensemble::Vector{Vector{Vector{Float64}}}, shot_budget::Int;
@@ -889,13 +935,7 @@ function estimate_gate_noise(d::Design, est_eigenvalues_experiment_ensemble::Vec
         elseif split
             split_project_gate_eigenvalues(dd, ls_type, unproj, gate_data; precision = precision)
         else
-            # simultaneous projection of all gates: the reference's SCS path with its own sparse precision matrix
-            design_matrix = convert(SparseMatrixCSC{Float64, Int}, d.matrix[clipped_indices, :])
-            cov_log = calc_covariance(dd, [mean.(e) for e in est_eigenvalues_experiment_ensemble],
-                [mean.(e) for e in est_covariance_experiment_ensemble]; weight_time = false, log_form = true)[clipped_indices, clipped_indices]
-            inv = ls_type == :gls ? Q.sparse_covariance_inv(cov_log, Q.get_clipped_mapping_lengths(dd.mapping_lengths, clipped_indices)) :
-                  sparse(Diagonal(diag(cov_log) .^ (-1)))
-            Q.full_project_gate_eigenvalues(unproj, Q.calc_precision_matrix(design_matrix, unproj, inv), gate_data; precision = precision)
+            full_project_gate_eigenvalues(dd, ls_type, unproj, gate_data; precision = precision)
         end
     end
     ols_unproj = fit(dd, :ols, est_eigenvalues, est_cov_eigenvalues; clipped_indices = kept)
