@@ -644,13 +644,12 @@ def main():
         if world > 1:
             stream.wait_event(free_ev[b])        # the collective that last read this buffer is done
         if world > 1 and xch is not None:
-            stream.wait_event(free_ev[1 - b])   # this rank's pull of the previous step: its slot parity is free again
+            stream.wait_event(free_ev[b])   # this rank's pull of step n - 2 (four slot sets rotate: see csrc/exchange.cuh)
         batches[b].launch()
         if world > 1 and xch is not None:
             # the push is fused into K1's prefix kernel (exchange attached to the context: the kernel that forms
             # the counts stores them into every rank's buffer over NVLink and releases the flags); the pull runs
-            # on the second stream (waits for every rank's flag); a slot parity is reused two steps later,
-            # after this rank's pull of the step in between
+            # on the second stream (waits for every rank's flag) and may finish behind the next step's kernel
             done_ev[b].record(stream)
             comm.wait_event(done_ev[b])
             xch.pull((reduced[b] if reduce_counts else gathered[b]).data_ptr(), reduce_counts, comm.cuda_stream)

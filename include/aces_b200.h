@@ -340,7 +340,8 @@ int32_t aces_design_fit_dist_solve(aces_ctx* ctx, aces_design* design);
  *                         separate push (the call must produce exactly n_counts counts, accumulate = 0)
  *   aces_exchange_status  ACES_E_CUDA if a pull gave up without a peer's flag (blocking: reads a flag); the wait is
  *                         bounded (about 10 s by default, aces_exchange_set_timeout) so that a dead peer cannot hang the GPU
- * Every rank must call push and pull once per step, in the same order.  Sums of integers: exact, identical on
+ * Every rank must call push and pull once per step, in the same order, and must not push exchange e before its own
+ * pull of exchange e - 2 has completed (four slot sets rotate; stream order or an event gives that for free).  Sums of integers: exact, identical on
  * every rank. */
 typedef struct aces_exchange aces_exchange;
 int64_t aces_exchange_bytes(int32_t world, int64_t n_counts);

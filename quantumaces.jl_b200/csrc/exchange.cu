@@ -6,17 +6,17 @@
 // size is latency bound (60 - 100 us on eight GPUs), which is as long as the parity kernel of a sharded
 // repetition itself.  Here every rank owns a buffer that all ranks of the node map (CUDA IPC):
 //
-//     slots [2][world][n]  int64   slot [e & 1][r] receives rank r's counts of exchange number e
-//     flags [2][world]     uint32  flag [e & 1][r] = e once those counts are complete
+//     slots [4][world][n]  int64   slot [e % 4][r] receives rank r's counts of exchange number e
+//     flags [4][world]     uint32  flag [e % 4][r] = e once those counts are complete
 //
 //   push (compute stream, right behind the prefix kernel): a grid-stride kernel stores the rank's counts
-//     into slot [e & 1][rank] of EVERY rank with 16-byte stores over NVLink; the last CTA to finish
-//     (ticket) fences at system scope and releases flag [e & 1][rank] = e on every rank.
+//     into slot [e % 4][rank] of EVERY rank with 16-byte stores over NVLink; the last CTA to finish
+//     (ticket) fences at system scope and releases flag [e % 4][rank] = e on every rank.
 //   pull (second stream): waits (acquire, system scope) until all `world` flags of this rank show e, then
 //     sums the slots (or copies them side by side) into the caller's output.
 //
-// The two parities alternate: rank A can only push exchange e + 2 after its pull of e + 1, which needed
-// B's flag of e + 1, which B released after (stream order) its own pull of e -- so nobody overwrites a slot
+// Four slot sets rotate.  The host lets a rank push exchange e only after its own pull of e - 2: that pull needed
+// every peer's push of e - 2, which (same rule) followed that peer's pull of e - 4 -- so nobody overwrites a slot
 // that is still being read.  Integer sums: the result is exact and identical on every rank.  A pull that
 // does not see its flags within its time-out (ten seconds by default) gives up and reports it (a dead peer must not hang the GPU).
 #include <algorithm>
@@ -40,7 +40,7 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 // counts of this rank -> slot [epoch & 1][rank] of every rank; then the flags
 __global__ void __launch_bounds__(256) exchange_push_kernel(uint8_t* const* base, int world, int rank, int64_t n, int64_t nc,
                                                             unsigned epoch, const int64_t* __restrict__ local, unsigned* ticket) {
-    const size_t slot = ((size_t)(epoch & 1u) * world + rank) * (size_t)n;  // even: 16-byte aligned
+    const size_t slot = ((size_t)(epoch % xchg::SLOTS) * world + rank) * (size_t)n;  // even: 16-byte aligned
     const int64_t n2 = nc / 2;
     const longlong2* src = reinterpret_cast<const longlong2*>(local);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) exchange_pull_kernel(uint8_t* mine, int w
     if (threadIdx.x == 0) ok = 1;
     __syncthreads();
     if ((int)threadIdx.x < world) {
-        const unsigned* f = reinterpret_cast<const unsigned*>(mine + flags_off(world, n)) + (size_t)(epoch & 1u) * world + threadIdx.x;
+        const unsigned* f = reinterpret_cast<const unsigned*>(mine + flags_off(world, n)) + (size_t)(epoch % xchg::SLOTS) * world + threadIdx.x;
         const long long t0 = clock64();
         while (ld_acquire_sys(f) != epoch) {
             __nanosleep(200);
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) exchange_pull_kernel(uint8_t* mine, int w
         if (threadIdx.x == 0 && blockIdx.x == 0) *err = 1;
         return;
     }
-    const int64_t* slots = reinterpret_cast<const int64_t*>(mine) + (size_t)(epoch & 1u) * world * (size_t)n;
+    const int64_t* slots = reinterpret_cast<const int64_t*>(mine) + (size_t)(epoch % xchg::SLOTS) * world * (size_t)n;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nc; i += (int64_t)gridDim.x * blockDim.x) {
         if (reduce) {
             int64_t s = 0;
@@ -100,7 +100,7 @@ extern "C" {
 int64_t aces_exchange_bytes(int32_t world, int64_t n_counts) {
     if (world < 1 || n_counts < 1) return 0;
     const int64_t n = (n_counts + 1) & ~(int64_t)1;
-    return (int64_t)(flags_off(world, n) + sizeof(unsigned) * 2 * (size_t)world + 256);
+    return (int64_t)(flags_off(world, n) + sizeof(unsigned) * xchg::SLOTS * (size_t)world + 256);
 }
 
 int32_t aces_peer_alloc(aces_ctx* ctx, int64_t bytes, void** dev_ptr, uint8_t* handle_out) {

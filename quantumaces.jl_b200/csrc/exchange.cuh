@@ -18,7 +18,11 @@ struct aces_exchange {
 };
 
 namespace xchg {
-__host__ __device__ inline size_t slots_bytes(int world, int64_t n) { return sizeof(int64_t) * 2 * (size_t)world * (size_t)n; }
+// Slot sets in rotation.  A rank pushes exchange e only after its own pull of e - 2 (so that the pull of e - 1 may
+// still be waiting for SMs behind the persistent parity kernel without holding up the next repetition); that pull
+// proves every peer has pushed e - 2, hence (same rule there) finished its pull of e - 4: slot e - 4 is free.
+constexpr unsigned SLOTS = 4;
+__host__ __device__ inline size_t slots_bytes(int world, int64_t n) { return sizeof(int64_t) * SLOTS * (size_t)world * (size_t)n; }
 __host__ __device__ inline size_t flags_off(int world, int64_t n) { return (slots_bytes(world, n) + 255) & ~(size_t)255; }
 
 // What a kernel needs to publish into slot [epoch & 1][rank] of every rank and to release the flags.
@@ -47,7 +51,7 @@ __device__ __forceinline__ void publish_flags(const PushArgs& a, unsigned n_ctas
         __threadfence_system();
         if ((int)threadIdx.x < a.world) {
             unsigned* f = reinterpret_cast<unsigned*>(a.base[threadIdx.x] + flags_off(a.world, a.n)) +
-                          (size_t)(a.epoch & 1u) * a.world + a.rank;
+                          (size_t)(a.epoch % SLOTS) * a.world + a.rank;
             st_release_sys(f, a.epoch);
         }
     }

@@ -158,7 +158,7 @@ __global__ void prefix_kernel(unsigned long long* __restrict__ seg,
                               long long* __restrict__ out, const int64_t* __restrict__ item_off,
                               const int32_t* __restrict__ item_E, int n_items, int K,
                               int accumulate, const xchg::PushArgs push) {
-    const size_t slot = push.base ? ((size_t)(push.epoch & 1u) * push.world + push.rank) * (size_t)push.n : 0;
+    const size_t slot = push.base ? ((size_t)(push.epoch % xchg::SLOTS) * push.world + push.rank) * (size_t)push.n : 0;
     for (int item = blockIdx.y; item < n_items; item += gridDim.y) {
         const int E = item_E[item];
         const int64_t off = item_off[item];
