@@ -68,6 +68,12 @@ FN(aces_design_fit); FN(aces_design_ls_covariance); FN(aces_design_precision_blo
 FN(aces_project_nonnegative_batched); FN(aces_last_rank_deficiency); FN(aces_synchronize);
 FN(aces_design_set_tuple_shard); FN(aces_design_fit_begin); FN(aces_design_fit_buffers); FN(aces_design_fit_solve);
 FN(aces_design_fit_refine_begin); FN(aces_design_fit_refine_end); FN(aces_design_fit_end);
+FN(aces_symmetric_eigenvalues); FN(aces_design_merit); FN(aces_design_merit_grad); FN(aces_design_project_full);
+FN(aces_design_fit_dist_begin); FN(aces_design_fit_dist_factor); FN(aces_design_fit_dist_update);
+FN(aces_design_fit_dist_buffers); FN(aces_design_fit_dist_solve);
+FN(aces_exchange_bytes); FN(aces_peer_alloc); FN(aces_peer_open); FN(aces_peer_close); FN(aces_peer_free);
+FN(aces_exchange_create); FN(aces_exchange_destroy); FN(aces_exchange_push); FN(aces_exchange_pull);
+FN(aces_exchange_attach); FN(aces_exchange_set_timeout); FN(aces_exchange_status);
 #define LOAD(name) do { *(void**)(&p_##name) = dlsym(h, #name); if (!p_##name) { fprintf(stderr, "missing symbol %s\n", #name); ++missing; } } while (0)
 
 #define CHECK(call) do { int32_t rc_ = (call); if (rc_ != 0) { fprintf(stderr, "%s -> %d: %s\n", #call, rc_, p_aces_last_error(ctx)); return 1; } } while (0)
@@ -85,6 +91,12 @@ int main(int argc, char** argv) {
     LOAD(aces_project_nonnegative_batched); LOAD(aces_last_rank_deficiency); LOAD(aces_synchronize);
     LOAD(aces_design_set_tuple_shard); LOAD(aces_design_fit_begin); LOAD(aces_design_fit_buffers); LOAD(aces_design_fit_solve);
     LOAD(aces_design_fit_refine_begin); LOAD(aces_design_fit_refine_end); LOAD(aces_design_fit_end);
+    LOAD(aces_symmetric_eigenvalues); LOAD(aces_design_merit); LOAD(aces_design_merit_grad); LOAD(aces_design_project_full);
+    LOAD(aces_design_fit_dist_begin); LOAD(aces_design_fit_dist_factor); LOAD(aces_design_fit_dist_update);
+    LOAD(aces_design_fit_dist_buffers); LOAD(aces_design_fit_dist_solve);
+    LOAD(aces_exchange_bytes); LOAD(aces_peer_alloc); LOAD(aces_peer_open); LOAD(aces_peer_close); LOAD(aces_peer_free);
+    LOAD(aces_exchange_create); LOAD(aces_exchange_destroy); LOAD(aces_exchange_push); LOAD(aces_exchange_pull);
+    LOAD(aces_exchange_attach); LOAD(aces_exchange_set_timeout); LOAD(aces_exchange_status);
     if (missing) return 1;
     if (!strcmp(argv[2], "--symbols")) {
         printf("ALL SYMBOLS RESOLVED (ABI version %d)\n", (int)p_aces_version());
@@ -224,6 +236,22 @@ int main(int argc, char** argv) {
         CHECK(p_aces_design_ls_covariance(ctx, dd, 2, F64("gate_eigenvalues"), F64("true_cov_log_nzval"), NULL, &tr, &trsq));
         const double e = fabs(tr - F64("tr_gls")[0]) / F64("tr_gls")[0];
         report("design_ls_covariance (GLS trace)", e <= 1e-9, e);
+    }
+    {   /* f2: eigvals(::Symmetric) -- the 1-D Laplacian has the spectrum 2 - 2 cos(k pi / (n + 1)); only the upper
+           triangle is read (Julia's Symmetric default), the lower one holds garbage here */
+        const int64_t n = 200;
+        double* a = (double*)malloc(sizeof(double) * (size_t)(n * n));
+        double* w = (double*)malloc(sizeof(double) * (size_t)n);
+        for (int64_t j = 0; j < n; ++j)
+            for (int64_t i = 0; i < n; ++i) a[i + j * n] = i > j ? 1e30 : (i == j ? 2.0 : (i + 1 == j ? -1.0 : 0.0));
+        CHECK(p_aces_symmetric_eigenvalues(ctx, n, a, n, w));
+        double worst = 0;
+        for (int64_t k = 0; k < n; ++k) {
+            const double want = 2.0 - 2.0 * cos((double)(k + 1) * 3.14159265358979323846 / (double)(n + 1));
+            if (fabs(w[k] - want) > worst) worst = fabs(w[k] - want);
+        }
+        report("symmetric_eigenvalues (1-D Laplacian, n = 200)", worst <= 4e-13, worst);
+        free(a); free(w);
     }
     free(g);
     CHECK(p_aces_design_destroy(ctx, dd));
